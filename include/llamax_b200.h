@@ -1,0 +1,136 @@
+/*
+ * llamax_b200 — C ABI of the B200-native (sm_100a) fine-tuning hot path of gau-nernst/llama-x.
+ *
+ * Every entry point replaces one Python/PyTorch seam of the reference (cited per function as file:line,
+ * relative to the reference repo).  Conventions:
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers owned by the caller
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it
+ *   - return 0 on success, a negative LLAMAX_ERR_* code otherwise; llamax_last_error() gives the text
+ *     (thread-local), so the Python seam can raise
+ *   - no allocation inside; scratch / workspace buffers are passed in by the caller
+ *   - bf16 tensors are row-major with an explicit leading dimension (elements) where noted
+ *   - thread-safe: forward (caller thread) and backward (autograd engine thread) may call concurrently
+ */
+#ifndef LLAMAX_B200_H_
+#define LLAMAX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLAMAX_B200_VERSION 100
+
+#define LLAMAX_OK 0
+#define LLAMAX_ERR_ARG (-1)  /* bad argument (shape / alignment / null) */
+#define LLAMAX_ERR_CUDA (-2) /* CUDA runtime or driver error */
+
+const char* llamax_last_error(void);
+int llamax_version(void);
+/* Select the device for subsequent calls of this thread (the library carries its own CUDA runtime). */
+int llamax_set_device(int device);
+/* 1 = single-CTA UMMA 128x256 tiles, 2 (default) = CTA pairs, UMMA 256x256 (tcgen05 cta_group::2). */
+int llamax_set_gemm_cta_group(int cg);
+
+/* Optional fused GEMM epilogue terms:  C = dequant(acc) + lora_scale * lora_h @ lora_b^T + resid
+ *   LoRA up-projection  : modelling/lora.py:43   (lora_h = x @ lora_a^T computed by the caller)
+ *   residual connection : modelling/llama.py:172-173 */
+typedef struct {
+  const void* lora_h; /* bf16 [M, lora_rank], row pitch ldh; NULL = no LoRA term */
+  int64_t ldh;
+  const void* lora_b; /* bf16 [N, lora_rank] contiguous */
+  int32_t lora_rank;  /* multiple of 4, <= 16 */
+  float lora_scale;   /* alpha / rank */
+  const void* resid;  /* bf16 [M, N], row pitch ldr; NULL = none */
+  int64_t ldr;
+} llamax_epilogue_t;
+
+/* ---- K3: int8 x int8 -> int32 GEMM with row/column-scale dequant --------------------------------
+ * Replaces torch.ops.torchao.int8_mm_dequant (subclasses/int8_mm.py:121-149, Triton kernel :50-118).
+ *   C[m,n] = bf16( (f32(sum_k A[m,k]*B[n,k]) * f32(a_scale[m])) * f32(b_scale[n]) )  [+ epilogue terms]
+ * A int8 [M,K] pitch lda; B int8 [N,K] pitch ldb (the reference passes weight.int_data.T, i.e. this
+ * matrix viewed as [K,N] with strides (1,K)); scales bf16 [M] / [N]; C bf16 [M,N] pitch ldc.
+ * The int32 accumulators are exact (|acc| <= K*127^2 < 2^31 for K <= 133143). */
+int llamax_int8_gemm_dequant(const void* A, int64_t lda, const void* B, int64_t ldb, const void* a_scale,
+                             const void* b_scale, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                             const llamax_epilogue_t* epi, void* stream);
+/* Same GEMM, raw int32 accumulators written to C (int32 [M,N]); parity/debug entry. */
+int llamax_int8_gemm_s32(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
+                         int64_t N, int64_t K, void* stream);
+
+/* ---- K4/K5/K6: bf16 x bf16 -> fp32 GEMM -----------------------------------------------------------
+ *   C[m,n] = bf16( acc[m,n] (* col_scale[n]) ) [+ epilogue terms],  acc = sum_k A[m,k]*B[n,k]
+ * weight-only forward   (subclasses/int8.py:118): B = bf16(int_data), col_scale = weight scale,
+ *                        round_before_scale = 1 reproduces the reference's two roundings
+ * grad_input            (subclasses/int8.py:127): B = (scale * int_data)^T from llamax_dequant_weight
+ * LoRA down / dh        (modelling/lora.py:43)  : N = rank (any multiple of 8) */
+int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
+                     int64_t N, int64_t K, const void* col_scale, int round_before_scale,
+                     const llamax_epilogue_t* epi, void* stream);
+
+/* De-quantise a frozen weight into a bf16 GEMM operand (scratch owned by the caller).
+ *   transpose = 0: out[n,k] = bf16(w8[n,k]) (* scale[n] if apply_scale)          out [N,K]
+ *   transpose = 1: out[k,n] = bf16(f32(w8[n,k]) * f32(scale[n])) (or unscaled)    out [K,N]
+ * Reference: weight.int_data.T.to(dtype) (int8.py:118), weight_i8.to(dtype) and grad*scale (int8.py:127). */
+int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t N, int64_t K, int transpose,
+                          int apply_scale, void* stream);
+
+/* ---- K2: row-wise int8 quantisation (subclasses/int8.py:10-16) ------------------------------------
+ *   s = amax(|x_f32|) / 127;  q = rint(x_f32 / max(s, 1e-12));  scale_out = bf16(s)        bit-exact */
+int llamax_rowquant_int8(const void* x, int64_t ldx, void* q8, void* scale_out, int64_t M, int64_t K,
+                         void* stream);
+
+/* ---- K1: RMSNorm (nn.RMSNorm(eps) at modelling/llama.py:158,160,182) ------------------------------
+ *   y = bf16( (x_f32 * rsqrt(mean(x_f32^2) + eps)) * w_f32 )
+ * optional outputs: rstd fp32 [M]; q8/qscale = rowquant_int8(y) fused (feeds the int8 GEMM). */
+int llamax_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, void* q8, void* qscale, int64_t M,
+                       int64_t D, float eps, void* stream);
+/* dx = [dres +] rmsnorm_backward(dy; x, w, rstd);  dw_partial fp32 [nparts, D] (summed by the caller or
+ * by llamax_reduce_partials).  nparts is chosen by the caller (<= 1024). */
+int llamax_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* rstd, const void* dres, void* dx,
+                       void* dw_partial, int32_t nparts, int64_t M, int64_t D, void* stream);
+/* out[d] (bf16) = sum_p partial[p, d] */
+int llamax_reduce_partials(const void* partial, void* out, int32_t nparts, int64_t D, void* stream);
+
+/* ---- K10: SwiGLU (modelling/llama.py:152) ---------------------------------------------------------
+ *   g = bf16( bf16(silu_f32(a)) * b );  optional g (bf16), q8/qscale = rowquant_int8(g) */
+int llamax_swiglu_fwd(const void* a, const void* b, int64_t ld, void* g, void* q8, void* qscale, int64_t M,
+                      int64_t F, void* stream);
+/* da, db from dg; optionally re-materialises g (needed for the LoRA-A gradient of w2). */
+int llamax_swiglu_bwd(const void* dg, const void* a, const void* b, int64_t ld, void* da, void* db, void* g,
+                      int64_t M, int64_t F, void* stream);
+
+/* ---- K7: RoPE (modelling/llama.py:63-73), interleaved pairs, fp32 math, in place ------------------
+ * x bf16 [B*S, ...] row pitch ld; rotates `nheads` heads of width D starting at column 0.
+ * rope fp32 [S, D/2, 2] (cos, sin) (build_rope, llama.py:54-60).  inverse = 1 applies the transpose
+ * (the backward of apply_rope). */
+int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_t S, int32_t nheads, int32_t D,
+                        int inverse, void* stream);
+
+/* ---- K8/K9: prefix-LM attention (modelling/llama.py:129-137) --------------------------------------
+ * mask(q, kv) = (kv < prefix_len) | (q >= kv);  prefix_len = 0 is plain causal.
+ * q bf16 [B,S,Hq,D] with row pitch ldq (elements between consecutive positions), k/v [B,S,Hkv,D] pitch
+ * ldk/ldv, o [B,S,Hq,D] pitch ldo, lse fp32 [B,Hq,S] (natural-log-sum-exp of scaled scores).
+ * GQA native: Hq % Hkv == 0, no K/V expansion.  D must be 128 (64 also supported).  scale = 1/sqrt(D). */
+int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                    int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
+                    int64_t prefix_len, float scale, void* stream);
+/* dq/dk/dv bf16 with pitches lddq/lddk/lddv; dq_accum fp32 workspace [B,S,Hq,D] (zeroed by the call);
+ * delta fp32 workspace [B,Hq,S]. */
+int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                    const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
+                    int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
+                    int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len, float scale,
+                    void* stream);
+
+/* ---- K6 backward: LoRA weight gradients (autograd of modelling/lora.py:43) ------------------------
+ *   out[p, r] (fp32, accumulated) += alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx, H bf16 [M,R]
+ * used for dB = scale * dY^T h and dA^T = x^T dh.  `out` must be zeroed by the caller before the first call. */
+int llamax_lora_wgrad(const void* X, int64_t ldx, const void* H, int64_t ldh, void* out, int64_t M, int64_t P,
+                      int32_t R, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLAMAX_B200_H_ */

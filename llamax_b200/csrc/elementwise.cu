@@ -1,0 +1,577 @@
+// HBM-bound passes of the decoder block: RMSNorm (+ fused row quantisation), row-wise int8 quantisation,
+// SwiGLU (+ fused row quantisation), RoPE, weight de-quantisation, and their backward passes.
+// All of them are one read + one write of each tensor with 16-byte vector accesses, fp32 math in registers
+// and warp-shuffle reductions; a row is held in registers between the reduction and the write so that no
+// element is read twice.
+#include "common.cuh"
+#include "host_utils.h"
+#include <algorithm>
+
+#include "llamax_b200.h"
+
+namespace lx {
+
+struct RowCfg {
+  int threads;
+  int nvec;
+  int V;  // 16-byte vectors (8 bf16) held per thread: 1, 2, 4 or 8
+};
+
+static inline bool row_cfg(int64_t D, RowCfg& c) {
+  if (D <= 0 || D % 8) return false;
+  const int nvec = (int)(D / 8);
+  int threads = std::min(512, ((nvec + 31) / 32) * 32);
+  int v = (nvec + threads - 1) / threads;
+  if (v > 8) return false;
+  c.V = v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : 8;
+  c.threads = threads;
+  c.nvec = nvec;
+  return true;
+}
+
+#define LX_DISPATCH_V(V_, ...)                    \
+  switch (V_) {                                   \
+    case 1: { constexpr int kV = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int kV = 2; __VA_ARGS__; } break; \
+    case 4: { constexpr int kV = 4; __VA_ARGS__; } break; \
+    default: { constexpr int kV = 8; __VA_ARGS__; } break; \
+  }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]);
+  u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]);
+  u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+template <bool kMax>
+__device__ __forceinline__ float block_reduce(float v, float* sm) {
+  v = kMax ? warp_max(v) : warp_sum(v);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // protect sm reuse between consecutive reductions
+  if (lane_id() == 0) sm[w] = v;
+  __syncthreads();
+  float r = kMax ? 0.f : 0.f;
+  if (kMax) {
+    r = sm[0];
+    for (int i = 1; i < nw; ++i) r = fmaxf(r, sm[i]);
+  } else {
+    for (int i = 0; i < nw; ++i) r += sm[i];
+  }
+  return r;
+}
+
+// quantise the (bf16-rounded) row held in registers; reference: subclasses/int8.py:10-16
+template <int kMaxV>
+__device__ __forceinline__ void quant_row_store(const float (&v)[kMaxV][8], int nvec, float amax, int8_t* qrow,
+                                                __nv_bfloat16* scale_out) {
+  const float s = amax / 127.0f;
+  const float sc = fmaxf(s, 1e-12f);
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+    if (idx < nvec) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q0 = (int)rintf(v[j][e] / sc);
+        const int q1 = (int)rintf(v[j][4 + e] / sc);
+        lo |= (uint32_t)(q0 & 0xff) << (8 * e);
+        hi |= (uint32_t)(q1 & 0xff) << (8 * e);
+      }
+      *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) = make_uint2(lo, hi);
+    }
+  }
+  if (threadIdx.x == 0) *scale_out = __float2bfloat16_rn(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm forward (+ optional fused row quantisation)
+// ------------------------------------------------------------------------------------------------
+template <int kMaxV>
+__global__ void rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                   __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
+                                   int8_t* __restrict__ q8, __nv_bfloat16* __restrict__ qscale, int D, int nvec,
+                                   float eps) {
+  __shared__ float sm[32];
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* xr = x + row * D;
+  float v[kMaxV][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+    if (idx < nvec) {
+      unpack8(ldg_nc_v4(xr + (int64_t)idx * 8), v[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(v[j][e], v[j][e], ss);
+    }
+  }
+  ss = block_reduce<false>(ss, sm);
+  const float rstd = 1.0f / sqrtf(ss / (float)D + eps);
+  if (threadIdx.x == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+    if (idx < nvec) {
+      float wf[8];
+      unpack8(*reinterpret_cast<const uint4*>(w + (int64_t)idx * 8), wf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[j][e] = round_bf16((v[j][e] * rstd) * wf[e]);
+        amax = fmaxf(amax, fabsf(v[j][e]));
+      }
+      if (y != nullptr) *reinterpret_cast<uint4*>(y + row * D + (int64_t)idx * 8) = pack8(v[j]);
+    }
+  }
+  if (q8 != nullptr) {
+    amax = block_reduce<true>(amax, sm);
+    quant_row_store(v, nvec, amax, q8 + row * D, qscale + row);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-wise int8 quantisation alone
+// ------------------------------------------------------------------------------------------------
+template <int kMaxV>
+__global__ void rowquant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int8_t* __restrict__ q8,
+                                __nv_bfloat16* __restrict__ qscale, int K, int nvec) {
+  __shared__ float sm[32];
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* xr = x + row * ldx;
+  float v[kMaxV][8];
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+    if (idx < nvec) {
+      unpack8(ldg_nc_v4(xr + (int64_t)idx * 8), v[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[j][e]));
+    }
+  }
+  amax = block_reduce<true>(amax, sm);
+  quant_row_store(v, nvec, amax, q8 + row * K, qscale + row);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SwiGLU forward: g = bf16( bf16(silu(a)) * b ), optional fused row quantisation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float a) { return a / (1.0f + expf(-a)); }
+
+template <int kMaxV>
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                  int64_t ld, __nv_bfloat16* __restrict__ g, int8_t* __restrict__ q8,
+                                  __nv_bfloat16* __restrict__ qscale, int F, int nvec) {
+  __shared__ float sm[32];
+  const int64_t row = blockIdx.x;
+  float v[kMaxV][8];
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+    if (idx < nvec) {
+      float af[8], bf[8];
+      unpack8(ldg_nc_v4(a + row * ld + (int64_t)idx * 8), af);
+      unpack8(ldg_nc_v4(b + row * ld + (int64_t)idx * 8), bf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[j][e] = round_bf16(round_bf16(silu_f(af[e])) * bf[e]);
+        amax = fmaxf(amax, fabsf(v[j][e]));
+      }
+      if (g != nullptr) *reinterpret_cast<uint4*>(g + row * F + (int64_t)idx * 8) = pack8(v[j]);
+    }
+  }
+  if (q8 != nullptr) {
+    amax = block_reduce<true>(amax, sm);
+    quant_row_store(v, nvec, amax, q8 + row * F, qscale + row);
+  }
+}
+
+// SwiGLU backward (grid-stride over 16-byte vectors)
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __restrict__ a,
+                                  const __nv_bfloat16* __restrict__ b, int64_t ld, __nv_bfloat16* __restrict__ da,
+                                  __nv_bfloat16* __restrict__ db, __nv_bfloat16* __restrict__ g, int64_t M,
+                                  int nvec) {
+  const int64_t total = M * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nvec;
+    const int c = (int)(i - row * nvec) * 8;
+    float af[8], bf[8], dgf[8], oa[8], ob[8], og[8];
+    unpack8(ldg_nc_v4(a + row * ld + c), af);
+    unpack8(ldg_nc_v4(b + row * ld + c), bf);
+    unpack8(ldg_nc_v4(dg + row * (int64_t)nvec * 8 + c), dgf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sig = 1.0f / (1.0f + expf(-af[e]));
+      const float sl = round_bf16(af[e] * sig);
+      ob[e] = dgf[e] * sl;
+      const float dsl = round_bf16(dgf[e] * bf[e]);
+      oa[e] = dsl * (sig * (1.0f + af[e] * (1.0f - sig)));
+      og[e] = sl * bf[e];
+    }
+    *reinterpret_cast<uint4*>(da + row * ld + c) = pack8(oa);
+    *reinterpret_cast<uint4*>(db + row * ld + c) = pack8(ob);
+    if (g != nullptr) *reinterpret_cast<uint4*>(g + row * (int64_t)nvec * 8 + c) = pack8(og);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm backward.  Persistent over rows: CTA p handles rows p, p+nparts, ...; dw partial sums stay in
+// registers and are written once per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int kMaxV>
+__global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                   const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
+                                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+                                   float* __restrict__ dw_partial, int64_t M, int D, int nvec) {
+  __shared__ float sm[32];
+  float wf[kMaxV][8], dwacc[kMaxV][8];
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dwacc[j][e] = 0.f;
+    if (idx < nvec) unpack8(*reinterpret_cast<const uint4*>(w + (int64_t)idx * 8), wf[j]);
+  }
+  for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+    const float rs = rstd[row];
+    float xh[kMaxV][8], gy[kMaxV][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float dyf[8];
+        unpack8(ldg_nc_v4(x + row * D + (int64_t)idx * 8), xh[j]);
+        unpack8(ldg_nc_v4(dy + row * D + (int64_t)idx * 8), dyf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[j][e] *= rs;
+          dwacc[j][e] = fmaf(dyf[e], xh[j][e], dwacc[j][e]);
+          gy[j][e] = dyf[e] * wf[j][e];
+          dot = fmaf(gy[j][e], xh[j][e], dot);
+        }
+      }
+    }
+    dot = block_reduce<false>(dot, sm) / (float)D;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float o[8];
+        if (dres != nullptr) unpack8(ldg_nc_v4(dres + row * D + (int64_t)idx * 8), o);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] += rs * (gy[j][e] - xh[j][e] * dot);
+        *reinterpret_cast<uint4*>(dx + row * D + (int64_t)idx * 8) = pack8(o);
+      }
+    }
+  }
+  if (dw_partial != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float* dst = dw_partial + (int64_t)blockIdx.x * D + (int64_t)idx * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(dwacc[j][0], dwacc[j][1], dwacc[j][2], dwacc[j][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(dwacc[j][4], dwacc[j][5], dwacc[j][6], dwacc[j][7]);
+      }
+    }
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int nparts,
+                                       int64_t D) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * D + d];
+  out[d] = __float2bfloat16_rn(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE in place, interleaved pairs (modelling/llama.py:63-73).  One thread = 8 bf16 = 4 pairs.
+// ------------------------------------------------------------------------------------------------
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ rope, int64_t rows,
+                            int S, int nheads, int D, int inverse) {
+  const int vec_per_row = nheads * D / 8;
+  const int64_t total = rows * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int c = (int)(i - row * vec_per_row) * 8;  // column within the row
+    const int s = (int)(row % S);
+    const int d = c % D;                             // offset inside the head, multiple of 8
+    __nv_bfloat16* p = x + row * ld + c;
+    float f[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), f);
+    const float4* cs = reinterpret_cast<const float4*>(rope + ((int64_t)s * (D / 2) + d / 2) * 2);
+    const float4 cs0 = cs[0], cs1 = cs[1];  // (c0,s0,c1,s1), (c2,s2,c3,s3)
+    const float cc[4] = {cs0.x, cs0.z, cs1.x, cs1.z};
+    float sn[4] = {cs0.y, cs0.w, cs1.y, cs1.w};
+    if (inverse) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sn[e] = -sn[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // out0 = x0*c - x1*s ; out1 = x1*c + x0*s   (each product rounded as in the fp32 reference)
+      o[2 * e] = __fsub_rn(__fmul_rn(f[2 * e], cc[e]), __fmul_rn(f[2 * e + 1], sn[e]));
+      o[2 * e + 1] = __fadd_rn(__fmul_rn(f[2 * e + 1], cc[e]), __fmul_rn(f[2 * e], sn[e]));
+    }
+    *reinterpret_cast<uint4*>(p) = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight de-quantisation into a bf16 GEMM operand
+// ------------------------------------------------------------------------------------------------
+__global__ void dequant_plain_kernel(const int8_t* __restrict__ w8, const __nv_bfloat16* __restrict__ scale,
+                                     __nv_bfloat16* __restrict__ out, int64_t N, int64_t K, int apply_scale) {
+  const int64_t nvec = N * K / 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = i * 16;
+    const float s = apply_scale ? __bfloat162float(scale[e0 / K]) : 1.0f;
+    const uint4 u = ldg_nc_v4(w8 + e0);
+    const uint32_t words[4] = {u.x, u.y, u.z, u.w};
+    float f[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f[q * 4 + e] = (float)(int8_t)((words[q] >> (8 * e)) & 0xff) * s;
+    float lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { lo[e] = f[e]; hi[e] = f[8 + e]; }
+    *reinterpret_cast<uint4*>(out + e0) = pack8(lo);
+    *reinterpret_cast<uint4*>(out + e0 + 8) = pack8(hi);
+  }
+}
+
+// out[k, n] = bf16(w8[n, k] * scale[n]); 64 x 64 tiles through shared memory
+__global__ void __launch_bounds__(256)
+dequant_transpose_kernel(const int8_t* __restrict__ w8, const __nv_bfloat16* __restrict__ scale,
+                         __nv_bfloat16* __restrict__ out, int N, int K, int apply_scale) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];
+  const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  {
+    const int n = threadIdx.x >> 2, kc = (threadIdx.x & 3) * 16;
+    if (n0 + n < N && k0 + kc < K) {
+      const float s = apply_scale ? __bfloat162float(scale[n0 + n]) : 1.0f;
+      const uint4 u = ldg_nc_v4(w8 + (int64_t)(n0 + n) * K + k0 + kc);
+      const uint32_t words[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          tile[kc + q * 4 + e][n] = __float2bfloat16_rn((float)(int8_t)((words[q] >> (8 * e)) & 0xff) * s);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) tile[kc + e][n] = __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int t = threadIdx.x + it * 256;
+    const int k = t >> 3, nc = (t & 7) * 8;
+    if (k0 + k < K && n0 + nc < N)
+      *reinterpret_cast<uint4*>(out + (int64_t)(k0 + k) * N + n0 + nc) = *reinterpret_cast<const uint4*>(&tile[k][nc]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LoRA weight gradient: out[p, r] += alpha * sum_m X[m, p] * H[m, r]   (R <= 16, fp32 atomics over M-chunks)
+// CTA = 128 columns of X (one 16-byte... 2 columns per thread on 64 threads x 2) x a chunk of rows.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128)
+lora_wgrad_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const __nv_bfloat16* __restrict__ H, int64_t ldh,
+                  float* __restrict__ out, int64_t M, int64_t P, int rows_per_cta, float alpha) {
+  // each thread owns 2 adjacent columns p, p+1 of X; block covers 256 columns
+  constexpr int kChunk = 32;
+  __shared__ __align__(16) float sh[kChunk][R];
+  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x * 2;
+  const int64_t m_begin = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t m_end = min(M, m_begin + rows_per_cta);
+  float acc0[R], acc1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc0[r] = acc1[r] = 0.f;
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += kChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk * R; i += 128) {
+      const int mm = i / R, r = i - mm * R;
+      sh[mm][r] = (m0 + mm < m_end) ? __bfloat162float(H[(m0 + mm) * ldh + r]) : 0.f;
+    }
+    __syncthreads();
+    if (p < P) {
+      uint32_t xv[kChunk];
+#pragma unroll
+      for (int mm = 0; mm < kChunk; ++mm)
+        xv[mm] = (m0 + mm < m_end) ? *reinterpret_cast<const uint32_t*>(X + (m0 + mm) * ldx + p) : 0u;
+#pragma unroll
+      for (int mm = 0; mm < kChunk; ++mm) {
+        const float x0 = bf16_lo(xv[mm]), x1 = bf16_hi(xv[mm]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc0[r] = fmaf(x0, sh[mm][r], acc0[r]);
+          acc1[r] = fmaf(x1, sh[mm][r], acc1[r]);
+        }
+      }
+    }
+  }
+  if (p < P) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      atomicAdd(out + p * R + r, alpha * acc0[r]);
+      atomicAdd(out + (p + 1) * R + r, alpha * acc1[r]);
+    }
+  }
+}
+
+}  // namespace lx
+
+using namespace lx;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int llamax_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, void* q8, void* qscale, int64_t M,
+                       int64_t D, float eps, void* stream) {
+  RowCfg c;
+  if (!x || !w) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: null input");
+  if ((q8 == nullptr) != (qscale == nullptr)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: q8 and qscale go together");
+  if (!row_cfg(D, c)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: D must be a multiple of 8 and <= 65536");
+  if (M == 0) return 0;
+  LX_DISPATCH_V(c.V, rmsnorm_fwd_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, (int)D, c.nvec, eps));
+  LX_CHECK_LAUNCH("rmsnorm_fwd");
+  return 0;
+}
+
+int llamax_rowquant_int8(const void* x, int64_t ldx, void* q8, void* scale_out, int64_t M, int64_t K,
+                         void* stream) {
+  RowCfg c;
+  if (!x || !q8 || !scale_out) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: null pointer");
+  if (!row_cfg(K, c) || ldx % 8) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: K and ldx must be multiples of 8");
+  if (M == 0) return 0;
+  LX_DISPATCH_V(c.V, rowquant_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, (int8_t*)q8, (bf16*)scale_out, (int)K, c.nvec));
+  LX_CHECK_LAUNCH("rowquant_int8");
+  return 0;
+}
+
+int llamax_swiglu_fwd(const void* a, const void* b, int64_t ld, void* g, void* q8, void* qscale, int64_t M,
+                      int64_t F, void* stream) {
+  RowCfg c;
+  if (!a || !b) return set_error(LLAMAX_ERR_ARG, "swiglu_fwd: null input");
+  if ((q8 == nullptr) != (qscale == nullptr)) return set_error(LLAMAX_ERR_ARG, "swiglu_fwd: q8 and qscale go together");
+  if (!row_cfg(F, c) || ld % 8) return set_error(LLAMAX_ERR_ARG, "swiglu_fwd: F and ld must be multiples of 8");
+  if (M == 0) return 0;
+  LX_DISPATCH_V(c.V, swiglu_fwd_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a, (const bf16*)b, ld, (bf16*)g, (int8_t*)q8, (bf16*)qscale, (int)F, c.nvec));
+  LX_CHECK_LAUNCH("swiglu_fwd");
+  return 0;
+}
+
+int llamax_swiglu_bwd(const void* dg, const void* a, const void* b, int64_t ld, void* da, void* db, void* g,
+                      int64_t M, int64_t F, void* stream) {
+  if (!dg || !a || !b || !da || !db) return set_error(LLAMAX_ERR_ARG, "swiglu_bwd: null pointer");
+  if (F % 8 || ld % 8) return set_error(LLAMAX_ERR_ARG, "swiglu_bwd: F and ld must be multiples of 8");
+  if (M == 0) return 0;
+  const int64_t total = M * (F / 8);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  swiglu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dg, (const bf16*)a, (const bf16*)b, ld,
+                                                              (bf16*)da, (bf16*)db, (bf16*)g, M, (int)(F / 8));
+  LX_CHECK_LAUNCH("swiglu_bwd");
+  return 0;
+}
+
+int llamax_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* rstd, const void* dres, void* dx,
+                       void* dw_partial, int32_t nparts, int64_t M, int64_t D, void* stream) {
+  RowCfg c;
+  if (!dy || !x || !w || !rstd || !dx) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: null pointer");
+  if (!row_cfg(D, c)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: D must be a multiple of 8 and <= 65536");
+  if (nparts <= 0 || nparts > 4096) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: nparts out of range");
+  LX_DISPATCH_V(c.V, rmsnorm_bwd_kernel<kV><<<nparts, c.threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)w, (const float*)rstd, (const bf16*)dres, (bf16*)dx,
+      (float*)dw_partial, M, (int)D, c.nvec));
+  LX_CHECK_LAUNCH("rmsnorm_bwd");
+  return 0;
+}
+
+int llamax_reduce_partials(const void* partial, void* out, int32_t nparts, int64_t D, void* stream) {
+  if (!partial || !out) return set_error(LLAMAX_ERR_ARG, "reduce_partials: null pointer");
+  reduce_partials_kernel<<<(unsigned)((D + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)partial,
+                                                                                        (bf16*)out, nparts, D);
+  LX_CHECK_LAUNCH("reduce_partials");
+  return 0;
+}
+
+int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_t S, int32_t nheads, int32_t D,
+                        int inverse, void* stream) {
+  if (!x || !rope) return set_error(LLAMAX_ERR_ARG, "rope: null pointer");
+  if (D % 8 || ld % 8) return set_error(LLAMAX_ERR_ARG, "rope: D and ld must be multiples of 8");
+  const int64_t total = B * S * (nheads * D / 8);
+  if (total == 0) return 0;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  rope_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)x, ld, (const float*)rope, B * S, (int)S, nheads, D,
+                                                        inverse);
+  LX_CHECK_LAUNCH("rope");
+  return 0;
+}
+
+int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t N, int64_t K, int transpose,
+                          int apply_scale, void* stream) {
+  if (!w8 || !out || (apply_scale && !scale)) return set_error(LLAMAX_ERR_ARG, "dequant_weight: null pointer");
+  if (K % 16 || N % 8) return set_error(LLAMAX_ERR_ARG, "dequant_weight: K % 16 and N % 8 required");
+  if (!transpose) {
+    const int64_t nvec = N * K / 16;
+    const int blocks = (int)std::min<int64_t>((nvec + 255) / 256, (int64_t)sm_count() * 16);
+    dequant_plain_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const int8_t*)w8, (const bf16*)scale, (bf16*)out,
+                                                                   N, K, apply_scale);
+  } else {
+    dim3 grid((unsigned)((K + 63) / 64), (unsigned)((N + 63) / 64));
+    dequant_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const int8_t*)w8, (const bf16*)scale,
+                                                                     (bf16*)out, (int)N, (int)K, apply_scale);
+  }
+  LX_CHECK_LAUNCH("dequant_weight");
+  return 0;
+}
+
+int llamax_lora_wgrad(const void* X, int64_t ldx, const void* H, int64_t ldh, void* out, int64_t M, int64_t P,
+                      int32_t R, float alpha, void* stream) {
+  if (!X || !H || !out) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: null pointer");
+  if (P % 2 || ldx % 2) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: P and ldx must be even");
+  if (M == 0) return 0;
+  const int col_blocks = (int)((P + 255) / 256);
+  int row_blocks = std::max(1, (sm_count() * 8) / col_blocks);
+  int rows_per_cta = (int)((M + row_blocks - 1) / row_blocks);
+  rows_per_cta = ((rows_per_cta + 31) / 32) * 32;
+  row_blocks = (int)((M + rows_per_cta - 1) / rows_per_cta);
+  dim3 grid(col_blocks, row_blocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 8)
+    lora_wgrad_kernel<8><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
+  else if (R == 16)
+    lora_wgrad_kernel<16><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
+  else if (R == 4)
+    lora_wgrad_kernel<4><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
+  else
+    return set_error(LLAMAX_ERR_ARG, "lora_wgrad: rank must be 4, 8 or 16");
+  LX_CHECK_LAUNCH("lora_wgrad");
+  return 0;
+}
+
+}  // extern "C"

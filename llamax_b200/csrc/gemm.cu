@@ -1,0 +1,428 @@
+// tcgen05 GEMM for the frozen-base projections of the Llama decoder block.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )       A, B both contraction-contiguous ("K-major")
+//
+// Two instantiations of one warp-specialised persistent kernel:
+//   kInt8 = true  : int8 x int8 -> int32 (tcgen05.mma.kind::i8), epilogue (f32(acc) * a_scale[m]) * b_scale[n]
+//                   replaces the Triton kernel of the reference (subclasses/int8_mm.py:50-118)
+//   kInt8 = false : bf16 x bf16 -> fp32 (tcgen05.mma.kind::f16); weight-only forward (subclasses/int8.py:118)
+//                   and grad_input (subclasses/int8.py:127) run on it with a de-quantised weight operand.
+// Fused epilogue options: LoRA up-projection (modelling/lora.py:43), residual add (modelling/llama.py:172-173).
+//
+// Structure (per CTA, 256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-7 = epilogue (TMEM -> registers -> global). smem ring of kStages {A,B} tiles with 128B swizzle,
+// two TMEM accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// CG = 2 runs CTA pairs (cta_group::2, UMMA 256 x 256): each CTA loads its 128 rows of A and half of B.
+#include "common.cuh"
+#include "host_utils.h"
+#include "llamax_b200.h"
+
+namespace lx {
+
+constexpr int kBM = 128;          // rows of A per CTA
+constexpr int kBN = 256;          // accumulator columns per tile
+constexpr int kBKBytes = 128;     // one 128B swizzle row of K per stage
+constexpr int kMaxLoraRank = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kGroupM = 8;        // m-tiles per scheduling group (L2 reuse of the B panel)
+
+struct GemmParams {
+  int M, N, K;
+  void* C;
+  int64_t ldc;
+  const __nv_bfloat16* row_scale;
+  const __nv_bfloat16* col_scale;
+  const __nv_bfloat16* lora_h;
+  int64_t ldh;
+  const __nv_bfloat16* lora_b;
+  int lora_rank;
+  float lora_scale;
+  const __nv_bfloat16* resid;
+  int64_t ldr;
+  int flags;  // 1: dump raw accumulator (int32 / fp32) to C; 2: round to bf16 before the column scale
+};
+
+template <int CG>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBKBytes;               // 16 KB
+  static constexpr int kBBytes = (kBN / CG) * kBKBytes;        // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = CG == 1 ? 4 : 6;
+  static constexpr int kAuxBytes = kBN * 4 + kBN * kMaxLoraRank * 4;  // col scale + lora_b (fp32)
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kStages * kStageBytes + kAuxBytes + kBarBytes + 1024;  // + align slack
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& tm, int& tn) {
+  const int per_group = kGroupM * num_n;
+  const int g = tile / per_group;
+  const int first_m = g * kGroupM;
+  const int gsize = min(num_m - first_m, kGroupM);
+  const int r = tile - g * per_group;
+  tm = first_m + r % gsize;
+  tn = r / gsize;
+}
+
+template <bool kInt8, int CG>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using S = GemmSmem<CG>;
+  constexpr int kStages = S::kStages;
+  constexpr int kElemPerRow = kInt8 ? 128 : 64;  // K elements per 128 B
+  constexpr int kTileM = kBM * CG;               // rows per cluster tile
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* s_colscale = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
+  float* s_lorab = s_colscale + kBN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lorab + kBN * kMaxLoraRank);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+  const bool is_leader = cta_rank == 0;
+
+  const int num_m = (p.M + kTileM - 1) / kTileM;
+  const int num_n = (p.N + kBN - 1) / kBN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + kElemPerRow - 1) / kElemPerRow;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_slot, 512);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_addr = CG == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int tm, tn;
+        tile_coords(tile, num_m, num_n, tm, tn);
+        const int row_a = tm * kTileM + cta_rank * kBM;
+        const int row_b = tn * kBN + cta_rank * (kBN / CG);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if constexpr (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kElemPerRow, row_a);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kElemPerRow, row_b);
+          } else {
+            if (is_leader) mbar_expect_tx(&full_bar[stage], S::kStageBytes * 2);
+            const uint32_t bar_addr = full_addr + stage * 8;
+            tma_load_2d_cg2(sa, &tmA, bar_addr, kb * kElemPerRow, row_a);
+            tma_load_2d_cg2(sb, &tmB, bar_addr, kb * kElemPerRow, row_b);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = kInt8 ? make_idesc(2, 1, kTileM, kBN) : make_idesc(1, 1, kTileM, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_tile = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
+        const int as = local_tile & 1;
+        const uint32_t aphase = (local_tile >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBKBytes / 32; ++k) {
+            // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_ss<kInt8, CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage], 3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 1) umma_commit(&tfull_bar[as]); else umma_commit_cg2(&tfull_bar[as], 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int ew = warp - 4;                 // TMEM lanes [32*ew, 32*ew+32)
+    const int et = threadIdx.x - 128;        // 0..127
+    const int R = p.lora_rank;
+    int local_tile = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
+      int tm, tn;
+      tile_coords(tile, num_m, num_n, tm, tn);
+      const int as = local_tile & 1;
+      const uint32_t aphase = (local_tile >> 1) & 1;
+      const int row = tm * kTileM + cta_rank * kBM + ew * 32 + lane_id();
+      const int col0 = tn * kBN;
+      const bool row_ok = row < p.M;
+
+      // stage per-column data for this tile (previous tile's readers are done: barrier below)
+      named_bar_sync(1, 128);
+      if (p.col_scale != nullptr) {
+        for (int i = et; i < kBN; i += 128)
+          s_colscale[i] = (col0 + i < p.N) ? __bfloat162float(p.col_scale[col0 + i]) : 0.f;
+      }
+      if (R > 0) {
+        for (int i = et; i < kBN * R; i += 128) {
+          const int n = i / R, r = i - n * R;
+          s_lorab[n * kMaxLoraRank + r] =
+              (col0 + n < p.N) ? __bfloat162float(p.lora_b[(int64_t)(col0 + n) * R + r]) * p.lora_scale : 0.f;
+        }
+      }
+      named_bar_sync(1, 128);
+
+      float rs = 1.f;
+      if (p.row_scale != nullptr && row_ok) rs = __bfloat162float(p.row_scale[row]);
+      float h[kMaxLoraRank];
+#pragma unroll
+      for (int r = 0; r < kMaxLoraRank; ++r)
+        h[r] = (r < R && row_ok) ? __bfloat162float(p.lora_h[(int64_t)row * p.ldh + r]) : 0.f;
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kBN;
+
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        const int col = col0 + c * 32;
+        if (col >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_wait_ld();
+        if (p.flags & 1) {
+          if (row_ok) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(p.C) + (int64_t)row * p.ldc + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (col + j < p.N) stg_v4(dst + j, make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          }
+          continue;
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = kInt8 ? static_cast<float>(static_cast<int32_t>(v[j])) : __uint_as_float(v[j]);
+          if constexpr (kInt8) {
+            a = (a * rs) * s_colscale[c * 32 + j];  // reference order: int8_mm.py:114
+          } else {
+            if (p.col_scale != nullptr) {
+              if (p.flags & 2) a = round_bf16(a);   // reference: bf16(x @ W^T) * s  (int8.py:118)
+              a = a * s_colscale[c * 32 + j];
+            }
+          }
+          f[j] = a;
+        }
+        if (R > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4* lb = reinterpret_cast<const float4*>(&s_lorab[(c * 32 + j) * kMaxLoraRank]);
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < kMaxLoraRank / 4; ++q) {
+              if (q * 4 < R) {
+                const float4 b4 = lb[q];
+                acc = fmaf(h[q * 4 + 0], b4.x, acc);
+                acc = fmaf(h[q * 4 + 1], b4.y, acc);
+                acc = fmaf(h[q * 4 + 2], b4.z, acc);
+                acc = fmaf(h[q * 4 + 3], b4.w, acc);
+              }
+            }
+            f[j] += acc;
+          }
+        }
+        if (row_ok) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col;
+          const __nv_bfloat16* rsd = p.resid ? p.resid + (int64_t)row * p.ldr + col : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col + j < p.N) {
+              if (rsd != nullptr) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(rsd + j);
+                f[j + 0] += bf16_lo(r4.x); f[j + 1] += bf16_hi(r4.x);
+                f[j + 2] += bf16_lo(r4.y); f[j + 3] += bf16_hi(r4.y);
+                f[j + 4] += bf16_lo(r4.z); f[j + 5] += bf16_hi(r4.z);
+                f[j + 6] += bf16_lo(r4.w); f[j + 7] += bf16_hi(r4.w);
+              }
+              uint4 o;
+              o.x = pack_bf16(f[j + 0], f[j + 1]);
+              o.y = pack_bf16(f[j + 2], f[j + 3]);
+              o.z = pack_bf16(f[j + 4], f[j + 5]);
+              o.w = pack_bf16(f[j + 6], f[j + 7]);
+              stg_v4(dst + j, o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tempty_bar[as]); else mbar_arrive_cluster(&tempty_bar[as], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <bool kInt8, int CG>
+static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
+                       cudaStream_t stream) {
+  using S = GemmSmem<CG>;
+  const int esz = kInt8 ? 1 : 2;
+  const int elem_per_row = kBKBytes / esz;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return set_error(LLAMAX_ERR_ARG, "gemm: empty problem");
+  if ((lda * esz) % 16 || (ldb * esz) % 16 || (reinterpret_cast<uintptr_t>(A) % 16) ||
+      (reinterpret_cast<uintptr_t>(B) % 16))
+    return set_error(LLAMAX_ERR_ARG, "gemm: operand base / leading dimension must be 16-byte aligned");
+  if (p.N % 8 || p.ldc % 8 || (reinterpret_cast<uintptr_t>(p.C) % 16))
+    return set_error(LLAMAX_ERR_ARG, "gemm: N and ldc must be multiples of 8, C 16-byte aligned");
+  if (p.resid && (p.ldr % 8 || reinterpret_cast<uintptr_t>(p.resid) % 16))
+    return set_error(LLAMAX_ERR_ARG, "gemm: residual must be 16-byte aligned with ldr % 8 == 0");
+  if (p.lora_rank < 0 || p.lora_rank > kMaxLoraRank || (p.lora_rank % 4))
+    return set_error(LLAMAX_ERR_ARG, "gemm: lora rank must be a multiple of 4 in [0, 16]");
+
+  CUtensorMap tmA, tmB;
+  const CUtensorMapDataType dt = kInt8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  int rc = make_tmap_2d(&tmA, dt, esz, A, p.K, p.M, lda, elem_per_row, kBM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, dt, esz, B, p.K, p.N, ldb, elem_per_row, kBN / CG);
+  if (rc) return rc;
+
+  auto kern = gemm_kernel<kInt8, CG>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const int num_sms = sm_count();
+  const int num_tiles = ((p.M + kBM * CG - 1) / (kBM * CG)) * ((p.N + kBN - 1) / kBN);
+  int clusters = num_sms / CG;
+  if (clusters > num_tiles) clusters = num_tiles;
+
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  if (e != cudaSuccess) return set_cuda_error(e, "gemm: launch");
+  return 0;
+}
+
+static int g_gemm_cg = 2;  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group
+
+}  // namespace lx
+
+using namespace lx;
+
+extern "C" {
+
+int llamax_set_gemm_cta_group(int cg) {
+  if (cg != 1 && cg != 2) return set_error(LLAMAX_ERR_ARG, "cta group must be 1 or 2");
+  g_gemm_cg = cg;
+  return 0;
+}
+
+static void fill_epilogue(GemmParams& p, const llamax_epilogue_t* epi) {
+  if (epi == nullptr) return;
+  p.lora_h = static_cast<const __nv_bfloat16*>(epi->lora_h);
+  p.ldh = epi->ldh;
+  p.lora_b = static_cast<const __nv_bfloat16*>(epi->lora_b);
+  p.lora_rank = epi->lora_h ? epi->lora_rank : 0;
+  p.lora_scale = epi->lora_scale;
+  p.resid = static_cast<const __nv_bfloat16*>(epi->resid);
+  p.ldr = epi->ldr;
+}
+
+int llamax_int8_gemm_dequant(const void* A, int64_t lda, const void* B, int64_t ldb, const void* a_scale,
+                             const void* b_scale, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                             const llamax_epilogue_t* epi, void* stream) {
+  if (!A || !B || !C || !a_scale || !b_scale) return set_error(LLAMAX_ERR_ARG, "int8_gemm_dequant: null pointer");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.C = C; p.ldc = ldc;
+  p.row_scale = static_cast<const __nv_bfloat16*>(a_scale);
+  p.col_scale = static_cast<const __nv_bfloat16*>(b_scale);
+  fill_epilogue(p, epi);
+  return g_gemm_cg == 2 ? launch_gemm<true, 2>(A, lda, B, ldb, p, (cudaStream_t)stream)
+                        : launch_gemm<true, 1>(A, lda, B, ldb, p, (cudaStream_t)stream);
+}
+
+int llamax_int8_gemm_s32(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
+                         int64_t N, int64_t K, void* stream) {
+  if (!A || !B || !C) return set_error(LLAMAX_ERR_ARG, "int8_gemm_s32: null pointer");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.C = C; p.ldc = ldc;
+  p.flags = 1;
+  return g_gemm_cg == 2 ? launch_gemm<true, 2>(A, lda, B, ldb, p, (cudaStream_t)stream)
+                        : launch_gemm<true, 1>(A, lda, B, ldb, p, (cudaStream_t)stream);
+}
+
+int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
+                     int64_t N, int64_t K, const void* col_scale, int round_before_scale,
+                     const llamax_epilogue_t* epi, void* stream) {
+  if (!A || !B || !C) return set_error(LLAMAX_ERR_ARG, "bf16_gemm: null pointer");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.C = C; p.ldc = ldc;
+  p.col_scale = static_cast<const __nv_bfloat16*>(col_scale);
+  p.flags = round_before_scale ? 2 : 0;
+  fill_epilogue(p, epi);
+  return g_gemm_cg == 2 ? launch_gemm<false, 2>(A, lda, B, ldb, p, (cudaStream_t)stream)
+                        : launch_gemm<false, 1>(A, lda, B, ldb, p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and TMA descriptor encoding.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lx {
+
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+int sm_count();
+
+// rank-2 tensor map: dims {inner, outer}, row pitch ld (elements), box {box_inner, box_outer}, 128B swizzle.
+int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* ptr, int64_t inner, int64_t outer,
+                 int64_t ld, int box_inner, int box_outer);
+
+// rank-4 tensor map over a [d3, d2, d1, d0] view (d0 contiguous) with element strides s1, s2, s3.
+int make_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* ptr, const int64_t dims[4],
+                 const int64_t strides[3], const int box[4]);
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace lx
+
+#define LX_CHECK_LAUNCH(where)                                  \
+  do {                                                          \
+    cudaError_t e__ = cudaGetLastError();                       \
+    if (e__ != cudaSuccess) return lx::set_cuda_error(e__, where); \
+  } while (0)

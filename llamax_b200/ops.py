@@ -1,0 +1,271 @@
+"""Tensor-level wrappers around the C ABI (include/llamax_b200.h).
+
+PyTorch is used here only for device memory and streams: every function takes CUDA tensors, passes raw pointers,
+sizes and the current stream to the library, and returns freshly allocated outputs. Nothing in this file computes
+on the host and nothing falls back to PyTorch math.
+"""
+
+import ctypes
+import threading
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import Epilogue, check
+
+_tls = threading.local()
+
+
+def _prep(t: Tensor):
+    """Select the tensor's device for this thread, return (lib, stream handle)."""
+    if not t.is_cuda:
+        raise _lib.LlamaxError("llamax_b200 ops need CUDA tensors: there is no CPU implementation of this path")
+    lib = _lib.load()
+    dev = t.device.index
+    if getattr(_tls, "dev", None) != dev:
+        check(lib.llamax_set_device(dev), "llamax_set_device")
+        _tls.dev = dev
+    return lib, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _rows(t: Tensor) -> Tensor:
+    """View as 2-D [rows, last] with unit inner stride."""
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def make_epilogue(lora_h=None, lora_b=None, lora_scale=1.0, resid=None):
+    if lora_h is None and resid is None:
+        return None, ()
+    ep = Epilogue()
+    keep = []
+    if lora_h is not None:
+        lora_h = _rows(lora_h)
+        lora_b = lora_b.contiguous()
+        assert lora_h.dtype is torch.bfloat16 and lora_b.dtype is torch.bfloat16
+        assert lora_b.shape[1] == lora_h.shape[1]
+        ep.lora_h, ep.ldh = lora_h.data_ptr(), lora_h.stride(0)
+        ep.lora_b, ep.lora_rank, ep.lora_scale = lora_b.data_ptr(), lora_h.shape[1], float(lora_scale)
+        keep += [lora_h, lora_b]
+    if resid is not None:
+        resid = _rows(resid)
+        assert resid.dtype is torch.bfloat16
+        ep.resid, ep.ldr = resid.data_ptr(), resid.stride(0)
+        keep.append(resid)
+    return ep, keep
+
+
+def set_gemm_cta_group(cg: int):
+    check(_lib.load().llamax_set_gemm_cta_group(cg), "llamax_set_gemm_cta_group")
+
+
+# ---------------------------------------------------------------------------------------------- GEMMs
+def int8_gemm_dequant(A: Tensor, W: Tensor, a_scale: Tensor, w_scale: Tensor, *, out: Tensor | None = None,
+                      lora_h=None, lora_b=None, lora_scale=1.0, resid=None) -> Tensor:
+    """C = dequant(A[M,K] @ W[N,K]^T) (+ LoRA + residual). A, W int8; scales bf16."""
+    lib, st = _prep(A)
+    assert A.dtype is torch.int8 and W.dtype is torch.int8 and A.dim() == 2 and W.dim() == 2
+    assert A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] == W.shape[1]
+    M, K = A.shape
+    N = W.shape[0]
+    a_scale = a_scale.reshape(-1).contiguous()
+    w_scale = w_scale.reshape(-1).contiguous()
+    assert a_scale.dtype is torch.bfloat16 and w_scale.dtype is torch.bfloat16
+    assert a_scale.numel() == M and w_scale.numel() == N
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
+    assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
+    check(lib.llamax_int8_gemm_dequant(_p(A), A.stride(0), _p(W), W.stride(0), _p(a_scale), _p(w_scale), _p(out),
+                                       out.stride(0), M, N, K, ctypes.byref(ep) if ep is not None else None, st),
+          "llamax_int8_gemm_dequant")
+    return out
+
+
+def int8_gemm_s32(A: Tensor, W: Tensor) -> Tensor:
+    """Raw int32 accumulators of A[M,K] @ W[N,K]^T (parity/debug)."""
+    lib, st = _prep(A)
+    assert A.dtype is torch.int8 and W.dtype is torch.int8 and A.stride(1) == 1 and W.stride(1) == 1
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, device=A.device, dtype=torch.int32)
+    check(lib.llamax_int8_gemm_s32(_p(A), A.stride(0), _p(W), W.stride(0), _p(out), out.stride(0), M, N, K, st),
+          "llamax_int8_gemm_s32")
+    return out
+
+
+def bf16_gemm(A: Tensor, B: Tensor, *, col_scale: Tensor | None = None, round_before_scale: bool = False,
+              out: Tensor | None = None, lora_h=None, lora_b=None, lora_scale=1.0, resid=None) -> Tensor:
+    """C = A[M,K] @ B[N,K]^T (* col_scale) (+ LoRA + residual); bf16 in/out, fp32 accumulate."""
+    lib, st = _prep(A)
+    assert A.dtype is torch.bfloat16 and B.dtype is torch.bfloat16 and A.dim() == 2 and B.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
+    M, K = A.shape
+    N = B.shape[0]
+    if col_scale is not None:
+        col_scale = col_scale.reshape(-1).contiguous()
+        assert col_scale.dtype is torch.bfloat16 and col_scale.numel() == N
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
+    assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
+    check(lib.llamax_bf16_gemm(_p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), M, N, K,
+                               _p(col_scale), int(round_before_scale),
+                               ctypes.byref(ep) if ep is not None else None, st),
+          "llamax_bf16_gemm")
+    return out
+
+
+def dequant_weight(w8: Tensor, scale: Tensor | None, *, transpose: bool, apply_scale: bool,
+                   out: Tensor | None = None) -> Tensor:
+    lib, st = _prep(w8)
+    assert w8.dtype is torch.int8 and w8.is_contiguous()
+    N, K = w8.shape
+    shape = (K, N) if transpose else (N, K)
+    if out is None:
+        out = torch.empty(shape, device=w8.device, dtype=torch.bfloat16)
+    else:
+        out = out.view(-1)[: N * K].view(shape)
+    if apply_scale:
+        scale = scale.contiguous()
+        assert scale.dtype is torch.bfloat16
+    check(lib.llamax_dequant_weight(_p(w8), _p(scale) if apply_scale else None, _p(out), N, K, int(transpose),
+                                    int(apply_scale), st), "llamax_dequant_weight")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ elementwise
+def rowquant_int8(x: Tensor):
+    """quantize_int8_rowwise (subclasses/int8.py:10-16): returns (int8 [M,K], bf16 scale [M])."""
+    x2 = _rows(x)
+    lib, st = _prep(x2)
+    assert x2.dtype is torch.bfloat16
+    M, K = x2.shape
+    q = torch.empty(M, K, device=x.device, dtype=torch.int8)
+    s = torch.empty(M, device=x.device, dtype=torch.bfloat16)
+    check(lib.llamax_rowquant_int8(_p(x2), x2.stride(0), _p(q), _p(s), M, K, st), "llamax_rowquant_int8")
+    return q, s
+
+
+def rmsnorm_fwd(x: Tensor, w: Tensor, eps: float, *, quant: bool = False, want_y: bool = True):
+    """Returns (y bf16 | None, rstd fp32 [M], q8 | None, qscale | None)."""
+    x2 = _rows(x)
+    assert x2.is_contiguous() and x2.dtype is torch.bfloat16 and w.dtype is torch.bfloat16 and w.is_contiguous()
+    lib, st = _prep(x2)
+    M, D = x2.shape
+    y = torch.empty_like(x2) if want_y else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    q8 = torch.empty(M, D, device=x.device, dtype=torch.int8) if quant else None
+    qs = torch.empty(M, device=x.device, dtype=torch.bfloat16) if quant else None
+    check(lib.llamax_rmsnorm_fwd(_p(x2), _p(w), _p(y), _p(rstd), _p(q8), _p(qs), M, D, float(eps), st),
+          "llamax_rmsnorm_fwd")
+    return y, rstd, q8, qs
+
+
+def rmsnorm_bwd(dy: Tensor, x: Tensor, w: Tensor, rstd: Tensor, dres: Tensor | None, *, want_dw: bool = True):
+    """Returns (dx bf16 [M,D], dw bf16 [D] | None). dx = dres + d(rmsnorm)/dx."""
+    dy2, x2 = _rows(dy), _rows(x)
+    assert dy2.is_contiguous() and x2.is_contiguous()
+    lib, st = _prep(x2)
+    M, D = x2.shape
+    dres2 = None
+    if dres is not None:
+        dres2 = _rows(dres)
+        assert dres2.is_contiguous()
+    dx = torch.empty_like(x2)
+    nparts = max(1, min(int(M), 4 * torch.cuda.get_device_properties(x.device).multi_processor_count))
+    partial = torch.empty(nparts, D, device=x.device, dtype=torch.float32) if want_dw else None
+    check(lib.llamax_rmsnorm_bwd(_p(dy2), _p(x2), _p(w), _p(rstd), _p(dres2), _p(dx), _p(partial), nparts, M, D, st),
+          "llamax_rmsnorm_bwd")
+    dw = None
+    if want_dw:
+        dw = torch.empty(D, device=x.device, dtype=torch.bfloat16)
+        check(lib.llamax_reduce_partials(_p(partial), _p(dw), nparts, D, st), "llamax_reduce_partials")
+    return dx, dw
+
+
+def swiglu_fwd(a: Tensor, b: Tensor, *, quant: bool = False, want_g: bool = True):
+    """g = bf16(bf16(silu(a)) * b). a, b: [M,F] views with a common row pitch. Returns (g, q8, qscale)."""
+    lib, st = _prep(a)
+    assert a.dtype is torch.bfloat16 and a.shape == b.shape and a.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1 and a.stride(0) == b.stride(0)
+    M, F = a.shape
+    g = torch.empty(M, F, device=a.device, dtype=torch.bfloat16) if want_g else None
+    q8 = torch.empty(M, F, device=a.device, dtype=torch.int8) if quant else None
+    qs = torch.empty(M, device=a.device, dtype=torch.bfloat16) if quant else None
+    check(lib.llamax_swiglu_fwd(_p(a), _p(b), a.stride(0), _p(g), _p(q8), _p(qs), M, F, st), "llamax_swiglu_fwd")
+    return g, q8, qs
+
+
+def swiglu_bwd(dg: Tensor, a: Tensor, b: Tensor, *, want_g: bool = False, out_ab: Tensor | None = None):
+    """Returns (da, db, g | None). If out_ab [M, 2F] is given, da/db are its two column halves."""
+    lib, st = _prep(a)
+    assert dg.is_contiguous() and a.stride(1) == 1 and a.stride(0) == b.stride(0)
+    M, F = a.shape
+    if out_ab is None:
+        out_ab = torch.empty(M, 2 * F, device=a.device, dtype=torch.bfloat16)
+    da, db = out_ab[:, :F], out_ab[:, F:]
+    assert da.stride(0) == a.stride(0), "da/db use the same row pitch as a/b"
+    g = torch.empty(M, F, device=a.device, dtype=torch.bfloat16) if want_g else None
+    check(lib.llamax_swiglu_bwd(_p(dg), _p(a), _p(b), a.stride(0), _p(da), _p(db), _p(g), M, F, st),
+          "llamax_swiglu_bwd")
+    return da, db, g
+
+
+def rope_(x: Tensor, rope: Tensor, B: int, S: int, nheads: int, D: int, *, inverse: bool = False) -> Tensor:
+    """In-place interleaved-pair RoPE on the first nheads*D columns of x [B*S, ld]."""
+    lib, st = _prep(x)
+    assert x.dtype is torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == B * S
+    assert rope.dtype is torch.float32 and rope.is_contiguous() and rope.shape[0] >= S and rope.shape[1] == D // 2
+    check(lib.llamax_rope_inplace(_p(x), x.stride(0), _p(rope), B, S, nheads, D, int(inverse), st),
+          "llamax_rope_inplace")
+    return x
+
+
+def lora_wgrad(X: Tensor, H: Tensor, alpha: float = 1.0) -> Tensor:
+    """out[P,R] (fp32) = alpha * X[M,P]^T @ H[M,R]."""
+    lib, st = _prep(X)
+    assert X.dtype is torch.bfloat16 and H.dtype is torch.bfloat16 and X.stride(1) == 1 and H.stride(1) == 1
+    M, Pn = X.shape
+    R = H.shape[1]
+    out = torch.zeros(Pn, R, device=X.device, dtype=torch.float32)
+    check(lib.llamax_lora_wgrad(_p(X), X.stride(0), _p(H), H.stride(0), _p(out), M, Pn, R, float(alpha), st),
+          "llamax_lora_wgrad")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, prefix_len: int,
+             scale: float | None = None):
+    """q [B*S, Hq*D] / k, v [B*S, Hkv*D] row views (unit inner stride). Returns (o [B*S, Hq*D], lse [B,Hq,S])."""
+    lib, st = _prep(q)
+    for t in (q, k, v):
+        assert t.dtype is torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == B * S
+    o = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
+    scale = float(scale) if scale is not None else D ** -0.5
+    check(lib.llamax_attn_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+                              _p(lse), B, S, Hq, Hkv, D, int(prefix_len), scale, st), "llamax_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, scale=None):
+    """Writes dq/dk/dv (row views like q/k/v)."""
+    lib, st = _prep(q)
+    dout = _rows(dout)
+    dq_accum = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.float32)
+    delta = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
+    scale = float(scale) if scale is not None else D ** -0.5
+    check(lib.llamax_attn_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+                              _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
+                              _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len),
+                              scale, st), "llamax_attn_bwd")
+    return dq, dk, dv
