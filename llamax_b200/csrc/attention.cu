@@ -1,14 +1,740 @@
-// placeholder until the prefix-LM attention kernels land (replaced in the next commit)
+// Prefix-LM flash attention for the Llama decoder block (modelling/llama.py:129-137), forward and backward,
+// on tcgen05 tensor cores with TMEM accumulators and TMA-fed 128B-swizzled shared-memory tiles.
+//
+//   mask(q, kv) = (kv < P) | (q >= kv)      P = prefix_len (bidirectional prefix, causal suffix; P = 0: causal)
+//
+// GQA native: the 4 (Hq/Hkv) query heads of a group read the same K/V tiles straight from the [B,S,Hkv,D]
+// projection output (no repeat_interleave, no transposes: TMA walks the strided layout). The mask is applied at
+// tile granularity: tiles that are fully masked are never visited, fully visible tiles skip the element test.
+//
+// Forward  : CTA = (128 query rows, 1 query head). warp0 TMA, warp1 MMA issue, warps4-7 softmax (thread = row).
+//            S = Q K^T double-buffered in TMEM, P staged through smem (bf16), O accumulated in TMEM with lazy
+//            rescaling; exp2-domain online softmax, LSE saved in natural log.
+// Backward : CTA = (128 kv rows, 1 kv head), loops over the group's query heads x 64-row query tiles.
+//            S^T = K Q^T and dP^T = V dO^T in TMEM (thread = kv row), P^T / dS^T staged through smem,
+//            dV += P^T dO and dK += dS^T Q accumulate in TMEM for the whole CTA lifetime,
+//            dQ^T = K^T dS^T is reduced into an fp32 buffer with coalesced red.global.add.
+#include "common.cuh"
 #include "host_utils.h"
 #include "llamax_b200.h"
+
+namespace lx {
+
+constexpr int kHD = 128;                    // head dim
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+struct AttnFwdParams {
+  __nv_bfloat16* o;
+  int64_t ldo;
+  float* lse;
+  int B, S, Hq, Hkv, P;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+namespace fwd {
+constexpr int kTile = 128;
+constexpr int kTileBytes = kTile * kHD * 2;       // 32 KB: two 16 KB boxes of [128 rows x 128 B]
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + kTileBytes;         // 2 stages
+constexpr int kOffV = kOffK + 2 * kTileBytes;     // 2 stages
+constexpr int kOffP = kOffV + 2 * kTileBytes;
+constexpr int kOffBar = kOffP + kTileBytes;
+constexpr int kNumBars = 1 + 4 + 4 + 4 + 2;       // q_full, k full/empty[2], v full/empty[2], s full/empty[2], p_full, pv_done
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+}  // namespace fwd
+
+__global__ void __launch_bounds__(256, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  using namespace fwd;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 11;
+  uint64_t* p_full = bars + 13;
+  uint64_t* pv_done = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int qt = gridDim.x - 1 - blockIdx.x;  // heaviest (largest q) tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.Hq / p.Hkv);
+  const int q0 = qt * kTile;
+  const int kv_end = min(p.S, max(p.P, q0 + kTile));
+  const int n_kv = (kv_end + kTile - 1) / kTile;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
+  const uint32_t tmem_O = tmem_base + 256;  // 128 columns
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (elect_one()) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_4d(smem + kOffQ, &tmQ, q_full, 0, h, q0, b);
+      tma_load_4d(smem + kOffQ + kTileBytes / 2, &tmQ, q_full, 64, h, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], kTileBytes);
+        uint8_t* sk = smem + kOffK + st * kTileBytes;
+        tma_load_4d(sk, &tmK, &k_full[st], 0, hk, j * kTile, b);
+        tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, j * kTile, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], kTileBytes);
+        uint8_t* sv = smem + kOffV + st * kTileBytes;
+        tma_load_4d(sv, &tmV, &v_full[st], 0, hk, j * kTile, b);
+        tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, j * kTile, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
+      const uint32_t sQ = smem_u32(smem + kOffQ);
+      const uint32_t sP = smem_u32(smem + kOffP);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t sK = smem_u32(smem + kOffK + st * kTileBytes);
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_smem_desc_sw128(sQ + dh * 16384 + ks * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(sK + dh * 16384 + ks * 32, 16, 1024);
+            umma_ss<false, 1>(tmem_S + st * 128, ad, bd, idesc_s, (dh | ks) != 0);
+          }
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_s(j + 1);
+        const int st = j & 1;
+        mbar_wait(&v_full[st], (j >> 1) & 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t sV = smem_u32(smem + kOffV + st * kTileBytes);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_smem_desc_sw128(sP + kb * 16384 + ks * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(sV + (kb * 64 + ks * 16) * 128, 16384, 1024);
+            umma_ss<false, 1>(tmem_O, ad, bd, idesc_pv, (j | kb | ks) != 0);
+          }
+        umma_commit(pv_done);
+        umma_commit(&v_empty[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------ softmax / correction / epilogue ------------------------------------
+    const int r = threadIdx.x - 128;  // row in tile == TMEM lane
+    const int ew = warp - 4;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const int q = q0 + r;
+    const uint32_t sP = smem_u32(smem + kOffP);
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const int kv0 = j * kTile;
+      // tile needs the element test unless every (q, kv) pair is visible and in range
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0));
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tS = tmem_S + st * 128 + lane_off;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c * 32, v);
+        tmem_wait_ld();
+        if (full_tile) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kv = kv0 + c * 32 + i;
+            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q));
+            mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
+          }
+        }
+      }
+      const float m_tile = mx * p.scale_log2;
+      float alpha = 1.f;
+      if (m_tile > m_used + 8.f) {  // lazy rescale: only when the running max grows by more than 2^8
+        alpha = ex2(m_used - m_tile);
+        m_used = m_tile;
+      }
+      // pass 2: probabilities
+      uint32_t preg[64];
+      float rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used));
+          float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used));
+          if (!full_tile) {
+            const int kv = kv0 + c * 32 + i;
+            if (!((kv < p.S) && ((kv < p.P) || (kv <= q)))) p0 = 0.f;
+            if (!((kv + 1 < p.S) && ((kv + 1 < p.P) || (kv + 1 <= q)))) p1 = 0.f;
+          }
+          rowsum += p0 + p1;
+          preg[c * 16 + i / 2] = pack_bf16(p0, p1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&s_empty[st]);
+      l = l * alpha + rowsum;
+
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // O stable, P buffer free
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_O + lane_off + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(tmem_O + lane_off + c * 32, v);
+          }
+          tmem_wait_st();
+        }
+      }
+      // P (bf16) -> smem, K-major 128B-swizzled: [kv-half][row][8 x 16 B chunks, chunk ^= row & 7]
+#pragma unroll
+      for (int c16 = 0; c16 < 16; ++c16) {
+        const int kb = c16 >> 3, c = c16 & 7;
+        const uint32_t addr = sP + kb * 16384 + r * 128 + ((c ^ (r & 7)) << 4);
+        sts_v4(addr, preg[c16 * 4], preg[c16 * 4 + 1], preg[c16 * 4 + 2], preg[c16 * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(p_full);
+    }
+    // epilogue
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool row_ok = q < p.S;
+    __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * kHD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_O + lane_off + c * 32, v);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 o4;
+          o4.x = pack_bf16(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+          o4.y = pack_bf16(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
+          o4.z = pack_bf16(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
+          o4.w = pack_bf16(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
+          stg_v4(orow + c * 32 + i, o4);
+        }
+      }
+    }
+    if (row_ok) p.lse[((int64_t)b * p.Hq + h) * p.S + q] = (m_used + log2f(l)) * kLn2;
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+struct AttnBwdParams {
+  const float* lse;    // [B, Hq, S]
+  const float* delta;  // [B, Hq, S]
+  float* dq_accum;     // [B*S, Hq*D] fp32
+  __nv_bfloat16* dk;
+  int64_t lddk;
+  __nv_bfloat16* dv;
+  int64_t lddv;
+  int B, S, Hq, Hkv, P;
+  float scale, scale_log2;
+};
+
+namespace bwd {
+constexpr int kKV = 128;                          // kv rows per CTA
+constexpr int kQ = 64;                            // query rows per step
+constexpr int kKVBytes = kKV * kHD * 2;           // 32 KB (2 boxes of [128 x 128 B])
+constexpr int kQBytes = kQ * kHD * 2;             // 16 KB (2 boxes of [64 x 128 B])
+constexpr int kPBytes = kKV * kQ * 2;             // 16 KB ([128 kv rows] x [64 q] bf16)
+constexpr int kOffK = 0;
+constexpr int kOffV = kOffK + kKVBytes;
+constexpr int kOffQ = kOffV + kKVBytes;           // 2 stages
+constexpr int kOffdO = kOffQ + 2 * kQBytes;       // 2 stages
+constexpr int kOffP = kOffdO + 2 * kQBytes;
+constexpr int kOffdS = kOffP + kPBytes;
+constexpr int kOffStat = kOffdS + kPBytes;        // lse2 / delta: 2 stages x 2 x 64 floats
+constexpr int kOffBar = kOffStat + 2 * 2 * kQ * 4;
+constexpr int kNumBars = 1 + 4 + 1 + 1 + 1 + 1 + 1;  // kv_full, qdo full/empty[2], sdp_full, pds_full, dq_full, dq_empty, acc_done
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+// TMEM columns
+constexpr int kColdV = 0, kColdK = 128, kColS = 256, kColdP = 320, kColdQ = 384;
+}  // namespace bwd
+
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const AttnBwdParams p) {
+  using namespace bwd;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_stat = reinterpret_cast<float*>(smem + kOffStat);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;
+  uint64_t* qdo_empty = bars + 3;
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_empty = bars + 8;
+  uint64_t* acc_done = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int kv0 = jt * kKV;
+  const int G = p.Hq / p.Hkv;
+  const int nq_tiles = (p.S + kQ - 1) / kQ;
+  const int i_start = (kv0 < p.P) ? 0 : kv0 / kQ;  // first query tile that sees this kv tile
+  const int steps_per_head = nq_tiles - i_start;
+  const int n_steps = G * steps_per_head;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * kKVBytes);
+      tma_load_4d(smem + kOffK, &tmK, kv_full, 0, hk, kv0, b);
+      tma_load_4d(smem + kOffK + kKVBytes / 2, &tmK, kv_full, 64, hk, kv0, b);
+      tma_load_4d(smem + kOffV, &tmV, kv_full, 0, hk, kv0, b);
+      tma_load_4d(smem + kOffV + kKVBytes / 2, &tmV, kv_full, 64, hk, kv0, b);
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s & 1;
+        const int hq = hk * G + s / steps_per_head;
+        const int q0 = (i_start + s % steps_per_head) * kQ;
+        mbar_wait(&qdo_empty[st], ((s >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * kQBytes);
+        uint8_t* sq = smem + kOffQ + st * kQBytes;
+        uint8_t* sdo = smem + kOffdO + st * kQBytes;
+        tma_load_4d(sq, &tmQ, &qdo_full[st], 0, hq, q0, b);
+        tma_load_4d(sq + kQBytes / 2, &tmQ, &qdo_full[st], 64, hq, q0, b);
+        tma_load_4d(sdo, &tmdO, &qdo_full[st], 0, hq, q0, b);
+        tma_load_4d(sdo + kQBytes / 2, &tmdO, &qdo_full[st], 64, hq, q0, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc_st = make_idesc(1, 1, 128, 64, 0, 0);    // S^T, dP^T : [kv x d] . [q x d]^T
+      constexpr uint32_t idesc_acc = make_idesc(1, 1, 128, 128, 0, 1);  // dV, dK    : [kv x q] . [q x d]   (B MN-major)
+      constexpr uint32_t idesc_dq = make_idesc(1, 1, 128, 64, 1, 1);    // dQ^T      : [kv x d]^T . [kv x q] (A, B MN-major)
+      const uint32_t sK = smem_u32(smem + kOffK), sV = smem_u32(smem + kOffV);
+      const uint32_t sP = smem_u32(smem + kOffP), sdS = smem_u32(smem + kOffdS);
+      mbar_wait(kv_full, 0);
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s & 1;
+        const uint32_t sQ = smem_u32(smem + kOffQ + st * kQBytes);
+        const uint32_t sdO = smem_u32(smem + kOffdO + st * kQBytes);
+        mbar_wait(&qdo_full[st], (s >> 1) & 1);
+        tc_fence_after();
+        // S^T = K Q^T, dP^T = V dO^T   (softmax threads finished reading the previous ones before pds_full)
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ak = make_smem_desc_sw128(sK + dh * 16384 + ks * 32, 16, 1024);
+            const uint64_t bq = make_smem_desc_sw128(sQ + dh * 8192 + ks * 32, 16, 1024);
+            umma_ss<false, 1>(tmem_base + kColS, ak, bq, idesc_st, (dh | ks) != 0);
+          }
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t av = make_smem_desc_sw128(sV + dh * 16384 + ks * 32, 16, 1024);
+            const uint64_t bo = make_smem_desc_sw128(sdO + dh * 8192 + ks * 32, 16, 1024);
+            umma_ss<false, 1>(tmem_base + kColdP, av, bo, idesc_st, (dh | ks) != 0);
+          }
+        umma_commit(sdp_full);
+        // wait for P^T / dS^T in smem, and for the previous dQ^T to be drained
+        mbar_wait(pds_full, s & 1);
+        mbar_wait(dq_empty, (s & 1) ^ 1);
+        tc_fence_after();
+        // dV += P^T dO ; dK += dS^T Q        (K dim = q, 64 -> 4 steps of 16)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ap = make_smem_desc_sw128(sP + ks * 32, 16, 1024);
+          const uint64_t bo = make_smem_desc_sw128(sdO + ks * 16 * 128, 8192, 1024);
+          umma_ss<false, 1>(tmem_base + kColdV, ap, bo, idesc_acc, (s | ks) != 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = make_smem_desc_sw128(sdS + ks * 32, 16, 1024);
+          const uint64_t bq = make_smem_desc_sw128(sQ + ks * 16 * 128, 8192, 1024);
+          umma_ss<false, 1>(tmem_base + kColdK, ad, bq, idesc_acc, (s | ks) != 0);
+        }
+        // dQ^T = K^T dS^T   (M = d, N = q, K dim = kv, 128 -> 8 steps of 16)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ak = make_smem_desc_sw128(sK + ks * 16 * 128, 16384, 1024);
+          const uint64_t bd = make_smem_desc_sw128(sdS + ks * 16 * 128, 16, 1024);
+          umma_ss<false, 1>(tmem_base + kColdQ, ak, bd, idesc_dq, ks != 0);
+        }
+        umma_commit(dq_full);
+        umma_commit(&qdo_empty[st]);
+      }
+      umma_commit(acc_done);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------ softmax-grad threads (thread = kv row / d row) ------------------------------------
+    const int t = threadIdx.x - 128;
+    const int ew = warp - 4;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const int kv = kv0 + t;
+    const uint32_t sP = smem_u32(smem + kOffP), sdS = smem_u32(smem + kOffdS);
+    for (int s = 0; s < n_steps; ++s) {
+      const int hq = hk * G + s / steps_per_head;
+      const int q0 = (i_start + s % steps_per_head) * kQ;
+      // stage lse (in log2 units) and delta of the 64 query rows
+      float* stat = s_stat + (s & 1) * 2 * kQ;
+      {
+        const int qq = q0 + (t & 63);
+        const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
+        if (t < 64) stat[t] = (qq < p.S) ? p.lse[idx] * kLog2e : INFINITY;
+        else stat[t] = (qq < p.S) ? p.delta[idx] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0));
+      mbar_wait(sdp_full, s & 1);
+      tc_fence_after();
+      uint32_t pr[32], dsr[32];  // packed bf16 pairs: 64 q values each
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tmem_base + kColS + lane_off + c * 32, sv);
+        tmem_ld_32x32(tmem_base + kColdP + lane_off + c * 32, dv);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int qi = c * 32 + i;
+          float p0 = ex2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -stat[qi]));
+          float p1 = ex2(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -stat[qi + 1]));
+          if (!full_tile) {
+            const int qa = q0 + qi;
+            if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)))) p0 = 0.f;
+            if (!((kv < p.S) && ((kv < p.P) || (kv <= qa + 1)))) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dv[i]) - stat[kQ + qi]) * p.scale;
+          const float d1 = p1 * (__uint_as_float(dv[i + 1]) - stat[kQ + qi + 1]) * p.scale;
+          pr[c * 16 + i / 2] = pack_bf16(p0, p1);
+          dsr[c * 16 + i / 2] = pack_bf16(d0, d1);
+        }
+      }
+      // rows of 64 q values = 128 B = 8 chunks, swizzled by (row & 7)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t off = t * 128 + ((c ^ (t & 7)) << 4);
+        sts_v4(sP + off, pr[c * 4], pr[c * 4 + 1], pr[c * 4 + 2], pr[c * 4 + 3]);
+        sts_v4(sdS + off, dsr[c * 4], dsr[c * 4 + 1], dsr[c * 4 + 2], dsr[c * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(pds_full);
+
+      // drain dQ^T: this thread owns head-dim element d = t for the 64 query rows of the step
+      mbar_wait(dq_full, s & 1);
+      tc_fence_after();
+      float* dq_base = p.dq_accum + ((int64_t)b * p.S + q0) * ((int64_t)p.Hq * kHD) + (int64_t)hq * kHD + t;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + kColdQ + lane_off + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int qi = c * 32 + i;
+          if (q0 + qi < p.S) atomicAdd(dq_base + (int64_t)qi * p.Hq * kHD, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(dq_empty);
+    }
+    // write dK, dV (thread = kv row)
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const bool row_ok = kv < p.S;
+    __nv_bfloat16* dkrow = p.dk + ((int64_t)b * p.S + kv) * p.lddk + (int64_t)hk * kHD;
+    __nv_bfloat16* dvrow = p.dv + ((int64_t)b * p.S + kv) * p.lddv + (int64_t)hk * kHD;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (c < 4 ? kColdV : kColdK) + lane_off + (c & 3) * 32, v);
+      tmem_wait_ld();
+      if (row_ok) {
+        __nv_bfloat16* dst = (c < 4 ? dvrow : dkrow) + (c & 3) * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 o4;
+          o4.x = pack_bf16(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          o4.y = pack_bf16(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          o4.z = pack_bf16(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+          o4.w = pack_bf16(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+          stg_v4(dst + i, o4);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// delta[b,h,s] = sum_d dO * O  (one warp per (row, head): 128 elements = 32 lanes x 4)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ dout,
+                                  int64_t lddo, float* __restrict__ delta, int64_t rows, int S, int Hq) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= rows * Hq) return;
+  const int64_t row = w / Hq;
+  const int h = (int)(w - row * Hq);
+  const int lane = threadIdx.x & 31;
+  const uint2 a = *reinterpret_cast<const uint2*>(o + row * ldo + h * kHD + lane * 4);
+  const uint2 g = *reinterpret_cast<const uint2*>(dout + row * lddo + h * kHD + lane * 4);
+  float s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+            bf16_hi(a.y) * bf16_hi(g.y);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int64_t bb = row / S, ss = row - bb * S;
+    delta[(bb * Hq + h) * S + ss] = s;
+  }
+}
+
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t lddq,
+                                       int64_t rows, int width) {
+  const int vec_per_row = width / 8;
+  const int64_t total = rows * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int c = (int)(i - row * vec_per_row) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(acc + row * width + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(acc + row * width + c + 4);
+    uint4 o4;
+    o4.x = pack_bf16(a.x, a.y);
+    o4.y = pack_bf16(a.z, a.w);
+    o4.z = pack_bf16(b4.x, b4.y);
+    o4.w = pack_bf16(b4.z, b4.w);
+    *reinterpret_cast<uint4*>(dq + row * lddq + c) = o4;
+  }
+}
+
+static int make_head_tmap(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t S, int H, int box_rows) {
+  const int64_t dims[4] = {kHD, H, S, B};
+  const int64_t strides[3] = {kHD, ld, S * ld};
+  const int box[4] = {64, 1, box_rows, 1};
+  return make_tmap_4d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box);
+}
+
+static int check_attn_args(int64_t B, int64_t S, int Hq, int Hkv, int D, int64_t P, const char* who) {
+  if (D != kHD) return set_error(LLAMAX_ERR_ARG, "attention: head_dim must be 128");
+  if (B <= 0 || S <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv) return set_error(LLAMAX_ERR_ARG, "attention: bad B/S/H");
+  if (P < 0) return set_error(LLAMAX_ERR_ARG, "attention: prefix_len < 0");
+  (void)who;
+  return 0;
+}
+
+}  // namespace lx
+
+using namespace lx;
+
 extern "C" {
-int llamax_attn_fwd(const void*, int64_t, const void*, int64_t, const void*, int64_t, void*, int64_t, void*, int64_t,
-                    int64_t, int32_t, int32_t, int32_t, int64_t, float, void*) {
-  return lx::set_error(LLAMAX_ERR_ARG, "attn_fwd: not built yet");
+
+int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                    int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
+                    int64_t prefix_len, float scale, void* stream) {
+  if (!q || !k || !v || !o || !lse) return set_error(LLAMAX_ERR_ARG, "attn_fwd: null pointer");
+  int rc = check_attn_args(B, S, Hq, Hkv, D, prefix_len, "attn_fwd");
+  if (rc) return rc;
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return set_error(LLAMAX_ERR_ARG, "attn_fwd: pitches must be multiples of 8");
+  CUtensorMap tq, tk, tv;
+  if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, fwd::kTile))) return rc;
+  if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, fwd::kTile))) return rc;
+  if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, fwd::kTile))) return rc;
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd: cudaFuncSetAttribute");
+    configured = true;
+  }
+  AttnFwdParams p;
+  p.o = (__nv_bfloat16*)o;
+  p.ldo = ldo;
+  p.lse = (float*)lse;
+  p.B = (int)B; p.S = (int)S; p.Hq = Hq; p.Hkv = Hkv;
+  p.P = (int)std::min<int64_t>(prefix_len, S);
+  p.scale_log2 = scale * kLog2e;
+  dim3 grid((unsigned)ceil_div(S, fwd::kTile), Hq, (unsigned)B);
+  attn_fwd_kernel<<<grid, 256, fwd::kSmemBytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  LX_CHECK_LAUNCH("attn_fwd");
+  return 0;
 }
-int llamax_attn_bwd(const void*, int64_t, const void*, int64_t, const void*, int64_t, const void*, int64_t, const void*,
-                    const void*, int64_t, void*, int64_t, void*, int64_t, void*, int64_t, void*, void*, int64_t, int64_t,
-                    int32_t, int32_t, int32_t, int64_t, float, void*) {
-  return lx::set_error(LLAMAX_ERR_ARG, "attn_bwd: not built yet");
+
+int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                    const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
+                    int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
+                    int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len, float scale,
+                    void* stream) {
+  if (!q || !k || !v || !o || !lse || !dout || !dq || !dk || !dv || !dq_accum || !delta)
+    return set_error(LLAMAX_ERR_ARG, "attn_bwd: null pointer");
+  int rc = check_attn_args(B, S, Hq, Hkv, D, prefix_len, "attn_bwd");
+  if (rc) return rc;
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || lddo % 8 || lddq % 8 || lddk % 8 || lddv % 8)
+    return set_error(LLAMAX_ERR_ARG, "attn_bwd: pitches must be multiples of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = B * S;
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)rows * Hq * kHD * sizeof(float), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: memset");
+  {
+    const int64_t warps = rows * Hq;
+    const int blocks = (int)ceil_div(warps * 32, 256);
+    attn_delta_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
+                                              (float*)delta, rows, (int)S, Hq);
+    LX_CHECK_LAUNCH("attn_bwd: delta");
+  }
+  CUtensorMap tq, tk, tv, tdo;
+  if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, bwd::kQ))) return rc;
+  if ((rc = make_head_tmap(&tdo, dout, lddo, B, S, Hq, bwd::kQ))) return rc;
+  if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, bwd::kKV))) return rc;
+  if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, bwd::kKV))) return rc;
+  static thread_local bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: cudaFuncSetAttribute");
+    configured = true;
+  }
+  AttnBwdParams p;
+  p.lse = (const float*)lse;
+  p.delta = (const float*)delta;
+  p.dq_accum = (float*)dq_accum;
+  p.dk = (__nv_bfloat16*)dk; p.lddk = lddk;
+  p.dv = (__nv_bfloat16*)dv; p.lddv = lddv;
+  p.B = (int)B; p.S = (int)S; p.Hq = Hq; p.Hkv = Hkv;
+  p.P = (int)std::min<int64_t>(prefix_len, S);
+  p.scale = scale;
+  p.scale_log2 = scale * kLog2e;
+  dim3 grid((unsigned)ceil_div(S, bwd::kKV), Hkv, (unsigned)B);
+  attn_bwd_kernel<<<grid, 256, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
+  LX_CHECK_LAUNCH("attn_bwd");
+  {
+    const int64_t total = rows * (Hq * kHD / 8);
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, rows, Hq * kHD);
+    LX_CHECK_LAUNCH("attn_bwd: dq convert");
+  }
+  return 0;
 }
-}
+
+}  // extern "C"

@@ -228,6 +228,94 @@ def elementwise():
     return ok
 
 
+def _attn_case(B, S, Hq, Hkv, P, do_bwd=True, seed=0):
+    import torch
+    from llamax_b200 import ops
+    from oracle import ref_ops as R
+    D = 128
+    torch.manual_seed(seed)
+    ld = (Hq + 2 * Hkv) * D
+    qkv = torch.randn(B * S, ld).bfloat16()
+    q, k, v = qkv[:, : Hq * D], qkv[:, Hq * D : (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D :]
+    dout = torch.randn(B * S, Hq * D).bfloat16()
+    to4 = lambda t, H: t.reshape(B, S, H, D).transpose(1, 2)
+    o_ref, dq_ref, dk_ref, dv_ref = R.attention_ref_grads(to4(q, Hq), to4(k, Hkv), to4(v, Hkv), to4(dout, Hq), P, torch.float64)
+    g = qkv.cuda()
+    qc, kc, vc = g[:, : Hq * D], g[:, Hq * D : (Hq + Hkv) * D], g[:, (Hq + Hkv) * D :]
+    o, lse = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, P)
+    torch.cuda.synchronize()
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    e_o = rel(to4(o.cpu(), Hq), o_ref)
+    # lse check
+    s = (to4(q, Hq).double() @ to4(k, Hkv).double().repeat_interleave(Hq // Hkv, 1).transpose(-1, -2)) / D ** 0.5
+    s = s.masked_fill(~R.prefix_lm_mask(S, P), float("-inf"))
+    e_l = (lse.cpu().double() - torch.logsumexp(s, -1)).abs().max().item()
+    msg = f"  attn B={B} S={S} Hq={Hq} Hkv={Hkv} P={P}: out err={e_o:.3e} lse abs err={e_l:.3e}"
+    ok = e_o < 1e-2 and e_l < 1e-2
+    if do_bwd:
+        dqkv = torch.zeros_like(g)
+        dq, dk, dv = dqkv[:, : Hq * D], dqkv[:, Hq * D : (Hq + Hkv) * D], dqkv[:, (Hq + Hkv) * D :]
+        ops.attn_bwd(qc, kc, vc, o, lse, dout.cuda(), dq, dk, dv, B, S, Hq, Hkv, D, P)
+        torch.cuda.synchronize()
+        e_q, e_k, e_v = rel(to4(dq.cpu(), Hq), dq_ref), rel(to4(dk.cpu(), Hkv), dk_ref), rel(to4(dv.cpu(), Hkv), dv_ref)
+        msg += f" | dq err={e_q:.3e} dk err={e_k:.3e} dv err={e_v:.3e}"
+        ok = ok and max(e_q, e_k, e_v) < 1e-2
+    print(msg, flush=True)
+    return ok
+
+
+@check
+def attn_fwd_small():
+    ok = True
+    for (B, S, Hq, Hkv, P) in [(1, 128, 1, 1, 0), (1, 256, 4, 1, 0), (2, 512, 8, 2, 128), (1, 300, 4, 2, 70), (1, 1628, 4, 1, 1500)]:
+        ok &= _attn_case(B, S, Hq, Hkv, P, do_bwd=False)
+    return ok
+
+
+@check
+def attn_bwd_small():
+    ok = True
+    for (B, S, Hq, Hkv, P) in [(1, 128, 1, 1, 0), (1, 256, 4, 1, 0), (2, 512, 8, 2, 128), (1, 300, 4, 2, 70), (1, 1628, 4, 1, 1500),
+                               (1, 2048, 8, 2, 0)]:
+        ok &= _attn_case(B, S, Hq, Hkv, P, do_bwd=True)
+    return ok
+
+
+@check
+def attn_perf():
+    import torch
+    from llamax_b200 import ops
+    import torch.nn.functional as F
+    D, Hq, Hkv = 128, 32, 8
+    for (B, S, P) in [(8, 2048, 0), (2, 8192, 0), (8, 2048, 1024), (9, 1756, 1500)]:
+        ld = (Hq + 2 * Hkv) * D
+        g = torch.randn(B * S, ld, device="cuda").bfloat16()
+        qc, kc, vc = g[:, : Hq * D], g[:, Hq * D : (Hq + Hkv) * D], g[:, (Hq + Hkv) * D :]
+        dout = torch.randn(B * S, Hq * D, device="cuda").bfloat16()
+        dqkv = torch.empty_like(g)
+        dq, dk, dv = dqkv[:, : Hq * D], dqkv[:, Hq * D : (Hq + Hkv) * D], dqkv[:, (Hq + Hkv) * D :]
+        o, lse = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, P)
+        pairs = S * P + (S - P) * (S - P + 1) / 2
+        fl_f = 4 * B * Hq * D * pairs
+        def timeit(fn, n=5):
+            for _ in range(2): fn()
+            ts = []
+            for _ in range(n):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+            return min(ts)
+        tf = timeit(lambda: ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, P))
+        tb = timeit(lambda: ops.attn_bwd(qc, kc, vc, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, P))
+        msg = f"  attn perf B={B} S={S} P={P}: fwd {tf:.3f} ms = {fl_f/tf/1e9:.0f} TF/s | bwd {tb:.3f} ms = {2.5*fl_f/tb/1e9:.0f} TF/s"
+        if P == 0:
+            q4 = qc.reshape(B, S, Hq, D).transpose(1, 2); k4 = kc.reshape(B, S, Hkv, D).transpose(1, 2); v4 = vc.reshape(B, S, Hkv, D).transpose(1, 2)
+            q4 = q4.detach().requires_grad_(True)
+            ts = timeit(lambda: F.scaled_dot_product_attention(q4, k4, v4, is_causal=True, enable_gqa=True))
+            msg += f" | torch SDPA fwd {ts:.3f} ms = {fl_f/ts/1e9:.0f} TF/s"
+        print(msg, flush=True)
+    return True
+
+
 def main():
     names = sys.argv[1:] or list(CHECKS)
     if len(names) == 1 and names[0].startswith("--run="):
