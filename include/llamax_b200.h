@@ -70,11 +70,11 @@ int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, voi
                      const llamax_epilogue_t* epi, void* stream);
 
 /* De-quantise a frozen weight into a bf16 GEMM operand (scratch owned by the caller).
- *   transpose = 0: out[n,k] = bf16(w8[n,k]) (* scale[n] if apply_scale)          out [N,K]
- *   transpose = 1: out[k,n] = bf16(f32(w8[n,k]) * f32(scale[n])) (or unscaled)    out [K,N]
+ *   transpose = 0: out[n,k] = bf16(w8[n,k]) (* scale[n] if apply_scale)          out [N,K], row pitch ldo
+ *   transpose = 1: out[k,n] = bf16(f32(w8[n,k]) * f32(scale[n])) (or unscaled)    out [K,N], row pitch ldo
  * Reference: weight.int_data.T.to(dtype) (int8.py:118), weight_i8.to(dtype) and grad*scale (int8.py:127). */
-int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t N, int64_t K, int transpose,
-                          int apply_scale, void* stream);
+int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t ldo, int64_t N, int64_t K,
+                          int transpose, int apply_scale, void* stream);
 
 /* ---- K2: row-wise int8 quantisation (subclasses/int8.py:10-16) ------------------------------------
  *   s = amax(|x_f32|) / 127;  q = rint(x_f32 / max(s, 1e-12));  scale_out = bf16(s)        bit-exact */
@@ -97,9 +97,9 @@ int llamax_reduce_partials(const void* partial, void* out, int32_t nparts, int64
  *   g = bf16( bf16(silu_f32(a)) * b );  optional g (bf16), q8/qscale = rowquant_int8(g) */
 int llamax_swiglu_fwd(const void* a, const void* b, int64_t ld, void* g, void* q8, void* qscale, int64_t M,
                       int64_t F, void* stream);
-/* da, db from dg; optionally re-materialises g (needed for the LoRA-A gradient of w2). */
-int llamax_swiglu_bwd(const void* dg, const void* a, const void* b, int64_t ld, void* da, void* db, void* g,
-                      int64_t M, int64_t F, void* stream);
+/* da, db (row pitch ldd) from dg; optionally re-materialises g (needed for the LoRA-A gradient of w2). */
+int llamax_swiglu_bwd(const void* dg, const void* a, const void* b, int64_t ld, void* da, void* db, int64_t ldd,
+                      void* g, int64_t M, int64_t F, void* stream);
 
 /* ---- K7: RoPE (modelling/llama.py:63-73), interleaved pairs, fp32 math, in place ------------------
  * x bf16 [B*S, ...] row pitch ld; rotates `nheads` heads of width D starting at column 0.

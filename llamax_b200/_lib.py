@@ -41,13 +41,13 @@ SIGNATURES = {
     "llamax_int8_gemm_dequant": [P, I64, P, I64, P, P, P, I64, I64, I64, I64, EP, P],
     "llamax_int8_gemm_s32": [P, I64, P, I64, P, I64, I64, I64, I64, P],
     "llamax_bf16_gemm": [P, I64, P, I64, P, I64, I64, I64, I64, P, c_int, EP, P],
-    "llamax_dequant_weight": [P, P, P, I64, I64, c_int, c_int, P],
+    "llamax_dequant_weight": [P, P, P, I64, I64, I64, c_int, c_int, P],
     "llamax_rowquant_int8": [P, I64, P, P, I64, I64, P],
     "llamax_rmsnorm_fwd": [P, P, P, P, P, P, I64, I64, c_float, P],
     "llamax_rmsnorm_bwd": [P, P, P, P, P, P, P, I32, I64, I64, P],
     "llamax_reduce_partials": [P, P, I32, I64, P],
     "llamax_swiglu_fwd": [P, P, I64, P, P, P, I64, I64, P],
-    "llamax_swiglu_bwd": [P, P, P, I64, P, P, P, I64, I64, P],
+    "llamax_swiglu_bwd": [P, P, P, I64, P, P, I64, P, I64, I64, P],
     "llamax_rope_inplace": [P, I64, P, I64, I64, I32, I32, c_int, P],
     "llamax_attn_fwd": [P, I64, P, I64, P, I64, P, I64, P, I64, I64, I32, I32, I32, I64, c_float, P],
     "llamax_attn_bwd": [P, I64, P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, P, I64, P, P,

@@ -200,8 +200,8 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __n
 // SwiGLU backward (grid-stride over 16-byte vectors)
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __restrict__ a,
                                   const __nv_bfloat16* __restrict__ b, int64_t ld, __nv_bfloat16* __restrict__ da,
-                                  __nv_bfloat16* __restrict__ db, __nv_bfloat16* __restrict__ g, int64_t M,
-                                  int nvec) {
+                                  __nv_bfloat16* __restrict__ db, int64_t ldd, __nv_bfloat16* __restrict__ g,
+                                  int64_t M, int nvec) {
   const int64_t total = M * nvec;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / nvec;
@@ -219,8 +219,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __
       oa[e] = dsl * (sig * (1.0f + af[e] * (1.0f - sig)));
       og[e] = sl * bf[e];
     }
-    *reinterpret_cast<uint4*>(da + row * ld + c) = pack8(oa);
-    *reinterpret_cast<uint4*>(db + row * ld + c) = pack8(ob);
+    *reinterpret_cast<uint4*>(da + row * ldd + c) = pack8(oa);
+    *reinterpret_cast<uint4*>(db + row * ldd + c) = pack8(ob);
     if (g != nullptr) *reinterpret_cast<uint4*>(g + row * (int64_t)nvec * 8 + c) = pack8(og);
   }
 }
@@ -339,11 +339,13 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const flo
 // weight de-quantisation into a bf16 GEMM operand
 // ------------------------------------------------------------------------------------------------
 __global__ void dequant_plain_kernel(const int8_t* __restrict__ w8, const __nv_bfloat16* __restrict__ scale,
-                                     __nv_bfloat16* __restrict__ out, int64_t N, int64_t K, int apply_scale) {
+                                     __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t N, int64_t K,
+                                     int apply_scale) {
   const int64_t nvec = N * K / 16;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = i * 16;
-    const float s = apply_scale ? __bfloat162float(scale[e0 / K]) : 1.0f;
+    const int64_t n = e0 / K, kk = e0 - n * K;
+    const float s = apply_scale ? __bfloat162float(scale[n]) : 1.0f;
     const uint4 u = ldg_nc_v4(w8 + e0);
     const uint32_t words[4] = {u.x, u.y, u.z, u.w};
     float f[16];
@@ -354,15 +356,15 @@ __global__ void dequant_plain_kernel(const int8_t* __restrict__ w8, const __nv_b
     float lo[8], hi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { lo[e] = f[e]; hi[e] = f[8 + e]; }
-    *reinterpret_cast<uint4*>(out + e0) = pack8(lo);
-    *reinterpret_cast<uint4*>(out + e0 + 8) = pack8(hi);
+    *reinterpret_cast<uint4*>(out + n * ldo + kk) = pack8(lo);
+    *reinterpret_cast<uint4*>(out + n * ldo + kk + 8) = pack8(hi);
   }
 }
 
 // out[k, n] = bf16(w8[n, k] * scale[n]); 64 x 64 tiles through shared memory
 __global__ void __launch_bounds__(256)
 dequant_transpose_kernel(const int8_t* __restrict__ w8, const __nv_bfloat16* __restrict__ scale,
-                         __nv_bfloat16* __restrict__ out, int N, int K, int apply_scale) {
+                         __nv_bfloat16* __restrict__ out, int64_t ldo, int N, int K, int apply_scale) {
   __shared__ __align__(16) __nv_bfloat16 tile[64][72];
   const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
   {
@@ -387,7 +389,7 @@ dequant_transpose_kernel(const int8_t* __restrict__ w8, const __nv_bfloat16* __r
     const int t = threadIdx.x + it * 256;
     const int k = t >> 3, nc = (t & 7) * 8;
     if (k0 + k < K && n0 + nc < N)
-      *reinterpret_cast<uint4*>(out + (int64_t)(k0 + k) * N + n0 + nc) = *reinterpret_cast<const uint4*>(&tile[k][nc]);
+      *reinterpret_cast<uint4*>(out + (int64_t)(k0 + k) * ldo + n0 + nc) = *reinterpret_cast<const uint4*>(&tile[k][nc]);
   }
 }
 
@@ -485,15 +487,15 @@ int llamax_swiglu_fwd(const void* a, const void* b, int64_t ld, void* g, void* q
   return 0;
 }
 
-int llamax_swiglu_bwd(const void* dg, const void* a, const void* b, int64_t ld, void* da, void* db, void* g,
-                      int64_t M, int64_t F, void* stream) {
+int llamax_swiglu_bwd(const void* dg, const void* a, const void* b, int64_t ld, void* da, void* db, int64_t ldd,
+                      void* g, int64_t M, int64_t F, void* stream) {
   if (!dg || !a || !b || !da || !db) return set_error(LLAMAX_ERR_ARG, "swiglu_bwd: null pointer");
-  if (F % 8 || ld % 8) return set_error(LLAMAX_ERR_ARG, "swiglu_bwd: F and ld must be multiples of 8");
+  if (F % 8 || ld % 8 || ldd % 8) return set_error(LLAMAX_ERR_ARG, "swiglu_bwd: F, ld and ldd must be multiples of 8");
   if (M == 0) return 0;
   const int64_t total = M * (F / 8);
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
   swiglu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dg, (const bf16*)a, (const bf16*)b, ld,
-                                                              (bf16*)da, (bf16*)db, (bf16*)g, M, (int)(F / 8));
+                                                              (bf16*)da, (bf16*)db, ldd, (bf16*)g, M, (int)(F / 8));
   LX_CHECK_LAUNCH("swiglu_bwd");
   return 0;
 }
@@ -532,19 +534,20 @@ int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_
   return 0;
 }
 
-int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t N, int64_t K, int transpose,
-                          int apply_scale, void* stream) {
+int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t ldo, int64_t N, int64_t K,
+                          int transpose, int apply_scale, void* stream) {
   if (!w8 || !out || (apply_scale && !scale)) return set_error(LLAMAX_ERR_ARG, "dequant_weight: null pointer");
-  if (K % 16 || N % 8) return set_error(LLAMAX_ERR_ARG, "dequant_weight: K % 16 and N % 8 required");
+  if (K % 16 || N % 8 || ldo % 8 || (reinterpret_cast<uintptr_t>(out) % 16))
+    return set_error(LLAMAX_ERR_ARG, "dequant_weight: K % 16, N % 8, ldo % 8 and 16-byte aligned out required");
   if (!transpose) {
     const int64_t nvec = N * K / 16;
     const int blocks = (int)std::min<int64_t>((nvec + 255) / 256, (int64_t)sm_count() * 16);
     dequant_plain_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const int8_t*)w8, (const bf16*)scale, (bf16*)out,
-                                                                   N, K, apply_scale);
+                                                                   ldo, N, K, apply_scale);
   } else {
     dim3 grid((unsigned)((K + 63) / 64), (unsigned)((N + 63) / 64));
     dequant_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const int8_t*)w8, (const bf16*)scale,
-                                                                     (bf16*)out, (int)N, (int)K, apply_scale);
+                                                                     (bf16*)out, ldo, (int)N, (int)K, apply_scale);
   }
   LX_CHECK_LAUNCH("dequant_weight");
   return 0;
@@ -566,10 +569,14 @@ int llamax_lora_wgrad(const void* X, int64_t ldx, const void* H, int64_t ldh, vo
     lora_wgrad_kernel<8><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
   else if (R == 16)
     lora_wgrad_kernel<16><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
+  else if (R == 24)
+    lora_wgrad_kernel<24><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
+  else if (R == 32)
+    lora_wgrad_kernel<32><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
   else if (R == 4)
     lora_wgrad_kernel<4><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)out, M, P, rows_per_cta, alpha);
   else
-    return set_error(LLAMAX_ERR_ARG, "lora_wgrad: rank must be 4, 8 or 16");
+    return set_error(LLAMAX_ERR_ARG, "lora_wgrad: rank must be 4, 8, 16, 24 or 32");
   LX_CHECK_LAUNCH("lora_wgrad");
   return 0;
 }

@@ -1,0 +1,3 @@
+from .audio import AudioConfig, LlamaAudio
+from .llama import Llama, LlamaConfig, PrefixLM, prefix_lm_attention, prefix_lm_block_mask
+from .lora import LoRALinear, apply_linear_adapter_

@@ -1,0 +1,273 @@
+"""Fused forward/backward of one Llama decoder block (TransformerLayer.forward, modelling/llama.py:163-174) for
+frozen-INT8 base weights (+ optional LoRA adapters), as ONE autograd.Function over this package's kernels.
+
+Why one Function instead of composing per-module autograd nodes:
+  * the save-set is chosen by hand (x, xn, post-RoPE qkv, O + LSE, x_mid, w1x|w3x, LoRA h): ~108 KB / token / layer
+    instead of the ~215 KB the eager reference keeps, so 16 k tokens x 32 layers fit HBM without recompute;
+  * residual adds, LoRA up-projections and dequant scales ride in GEMM epilogues; row quantisation rides in the
+    RMSNorm / SwiGLU passes; q|k|v and w1|w3 share one quantised activation and one backward GEMM
+    (their grad_input GEMMs are concatenated along the contraction dimension together with the LoRA terms).
+
+Data layout (M = B*S tokens):
+  qkv   [M, (Hq + 2 Hkv) * D]   q | k | v column blocks, RoPE applied in place on q | k, read by the attention
+                                kernels through strided TMA (no [B,H,S,D] transposes)
+  ab    [M, 2F]                 w1 x | w3 x
+  dqkv  [M, (Hq+2Hkv)*D + Rq+Rk+Rv]   gradient blocks followed by the LoRA dh columns (same for dab)
+"""
+
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from .. import ops
+from ..subclasses.int8 import Int8LinearWeight
+
+EPS = 1e-5
+
+_scratch: dict = {}
+
+
+def _get_scratch(device, numel: int) -> Tensor:
+    """One growing bf16 scratch per device for de-quantised weight operands (re-used by every layer)."""
+    buf = _scratch.get(device)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(numel, device=device, dtype=torch.bfloat16)
+        _scratch[device] = buf
+    return buf
+
+
+class LinearSpec:
+    """Raw tensors of one (LoRA)Linear with an Int8LinearWeight base."""
+
+    __slots__ = ("w8", "ws", "dynamic", "lora_a", "lora_b", "lora_scale", "N", "K", "R")
+
+    def __init__(self, module):
+        w = module.weight
+        if not isinstance(w, Int8LinearWeight):
+            raise NotImplementedError("fused decoder block needs Int8LinearWeight base weights (quantize_linear_)")
+        if module.bias is not None:
+            raise NotImplementedError("fused decoder block: bias is not supported (Llama has none)")
+        self.w8, self.ws, self.dynamic = w.int_data, w.scale, w.dynamic_int8_act
+        self.N, self.K = w.shape
+        rank = getattr(module, "rank", 0)
+        if rank and rank > 0:
+            self.lora_a, self.lora_b, self.lora_scale, self.R = module.lora_a, module.lora_b, float(module.scale), rank
+        else:
+            self.lora_a = self.lora_b = None
+            self.lora_scale, self.R = 1.0, 0
+
+
+def _lora_down(x: Tensor, specs) -> Tensor | None:
+    """h = x @ [A_1; A_2; ...]^T for the adapters that share the input x. [M, sum R]."""
+    a_list = [s.lora_a for s in specs if s.R > 0]
+    if not a_list:
+        return None
+    a_cat = a_list[0] if len(a_list) == 1 else torch.cat(a_list, 0)
+    return ops.bf16_gemm(x, a_cat.detach())
+
+
+def _linear(spec: LinearSpec, x_bf16, x_q8, x_qs, h, out=None, resid=None):
+    ep = {}
+    if h is not None:
+        ep.update(lora_h=h, lora_b=spec.lora_b.detach(), lora_scale=spec.lora_scale)
+    if resid is not None:
+        ep["resid"] = resid
+    if spec.dynamic:
+        return ops.int8_gemm_dequant(x_q8, spec.w8, x_qs, spec.ws, out=out, **ep)
+    wd = ops.dequant_weight(spec.w8, None, transpose=False, apply_scale=False,
+                            out=_get_scratch(x_bf16.device, spec.N * spec.K)[: spec.N * spec.K].view(spec.N, spec.K))
+    return ops.bf16_gemm(x_bf16, wd, col_scale=spec.ws, round_before_scale=True, out=out, **ep)
+
+
+def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Tensor | None, need_dx=True):
+    """Backward of linears that share one input. dy_cat [M, n_total + r_total]: gradient blocks already written in
+    the first n_total columns (block i = specs[i].N columns); the LoRA dh columns are filled here.
+    Returns (dx [M,K], [(dA_i, dB_i) | None per spec])."""
+    M = dy_cat.shape[0]
+    K = specs[0].K
+    r_total = sum(s.R for s in specs)
+    width = n_total + r_total
+    assert dy_cat.shape[1] == width
+    wt = _get_scratch(dy_cat.device, K * width)[: K * width].view(K, width)
+    n_off, r_off = 0, 0
+    lora_grads = []
+    for s in specs:
+        dy_i = dy_cat[:, n_off : n_off + s.N]
+        ops.dequant_weight(s.w8, s.ws, transpose=True, apply_scale=True, out=wt[:, n_off : n_off + s.N])
+        if s.R > 0:
+            c0 = n_total + r_off
+            # dh_i = scale * dy_i @ B_i    -> columns [c0, c0+R) of dy_cat
+            bt = (s.lora_b.detach().t() * s.lora_scale).contiguous()
+            ops.bf16_gemm(dy_i, bt, out=dy_cat[:, c0 : c0 + s.R])
+            wt[:, c0 : c0 + s.R].copy_(s.lora_a.detach().t())
+            h_i = h_cat[:, r_off : r_off + s.R]
+            dB = ops.lora_wgrad(dy_i, h_i, s.lora_scale)  # [N, R] fp32
+            lora_grads.append([None, dB.to(s.lora_b.dtype)])
+            r_off += s.R
+        else:
+            lora_grads.append(None)
+        n_off += s.N
+    if r_total > 0:
+        dA_t = ops.lora_wgrad(x_in, dy_cat[:, n_total:], 1.0)  # [K, r_total] = x^T dh
+        r_off = 0
+        for s, lg in zip(specs, lora_grads):
+            if lg is not None:
+                lg[0] = dA_t[:, r_off : r_off + s.R].t().to(s.lora_a.dtype).contiguous()
+                r_off += s.R
+    dx = ops.bf16_gemm(dy_cat, wt) if need_dx else None
+    return dx, lora_grads
+
+
+def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, h: Tensor | None):
+    """Backward of one linear whose incoming gradient buffer we do not own: LoRA term in the GEMM epilogue."""
+    wt = ops.dequant_weight(spec.w8, spec.ws, transpose=True, apply_scale=True,
+                            out=_get_scratch(dy.device, spec.N * spec.K)[: spec.N * spec.K].view(spec.K, spec.N))
+    if spec.R > 0:
+        bt = (spec.lora_b.detach().t() * spec.lora_scale).contiguous()
+        dh = ops.bf16_gemm(dy, bt)                                     # [M, R]
+        at = spec.lora_a.detach().t().contiguous()                     # [K, R]
+        dx = ops.bf16_gemm(dy, wt, lora_h=dh, lora_b=at, lora_scale=1.0)
+        dB = ops.lora_wgrad(dy, h, spec.lora_scale).to(spec.lora_b.dtype)
+        dA = ops.lora_wgrad(x_in, dh, 1.0).t().to(spec.lora_a.dtype).contiguous()
+        return dx, (dA, dB)
+    return ops.bf16_gemm(dy, wt), None
+
+
+class FusedDecoderBlock(torch.autograd.Function):
+    """out = TransformerLayer(x). Inputs after `meta` are the trainable tensors, in the order of
+    `block_trainables(layer)`: attention_norm.weight, ffn_norm.weight, then (lora_a, lora_b) of
+    wq, wk, wv, wo, w1, w3, w2 for the adapters that exist."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, rope: Tensor, meta, *trainables):
+        layer, prefix_len = meta
+        att, ff = layer.attention, layer.feed_forward
+        B, S, Dm = x.shape
+        M = B * S
+        Hq, Hkv, D = att.num_heads, att.num_kv_heads, att.head_dim
+        sq, sk, sv, so = (LinearSpec(m) for m in (att.wq, att.wk, att.wv, att.wo))
+        s1, s3, s2 = (LinearSpec(m) for m in (ff.w1, ff.w3, ff.w2))
+        w_an, w_fn = layer.attention_norm.weight.detach(), layer.ffn_norm.weight.detach()
+        x2 = x.reshape(M, Dm)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        dyn_qkv, dyn_13 = sq.dynamic, s1.dynamic
+
+        # --- attention half ---
+        xn1, rstd1, xq, xs = ops.rmsnorm_fwd(x2, w_an, EPS, quant=dyn_qkv)
+        h_qkv = _lora_down(xn1, (sq, sk, sv))
+        nq, nk = Hq * D, Hkv * D
+        qkv = torch.empty(M, nq + 2 * nk, device=x.device, dtype=torch.bfloat16)
+        r_off = 0
+        for spec, c0, c1 in ((sq, 0, nq), (sk, nq, nq + nk), (sv, nq + nk, nq + 2 * nk)):
+            h = h_qkv[:, r_off : r_off + spec.R] if spec.R > 0 else None
+            r_off += spec.R
+            _linear(spec, xn1, xq, xs, h, out=qkv[:, c0:c1])
+        ops.rope_(qkv, rope, B, S, Hq + Hkv, D)
+        o, lse = ops.attn_fwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], B, S, Hq, Hkv, D, prefix_len)
+        oq = osc = None
+        if so.dynamic:
+            oq, osc = ops.rowquant_int8(o)
+        h_o = _lora_down(o, (so,))
+        x1 = _linear(so, o, oq, osc, h_o, resid=x2)
+
+        # --- feed-forward half ---
+        xn2, rstd2, xq2, xs2 = ops.rmsnorm_fwd(x1, w_fn, EPS, quant=dyn_13)
+        h_13 = _lora_down(xn2, (s1, s3))
+        F_ = s1.N
+        ab = torch.empty(M, 2 * F_, device=x.device, dtype=torch.bfloat16)
+        _linear(s1, xn2, xq2, xs2, h_13[:, : s1.R] if s1.R > 0 else None, out=ab[:, :F_])
+        _linear(s3, xn2, xq2, xs2, h_13[:, s1.R : s1.R + s3.R] if s3.R > 0 else None, out=ab[:, F_:])
+        need_g = (s2.R > 0) or (not s2.dynamic)
+        g, gq, gs = ops.swiglu_fwd(ab[:, :F_], ab[:, F_:], quant=s2.dynamic, want_g=need_g)
+        h_2 = _lora_down(g, (s2,)) if s2.R > 0 else None
+        out = _linear(s2, g, gq, gs, h_2, resid=x1)
+
+        ctx.meta = meta
+        ctx.shape = (B, S, Dm)
+        ctx.save_for_backward(x2, xn1, rstd1, qkv, o, lse, x1, xn2, rstd2, ab, h_qkv, h_o, h_13, h_2, rope)
+        return out.view(B, S, Dm)
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        layer, prefix_len = ctx.meta
+        x2, xn1, rstd1, qkv, o, lse, x1, xn2, rstd2, ab, h_qkv, h_o, h_13, h_2, rope = ctx.saved_tensors
+        att, ff = layer.attention, layer.feed_forward
+        B, S, Dm = ctx.shape
+        M = B * S
+        Hq, Hkv, D = att.num_heads, att.num_kv_heads, att.head_dim
+        sq, sk, sv, so = (LinearSpec(m) for m in (att.wq, att.wk, att.wv, att.wo))
+        s1, s3, s2 = (LinearSpec(m) for m in (ff.w1, ff.w3, ff.w2))
+        w_an, w_fn = layer.attention_norm.weight, layer.ffn_norm.weight
+        F_ = s1.N
+        dout2 = dout.reshape(M, Dm)
+        if not dout2.is_contiguous():
+            dout2 = dout2.contiguous()
+
+        # --- w2 ---  (needs g = silu(a) * b only for dA of w2: re-materialised by the SwiGLU backward kernel)
+        r13 = s1.R + s3.R
+        dab = torch.empty(M, 2 * F_ + r13, device=dout.device, dtype=torch.bfloat16)
+        wt2 = ops.dequant_weight(s2.w8, s2.ws, transpose=True, apply_scale=True,
+                                 out=_get_scratch(dout.device, s2.N * s2.K)[: s2.N * s2.K].view(s2.K, s2.N))
+        g2 = None
+        if s2.R > 0:
+            dh2 = ops.bf16_gemm(dout2, (s2.lora_b.detach().t() * s2.lora_scale).contiguous())
+            dg = ops.bf16_gemm(dout2, wt2, lora_h=dh2, lora_b=s2.lora_a.detach().t().contiguous(), lora_scale=1.0)
+            dB2 = ops.lora_wgrad(dout2, h_2, s2.lora_scale).to(s2.lora_b.dtype)
+        else:
+            dg = ops.bf16_gemm(dout2, wt2)
+        _, _, g = ops.swiglu_bwd(dg, ab[:, :F_], ab[:, F_:], want_g=s2.R > 0, out_ab=dab)
+        if s2.R > 0:
+            dA2 = ops.lora_wgrad(g, dh2, 1.0).t().to(s2.lora_a.dtype).contiguous()
+            g2 = (dA2, dB2)
+        del dg, g
+
+        # --- w1 | w3 ---
+        dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, h_13)
+        del dab
+        want_dw_fn, want_dw_an = w_fn.requires_grad, w_an.requires_grad
+        dx1, dw_fn = ops.rmsnorm_bwd(dxn2, x1, w_fn.detach(), rstd2, dout2, want_dw=want_dw_fn)
+        del dxn2
+
+        # --- wo ---
+        do, go = _single_backward(so, dx1, o, h_o)
+
+        # --- attention ---
+        nq, nk = Hq * D, Hkv * D
+        rqkv = sq.R + sk.R + sv.R
+        dqkv = torch.empty(M, nq + 2 * nk + rqkv, device=dout.device, dtype=torch.bfloat16)
+        ops.attn_bwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], o, lse, do,
+                     dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len)
+        ops.rope_(dqkv, rope, B, S, Hq + Hkv, D, inverse=True)
+        dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, h_qkv)
+        del dqkv
+        dx, dw_an = ops.rmsnorm_bwd(dxn1, x2, w_an.detach(), rstd1, dx1, want_dw=want_dw_an)
+
+        grads = [dw_an, dw_fn]
+        for spec, g_ in zip((sq, sk, sv, so, s1, s3, s2), (*gqkv, go, *g13, g2)):
+            if spec.R > 0:
+                grads += [g_[0], g_[1]]
+        return (dx.view(B, S, Dm), None, None, *grads)
+
+
+def block_trainables(layer):
+    """Tensors passed to FusedDecoderBlock.apply after `meta`, in the order backward() returns their gradients."""
+    att, ff = layer.attention, layer.feed_forward
+    ts = [layer.attention_norm.weight, layer.ffn_norm.weight]
+    for m in (att.wq, att.wk, att.wv, att.wo, ff.w1, ff.w3, ff.w2):
+        if getattr(m, "rank", 0) > 0:
+            ts += [m.lora_a, m.lora_b]
+    return ts
+
+
+def fused_block_supported(layer, x: Tensor) -> bool:
+    att, ff = layer.attention, layer.feed_forward
+    mods = (att.wq, att.wk, att.wv, att.wo, ff.w1, ff.w3, ff.w2)
+    return (
+        x.is_cuda and x.dtype is torch.bfloat16 and att.kv_cache is None and att.head_dim == 128
+        and all(isinstance(m.weight, Int8LinearWeight) and m.bias is None for m in mods)
+        and all(getattr(m, "rank", 0) <= 16 and getattr(m, "rank", 0) % 8 == 0 for m in mods)
+        and att.wq.weight.dynamic_int8_act == att.wk.weight.dynamic_int8_act == att.wv.weight.dynamic_int8_act
+        and ff.w1.weight.dynamic_int8_act == ff.w3.weight.dynamic_int8_act
+    )

@@ -1,0 +1,329 @@
+"""Llama decoder — drop-in for modelling/llama.py of the reference (module / parameter names, constructor and
+forward signatures kept, so reference state_dicts load unchanged), with the decoder block running on this package's
+sm_100a kernels.
+
+  LlamaConfig                      llama.py:17-29      same fields
+  build_rope / apply_rope          llama.py:32-73      same table [max_seq_len, head_dim/2, 2] fp32; in-place kernel
+  Attention / FeedForward          llama.py:93-152     wq wk wv wo / w1 w2 w3
+  TransformerLayer                 llama.py:155-174    -> FusedDecoderBlock when the base is Int8LinearWeight
+  Llama                            llama.py:177-219    embed -> layers -> norm -> output -> cross-entropy
+
+Masking: the reference wires FlexAttention `block_mask`s and dense SDPA `mask`s (llama.py:129-137). The kernels here
+implement the prefix-LM family  mask(q, kv) = (kv < P) | (q >= kv)  (P = 0: causal). Pass it as
+`block_mask=PrefixLM(P)` (or anything with a `.prefix_len` attribute, e.g. a FlexAttention BlockMask produced by
+`prefix_lm_block_mask`). Arbitrary dense masks, KV caches / `input_pos` (the inference path) are out of scope and
+raise.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import NamedTuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from .. import ops
+from .fused_block import FusedDecoderBlock, block_trainables, fused_block_supported
+
+
+class LlamaConfig(NamedTuple):
+    embed_dim: int
+    num_layers: int
+    head_dim: int
+    num_heads: int
+    num_kv_heads: int
+    intermediate_dim: int
+    max_seq_len: int = 2048
+    vocab_size: int = 128_256  # Llama3
+    attn_dropout: float = 0.0
+    rope_base: int = 50_000
+    is_llama3_1: bool = False
+    activation_checkpointing: bool = False
+
+
+class PrefixLM:
+    """Mask descriptor: keys [0, prefix_len) are visible to every query, the rest is causal."""
+
+    def __init__(self, prefix_len: int):
+        self.prefix_len = int(prefix_len)
+
+    def __repr__(self):
+        return f"PrefixLM(prefix_len={self.prefix_len})"
+
+
+def prefix_lm_block_mask(prefix_len: int, seq_len: int, device="cuda"):
+    """A real FlexAttention BlockMask for the prefix-LM mask, tagged with `.prefix_len` so that both this package
+    and the reference's flex_attention branch (llama.py:129-132) accept it."""
+    from torch.nn.attention.flex_attention import create_block_mask
+
+    def mask_mod(b, h, q_idx, kv_idx):
+        return (kv_idx < prefix_len) | (q_idx >= kv_idx)
+
+    bm = create_block_mask(mask_mod, None, None, seq_len, seq_len, device=device)
+    bm.prefix_len = int(prefix_len)
+    return bm
+
+
+def _prefix_len_of(mask, block_mask, input_pos) -> int:
+    if mask is not None or input_pos is not None:
+        raise NotImplementedError(
+            "llamax_b200: dense `mask` / `input_pos` (KV-cache inference path, llama.py:126-127,135-137) is outside "
+            "the fine-tuning hot path; use block_mask=PrefixLM(P)"
+        )
+    if block_mask is None:
+        return 0
+    p = getattr(block_mask, "prefix_len", None)
+    if p is None:
+        raise NotImplementedError(
+            "llamax_b200: block_mask must describe a prefix-LM mask (PrefixLM(P) or prefix_lm_block_mask(P, L)); "
+            "generic FlexAttention mask_mods are not implemented"
+        )
+    return int(p)
+
+
+def scale_llama3_1_rope(freqs: Tensor) -> Tensor:
+    """Llama-3.1 long-context frequency rescale (llama.py:32-51), vectorised."""
+    factor, low, high, old_ctx = 8.0, 1.0, 4.0, 8192.0
+    wavelen = 2 * torch.pi / freqs
+    smooth = (old_ctx / wavelen - low) / (high - low)
+    mid = (1 - smooth) * freqs / factor + smooth * freqs
+    out = torch.where(wavelen < old_ctx / high, freqs, torch.where(wavelen > old_ctx / low, freqs / factor, mid))
+    return out.to(freqs.dtype)
+
+
+def build_rope(config: LlamaConfig) -> Tensor:
+    theta = 1.0 / (config.rope_base ** (torch.arange(0, config.head_dim, 2, dtype=torch.float32) / config.head_dim))
+    if config.is_llama3_1:
+        theta = scale_llama3_1_rope(theta)
+    angles = torch.outer(torch.arange(config.max_seq_len, dtype=torch.float32), theta)
+    return torch.stack([angles.cos(), angles.sin()], dim=-1)
+
+
+class _RopeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, rope: Tensor):
+        B, S, H, D = x.shape
+        y = x.reshape(B * S, H * D).clone()
+        ops.rope_(y, rope, B, S, H, D)
+        ctx.save_for_backward(rope)
+        return y.view(B, S, H, D)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        (rope,) = ctx.saved_tensors
+        B, S, H, D = dy.shape
+        dx = dy.reshape(B * S, H * D).clone()
+        ops.rope_(dx, rope, B, S, H, D, inverse=True)
+        return dx.view(B, S, H, D), None
+
+
+def apply_rope(x: Tensor, rope: Tensor) -> Tensor:
+    """x [B, S, H, D]; interleaved-pair rotation in fp32 (llama.py:63-73)."""
+    return _RopeFn.apply(x, rope.contiguous())
+
+
+class _PrefixLMAttentionFn(torch.autograd.Function):
+    """o = softmax(q k^T / sqrt(D) + mask) v on [B, S, H, D] tensors (GQA native)."""
+
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, prefix_len: int):
+        B, S, Hq, D = q.shape
+        Hkv = k.shape[2]
+        q2, k2, v2 = (t.reshape(B * S, -1) for t in (q, k, v))
+        q2, k2, v2 = (t if t.stride(1) == 1 else t.contiguous() for t in (q2, k2, v2))
+        o, lse = ops.attn_fwd(q2, k2, v2, B, S, Hq, Hkv, D, prefix_len)
+        ctx.save_for_backward(q2, k2, v2, o, lse)
+        ctx.dims = (B, S, Hq, Hkv, D, prefix_len)
+        return o.view(B, S, Hq, D)
+
+    @staticmethod
+    def backward(ctx, do: Tensor):
+        q2, k2, v2, o, lse = ctx.saved_tensors
+        B, S, Hq, Hkv, D, prefix_len = ctx.dims
+        dq, dk, dv = torch.empty_like(q2), torch.empty_like(k2), torch.empty_like(v2)
+        ops.attn_bwd(q2, k2, v2, o, lse, do.reshape(B * S, Hq * D), dq, dk, dv, B, S, Hq, Hkv, D, prefix_len)
+        return dq.view(B, S, Hq, D), dk.view(B, S, Hkv, D), dv.view(B, S, Hkv, D), None
+
+
+def prefix_lm_attention(q: Tensor, k: Tensor, v: Tensor, prefix_len: int = 0) -> Tensor:
+    return _PrefixLMAttentionFn.apply(q, k, v, prefix_len)
+
+
+class Attention(nn.Module):
+    def __init__(self, config: LlamaConfig) -> None:
+        super().__init__()
+        self.num_heads = config.num_heads
+        self.num_kv_heads = config.num_kv_heads
+        self.embed_dim = config.embed_dim
+        self.attn_dropout = config.attn_dropout
+        self.head_dim = config.head_dim
+        self.wq = nn.Linear(self.embed_dim, self.num_heads * self.head_dim, bias=False)
+        self.wk = nn.Linear(self.embed_dim, self.num_kv_heads * self.head_dim, bias=False)
+        self.wv = nn.Linear(self.embed_dim, self.num_kv_heads * self.head_dim, bias=False)
+        self.wo = nn.Linear(self.num_heads * self.head_dim, self.embed_dim, bias=False)
+        self.kv_cache = None
+
+    def forward(self, x: Tensor, rope: Tensor, *, mask: Tensor | None = None, input_pos: Tensor | None = None,
+                block_mask=None) -> Tensor:
+        if self.kv_cache is not None:
+            raise NotImplementedError("llamax_b200: KV-cache decoding is outside the fine-tuning hot path")
+        if self.training and self.attn_dropout > 0:
+            raise NotImplementedError("llamax_b200: attention dropout is not implemented")
+        prefix_len = _prefix_len_of(mask, block_mask, input_pos)
+        B, L, _ = x.shape
+        q = self.wq(x).view(B, L, self.num_heads, self.head_dim)
+        k = self.wk(x).view(B, L, self.num_kv_heads, self.head_dim)
+        v = self.wv(x).view(B, L, self.num_kv_heads, self.head_dim)
+        q, k = apply_rope(q, rope), apply_rope(k, rope)
+        out = prefix_lm_attention(q, k, v, prefix_len)
+        return self.wo(out.reshape(B, L, self.num_heads * self.head_dim))
+
+
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ab: Tensor):
+        M, F2 = ab.shape
+        g, _, _ = ops.swiglu_fwd(ab[:, : F2 // 2], ab[:, F2 // 2 :])
+        ctx.save_for_backward(ab)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg: Tensor):
+        (ab,) = ctx.saved_tensors
+        F_ = ab.shape[1] // 2
+        dab = torch.empty_like(ab)
+        ops.swiglu_bwd(dg.contiguous(), ab[:, :F_], ab[:, F_:], out_ab=dab)
+        return dab
+
+
+class FeedForward(nn.Module):
+    def __init__(self, config: LlamaConfig):
+        super().__init__()
+        self.w1 = nn.Linear(config.embed_dim, config.intermediate_dim, bias=False)
+        self.w3 = nn.Linear(config.embed_dim, config.intermediate_dim, bias=False)
+        self.w2 = nn.Linear(config.intermediate_dim, config.embed_dim, bias=False)
+        self.act = nn.SiLU()
+
+    def forward(self, x: Tensor) -> Tensor:
+        shape = x.shape
+        ab = torch.cat([self.w1(x), self.w3(x)], dim=-1).reshape(-1, 2 * self.w1.out_features)
+        g = _SwiGLUFn.apply(ab).view(*shape[:-1], -1)
+        return self.w2(g)
+
+
+class TransformerLayer(nn.Module):
+    def __init__(self, config: LlamaConfig) -> None:
+        super().__init__()
+        self.attention_norm = nn.RMSNorm(config.embed_dim, eps=1e-5)
+        self.attention = Attention(config)
+        self.ffn_norm = nn.RMSNorm(config.embed_dim, eps=1e-5)
+        self.feed_forward = FeedForward(config)
+
+    def forward(self, x: Tensor, rope: Tensor, *, mask: Tensor | None = None, input_pos: Tensor | None = None,
+                block_mask=None) -> Tensor:
+        if fused_block_supported(self, x):
+            prefix_len = _prefix_len_of(mask, block_mask, input_pos)
+            return FusedDecoderBlock.apply(x, rope, (self, prefix_len), *block_trainables(self))
+        # unfused composition (e.g. bf16 base weights): same math, module by module
+        x = x + self.attention(self.attention_norm(x), rope, mask=mask, input_pos=input_pos, block_mask=block_mask)
+        x = x + self.feed_forward(self.ffn_norm(x))
+        return x
+
+
+class Llama(nn.Module):
+    def __init__(self, config: LlamaConfig) -> None:
+        super().__init__()
+        self.tok_embeddings = nn.Embedding(config.vocab_size, config.embed_dim)
+        self.layers = nn.ModuleList([TransformerLayer(config) for _ in range(config.num_layers)])
+        self.norm = nn.RMSNorm(config.embed_dim, eps=1e-5)
+        self.output = nn.Linear(config.embed_dim, config.vocab_size, bias=False)
+        self.config = config
+
+    def build_cache(self, inference: bool = False):
+        if inference:
+            raise NotImplementedError("llamax_b200: build_cache(inference=True) (KV cache) is out of scope")
+        device = self.tok_embeddings.weight.device
+        self.register_buffer("rope", build_rope(self.config).to(device), persistent=False)
+
+    def _run_layers(self, x: Tensor, block_mask) -> Tensor:
+        rope = self.rope[: x.shape[1]]
+        for layer in self.layers:
+            if self.config.activation_checkpointing:
+                from torch.utils.checkpoint import checkpoint
+
+                x = checkpoint(layer, x, rope, block_mask=block_mask, use_reentrant=False)
+            else:
+                x = layer(x, rope, block_mask=block_mask)
+        return x
+
+    def _head(self, x: Tensor, labels: Tensor | None) -> Tensor:
+        x = self.norm(x)
+        if labels is None:
+            return self.output(x)
+        return chunked_lm_loss(x, self.output.weight, labels)
+
+    def forward(self, x: Tensor, *, input_pos: Tensor | None = None, block_mask=None,
+                labels: Tensor | None = None) -> Tensor:
+        if input_pos is not None:
+            raise NotImplementedError("llamax_b200: input_pos (inference) is outside the fine-tuning hot path")
+        x = self.tok_embeddings(x)
+        x = self._run_layers(x, block_mask)
+        return self._head(x, labels)
+
+
+class _ChunkedLMLoss(torch.autograd.Function):
+    """mean cross-entropy of (x @ W^T).float() against labels (ignore_index = -100) without materialising the
+    [M, vocab] fp32 logits (llama.py:216-218 keeps 8.4 GB of them at M = 16384). Row chunks; per chunk the bf16
+    logits GEMM, an fp32 log-sum-exp, and — since the head is frozen in this workload — dx = (softmax - onehot) W.
+    (LM head + CE are a 'next' row of the scope table: library GEMMs here, not hand-written kernels.)"""
+
+    CHUNK = 4096
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, labels: Tensor):
+        x2 = x.reshape(-1, x.shape[-1])
+        lab = labels.reshape(-1)
+        n_valid = (lab != -100).sum().clamp(min=1)
+        loss = torch.zeros((), device=x.device, dtype=torch.float32)
+        need_dx = x.requires_grad
+        need_dw = weight.requires_grad
+        dx = torch.empty_like(x2) if need_dx else None
+        dw = torch.zeros_like(weight, dtype=torch.float32) if need_dw else None
+        for i in range(0, x2.shape[0], _ChunkedLMLoss.CHUNK):
+            xs, ls = x2[i : i + _ChunkedLMLoss.CHUNK], lab[i : i + _ChunkedLMLoss.CHUNK]
+            logits = (xs @ weight.T).float()
+            lse = torch.logsumexp(logits, dim=-1)
+            valid = ls != -100
+            tgt = logits.gather(1, ls.clamp(min=0).unsqueeze(1)).squeeze(1)
+            loss += ((lse - tgt) * valid).sum()
+            if need_dx or need_dw:
+                p = torch.exp(logits - lse.unsqueeze(1))
+                p.scatter_add_(1, ls.clamp(min=0).unsqueeze(1), -torch.ones_like(lse).unsqueeze(1))
+                p *= (valid / n_valid).unsqueeze(1)
+                p = p.to(x.dtype)
+                if need_dx:
+                    dx[i : i + _ChunkedLMLoss.CHUNK] = p @ weight
+                if need_dw:
+                    dw += (p.T @ xs).float()
+        ctx.save_for_backward(dx, dw)
+        ctx.x_shape = x.shape
+        ctx.w_dtype = weight.dtype
+        return loss / n_valid
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        dx, dw = ctx.saved_tensors
+        gx = (dx * g).view(ctx.x_shape) if dx is not None else None
+        gw = (dw * g).to(ctx.w_dtype) if dw is not None else None
+        return gx, gw, None
+
+
+def chunked_lm_loss(x: Tensor, weight: Tensor, labels: Tensor) -> Tensor:
+    from ..subclasses.int8 import Int8LinearWeight
+
+    if isinstance(weight, Int8LinearWeight):  # quantised head: go through the module path
+        logits = F.linear(x, weight)
+        return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), labels.view(-1))
+    return _ChunkedLMLoss.apply(x, weight, labels)

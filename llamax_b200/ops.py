@@ -132,13 +132,12 @@ def dequant_weight(w8: Tensor, scale: Tensor | None, *, transpose: bool, apply_s
     shape = (K, N) if transpose else (N, K)
     if out is None:
         out = torch.empty(shape, device=w8.device, dtype=torch.bfloat16)
-    else:
-        out = out.view(-1)[: N * K].view(shape)
+    assert out.shape == shape and out.stride(1) == 1 and out.dtype is torch.bfloat16
     if apply_scale:
         scale = scale.contiguous()
         assert scale.dtype is torch.bfloat16
-    check(lib.llamax_dequant_weight(_p(w8), _p(scale) if apply_scale else None, _p(out), N, K, int(transpose),
-                                    int(apply_scale), st), "llamax_dequant_weight")
+    check(lib.llamax_dequant_weight(_p(w8), _p(scale) if apply_scale else None, _p(out), out.stride(0), N, K,
+                                    int(transpose), int(apply_scale), st), "llamax_dequant_weight")
     return out
 
 
@@ -206,16 +205,15 @@ def swiglu_fwd(a: Tensor, b: Tensor, *, quant: bool = False, want_g: bool = True
 
 
 def swiglu_bwd(dg: Tensor, a: Tensor, b: Tensor, *, want_g: bool = False, out_ab: Tensor | None = None):
-    """Returns (da, db, g | None). If out_ab [M, 2F] is given, da/db are its two column halves."""
+    """Returns (da, db, g | None). If out_ab [M, >= 2F] is given, da/db are its first two F-wide column blocks."""
     lib, st = _prep(a)
     assert dg.is_contiguous() and a.stride(1) == 1 and a.stride(0) == b.stride(0)
     M, F = a.shape
     if out_ab is None:
         out_ab = torch.empty(M, 2 * F, device=a.device, dtype=torch.bfloat16)
-    da, db = out_ab[:, :F], out_ab[:, F:]
-    assert da.stride(0) == a.stride(0), "da/db use the same row pitch as a/b"
+    da, db = out_ab[:, :F], out_ab[:, F : 2 * F]
     g = torch.empty(M, F, device=a.device, dtype=torch.bfloat16) if want_g else None
-    check(lib.llamax_swiglu_bwd(_p(dg), _p(a), _p(b), a.stride(0), _p(da), _p(db), _p(g), M, F, st),
+    check(lib.llamax_swiglu_bwd(_p(dg), _p(a), _p(b), a.stride(0), _p(da), _p(db), out_ab.stride(0), _p(g), M, F, st),
           "llamax_swiglu_bwd")
     return da, db, g
 

@@ -213,8 +213,24 @@ class LayerWeights:
         self.ffn_norm = None
 
 
+class Int8LinearRef(torch.autograd.Function):
+    """The reference's custom autograd node (subclasses/int8.py:106-130): forward in either INT8 mode, backward
+    grad_input = (grad * scale) @ W8 in the gradient's dtype — a straight-through estimator that ignores the
+    activation quantisation of the dynamic mode; the frozen weight gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w8, w_scale, dynamic_int8_act):
+        ctx.save_for_backward(w8, w_scale)
+        return int8_linear_fwd_ref(x, w8, w_scale, dynamic_int8_act)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        w8, w_scale = ctx.saved_tensors
+        return int8_linear_bwd_ref(grad_out, w8, w_scale), None, None, None
+
+
 def lora_linear_ref(x, lw: LayerWeights, name: str, dynamic: bool):
-    out = int8_linear_fwd_ref(x, lw.w8[name], lw.ws[name], dynamic)
+    out = Int8LinearRef.apply(x, lw.w8[name], lw.ws[name], dynamic)
     if name in lw.lora_a:
         out = out + lora_delta_ref(x, lw.lora_a[name], lw.lora_b[name], lw.lora_scale)
     return out
