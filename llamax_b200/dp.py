@@ -1,0 +1,68 @@
+"""Data parallelism for the fine-tuning step: one process per GPU, full replica per rank, ONE all-reduce (average)
+of the trainable gradients per optimizer step over NCCL / NVLink.
+
+The reference has no distributed code at all (both train scripts are single-process); the payload here is small
+(LoRA r=8 on Llama-3.1-8B: 20.97 M elements = 41.9 MB bf16, + 65 RMSNorm weights), so a single flat bucket and a
+plain NCCL all-reduce is the right tool: there is no compute step to fuse with and nothing to overlap that would
+show up in a >= 200 ms step.
+"""
+
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: str | None = None):
+    """Initialise torch.distributed from the torchrun environment. Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+class GradBucket:
+    """Flat bucket over the gradients of `params`; `allreduce_()` averages them across ranks in one collective."""
+
+    def __init__(self, params, dtype=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.numel = sum(p.numel() for p in self.params)
+        self.dtype = dtype
+        self._flat = None
+
+    def nbytes(self) -> int:
+        dt = self.dtype or (self.params[0].dtype if self.params else torch.bfloat16)
+        return self.numel * torch.empty((), dtype=dt).element_size()
+
+    def allreduce_(self, group=None):
+        if not dist.is_initialized() or dist.get_world_size(group) == 1 or not self.params:
+            return
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        dt = self.dtype or grads[0].dtype
+        if self._flat is None or self._flat.device != grads[0].device or self._flat.dtype != dt:
+            self._flat = torch.empty(self.numel, device=grads[0].device, dtype=dt)
+        views = list(self._flat.split([g.numel() for g in grads]))
+        torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(self._flat, op=dist.ReduceOp.AVG, group=group)
+        else:  # gloo has no AVG (and no bf16 sum on some builds): sum in fp32, divide
+            tmp = self._flat.float()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+            self._flat.copy_(tmp / dist.get_world_size(group))
+        for p, g, v in zip(self.params, grads, views):
+            if p.grad is None:
+                p.grad = v.view_as(p).clone()
+            else:
+                g.copy_(v.view_as(g))

@@ -17,6 +17,49 @@ from ._lib import Epilogue, check
 _tls = threading.local()
 
 
+class _KernelTiming:
+    """Optional CUDA-event timing of every library launch, by kernel class (used by bench.py for the live
+    per-kernel roofline). Off by default: zero overhead on the training path."""
+
+    def __init__(self):
+        self.on = False
+        self.records = []
+
+    def enable(self):
+        self.records, self.on = [], True
+
+    def disable(self):
+        self.on = False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, flops, nbytes in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["n"] += 1
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+TIMING = _KernelTiming()
+
+
+def _call(lib, name: str, args: tuple, kclass: str, flops: float = 0.0, nbytes: float = 0.0):
+    """Invoke one C-ABI entry point; raise on a non-zero return; optionally time it with CUDA events."""
+    fn = getattr(lib, name)
+    if TIMING.on:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TIMING.records.append((kclass, e0, e1, flops, nbytes))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+
+
 def _prep(t: Tensor):
     """Select the tensor's device for this thread, return (lib, stream handle)."""
     if not t.is_cuda:
@@ -84,9 +127,9 @@ def int8_gemm_dequant(A: Tensor, W: Tensor, a_scale: Tensor, w_scale: Tensor, *,
         out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
     assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
     ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
-    check(lib.llamax_int8_gemm_dequant(_p(A), A.stride(0), _p(W), W.stride(0), _p(a_scale), _p(w_scale), _p(out),
-                                       out.stride(0), M, N, K, ctypes.byref(ep) if ep is not None else None, st),
-          "llamax_int8_gemm_dequant")
+    _call(lib, "llamax_int8_gemm_dequant",
+          (_p(A), A.stride(0), _p(W), W.stride(0), _p(a_scale), _p(w_scale), _p(out), out.stride(0), M, N, K, ctypes.byref(ep) if ep is not None else None, st,),
+          "int8_gemm", 2.0 * M * N * K, 0.0)
     return out
 
 
@@ -97,8 +140,9 @@ def int8_gemm_s32(A: Tensor, W: Tensor) -> Tensor:
     M, K = A.shape
     N = W.shape[0]
     out = torch.empty(M, N, device=A.device, dtype=torch.int32)
-    check(lib.llamax_int8_gemm_s32(_p(A), A.stride(0), _p(W), W.stride(0), _p(out), out.stride(0), M, N, K, st),
-          "llamax_int8_gemm_s32")
+    _call(lib, "llamax_int8_gemm_s32",
+          (_p(A), A.stride(0), _p(W), W.stride(0), _p(out), out.stride(0), M, N, K, st,),
+          "int8_gemm", 2.0 * M * N * K, 0.0)
     return out
 
 
@@ -117,10 +161,9 @@ def bf16_gemm(A: Tensor, B: Tensor, *, col_scale: Tensor | None = None, round_be
         out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
     assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
     ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
-    check(lib.llamax_bf16_gemm(_p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), M, N, K,
-                               _p(col_scale), int(round_before_scale),
-                               ctypes.byref(ep) if ep is not None else None, st),
-          "llamax_bf16_gemm")
+    _call(lib, "llamax_bf16_gemm",
+          (_p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), M, N, K, _p(col_scale), int(round_before_scale), ctypes.byref(ep) if ep is not None else None, st,),
+          "bf16_gemm", 2.0 * M * N * K, 0.0)
     return out
 
 
@@ -136,8 +179,9 @@ def dequant_weight(w8: Tensor, scale: Tensor | None, *, transpose: bool, apply_s
     if apply_scale:
         scale = scale.contiguous()
         assert scale.dtype is torch.bfloat16
-    check(lib.llamax_dequant_weight(_p(w8), _p(scale) if apply_scale else None, _p(out), out.stride(0), N, K,
-                                    int(transpose), int(apply_scale), st), "llamax_dequant_weight")
+    _call(lib, "llamax_dequant_weight",
+          (_p(w8), _p(scale) if apply_scale else None, _p(out), out.stride(0), N, K, int(transpose), int(apply_scale), st,),
+          "dequant_weight", 0.0, 3.0 * N * K)
     return out
 
 
@@ -150,7 +194,9 @@ def rowquant_int8(x: Tensor):
     M, K = x2.shape
     q = torch.empty(M, K, device=x.device, dtype=torch.int8)
     s = torch.empty(M, device=x.device, dtype=torch.bfloat16)
-    check(lib.llamax_rowquant_int8(_p(x2), x2.stride(0), _p(q), _p(s), M, K, st), "llamax_rowquant_int8")
+    _call(lib, "llamax_rowquant_int8",
+          (_p(x2), x2.stride(0), _p(q), _p(s), M, K, st,),
+          "rowquant", 0.0, 3.0 * M * K)
     return q, s
 
 
@@ -164,8 +210,9 @@ def rmsnorm_fwd(x: Tensor, w: Tensor, eps: float, *, quant: bool = False, want_y
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
     q8 = torch.empty(M, D, device=x.device, dtype=torch.int8) if quant else None
     qs = torch.empty(M, device=x.device, dtype=torch.bfloat16) if quant else None
-    check(lib.llamax_rmsnorm_fwd(_p(x2), _p(w), _p(y), _p(rstd), _p(q8), _p(qs), M, D, float(eps), st),
-          "llamax_rmsnorm_fwd")
+    _call(lib, "llamax_rmsnorm_fwd",
+          (_p(x2), _p(w), _p(y), _p(rstd), _p(q8), _p(qs), M, D, float(eps), st,),
+          "rmsnorm_fwd", 0.0, (2.0 + 2.0 * (y is not None) + 1.0 * (q8 is not None)) * M * D)
     return y, rstd, q8, qs
 
 
@@ -182,12 +229,15 @@ def rmsnorm_bwd(dy: Tensor, x: Tensor, w: Tensor, rstd: Tensor, dres: Tensor | N
     dx = torch.empty_like(x2)
     nparts = max(1, min(int(M), 4 * torch.cuda.get_device_properties(x.device).multi_processor_count))
     partial = torch.empty(nparts, D, device=x.device, dtype=torch.float32) if want_dw else None
-    check(lib.llamax_rmsnorm_bwd(_p(dy2), _p(x2), _p(w), _p(rstd), _p(dres2), _p(dx), _p(partial), nparts, M, D, st),
-          "llamax_rmsnorm_bwd")
+    _call(lib, "llamax_rmsnorm_bwd",
+          (_p(dy2), _p(x2), _p(w), _p(rstd), _p(dres2), _p(dx), _p(partial), nparts, M, D, st,),
+          "rmsnorm_bwd", 0.0, (6.0 + 2.0 * (dres2 is not None)) * M * D)
     dw = None
     if want_dw:
         dw = torch.empty(D, device=x.device, dtype=torch.bfloat16)
-        check(lib.llamax_reduce_partials(_p(partial), _p(dw), nparts, D, st), "llamax_reduce_partials")
+        _call(lib, "llamax_reduce_partials",
+          (_p(partial), _p(dw), nparts, D, st,),
+          "rmsnorm_bwd", 0.0, 4.0 * nparts * D)
     return dx, dw
 
 
@@ -200,7 +250,9 @@ def swiglu_fwd(a: Tensor, b: Tensor, *, quant: bool = False, want_g: bool = True
     g = torch.empty(M, F, device=a.device, dtype=torch.bfloat16) if want_g else None
     q8 = torch.empty(M, F, device=a.device, dtype=torch.int8) if quant else None
     qs = torch.empty(M, device=a.device, dtype=torch.bfloat16) if quant else None
-    check(lib.llamax_swiglu_fwd(_p(a), _p(b), a.stride(0), _p(g), _p(q8), _p(qs), M, F, st), "llamax_swiglu_fwd")
+    _call(lib, "llamax_swiglu_fwd",
+          (_p(a), _p(b), a.stride(0), _p(g), _p(q8), _p(qs), M, F, st,),
+          "swiglu_fwd", 0.0, (4.0 + 2.0 * (g is not None) + 1.0 * (q8 is not None)) * M * F)
     return g, q8, qs
 
 
@@ -213,8 +265,9 @@ def swiglu_bwd(dg: Tensor, a: Tensor, b: Tensor, *, want_g: bool = False, out_ab
         out_ab = torch.empty(M, 2 * F, device=a.device, dtype=torch.bfloat16)
     da, db = out_ab[:, :F], out_ab[:, F : 2 * F]
     g = torch.empty(M, F, device=a.device, dtype=torch.bfloat16) if want_g else None
-    check(lib.llamax_swiglu_bwd(_p(dg), _p(a), _p(b), a.stride(0), _p(da), _p(db), out_ab.stride(0), _p(g), M, F, st),
-          "llamax_swiglu_bwd")
+    _call(lib, "llamax_swiglu_bwd",
+          (_p(dg), _p(a), _p(b), a.stride(0), _p(da), _p(db), out_ab.stride(0), _p(g), M, F, st,),
+          "swiglu_bwd", 0.0, (10.0 + 2.0 * (g is not None)) * M * F)
     return da, db, g
 
 
@@ -223,8 +276,9 @@ def rope_(x: Tensor, rope: Tensor, B: int, S: int, nheads: int, D: int, *, inver
     lib, st = _prep(x)
     assert x.dtype is torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == B * S
     assert rope.dtype is torch.float32 and rope.is_contiguous() and rope.shape[0] >= S and rope.shape[1] == D // 2
-    check(lib.llamax_rope_inplace(_p(x), x.stride(0), _p(rope), B, S, nheads, D, int(inverse), st),
-          "llamax_rope_inplace")
+    _call(lib, "llamax_rope_inplace",
+          (_p(x), x.stride(0), _p(rope), B, S, nheads, D, int(inverse), st,),
+          "rope", 0.0, 4.0 * B * S * nheads * D)
     return x
 
 
@@ -235,12 +289,19 @@ def lora_wgrad(X: Tensor, H: Tensor, alpha: float = 1.0) -> Tensor:
     M, Pn = X.shape
     R = H.shape[1]
     out = torch.zeros(Pn, R, device=X.device, dtype=torch.float32)
-    check(lib.llamax_lora_wgrad(_p(X), X.stride(0), _p(H), H.stride(0), _p(out), M, Pn, R, float(alpha), st),
-          "llamax_lora_wgrad")
+    _call(lib, "llamax_lora_wgrad",
+          (_p(X), X.stride(0), _p(H), H.stride(0), _p(out), M, Pn, R, float(alpha), st,),
+          "lora_wgrad", 2.0 * M * Pn * R, 2.0 * M * (Pn + R))
     return out
 
 
 # ---------------------------------------------------------------------------------------------- attention
+def _pairs(S: int, prefix_len: int) -> float:
+    """Unmasked (q, kv) pairs of the prefix-LM mask: S*P + (S-P)(S-P+1)/2."""
+    P_ = min(int(prefix_len), S)
+    return S * P_ + (S - P_) * (S - P_ + 1) / 2
+
+
 def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, prefix_len: int,
              scale: float | None = None):
     """q [B*S, Hq*D] / k, v [B*S, Hkv*D] row views (unit inner stride). Returns (o [B*S, Hq*D], lse [B,Hq,S])."""
@@ -250,8 +311,9 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int,
     o = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.bfloat16)
     lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     scale = float(scale) if scale is not None else D ** -0.5
-    check(lib.llamax_attn_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
-                              _p(lse), B, S, Hq, Hkv, D, int(prefix_len), scale, st), "llamax_attn_fwd")
+    _call(lib, "llamax_attn_fwd",
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), B, S, Hq, Hkv, D, int(prefix_len), scale, st,),
+          "attn_fwd", 4.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return o, lse
 
 
@@ -262,8 +324,7 @@ def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, sc
     dq_accum = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.float32)
     delta = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     scale = float(scale) if scale is not None else D ** -0.5
-    check(lib.llamax_attn_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
-                              _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
-                              _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len),
-                              scale, st), "llamax_attn_bwd")
+    _call(lib, "llamax_attn_bwd",
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len), scale, st,),
+          "attn_bwd", 10.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return dq, dk, dv
