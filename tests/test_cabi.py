@@ -1,0 +1,52 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/llamax_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+from llamax_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "llamax_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = re.findall(r"\b(?:int|const char\*)\s+(llamax_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    return {name: [a for a in args.split(",") if a.strip() not in ("", "void")] for name, args in decls}
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+
+    g.build()
+    lib = _lib.load()
+    declared = _declared()
+    assert len(declared) >= 18
+    for name, args in declared.items():
+        fn = getattr(lib, name)  # raises AttributeError when missing
+        assert fn is not None
+        if name in _lib.SIGNATURES:
+            assert len(_lib.SIGNATURES[name]) == len(args), f"{name}: binding has {len(_lib.SIGNATURES[name])} args, header {len(args)}"
+    assert set(_lib.SIGNATURES) <= set(declared)
+    assert lib.llamax_version() == 100
+    assert isinstance(lib.llamax_last_error(), bytes)
+
+
+def test_epilogue_struct_layout_matches_header():
+    e = _lib.Epilogue
+    assert [f[0] for f in e._fields_] == ["lora_h", "ldh", "lora_b", "lora_rank", "lora_scale", "resid", "ldr"]
+    assert ctypes.sizeof(e) == 48 and e.lora_rank.offset == 24 and e.lora_scale.offset == 28 and e.resid.offset == 32
+
+
+def test_argument_validation_without_gpu():
+    """Entry points reject bad arguments before touching the device."""
+    lib = _lib.load()
+    rc = lib.llamax_rowquant_int8(None, 0, None, None, 4, 16, None)
+    assert rc == -1 and b"null" in lib.llamax_last_error()
+    rc = lib.llamax_set_gemm_cta_group(3)
+    assert rc == -1
+    assert lib.llamax_set_gemm_cta_group(2) == 0
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.llamax_attn_fwd(p, 64, p, 64, p, 64, p, 64, p, 1, 16, 2, 1, 64, 0, 1.0, None)
+    assert rc == -1 and b"head_dim" in lib.llamax_last_error()

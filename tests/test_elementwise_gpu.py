@@ -1,0 +1,100 @@
+"""GPU parity of the HBM-bound passes (row quantisation bit-exact; norm / SwiGLU / RoPE against the reference
+formulas; backward passes within 1e-2 of the fp32 evaluation)."""
+import pytest
+import torch
+
+from llamax_b200 import ops
+from oracle import ref_ops as R
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,K", [(64, 512), (300, 4096), (128, 14336), (5, 1792), (1, 8), (3, 32768)])
+def test_rowquant_bit_exact(M, K):
+    g = torch.Generator().manual_seed(K)
+    x = (torch.randn(M, K, generator=g) * 3).bfloat16()
+    x[0].zero_()                                   # all-zero row -> scale 0, codes 0
+    if M > 2:
+        x[1] = 1e-30                               # below the 1e-12 clip
+        x[2, 0] = 3.0e38                           # huge dynamic range
+    q_ref, s_ref = R.quantize_int8_rowwise(x)
+    q, s = ops.rowquant_int8(x.cuda())
+    assert torch.equal(q.cpu(), q_ref) and torch.equal(s.cpu(), s_ref)
+
+
+def test_rowquant_pitched_input():
+    x = torch.randn(40, 1024).bfloat16()
+    q, s = ops.rowquant_int8(x.cuda()[:, 256:768])
+    q_ref, s_ref = R.quantize_int8_rowwise(x[:, 256:768].contiguous())
+    assert torch.equal(q.cpu(), q_ref) and torch.equal(s.cpu(), s_ref)
+
+
+@pytest.mark.parametrize("M,D", [(64, 512), (300, 4096), (7, 8192)])
+def test_rmsnorm_fwd_bwd(M, D):
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(M, D, generator=g).bfloat16()
+    w = (1 + 0.1 * torch.randn(D, generator=g)).bfloat16()
+    y_ref = R.rmsnorm_ref(x, w)
+    y, rstd, q8, qs = ops.rmsnorm_fwd(x.cuda(), w.cuda(), 1e-5, quant=True)
+    assert (y.cpu() != y_ref).float().mean().item() < 1e-3       # 1-ulp flips from the reduction order only
+    assert rel_err(y, y_ref.float()) < 8e-3
+    q_ref, s_ref = R.quantize_int8_rowwise(y.cpu())               # fused quantisation == quantising y
+    assert torch.equal(q8.cpu(), q_ref) and torch.equal(qs.cpu(), s_ref)
+    dy = torch.randn(M, D, generator=g).bfloat16()
+    dres = torch.randn(M, D, generator=g).bfloat16()
+    dx_ref, dw_ref = R.rmsnorm_bwd_f32(dy, x, w)
+    dx, dw = ops.rmsnorm_bwd(dy.cuda(), x.cuda(), w.cuda(), rstd, dres.cuda())
+    assert rel_err(dx, dx_ref + dres.float()) <= 1e-2 and rel_err(dw, dw_ref) <= 1e-2
+    dx2, dw2 = ops.rmsnorm_bwd(dy.cuda(), x.cuda(), w.cuda(), rstd, None, want_dw=False)
+    assert dw2 is None and rel_err(dx2, dx_ref) <= 1e-2
+
+
+@pytest.mark.parametrize("M,F", [(64, 1792), (100, 14336)])
+def test_swiglu_fwd_bwd(M, F):
+    g = torch.Generator().manual_seed(F)
+    ab = (torch.randn(M, 2 * F, generator=g) * 2).bfloat16()
+    a, b = ab[:, :F], ab[:, F:]
+    g_ref = R.swiglu_ref(a, b)
+    abc = ab.cuda()
+    gg, q8, qs = ops.swiglu_fwd(abc[:, :F], abc[:, F:], quant=True)
+    assert (gg.cpu() != g_ref).float().mean().item() < 1e-3
+    q_ref, s_ref = R.quantize_int8_rowwise(gg.cpu())
+    assert torch.equal(q8.cpu(), q_ref) and torch.equal(qs.cpu(), s_ref)
+    dg = torch.randn(M, F, generator=g).bfloat16()
+    da_ref, db_ref = R.swiglu_bwd_f32(dg, a, b)
+    wide = torch.zeros(M, 2 * F + 16, dtype=torch.bfloat16, device="cuda")
+    da, db, g2 = ops.swiglu_bwd(dg.cuda(), abc[:, :F], abc[:, F:], want_g=True, out_ab=wide)
+    assert rel_err(da, da_ref) <= 1e-2 and rel_err(db, db_ref) <= 1e-2
+    assert torch.equal(g2.cpu(), gg.cpu()) and (wide[:, 2 * F :] == 0).all()
+
+
+def test_rope_bit_exact_and_inverse():
+    B, S, H, D = 2, 300, 6, 128
+    rope = R.build_rope(D, 512, 500000, True)
+    x = torch.randn(B, S, H, D).bfloat16()
+    y_ref = R.apply_rope(x, rope[:S])
+    xc = torch.cat([x.reshape(B * S, H * D), torch.zeros(B * S, 256).bfloat16()], 1).cuda()
+    ops.rope_(xc, rope.cuda(), B, S, H, D)
+    assert torch.equal(xc[:, : H * D].cpu().view(B, S, H, D), y_ref)
+    assert (xc[:, H * D :] == 0).all()
+    dy = torch.randn(B, S, H, D).bfloat16()
+    dyc = dy.reshape(B * S, H * D).clone().cuda()
+    ops.rope_(dyc, rope.cuda(), B, S, H, D, inverse=True)
+    assert torch.equal(dyc.cpu().view(B, S, H, D), R.apply_rope_inverse(dy, rope[:S]))
+
+
+def test_dequant_weight_and_lora_wgrad():
+    N, K = 264, 256
+    w8 = torch.randint(-127, 128, (N, K), dtype=torch.int8)
+    s = (torch.rand(N) * 0.01).bfloat16()
+    o1 = ops.dequant_weight(w8.cuda(), s.cuda(), transpose=False, apply_scale=False).cpu()
+    assert torch.equal(o1, w8.bfloat16())
+    wide = torch.zeros(K, N + 24, dtype=torch.bfloat16, device="cuda")
+    ops.dequant_weight(w8.cuda(), s.cuda(), transpose=True, apply_scale=True, out=wide[:, :N])
+    assert torch.equal(wide[:, :N].cpu(), (w8.float() * s.float()[:, None]).bfloat16().T) and (wide[:, N:] == 0).all()
+    for Rr in (8, 16, 24):
+        M, Pn = 1000, 512
+        X, Hh = torch.randn(M, Pn).bfloat16(), torch.randn(M, Rr).bfloat16()
+        o = ops.lora_wgrad(X.cuda(), Hh.cuda(), 0.5).cpu()
+        assert rel_err(o, 0.5 * X.float().T @ Hh.float()) < 1e-4

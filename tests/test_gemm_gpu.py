@@ -1,0 +1,131 @@
+"""GPU parity of the tcgen05 GEMMs through the C ABI.
+INT8: int32 accumulators and the dequantised bf16 output are BIT-EXACT against the oracle (subclasses/int8_mm.py).
+bf16: max |err| / max |ref_fp32| <= 1e-2 (north_star tolerance)."""
+import pytest
+import torch
+
+from llamax_b200 import ops
+from oracle import ref_ops as R
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_i8(*shape, gen=None):
+    return torch.randint(-127, 128, shape, dtype=torch.int8, generator=gen)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (256, 512, 512), (300, 264, 208), (1, 8, 16), (513, 1024, 4096),
+                                   (1024, 128, 1792), (77, 6144, 512)])
+def test_int8_accumulators_bit_exact(cg, M, N, K):
+    ops.set_gemm_cta_group(cg)
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A, W = _rand_i8(M, K, gen=g), _rand_i8(N, K, gen=g)
+    out = ops.int8_gemm_s32(A.cuda(), W.cuda()).cpu()
+    assert torch.equal(out, A.int() @ W.int().T)
+    ops.set_gemm_cta_group(2)
+
+
+def test_int8_adversarial_range():
+    """All-(+-127) operands at K = 14336: |acc| = K * 127^2 = 231,225,344 < 2^31, no saturation."""
+    M, N, K = 130, 264, 14336
+    A = torch.full((M, K), 127, dtype=torch.int8)
+    W = torch.full((N, K), -127, dtype=torch.int8)
+    W[::2] = 127
+    out = ops.int8_gemm_s32(A.cuda(), W.cuda()).cpu()
+    assert torch.equal(out, R.int8_mm_s32(A, W.T))
+    assert out.abs().max().item() == K * 127 * 127
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 768, 1024), (300, 264, 208)])
+def test_int8_dequant_output_bit_exact(M, N, K):
+    g = torch.Generator().manual_seed(1)
+    A, W = _rand_i8(M, K, gen=g), _rand_i8(N, K, gen=g)
+    sa = (torch.rand(M, generator=g) * 0.1).bfloat16()
+    sw = (torch.rand(N, generator=g) * 0.01).bfloat16()
+    ref = R.int8_mm_dequant(A, W.T, sa, sw)
+    out = ops.int8_gemm_dequant(A.cuda(), W.cuda(), sa.cuda(), sw.cuda()).cpu()
+    assert torch.equal(out, ref)
+    # the torch.library seam (reference schema: B is the [K,N] transposed view)
+    from llamax_b200.subclasses import int8_mm_dequant
+
+    out2 = int8_mm_dequant(A.cuda(), W.cuda().T, sa.cuda(), sw.cuda()).cpu()
+    assert torch.equal(out2, ref)
+    out3 = int8_mm_dequant(A.cuda(), W.T.contiguous().cuda(), sa.cuda(), sw.cuda()).cpu()  # non-view B: copied
+    assert torch.equal(out3, ref)
+
+
+def test_int8_full_size_checksum():
+    """BASELINE config 4 at full size (M=16384, N=14336, K=4096): every row's sum of accumulators equals
+    A[m,:] . colsum(W) exactly (int64) — a checksum of the whole 235 M-element result."""
+    M, N, K = 16384, 14336, 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randint(-127, 128, (M, K), dtype=torch.int8, device="cuda", generator=g)
+    W = torch.randint(-127, 128, (N, K), dtype=torch.int8, device="cuda", generator=g)
+    out = ops.int8_gemm_s32(A, W)
+    rows = out.sum(1, dtype=torch.int64)
+    wsum = W.sum(0, dtype=torch.int64).double()
+    expect = (A.double() @ wsum).to(torch.int64)  # |values| < 2^53: exact in fp64
+    assert torch.equal(rows, expect)
+    cols = out.sum(0, dtype=torch.int64)
+    expect_c = (W.double() @ A.sum(0, dtype=torch.int64).double()).to(torch.int64)
+    assert torch.equal(cols, expect_c)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 264, 200), (2048, 1024, 4096), (1000, 16, 4096), (640, 4096, 6168)])
+def test_bf16_gemm_tolerance(cg, M, N, K):
+    ops.set_gemm_cta_group(cg)
+    g = torch.Generator().manual_seed(2)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    B = torch.randn(N, K, generator=g).bfloat16()
+    out = ops.bf16_gemm(A.cuda(), B.cuda())
+    assert rel_err(out, A.float() @ B.float().T) <= 1e-2
+    ops.set_gemm_cta_group(2)
+
+
+def test_epilogue_lora_residual_and_pitched_output():
+    M, N, K, Rk = 384, 520, 512, 8
+    g = torch.Generator().manual_seed(3)
+    A, W = _rand_i8(M, K, gen=g), _rand_i8(N, K, gen=g)
+    sa, sw = (torch.rand(M, generator=g) * 0.1).bfloat16(), (torch.rand(N, generator=g) * 0.01).bfloat16()
+    h = torch.randn(M, 24, generator=g).bfloat16()            # rank-8 slice of a wider h (pitch 24)
+    lb = (torch.randn(N, Rk, generator=g) * 0.1).bfloat16()
+    res = torch.randn(M, N, generator=g).bfloat16()
+    buf = torch.zeros(M, N + 64, dtype=torch.bfloat16, device="cuda")
+    ops.int8_gemm_dequant(A.cuda(), W.cuda(), sa.cuda(), sw.cuda(), out=buf[:, 32 : 32 + N], lora_h=h.cuda()[:, 8:16],
+                          lora_b=lb.cuda(), lora_scale=2.0, resid=res.cuda())
+    ref = ((A.int() @ W.int().T).float() * sa.float()[:, None]) * sw.float()[None, :] \
+        + 2.0 * (h[:, 8:16].float() @ lb.float().T) + res.float()
+    assert rel_err(buf[:, 32 : 32 + N], ref) <= 5e-3
+    assert (buf[:, :32] == 0).all() and (buf[:, 32 + N :] == 0).all()  # nothing written outside the slice
+
+
+def test_weight_only_forward_and_grad_input_vs_reference_formulas():
+    """int8.py:118 / :127 — bf16 reference op sequence and its fp32 evaluation."""
+    M, N, K = 256, 384, 512
+    g = torch.Generator().manual_seed(4)
+    w8, ws = R.quantize_int8_rowwise((torch.randn(N, K, generator=g) * 0.05).bfloat16())
+    x = torch.randn(M, K, generator=g).bfloat16()
+    dy = torch.randn(M, N, generator=g).bfloat16()
+    from llamax_b200.subclasses.int8 import int8_linear_forward, int8_linear_grad_input
+
+    y = int8_linear_forward(x.cuda(), w8.cuda(), ws.cuda(), False).cpu()
+    y_ref = R.int8_linear_fwd_ref(x, w8, ws, False)
+    assert rel_err(y, R.int8_linear_fwd_f32(x, w8, ws)) <= 1e-2
+    assert (y != y_ref).float().mean().item() < 0.02  # same two roundings; fp32 summation order may flip an ulp
+    gx = int8_linear_grad_input(dy.cuda(), w8.cuda(), ws.cuda()).cpu()
+    assert rel_err(gx, R.int8_linear_bwd_f32(dy, w8, ws)) <= 1e-2
+    assert rel_err(gx, R.int8_linear_bwd_ref(dy, w8, ws).float()) <= 1e-2
+
+
+def test_bad_arguments_raise():
+    from llamax_b200._lib import LlamaxError
+
+    A = torch.zeros(16, 24, dtype=torch.int8, device="cuda")  # K = 24: row pitch not 16-byte aligned
+    W = torch.zeros(8, 24, dtype=torch.int8, device="cuda")
+    with pytest.raises(LlamaxError):
+        ops.int8_gemm_s32(A, W)
+    with pytest.raises(LlamaxError):
+        ops.rowquant_int8(torch.zeros(4, 16, dtype=torch.bfloat16))  # CPU tensor: no fallback
