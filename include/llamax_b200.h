@@ -125,10 +125,19 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     void* stream);
 
 /* ---- K6 backward: LoRA weight gradients (autograd of modelling/lora.py:43) ------------------------
- *   out[p, r] (fp32, accumulated) += alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx, H bf16 [M,R]
- * used for dB = scale * dY^T h and dA^T = x^T dh.  `out` must be zeroed by the caller before the first call. */
-int llamax_lora_wgrad(const void* X, int64_t ldx, const void* H, int64_t ldh, void* out, int64_t M, int64_t P,
-                      int32_t R, float alpha, void* stream);
+ *   out[p, r] (fp32) = alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx, H bf16 [M,R] pitch ldh
+ * used for dB = scale * dY^T h and dA^T = x^T dh.  workspace: fp32 [nparts, P, R]; the M rows are split into
+ * nparts chunks whose partial sums are reduced by a second kernel (no atomics). */
+int llamax_lora_wgrad(const void* X, int64_t ldx, const void* H, int64_t ldh, void* out, void* workspace,
+                      int32_t nparts, int64_t M, int64_t P, int32_t R, float alpha, void* stream);
+
+/* ---- K12 (next row): cross-entropy over bf16 logits, forward + backward in place -------------------
+ * F.cross_entropy(logits.float(), labels) (modelling/llama.py:216-218, audio.py:74-76), ignore_index = -100:
+ *   loss_sum[0] += sum_rows (logsumexp(f32(logits[m,:])) - logits[m, label]);
+ *   if write_grad: logits[m,:] <- (softmax(logits[m,:]) - onehot(label)) * inv_n[0]   (0 for ignored rows)
+ * logits bf16 [M, V] pitch ld; labels int64 [M]; loss_sum, inv_n: fp32 device scalars. */
+int llamax_cross_entropy(void* logits, int64_t ld, const void* labels, void* loss_sum, const void* inv_n, int64_t M,
+                         int64_t V, int write_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -198,55 +198,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tmem_S + st * 128 + lane_off;
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
-        tmem_wait_ld();
-        if (full_tile) {
+      // single pass over TMEM: the whole score row (128 fp32) lives in registers
+      uint32_t sv[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, sv[c]);
+      tmem_wait_ld_regs(sv[0]);
+      tmem_wait_ld_regs(sv[1]);
+      tmem_wait_ld_regs(sv[2]);
+      tmem_wait_ld_regs(sv[3]);
+      // S is in registers: release the TMEM buffer for the next QK^T right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&s_empty[st]);
+      if (!full_tile) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kv = kv0 + c * 32 + i;
             const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q));
-            mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
+            if (!ok) sv[c][i] = 0xff800000u;  // -inf
           }
-        }
       }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
       const float m_tile = mx * p.scale_log2;
       float alpha = 1.f;
       if (m_tile > m_used + 8.f) {  // lazy rescale: only when the running max grows by more than 2^8
         alpha = ex2(m_used - m_tile);
         m_used = m_tile;
       }
-      // pass 2: probabilities
       uint32_t preg[64];
       float rowsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
-        tmem_wait_ld();
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used));
-          float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used));
-          if (!full_tile) {
-            const int kv = kv0 + c * 32 + i;
-            if (!((kv < p.S) && ((kv < p.P) || (kv <= q)))) p0 = 0.f;
-            if (!((kv + 1 < p.S) && ((kv + 1 < p.P) || (kv + 1 <= q)))) p1 = 0.f;
-          }
+          const float p0 = ex2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_used));      // -inf -> 0
+          const float p1 = ex2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_used));
           rowsum += p0 + p1;
           preg[c * 16 + i / 2] = pack_bf16(p0, p1);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&s_empty[st]);
+
       l = l * alpha + rowsum;
 
       if (j > 0) {
@@ -315,7 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 struct AttnBwdParams {
   const float* lse;    // [B, Hq, S]
   const float* delta;  // [B, Hq, S]
-  float* dq_accum;     // [B*S, Hq*D] fp32
+  float* dq_accum;     // [B, Hq, S, D] fp32 (tile-contiguous for the bulk reduce)
   __nv_bfloat16* dk;
   int64_t lddk;
   __nv_bfloat16* dv;
@@ -336,7 +332,9 @@ constexpr int kOffQ = kOffV + kKVBytes;           // 2 stages
 constexpr int kOffdO = kOffQ + 2 * kQBytes;       // 2 stages
 constexpr int kOffP = kOffdO + 2 * kQBytes;
 constexpr int kOffdS = kOffP + kPBytes;
-constexpr int kOffStat = kOffdS + kPBytes;        // lse2 / delta: 2 stages x 2 x 64 floats
+constexpr int kOffdQ = kOffdS + kPBytes;          // fp32 [64 q][128 d] staging for the bulk reduce-add
+constexpr int kdQBytes = kQ * kHD * 4;            // 32 KB
+constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta: 2 stages x 2 x 64 floats
 constexpr int kOffBar = kOffStat + 2 * 2 * kQ * 4;
 constexpr int kNumBars = 1 + 4 + 1 + 1 + 1 + 1 + 1;  // kv_full, qdo full/empty[2], sdp_full, pds_full, dq_full, dq_empty, acc_done
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
@@ -543,25 +541,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(pds_full);
 
-      // drain dQ^T: this thread owns head-dim element d = t for the 64 query rows of the step
+      // drain dQ^T: this thread owns head-dim element d = t for the 64 query rows of the step.
+      // TMEM -> fp32 smem tile [q][d] (conflict-free: a warp writes 128 contiguous bytes per q) -> one bulk
+      // reduce-add of the whole tile into dq_accum[b, hq, q0:q0+64, :] (contiguous 32 KB).
       mbar_wait(dq_full, s & 1);
       tc_fence_after();
-      float* dq_base = p.dq_accum + ((int64_t)b * p.S + q0) * ((int64_t)p.Hq * kHD) + (int64_t)hq * kHD + t;
+      if (t == 0) tma_store_wait_read<0>();   // previous step's bulk reduce has finished reading the staging tile
+      named_bar_sync(2, 128);
+      float* stage = reinterpret_cast<float*>(smem + kOffdQ);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + kColdQ + lane_off + c * 32, v);
-        tmem_wait_ld();
+        tmem_wait_ld_regs(v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int qi = c * 32 + i;
-          if (q0 + qi < p.S) atomicAdd(dq_base + (int64_t)qi * p.Hq * kHD, __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < 32; ++i) stage[(c * 32 + i) * kHD + t] = __uint_as_float(v[i]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (t == 0) {
+        const int rows = min(kQ, p.S - q0);
+        float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0) * kHD;
+        bulk_reduce_add_f32(dst, stage, (uint32_t)rows * kHD * 4);
+        tma_store_commit();
       }
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(dq_empty);
     }
+    if (t == 0) tma_store_wait<0>();  // all bulk reductions of this CTA have completed
     // write dK, dV (thread = kv row)
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -613,21 +621,26 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t l
   }
 }
 
+// dq_accum fp32 [B, Hq, S, D] -> dq bf16 [B*S, Hq*D] (row pitch lddq); one thread = 8 head-dim elements
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t lddq,
-                                       int64_t rows, int width) {
-  const int vec_per_row = width / 8;
-  const int64_t total = rows * vec_per_row;
+                                       int64_t B, int S, int Hq) {
+  const int64_t total = B * Hq * (int64_t)S * (kHD / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / vec_per_row;
-    const int c = (int)(i - row * vec_per_row) * 8;
-    const float4 a = *reinterpret_cast<const float4*>(acc + row * width + c);
-    const float4 b4 = *reinterpret_cast<const float4*>(acc + row * width + c + 4);
+    const int c = (int)(i % (kHD / 8)) * 8;
+    int64_t r = i / (kHD / 8);        // (b * Hq + h) * S + s
+    const int s_ = (int)(r % S);
+    r /= S;
+    const int h = (int)(r % Hq);
+    const int64_t b = r / Hq;
+    const float* src = acc + (((b * Hq + h) * S + s_) * kHD + c);
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b4 = *reinterpret_cast<const float4*>(src + 4);
     uint4 o4;
     o4.x = pack_bf16(a.x, a.y);
     o4.y = pack_bf16(a.z, a.w);
     o4.z = pack_bf16(b4.x, b4.y);
     o4.w = pack_bf16(b4.z, b4.w);
-    *reinterpret_cast<uint4*>(dq + row * lddq + c) = o4;
+    *reinterpret_cast<uint4*>(dq + (b * S + s_) * lddq + (int64_t)h * kHD + c) = o4;
   }
 }
 
@@ -731,7 +744,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   {
     const int64_t total = rows * (Hq * kHD / 8);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, rows, Hq * kHD);
+    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq);
     LX_CHECK_LAUNCH("attn_bwd: dq convert");
   }
   return 0;

@@ -63,7 +63,19 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
   tn = r / gsize;
 }
 
-template <bool kInt8, int CG>
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// kRank: compile-time LoRA rank of the epilogue (0 = none, 8, 16); runtime ranks are zero-padded up to it.
+template <bool kInt8, int CG, int kRank>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<CG>;
@@ -185,6 +197,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int ew = warp - 4;                 // TMEM lanes [32*ew, 32*ew+32)
     const int et = threadIdx.x - 128;        // 0..127
     const int R = p.lora_rank;
+    constexpr int kRS = kRank > 0 ? kRank : 4;  // floats per staged lora_b row
+    const uint32_t s_cs = smem_u32(s_colscale);
+    const uint32_t s_lb = smem_u32(s_lorab);
+    const bool dump = (p.flags & 1) != 0;
+    const bool has_cs = p.col_scale != nullptr;
+    const bool pre_round = (p.flags & 2) != 0;
     int local_tile = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
       int tm, tn;
@@ -197,97 +215,116 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       // stage per-column data for this tile (previous tile's readers are done: barrier below)
       named_bar_sync(1, 128);
-      if (p.col_scale != nullptr) {
+      if (has_cs) {
         for (int i = et; i < kBN; i += 128)
           s_colscale[i] = (col0 + i < p.N) ? __bfloat162float(p.col_scale[col0 + i]) : 0.f;
       }
-      if (R > 0) {
-        for (int i = et; i < kBN * R; i += 128) {
-          const int n = i / R, r = i - n * R;
-          s_lorab[n * kMaxLoraRank + r] =
-              (col0 + n < p.N) ? __bfloat162float(p.lora_b[(int64_t)(col0 + n) * R + r]) * p.lora_scale : 0.f;
+      if constexpr (kRank > 0) {
+        for (int i = et; i < kBN * kRank; i += 128) {
+          const int n = i / kRank, r = i % kRank;
+          s_lorab[i] = (col0 + n < p.N && r < R) ? __bfloat162float(p.lora_b[(int64_t)(col0 + n) * R + r]) * p.lora_scale
+                                                  : 0.f;
         }
       }
       named_bar_sync(1, 128);
 
       float rs = 1.f;
       if (p.row_scale != nullptr && row_ok) rs = __bfloat162float(p.row_scale[row]);
-      float h[kMaxLoraRank];
+      float h[kRS];
 #pragma unroll
-      for (int r = 0; r < kMaxLoraRank; ++r)
-        h[r] = (r < R && row_ok) ? __bfloat162float(p.lora_h[(int64_t)row * p.ldh + r]) : 0.f;
+      for (int r = 0; r < kRS; ++r) h[r] = 0.f;
+      if constexpr (kRank > 0) {
+        if (row_ok) {
+          const __nv_bfloat16* hp = p.lora_h + (int64_t)row * p.ldh;
+          if (R == kRank) {  // 16-byte vector loads (h rows are 16-byte aligned for rank 8 / 16)
+#pragma unroll
+            for (int r = 0; r < kRank; r += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(hp + r);
+              h[r + 0] = bf16_lo(u.x); h[r + 1] = bf16_hi(u.x); h[r + 2] = bf16_lo(u.y); h[r + 3] = bf16_hi(u.y);
+              h[r + 4] = bf16_lo(u.z); h[r + 5] = bf16_hi(u.z); h[r + 6] = bf16_lo(u.w); h[r + 7] = bf16_hi(u.w);
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < kRank; ++r)
+              if (r < R) h[r] = __bfloat162float(hp[r]);
+          }
+        }
+      }
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kBN;
+      const int n_chunks = min(kBN / 32, (p.N - col0 + 31) / 32);
 
+      uint32_t v[2][32];
+      tmem_ld_32x32(taddr, v[0]);
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        const int col = col0 + c * 32;
-        if (col >= p.N) break;
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_wait_ld();
-        if (p.flags & 1) {
-          if (row_ok) {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(p.C) + (int64_t)row * p.ldc + col;
+      for (int c = 0; c < n_chunks; c += 2) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (col + j < p.N) stg_v4(dst + j, make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          }
-          continue;
-        }
-        float f[32];
+        for (int half = 0; half < 2; ++half) {
+          const int cc = c + half;
+          if (cc >= n_chunks) break;
+          uint32_t(&vv)[32] = v[half];
+          tmem_wait_ld_regs(vv);
+          if (cc + 1 < n_chunks) tmem_ld_32x32(taddr + (cc + 1) * 32, v[half ^ 1]);  // prefetch next chunk
+          const int col = col0 + cc * 32;
+          if (dump) {
+            if (row_ok) {
+              uint32_t* dst = reinterpret_cast<uint32_t*>(p.C) + (int64_t)row * p.ldc + col;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = kInt8 ? static_cast<float>(static_cast<int32_t>(v[j])) : __uint_as_float(v[j]);
-          if constexpr (kInt8) {
-            a = (a * rs) * s_colscale[c * 32 + j];  // reference order: int8_mm.py:114
-          } else {
-            if (p.col_scale != nullptr) {
-              if (p.flags & 2) a = round_bf16(a);   // reference: bf16(x @ W^T) * s  (int8.py:118)
-              a = a * s_colscale[c * 32 + j];
+              for (int j = 0; j < 32; j += 4)
+                if (col + j < p.N) stg_v4(dst + j, make_uint4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]));
             }
+            continue;
           }
-          f[j] = a;
-        }
-        if (R > 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float4* lb = reinterpret_cast<const float4*>(&s_lorab[(c * 32 + j) * kMaxLoraRank]);
-            float acc = 0.f;
-#pragma unroll
-            for (int q = 0; q < kMaxLoraRank / 4; ++q) {
-              if (q * 4 < R) {
-                const float4 b4 = lb[q];
-                acc = fmaf(h[q * 4 + 0], b4.x, acc);
-                acc = fmaf(h[q * 4 + 1], b4.y, acc);
-                acc = fmaf(h[q * 4 + 2], b4.z, acc);
-                acc = fmaf(h[q * 4 + 3], b4.w, acc);
-              }
-            }
-            f[j] += acc;
-          }
-        }
-        if (row_ok) {
+          const __nv_bfloat16* rsd = (p.resid && row_ok) ? p.resid + (int64_t)row * p.ldr + col : nullptr;
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col;
-          const __nv_bfloat16* rsd = p.resid ? p.resid + (int64_t)row * p.ldr + col : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col + j < p.N) {
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            float f[8];
+            float cs[8];
+            if (kInt8 || has_cs) {
+              const float4 c0 = lds_f4(s_cs + (cc * 32 + j8) * 4), c1 = lds_f4(s_cs + (cc * 32 + j8 + 4) * 4);
+              cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = kInt8 ? static_cast<float>(static_cast<int32_t>(vv[j8 + j])) : __uint_as_float(vv[j8 + j]);
+              if constexpr (kInt8) {
+                a = (a * rs) * cs[j];              // reference order: int8_mm.py:114
+              } else if (has_cs) {
+                if (pre_round) a = round_bf16(a);  // reference: bf16(x @ W^T) * s  (int8.py:118)
+                a = a * cs[j];
+              }
+              if constexpr (kRank > 0) {
+                const uint32_t lb = s_lb + (cc * 32 + j8 + j) * (kRank * 4);
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < kRank; q += 4) {
+                  const float4 b4 = lds_f4(lb + q * 4);
+                  acc = fmaf(h[q + 0], b4.x, acc);
+                  acc = fmaf(h[q + 1], b4.y, acc);
+                  acc = fmaf(h[q + 2], b4.z, acc);
+                  acc = fmaf(h[q + 3], b4.w, acc);
+                }
+                a += acc;
+              }
+              f[j] = a;
+            }
+            if (row_ok && col + j8 < p.N) {
               if (rsd != nullptr) {
-                const uint4 r4 = *reinterpret_cast<const uint4*>(rsd + j);
-                f[j + 0] += bf16_lo(r4.x); f[j + 1] += bf16_hi(r4.x);
-                f[j + 2] += bf16_lo(r4.y); f[j + 3] += bf16_hi(r4.y);
-                f[j + 4] += bf16_lo(r4.z); f[j + 5] += bf16_hi(r4.z);
-                f[j + 6] += bf16_lo(r4.w); f[j + 7] += bf16_hi(r4.w);
+                const uint4 r4 = *reinterpret_cast<const uint4*>(rsd + j8);
+                f[0] += bf16_lo(r4.x); f[1] += bf16_hi(r4.x);
+                f[2] += bf16_lo(r4.y); f[3] += bf16_hi(r4.y);
+                f[4] += bf16_lo(r4.z); f[5] += bf16_hi(r4.z);
+                f[6] += bf16_lo(r4.w); f[7] += bf16_hi(r4.w);
               }
               uint4 o;
-              o.x = pack_bf16(f[j + 0], f[j + 1]);
-              o.y = pack_bf16(f[j + 2], f[j + 3]);
-              o.z = pack_bf16(f[j + 4], f[j + 5]);
-              o.w = pack_bf16(f[j + 6], f[j + 7]);
-              stg_v4(dst + j, o);
+              o.x = pack_bf16(f[0], f[1]);
+              o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]);
+              o.w = pack_bf16(f[6], f[7]);
+              stg_v4(dst + j8, o);
             }
           }
         }
@@ -308,8 +345,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <bool kInt8, int CG>
-static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
+template <bool kInt8, int CG, int kRank>
+static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
   using S = GemmSmem<CG>;
   const int esz = kInt8 ? 1 : 2;
@@ -332,7 +369,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
   rc = make_tmap_2d(&tmB, dt, esz, B, p.K, p.N, ldb, elem_per_row, kBN / CG);
   if (rc) return rc;
 
-  auto kern = gemm_kernel<kInt8, CG>;
+  auto kern = gemm_kernel<kInt8, CG, kRank>;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -359,6 +396,14 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
   if (e != cudaSuccess) return set_cuda_error(e, "gemm: launch");
   return 0;
+}
+
+template <bool kInt8, int CG>
+static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
+                       cudaStream_t stream) {
+  if (p.lora_rank <= 0) return launch_gemm_r<kInt8, CG, 0>(A, lda, B, ldb, p, stream);
+  if (p.lora_rank <= 8) return launch_gemm_r<kInt8, CG, 8>(A, lda, B, ldb, p, stream);
+  return launch_gemm_r<kInt8, CG, 16>(A, lda, B, ldb, p, stream);
 }
 
 static int g_gemm_cg = 2;  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group

@@ -262,7 +262,19 @@ class Llama(nn.Module):
         x = self.norm(x)
         if labels is None:
             return self.output(x)
-        return chunked_lm_loss(x, self.output.weight, labels)
+        return chunked_lm_loss(x, self.output.weight, labels, self._output_weight_t(x))
+
+    def _output_weight_t(self, x: Tensor):
+        """W_out^T [embed, vocab] as the grad_input GEMM operand; cached while the weight is unchanged."""
+        w = self.output.weight
+        if not (x.requires_grad and x.is_cuda and isinstance(w, nn.Parameter) and w.dtype is torch.bfloat16):
+            return None
+        key = (w.data_ptr(), w._version)
+        cached = getattr(self, "_w_out_t", None)
+        if cached is None or cached[0] != key:
+            cached = (key, w.detach().t().contiguous())
+            self._w_out_t = cached
+        return cached[1]
 
     def forward(self, x: Tensor, *, input_pos: Tensor | None = None, block_mask=None,
                 labels: Tensor | None = None) -> Tensor:
@@ -275,55 +287,52 @@ class Llama(nn.Module):
 
 class _ChunkedLMLoss(torch.autograd.Function):
     """mean cross-entropy of (x @ W^T).float() against labels (ignore_index = -100) without materialising the
-    [M, vocab] fp32 logits (llama.py:216-218 keeps 8.4 GB of them at M = 16384). Row chunks; per chunk the bf16
-    logits GEMM, an fp32 log-sum-exp, and — since the head is frozen in this workload — dx = (softmax - onehot) W.
-    (LM head + CE are a 'next' row of the scope table: library GEMMs here, not hand-written kernels.)"""
+    [M, vocab] fp32 logits (llama.py:216-218 keeps 8.4 GB of them at M = 16384). Row chunks; per chunk: bf16 logits
+    by the tcgen05 bf16 GEMM, one fused cross-entropy pass that turns the logits into d(loss)/d(logits) in place,
+    and dx = dlogits @ W on the same GEMM kernel (W^T is cached while the head is frozen)."""
 
     CHUNK = 4096
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, labels: Tensor):
+    def forward(ctx, x: Tensor, weight: Tensor, labels: Tensor, weight_t: Tensor | None):
         x2 = x.reshape(-1, x.shape[-1])
-        lab = labels.reshape(-1)
-        n_valid = (lab != -100).sum().clamp(min=1)
-        loss = torch.zeros((), device=x.device, dtype=torch.float32)
-        need_dx = x.requires_grad
-        need_dw = weight.requires_grad
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        lab = labels.reshape(-1).contiguous()
+        need_dx, need_dw = x.requires_grad, weight.requires_grad
+        n_valid = (lab != -100).sum().clamp(min=1).float()
+        inv_n = n_valid.reciprocal()
+        loss_sum = torch.zeros((), device=x.device, dtype=torch.float32)
         dx = torch.empty_like(x2) if need_dx else None
         dw = torch.zeros_like(weight, dtype=torch.float32) if need_dw else None
-        for i in range(0, x2.shape[0], _ChunkedLMLoss.CHUNK):
-            xs, ls = x2[i : i + _ChunkedLMLoss.CHUNK], lab[i : i + _ChunkedLMLoss.CHUNK]
-            logits = (xs @ weight.T).float()
-            lse = torch.logsumexp(logits, dim=-1)
-            valid = ls != -100
-            tgt = logits.gather(1, ls.clamp(min=0).unsqueeze(1)).squeeze(1)
-            loss += ((lse - tgt) * valid).sum()
-            if need_dx or need_dw:
-                p = torch.exp(logits - lse.unsqueeze(1))
-                p.scatter_add_(1, ls.clamp(min=0).unsqueeze(1), -torch.ones_like(lse).unsqueeze(1))
-                p *= (valid / n_valid).unsqueeze(1)
-                p = p.to(x.dtype)
-                if need_dx:
-                    dx[i : i + _ChunkedLMLoss.CHUNK] = p @ weight
-                if need_dw:
-                    dw += (p.T @ xs).float()
+        wd = weight.detach()
+        C = _ChunkedLMLoss.CHUNK
+        buf = torch.empty(min(C, x2.shape[0]), wd.shape[0], device=x.device, dtype=torch.bfloat16)
+        for i in range(0, x2.shape[0], C):
+            xs, ls = x2[i : i + C], lab[i : i + C]
+            logits = ops.bf16_gemm(xs, wd, out=buf[: xs.shape[0]])
+            ops.cross_entropy_(logits, ls, loss_sum, inv_n, need_dx or need_dw)
+            if need_dx:
+                ops.bf16_gemm(logits, weight_t, out=dx[i : i + C])
+            if need_dw:
+                dw += (logits.T @ xs).float()  # trainable head: library GEMM (contraction over tokens)
         ctx.save_for_backward(dx, dw)
         ctx.x_shape = x.shape
         ctx.w_dtype = weight.dtype
-        return loss / n_valid
+        return loss_sum * inv_n
 
     @staticmethod
     def backward(ctx, g: Tensor):
         dx, dw = ctx.saved_tensors
         gx = (dx * g).view(ctx.x_shape) if dx is not None else None
         gw = (dw * g).to(ctx.w_dtype) if dw is not None else None
-        return gx, gw, None
+        return gx, gw, None, None
 
 
-def chunked_lm_loss(x: Tensor, weight: Tensor, labels: Tensor) -> Tensor:
+def chunked_lm_loss(x: Tensor, weight: Tensor, labels: Tensor, weight_t: Tensor | None = None) -> Tensor:
     from ..subclasses.int8 import Int8LinearWeight
 
-    if isinstance(weight, Int8LinearWeight):  # quantised head: go through the module path
-        logits = F.linear(x, weight)
+    if isinstance(weight, Int8LinearWeight) or not x.is_cuda or x.dtype is not torch.bfloat16 or weight.shape[0] % 8:
+        logits = F.linear(x, weight)  # quantised / odd head: module path + library cross-entropy
         return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), labels.view(-1))
-    return _ChunkedLMLoss.apply(x, weight, labels)
+    return _ChunkedLMLoss.apply(x, weight, labels, weight_t)

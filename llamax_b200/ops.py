@@ -288,11 +288,29 @@ def lora_wgrad(X: Tensor, H: Tensor, alpha: float = 1.0) -> Tensor:
     assert X.dtype is torch.bfloat16 and H.dtype is torch.bfloat16 and X.stride(1) == 1 and H.stride(1) == 1
     M, Pn = X.shape
     R = H.shape[1]
-    out = torch.zeros(Pn, R, device=X.device, dtype=torch.float32)
+    cols = 8 if R == 8 else 4
+    col_blocks = (Pn + 128 * cols - 1) // (128 * cols)
+    sms = torch.cuda.get_device_properties(X.device).multi_processor_count
+    nparts = max(1, min((M + 63) // 64, (2 * sms) // col_blocks))
+    out = torch.empty(Pn, R, device=X.device, dtype=torch.float32)
+    work = torch.empty(nparts, Pn, R, device=X.device, dtype=torch.float32)
     _call(lib, "llamax_lora_wgrad",
-          (_p(X), X.stride(0), _p(H), H.stride(0), _p(out), M, Pn, R, float(alpha), st,),
+          (_p(X), X.stride(0), _p(H), H.stride(0), _p(out), _p(work), nparts, M, Pn, R, float(alpha), st),
           "lora_wgrad", 2.0 * M * Pn * R, 2.0 * M * (Pn + R))
     return out
+
+
+def cross_entropy_(logits: Tensor, labels: Tensor, loss_sum: Tensor, inv_n: Tensor | None, write_grad: bool):
+    """In place: accumulates sum of per-row CE into loss_sum (fp32 scalar tensor); if write_grad, overwrites logits
+    with (softmax - onehot) * inv_n (rows with label -100 -> 0)."""
+    lib, st = _prep(logits)
+    assert logits.dtype is torch.bfloat16 and logits.dim() == 2 and logits.stride(1) == 1
+    assert labels.dtype is torch.int64 and labels.is_contiguous() and labels.numel() == logits.shape[0]
+    assert loss_sum.dtype is torch.float32 and (inv_n is None or inv_n.dtype is torch.float32)
+    M, V = logits.shape
+    _call(lib, "llamax_cross_entropy",
+          (_p(logits), logits.stride(0), _p(labels), _p(loss_sum), _p(inv_n), M, V, int(write_grad), st),
+          "cross_entropy", 0.0, (4.0 if write_grad else 2.0) * M * V)
 
 
 # ---------------------------------------------------------------------------------------------- attention

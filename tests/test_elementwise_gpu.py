@@ -98,3 +98,22 @@ def test_dequant_weight_and_lora_wgrad():
         X, Hh = torch.randn(M, Pn).bfloat16(), torch.randn(M, Rr).bfloat16()
         o = ops.lora_wgrad(X.cuda(), Hh.cuda(), 0.5).cpu()
         assert rel_err(o, 0.5 * X.float().T @ Hh.float()) < 1e-4
+
+
+@pytest.mark.parametrize("M,V", [(37, 1024), (16, 128256)])
+def test_cross_entropy_fwd_bwd(M, V):
+    """F.cross_entropy(logits.float(), labels) with ignore_index -100 (llama.py:216-218), loss and d/dlogits."""
+    g = torch.Generator().manual_seed(V)
+    logits = (torch.randn(M, V, generator=g) * 3).bfloat16()
+    labels = torch.randint(0, V, (M,), generator=g)
+    labels[::5] = -100
+    lf = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf, labels)
+    ref.backward()
+    lc = logits.cuda().clone()
+    loss_sum = torch.zeros((), device="cuda", dtype=torch.float32)
+    inv_n = torch.tensor(1.0 / (labels != -100).sum().item(), device="cuda", dtype=torch.float32)
+    ops.cross_entropy_(lc, labels.cuda(), loss_sum, inv_n, True)
+    assert abs((loss_sum * inv_n).item() - ref.item()) <= 1e-4 * abs(ref.item())
+    assert rel_err(lc, lf.grad) <= 1e-2
+    assert (lc[::5] == 0).all()
