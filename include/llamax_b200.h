@@ -125,11 +125,11 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     void* stream);
 
 /* ---- K6 backward: LoRA weight gradients (autograd of modelling/lora.py:43) ------------------------
- *   out[p, r] (fp32) = alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx, H bf16 [M,R] pitch ldh
- * used for dB = scale * dY^T h and dA^T = x^T dh.  workspace: fp32 [nparts, P, R]; the M rows are split into
- * nparts chunks whose partial sums are reduced by a second kernel (no atomics). */
-int llamax_lora_wgrad(const void* X, int64_t ldx, const void* H, int64_t ldh, void* out, void* workspace,
-                      int32_t nparts, int64_t M, int64_t P, int32_t R, float alpha, void* stream);
+ *   out[p, r] (fp32) = alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx;  Ht = H^T bf16 [R, M] pitch ldht
+ * used for dB = scale * dY^T h and dA^T = x^T dh.  tcgen05 GEMM with X read as an MN-major operand (no transpose
+ * of the big tensor); rank <= 32; `out` is zeroed by the call, token-dimension splits are reduced with fp32 red.add. */
+int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, void* out, int64_t M, int64_t P,
+                      int32_t R, float alpha, void* stream);
 
 /* ---- K12 (next row): cross-entropy over bf16 logits, forward + backward in place -------------------
  * F.cross_entropy(logits.float(), labels) (modelling/llama.py:216-218, audio.py:74-76), ignore_index = -100:

@@ -323,6 +323,7 @@ struct AttnBwdParams {
 namespace bwd {
 constexpr int kKV = 128;                          // kv rows per CTA
 constexpr int kQ = 64;                            // query rows per step
+constexpr int kThreads = 384;                     // warps 0-3 control, 4-7 softmax-grad, 8-11 dQ drain
 constexpr int kKVBytes = kKV * kHD * 2;           // 32 KB (2 boxes of [128 x 128 B])
 constexpr int kQBytes = kQ * kHD * 2;             // 16 KB (2 boxes of [64 x 128 B])
 constexpr int kPBytes = kKV * kQ * 2;             // 16 KB ([128 kv rows] x [64 q] bf16)
@@ -330,19 +331,21 @@ constexpr int kOffK = 0;
 constexpr int kOffV = kOffK + kKVBytes;
 constexpr int kOffQ = kOffV + kKVBytes;           // 2 stages
 constexpr int kOffdO = kOffQ + 2 * kQBytes;       // 2 stages
-constexpr int kOffP = kOffdO + 2 * kQBytes;
-constexpr int kOffdS = kOffP + kPBytes;
-constexpr int kOffdQ = kOffdS + kPBytes;          // fp32 [64 q][128 d] staging for the bulk reduce-add
+constexpr int kOffP = kOffdO + 2 * kQBytes;       // 2 buffers
+constexpr int kOffdS = kOffP + 2 * kPBytes;       // 2 buffers
+constexpr int kOffdQ = kOffdS + 2 * kPBytes;      // fp32 [64 q][128 d] staging for the bulk reduce-add
 constexpr int kdQBytes = kQ * kHD * 4;            // 32 KB
 constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta: 2 stages x 2 x 64 floats
 constexpr int kOffBar = kOffStat + 2 * 2 * kQ * 4;
-constexpr int kNumBars = 1 + 4 + 1 + 1 + 1 + 1 + 1;  // kv_full, qdo full/empty[2], sdp_full, pds_full, dq_full, dq_empty, acc_done
+// kv_full, qdo full/empty[2], sdp_full, pds full/empty[2], dq_full, dq_empty, acc_done
+constexpr int kNumBars = 1 + 4 + 1 + 4 + 1 + 1 + 1;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+static_assert(kSmemBytes <= 232448, "attention backward shared memory budget");
 // TMEM columns
 constexpr int kColdV = 0, kColdK = 128, kColS = 256, kColdP = 320, kColdQ = 384;
 }  // namespace bwd
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const AttnBwdParams p) {
@@ -356,9 +359,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* qdo_empty = bars + 3;
   uint64_t* sdp_full = bars + 5;
   uint64_t* pds_full = bars + 6;
-  uint64_t* dq_full = bars + 7;
-  uint64_t* dq_empty = bars + 8;
-  uint64_t* acc_done = bars + 9;
+  uint64_t* pds_empty = bars + 8;
+  uint64_t* dq_full = bars + 10;
+  uint64_t* dq_empty = bars + 11;
+  uint64_t* acc_done = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int warp = threadIdx.x >> 5;
@@ -381,9 +385,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_empty[i], 1);
+      mbar_init(&pds_full[i], 4);
+      mbar_init(&pds_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 4);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 4);
     mbar_init(acc_done, 1);
@@ -423,20 +428,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
+    // issue order per step s:  [S^T, dP^T](s+1)  then  [dV, dK, dQ^T](s)  so that the softmax-grad warps work on
+    // step s+1 while the three accumulation GEMMs of step s run.
     if (elect_one()) {
       constexpr uint32_t idesc_st = make_idesc(1, 1, 128, 64, 0, 0);    // S^T, dP^T : [kv x d] . [q x d]^T
       constexpr uint32_t idesc_acc = make_idesc(1, 1, 128, 128, 0, 1);  // dV, dK    : [kv x q] . [q x d]   (B MN-major)
       constexpr uint32_t idesc_dq = make_idesc(1, 1, 128, 64, 1, 1);    // dQ^T      : [kv x d]^T . [kv x q] (A, B MN-major)
       const uint32_t sK = smem_u32(smem + kOffK), sV = smem_u32(smem + kOffV);
-      const uint32_t sP = smem_u32(smem + kOffP), sdS = smem_u32(smem + kOffdS);
-      mbar_wait(kv_full, 0);
-      for (int s = 0; s < n_steps; ++s) {
+      auto issue_sdp = [&](int s) {
         const int st = s & 1;
         const uint32_t sQ = smem_u32(smem + kOffQ + st * kQBytes);
         const uint32_t sdO = smem_u32(smem + kOffdO + st * kQBytes);
         mbar_wait(&qdo_full[st], (s >> 1) & 1);
         tc_fence_after();
-        // S^T = K Q^T, dP^T = V dO^T   (softmax threads finished reading the previous ones before pds_full)
 #pragma unroll
         for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
@@ -454,9 +458,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_ss<false, 1>(tmem_base + kColdP, av, bo, idesc_st, (dh | ks) != 0);
           }
         umma_commit(sdp_full);
-        // wait for P^T / dS^T in smem, and for the previous dQ^T to be drained
-        mbar_wait(pds_full, s & 1);
-        mbar_wait(dq_empty, (s & 1) ^ 1);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s & 1;
+        const uint32_t sQ = smem_u32(smem + kOffQ + st * kQBytes);
+        const uint32_t sdO = smem_u32(smem + kOffdO + st * kQBytes);
+        const uint32_t sP = smem_u32(smem + kOffP + st * kPBytes);
+        const uint32_t sdS = smem_u32(smem + kOffdS + st * kPBytes);
+        // softmax-grad of step s done: S^T/dP^T columns are free and P^T/dS^T[st] are in smem
+        mbar_wait(&pds_full[st], (s >> 1) & 1);
+        if (s + 1 < n_steps) issue_sdp(s + 1);
+        mbar_wait(dq_empty, (s & 1) ^ 1);  // previous dQ^T drained from TMEM
         tc_fence_after();
         // dV += P^T dO ; dK += dS^T Q        (K dim = q, 64 -> 4 steps of 16)
 #pragma unroll
@@ -480,22 +494,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         umma_commit(dq_full);
         umma_commit(&qdo_empty[st]);
+        umma_commit(&pds_empty[st]);
       }
       umma_commit(acc_done);
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ------------------------------------ softmax-grad threads (thread = kv row / d row) ------------------------------------
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------ softmax-grad threads (thread = kv row) ------------------------------------
     const int t = threadIdx.x - 128;
     const int ew = warp - 4;
     const uint32_t lane_off = uint32_t(ew * 32) << 16;
     const int kv = kv0 + t;
-    const uint32_t sP = smem_u32(smem + kOffP), sdS = smem_u32(smem + kOffdS);
     for (int s = 0; s < n_steps; ++s) {
+      const int st = s & 1;
       const int hq = hk * G + s / steps_per_head;
       const int q0 = (i_start + s % steps_per_head) * kQ;
+      const uint32_t sP = smem_u32(smem + kOffP + st * kPBytes), sdS = smem_u32(smem + kOffdS + st * kPBytes);
       // stage lse (in log2 units) and delta of the 64 query rows
-      float* stat = s_stat + (s & 1) * 2 * kQ;
+      float* stat = s_stat + st * 2 * kQ;
       {
         const int qq = q0 + (t & 63);
         const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
@@ -504,15 +520,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       named_bar_sync(1, 128);
       const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0));
+      mbar_wait(&pds_empty[st], ((s >> 1) & 1) ^ 1);  // P^T/dS^T[st] no longer read by the MMAs of step s-2
       mbar_wait(sdp_full, s & 1);
       tc_fence_after();
-      uint32_t pr[32], dsr[32];  // packed bf16 pairs: 64 q values each
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + kColS + lane_off + c * 32, sv);
         tmem_ld_32x32(tmem_base + kColdP + lane_off + c * 32, dv);
-        tmem_wait_ld();
+        tmem_wait_ld_regs(sv);
+        tmem_wait_ld_regs(dv);
+        uint32_t pr[16], dsr[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const int qi = c * 32 + i;
@@ -525,51 +543,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           const float d0 = p0 * (__uint_as_float(dv[i]) - stat[kQ + qi]) * p.scale;
           const float d1 = p1 * (__uint_as_float(dv[i + 1]) - stat[kQ + qi + 1]) * p.scale;
-          pr[c * 16 + i / 2] = pack_bf16(p0, p1);
-          dsr[c * 16 + i / 2] = pack_bf16(d0, d1);
+          pr[i / 2] = pack_bf16(p0, p1);
+          dsr[i / 2] = pack_bf16(d0, d1);
+        }
+        // rows of 64 q values = 128 B = 8 chunks of 16 B, swizzled by (row & 7); this half = chunks 4c .. 4c+3
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint32_t off = t * 128 + (((c * 4 + cc) ^ (t & 7)) << 4);
+          sts_v4(sP + off, pr[cc * 4], pr[cc * 4 + 1], pr[cc * 4 + 2], pr[cc * 4 + 3]);
+          sts_v4(sdS + off, dsr[cc * 4], dsr[cc * 4 + 1], dsr[cc * 4 + 2], dsr[cc * 4 + 3]);
         }
       }
-      // rows of 64 q values = 128 B = 8 chunks, swizzled by (row & 7)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t off = t * 128 + ((c ^ (t & 7)) << 4);
-        sts_v4(sP + off, pr[c * 4], pr[c * 4 + 1], pr[c * 4 + 2], pr[c * 4 + 3]);
-        sts_v4(sdS + off, dsr[c * 4], dsr[c * 4 + 1], dsr[c * 4 + 2], dsr[c * 4 + 3]);
-      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(pds_full);
-
-      // drain dQ^T: this thread owns head-dim element d = t for the 64 query rows of the step.
-      // TMEM -> fp32 smem tile [q][d] (conflict-free: a warp writes 128 contiguous bytes per q) -> one bulk
-      // reduce-add of the whole tile into dq_accum[b, hq, q0:q0+64, :] (contiguous 32 KB).
-      mbar_wait(dq_full, s & 1);
-      tc_fence_after();
-      if (t == 0) tma_store_wait_read<0>();   // previous step's bulk reduce has finished reading the staging tile
-      named_bar_sync(2, 128);
-      float* stage = reinterpret_cast<float*>(smem + kOffdQ);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + kColdQ + lane_off + c * 32, v);
-        tmem_wait_ld_regs(v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) stage[(c * 32 + i) * kHD + t] = __uint_as_float(v[i]);
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(2, 128);
-      if (t == 0) {
-        const int rows = min(kQ, p.S - q0);
-        float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0) * kHD;
-        bulk_reduce_add_f32(dst, stage, (uint32_t)rows * kHD * 4);
-        tma_store_commit();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(dq_empty);
+      if (lane_id() == 0) mbar_arrive(&pds_full[st]);
     }
-    if (t == 0) tma_store_wait<0>();  // all bulk reductions of this CTA have completed
     // write dK, dV (thread = kv row)
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -580,7 +569,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int c = 0; c < 8; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (c < 4 ? kColdV : kColdK) + lane_off + (c & 3) * 32, v);
-      tmem_wait_ld();
+      tmem_wait_ld_regs(v);
       if (row_ok) {
         __nv_bfloat16* dst = (c < 4 ? dvrow : dkrow) + (c & 3) * 32;
 #pragma unroll
@@ -595,6 +584,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     tc_fence_before();
+  } else if (warp >= 8) {
+    // ------------------------------------ dQ drain threads (thread = head-dim element d) ------------------------------------
+    // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> ONE bulk
+    // reduce-add of the tile into dq_accum[b, hq, q0:q0+64, :] (contiguous 32 KB, fp32 add performed at L2).
+    const int t = threadIdx.x - 256;
+    const uint32_t lane_off = uint32_t((warp - 8) * 32) << 16;
+    float* stage = reinterpret_cast<float*>(smem + kOffdQ);
+    for (int s = 0; s < n_steps; ++s) {
+      const int hq = hk * G + s / steps_per_head;
+      const int q0 = (i_start + s % steps_per_head) * kQ;
+      mbar_wait(dq_full, s & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + kColdQ + lane_off, v0);
+      tmem_ld_32x32(tmem_base + kColdQ + lane_off + 32, v1);
+      tmem_wait_ld_regs(v0);
+      tmem_wait_ld_regs(v1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(dq_empty);  // TMEM columns free for the next dQ^T
+      if (t == 0) tma_store_wait_read<0>();       // previous bulk reduce finished reading the staging tile
+      named_bar_sync(2, 128);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) stage[i * kHD + t] = __uint_as_float(v0[i]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) stage[(32 + i) * kHD + t] = __uint_as_float(v1[i]);
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (t == 0) {
+        const int rows = min(kQ, p.S - q0);
+        float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0) * kHD;
+        bulk_reduce_add_f32(dst, stage, (uint32_t)rows * kHD * 4);
+        tma_store_commit();
+      }
+    }
+    if (t == 0) tma_store_wait<0>();  // all bulk reductions of this CTA have completed
   }
 
   tc_fence_before();
@@ -739,7 +764,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.scale = scale;
   p.scale_log2 = scale * kLog2e;
   dim3 grid((unsigned)ceil_div(S, bwd::kKV), Hkv, (unsigned)B);
-  attn_bwd_kernel<<<grid, 256, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
+  attn_bwd_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");
   {
     const int64_t total = rows * (Hq * kHD / 8);

@@ -394,95 +394,6 @@ dequant_transpose_kernel(const int8_t* __restrict__ w8, const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// LoRA weight gradient: out[p, r] += alpha * sum_m X[m, p] * H[m, r]   (R <= 16, fp32 atomics over M-chunks)
-// CTA = 128 columns of X (one 16-byte... 2 columns per thread on 64 threads x 2) x a chunk of rows.
-// ------------------------------------------------------------------------------------------------
-template <int R, int COLS>
-__global__ void __launch_bounds__(128)
-lora_wgrad_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const __nv_bfloat16* __restrict__ H, int64_t ldh,
-                  float* __restrict__ partial, int64_t M, int64_t P, int rows_per_cta) {
-  // thread owns COLS adjacent columns of X (one 16- or 8-byte load per row); block covers 128*COLS columns;
-  // blockIdx.y owns a chunk of rows; COLS*R register accumulators, written to partial[blockIdx.y][p][r]
-  // (plain stores; summed by lora_wgrad_reduce_kernel — fp32 atomics were the bottleneck of the first version).
-  constexpr int kChunk = 16;
-  __shared__ __align__(16) float sh[kChunk][R];
-  const int64_t p0 = ((int64_t)blockIdx.x * 128 + threadIdx.x) * COLS;
-  const int64_t m_begin = (int64_t)blockIdx.y * rows_per_cta;
-  const int64_t m_end = min(M, m_begin + rows_per_cta);
-  const bool active = p0 < P;
-  float acc[COLS][R];
-#pragma unroll
-  for (int c = 0; c < COLS; ++c)
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[c][r] = 0.f;
-  for (int64_t m0 = m_begin; m0 < m_end; m0 += kChunk) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kChunk * R; i += 128) {
-      const int mm = i / R, r = i - mm * R;
-      sh[mm][r] = (m0 + mm < m_end) ? __bfloat162float(H[(m0 + mm) * ldh + r]) : 0.f;
-    }
-    __syncthreads();
-    if (active) {
-      uint32_t xv[kChunk][COLS / 2];
-#pragma unroll
-      for (int mm = 0; mm < kChunk; ++mm) {
-        if (m0 + mm < m_end) {
-          const __nv_bfloat16* src = X + (m0 + mm) * ldx + p0;
-          if constexpr (COLS == 8) {
-            const uint4 u = ldg_nc_v4(src);
-            xv[mm][0] = u.x; xv[mm][1] = u.y; xv[mm][2] = u.z; xv[mm][3] = u.w;
-          } else {
-            const uint2 u = *reinterpret_cast<const uint2*>(src);
-            xv[mm][0] = u.x; xv[mm][1] = u.y;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < COLS / 2; ++c) xv[mm][c] = 0u;
-        }
-      }
-#pragma unroll
-      for (int mm = 0; mm < kChunk; ++mm) {
-        float hr[R];
-#pragma unroll
-        for (int r = 0; r < R; r += 4) {
-          const float4 h4 = *reinterpret_cast<const float4*>(&sh[mm][r]);
-          hr[r] = h4.x; hr[r + 1] = h4.y; hr[r + 2] = h4.z; hr[r + 3] = h4.w;
-        }
-#pragma unroll
-        for (int c = 0; c < COLS / 2; ++c) {
-          const float x0 = bf16_lo(xv[mm][c]), x1 = bf16_hi(xv[mm][c]);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            acc[2 * c][r] = fmaf(x0, hr[r], acc[2 * c][r]);
-            acc[2 * c + 1][r] = fmaf(x1, hr[r], acc[2 * c + 1][r]);
-          }
-        }
-      }
-    }
-  }
-  if (active) {
-    float* dst = partial + ((int64_t)blockIdx.y * P + p0) * R;
-#pragma unroll
-    for (int c = 0; c < COLS; ++c)
-#pragma unroll
-      for (int r = 0; r < R; r += 4)
-        *reinterpret_cast<float4*>(dst + c * R + r) = make_float4(acc[c][r], acc[c][r + 1], acc[c][r + 2], acc[c][r + 3]);
-  }
-}
-
-__global__ void lora_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts,
-                                         int64_t n, float alpha) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= n) return;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = 0; p < nparts; ++p) {
-    const float4 v = *reinterpret_cast<const float4*>(partial + (int64_t)p * n + i);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-  }
-  *reinterpret_cast<float4*>(out + i) = make_float4(alpha * s.x, alpha * s.y, alpha * s.z, alpha * s.w);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Cross-entropy over bf16 logits, forward + backward in place (F.cross_entropy(logits.float(), labels),
 // modelling/llama.py:216-218): per row lse = logsumexp(f32(logits)); loss_sum += lse - logit[label];
 // logits <- (softmax - onehot(label)) * inv_n   (0 for ignored rows, label == -100).
@@ -657,35 +568,6 @@ int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t 
                                                                      (bf16*)out, ldo, (int)N, (int)K, apply_scale);
   }
   LX_CHECK_LAUNCH("dequant_weight");
-  return 0;
-}
-
-int llamax_lora_wgrad(const void* X, int64_t ldx, const void* H, int64_t ldh, void* out, void* workspace,
-                      int32_t nparts, int64_t M, int64_t P, int32_t R, float alpha, void* stream) {
-  if (!X || !H || !out || !workspace) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: null pointer");
-  if (R != 8 && R != 16 && R != 24 && R != 32) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: rank must be 8, 16, 24 or 32");
-  const int cols = (R == 8) ? 8 : 4;
-  if (P % cols || ldx % cols || (reinterpret_cast<uintptr_t>(X) % (2 * cols)))
-    return set_error(LLAMAX_ERR_ARG, "lora_wgrad: P, ldx and the base of X must be aligned to the per-thread vector");
-  if (nparts < 1 || nparts > 65535) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: nparts out of range");
-  if (M <= 0) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: M must be positive");
-  const int col_blocks = (int)((P + 128 * cols - 1) / (128 * cols));
-  int rows_per_cta = (int)((M + nparts - 1) / nparts);
-  dim3 grid(col_blocks, nparts);
-  cudaStream_t st = (cudaStream_t)stream;
-#define LX_WGRAD(RR, CC)                                                                                              \
-  lora_wgrad_kernel<RR, CC><<<grid, 128, 0, st>>>((const bf16*)X, ldx, (const bf16*)H, ldh, (float*)workspace, M, P, \
-                                                   rows_per_cta)
-  if (R == 8) LX_WGRAD(8, 8);
-  else if (R == 16) LX_WGRAD(16, 4);
-  else if (R == 24) LX_WGRAD(24, 4);
-  else LX_WGRAD(32, 4);
-#undef LX_WGRAD
-  LX_CHECK_LAUNCH("lora_wgrad");
-  const int64_t n = P * R;
-  lora_wgrad_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>((const float*)workspace, (float*)out, nparts,
-                                                                            n, alpha);
-  LX_CHECK_LAUNCH("lora_wgrad: reduce");
   return 0;
 }
 

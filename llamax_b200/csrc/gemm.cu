@@ -15,6 +15,8 @@
 // CG = 2 runs CTA pairs (cta_group::2, UMMA 256 x 256): each CTA loads its 128 rows of A and half of B.
 #include "common.cuh"
 #include "host_utils.h"
+#include <algorithm>
+
 #include "llamax_b200.h"
 
 namespace lx {
@@ -406,6 +408,114 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
   return launch_gemm_r<kInt8, CG, 16>(A, lda, B, ldb, p, stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// LoRA weight gradient on tensor cores:  out[p, r] += alpha * sum_m X[m, p] * H[m, r]
+//   = GEMM with M' = P (128 per CTA), N' = 32 (rank zero-padded), K' = tokens.
+// A' = X^T is read straight from X [tokens, P] as an MN-major operand (64-column boxes, like V in attention),
+// B' = H^T [R, tokens] K-major.  grid = (P / 128, splits over tokens); fp32 red.add of the few outputs.
+// ------------------------------------------------------------------------------------------------
+namespace wg {
+constexpr int kStages = 8;
+constexpr int kABytes = 128 * 64 * 2;  // [64 tokens] x [128 P-columns] bf16 = two boxes of [64 x 128 B]
+constexpr int kBBytes = 32 * 64 * 2;   // [32 rank rows] x [64 tokens]
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmem = kStages * kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
+}  // namespace wg
+
+__global__ void __launch_bounds__(192, 1)
+lora_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmHt,
+                     float* __restrict__ out, int P, int R, int M, int k_per_split, float alpha) {
+  using namespace wg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* done_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 128;
+  const int k_begin = blockIdx.y * k_per_split;
+  const int k_end = min(M, k_begin + k_per_split);
+  const int num_kb = (k_end - k_begin + 63) / 64;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmHt);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_slot, 32);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStageBytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        const int k0 = k_begin + kb * 64;
+        tma_load_2d(sa, &tmX, &full_bar[stage], p0, k0);
+        tma_load_2d(sa + kABytes / 2, &tmX, &full_bar[stage], p0 + 64, k0);
+        tma_load_2d(sa + kABytes, &tmHt, &full_bar[stage], k0, 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(1, 1, 128, 32, 1, 0);  // A MN-major, B K-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = make_smem_desc_sw128(sa + ks * 16 * 128, 8192, 1024);
+          const uint64_t bd = make_smem_desc_sw128(sb + ks * 32, 16, 1024);
+          umma_ss<false, 1>(tmem_base, ad, bd, idesc, (kb | ks) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    // epilogue warps 2..5: TMEM lanes 32*(warp % 4)
+    const int lq = warp & 3;
+    const int row = p0 + lq * 32 + lane_id();
+    if (num_kb > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(lq * 32) << 16), v);
+      tmem_wait_ld_regs(v);
+      if (row < P) {
+        for (int r = 0; r < R; ++r) atomicAdd(out + (int64_t)row * R + r, alpha * __uint_as_float(v[r]));
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, 32);
+}
+
 static int g_gemm_cg = 2;  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group
 
 }  // namespace lx
@@ -468,6 +578,38 @@ int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   fill_epilogue(p, epi);
   return g_gemm_cg == 2 ? launch_gemm<false, 2>(A, lda, B, ldb, p, (cudaStream_t)stream)
                         : launch_gemm<false, 1>(A, lda, B, ldb, p, (cudaStream_t)stream);
+}
+
+int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, void* out, int64_t M, int64_t P,
+                      int32_t R, float alpha, void* stream) {
+  if (!X || !Ht || !out) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: null pointer");
+  if (R < 1 || R > 32) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: rank must be in [1, 32]");
+  if (M <= 0 || P <= 0) return set_error(LLAMAX_ERR_ARG, "lora_wgrad: empty problem");
+  if (ldx % 8 || ldht % 8 || (reinterpret_cast<uintptr_t>(X) % 16) || (reinterpret_cast<uintptr_t>(Ht) % 16))
+    return set_error(LLAMAX_ERR_ARG, "lora_wgrad: X / H^T must be 16-byte aligned with pitches multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)P * R * sizeof(float), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "lora_wgrad: memset");
+  CUtensorMap tmX, tmHt;
+  int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, X, P, M, ldx, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmHt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Ht, M, R, ldht, 64, 32);
+  if (rc) return rc;
+  static thread_local bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(lora_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "lora_wgrad: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const int p_tiles = (int)((P + 127) / 128);
+  int splits = std::max(1, std::min(32, (sm_count() + p_tiles - 1) / p_tiles));
+  int k_per_split = (int)((M + splits - 1) / splits);
+  k_per_split = ((k_per_split + 63) / 64) * 64;
+  splits = (int)((M + k_per_split - 1) / k_per_split);
+  dim3 grid(p_tiles, splits);
+  lora_wgrad_tc_kernel<<<grid, 192, wg::kSmem, st>>>(tmX, tmHt, (float*)out, (int)P, R, (int)M, k_per_split, alpha);
+  LX_CHECK_LAUNCH("lora_wgrad");
+  return 0;
 }
 
 }  // extern "C"

@@ -283,19 +283,17 @@ def rope_(x: Tensor, rope: Tensor, B: int, S: int, nheads: int, D: int, *, inver
 
 
 def lora_wgrad(X: Tensor, H: Tensor, alpha: float = 1.0) -> Tensor:
-    """out[P,R] (fp32) = alpha * X[M,P]^T @ H[M,R]."""
+    """out[P,R] (fp32) = alpha * X[M,P]^T @ H[M,R]  (tensor cores; X is consumed in place, H^T is a tiny copy)."""
     lib, st = _prep(X)
-    assert X.dtype is torch.bfloat16 and H.dtype is torch.bfloat16 and X.stride(1) == 1 and H.stride(1) == 1
+    assert X.dtype is torch.bfloat16 and H.dtype is torch.bfloat16 and X.stride(1) == 1
     M, Pn = X.shape
     R = H.shape[1]
-    cols = 8 if R == 8 else 4
-    col_blocks = (Pn + 128 * cols - 1) // (128 * cols)
-    sms = torch.cuda.get_device_properties(X.device).multi_processor_count
-    nparts = max(1, min((M + 63) // 64, (2 * sms) // col_blocks))
+    Mp = (M + 7) // 8 * 8
+    Ht = torch.zeros(R, Mp, device=X.device, dtype=torch.bfloat16) if Mp != M else torch.empty(R, M, device=X.device, dtype=torch.bfloat16)
+    Ht[:, :M].copy_(H.t())
     out = torch.empty(Pn, R, device=X.device, dtype=torch.float32)
-    work = torch.empty(nparts, Pn, R, device=X.device, dtype=torch.float32)
     _call(lib, "llamax_lora_wgrad",
-          (_p(X), X.stride(0), _p(H), H.stride(0), _p(out), _p(work), nparts, M, Pn, R, float(alpha), st),
+          (_p(X), X.stride(0), _p(Ht), Ht.stride(0), _p(out), M, Pn, R, float(alpha), st),
           "lora_wgrad", 2.0 * M * Pn * R, 2.0 * M * (Pn + R))
     return out
 
