@@ -30,6 +30,12 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -140,23 +146,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
-      const uint32_t sQ = smem_u32(smem + kOffQ);
-      const uint32_t sP = smem_u32(smem + kOffP);
+      constexpr uint32_t kHi = desc_hi(1024);
+      const uint32_t loQ = desc_lo(smem_u32(smem + kOffQ), 16), loP = desc_lo(smem_u32(smem + kOffP), 16);
+      const uint32_t loK0 = desc_lo(smem_u32(smem + kOffK), 16), loV0 = desc_lo(smem_u32(smem + kOffV), 16384);
       auto issue_s = [&](int j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t sK = smem_u32(smem + kOffK + st * kTileBytes);
+        const uint32_t loK = loK0 + st * (kTileBytes / 16);
 #pragma unroll
         for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_smem_desc_sw128(sQ + dh * 16384 + ks * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc_sw128(sK + dh * 16384 + ks * 32, 16, 1024);
-            umma_ss<false, 1>(tmem_S + st * 128, ad, bd, idesc_s, (dh | ks) != 0);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss<false, 1>(tmem_S + st * 128, desc_join(loQ + dh * 1024 + ks * 2, kHi),
+                              desc_join(loK + dh * 1024 + ks * 2, kHi), idesc_s, (dh | ks) != 0);
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);
       };
@@ -168,15 +173,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&v_full[st], (j >> 1) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t sV = smem_u32(smem + kOffV + st * kTileBytes);
+        const uint32_t loV = loV0 + st * (kTileBytes / 16);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_smem_desc_sw128(sP + kb * 16384 + ks * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc_sw128(sV + (kb * 64 + ks * 16) * 128, 16384, 1024);
-            umma_ss<false, 1>(tmem_O, ad, bd, idesc_pv, (j | kb | ks) != 0);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss<false, 1>(tmem_O, desc_join(loP + kb * 1024 + ks * 2, kHi),
+                              desc_join(loV + (kb * 64 + ks * 16) * 8, kHi), idesc_pv, (j | kb | ks) != 0);
         umma_commit(pv_done);
         umma_commit(&v_empty[st]);
       }
@@ -323,7 +326,8 @@ struct AttnBwdParams {
 namespace bwd {
 constexpr int kKV = 128;                          // kv rows per CTA
 constexpr int kQ = 64;                            // query rows per step
-constexpr int kThreads = 384;                     // warps 0-3 control, 4-7 softmax-grad, 8-11 dQ drain
+constexpr int kThreads = 384;                     // warps 0-3 control, warps 4-11 workers (softmax-grad + dQ drain)
+constexpr int kWorkers = 256;
 constexpr int kKVBytes = kKV * kHD * 2;           // 32 KB (2 boxes of [128 x 128 B])
 constexpr int kQBytes = kQ * kHD * 2;             // 16 KB (2 boxes of [64 x 128 B])
 constexpr int kPBytes = kKV * kQ * 2;             // 16 KB ([128 kv rows] x [64 q] bf16)
@@ -337,11 +341,11 @@ constexpr int kOffdQ = kOffdS + 2 * kPBytes;      // fp32 [64 q][128 d] staging 
 constexpr int kdQBytes = kQ * kHD * 4;            // 32 KB
 constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta: 2 stages x 2 x 64 floats
 constexpr int kOffBar = kOffStat + 2 * 2 * kQ * 4;
-// kv_full, qdo full/empty[2], sdp_full, pds full/empty[2], dq_full, dq_empty, acc_done
-constexpr int kNumBars = 1 + 4 + 1 + 4 + 1 + 1 + 1;
+// kv_full, qdo full/empty[2], sdp_full, pds full/empty[2], dq full/empty[2], acc_done
+constexpr int kNumBars = 1 + 4 + 1 + 4 + 4 + 1;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "attention backward shared memory budget");
-// TMEM columns
+// TMEM columns: dV, dK accumulators; S^T, dP^T; dQ^T double-buffered
 constexpr int kColdV = 0, kColdK = 128, kColS = 256, kColdP = 320, kColdQ = 384;
 }  // namespace bwd
 
@@ -361,8 +365,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* pds_full = bars + 6;
   uint64_t* pds_empty = bars + 8;
   uint64_t* dq_full = bars + 10;
-  uint64_t* dq_empty = bars + 11;
-  uint64_t* acc_done = bars + 12;
+  uint64_t* dq_empty = bars + 12;
+  uint64_t* acc_done = bars + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int warp = threadIdx.x >> 5;
@@ -385,12 +389,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_empty[i], 1);
-      mbar_init(&pds_full[i], 4);
+      mbar_init(&pds_full[i], 8);
       mbar_init(&pds_empty[i], 1);
+      mbar_init(&dq_full[i], 1);
+      mbar_init(&dq_empty[i], 8);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -428,128 +432,172 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
-    // issue order per step s:  [S^T, dP^T](s+1)  then  [dV, dK, dQ^T](s)  so that the softmax-grad warps work on
-    // step s+1 while the three accumulation GEMMs of step s run.
+    // issue order per step s:  [S^T, dP^T](s+1)  then  [dV, dK, dQ^T](s)  so that the worker warps process step s+1
+    // while the three accumulation GEMMs of step s run.
     if (elect_one()) {
       constexpr uint32_t idesc_st = make_idesc(1, 1, 128, 64, 0, 0);    // S^T, dP^T : [kv x d] . [q x d]^T
       constexpr uint32_t idesc_acc = make_idesc(1, 1, 128, 128, 0, 1);  // dV, dK    : [kv x q] . [q x d]   (B MN-major)
       constexpr uint32_t idesc_dq = make_idesc(1, 1, 128, 64, 1, 1);    // dQ^T      : [kv x d]^T . [kv x q] (A, B MN-major)
-      const uint32_t sK = smem_u32(smem + kOffK), sV = smem_u32(smem + kOffV);
+      constexpr uint32_t kHi = desc_hi(1024);
+      // descriptor low words (address >> 4 | LBO): K-major operands carry LBO 16 (unused), MN-major the atom stride
+      const uint32_t loK = desc_lo(smem_u32(smem + kOffK), 16), loV = desc_lo(smem_u32(smem + kOffV), 16);
+      const uint32_t loKmn = desc_lo(smem_u32(smem + kOffK), 16384);
+      uint32_t loQ[2], lodO[2], loQmn[2], lodOmn[2], loP[2], lodS[2];
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        loQ[st] = desc_lo(smem_u32(smem + kOffQ + st * kQBytes), 16);
+        lodO[st] = desc_lo(smem_u32(smem + kOffdO + st * kQBytes), 16);
+        loQmn[st] = desc_lo(smem_u32(smem + kOffQ + st * kQBytes), 8192);
+        lodOmn[st] = desc_lo(smem_u32(smem + kOffdO + st * kQBytes), 8192);
+        loP[st] = desc_lo(smem_u32(smem + kOffP + st * kPBytes), 16);
+        lodS[st] = desc_lo(smem_u32(smem + kOffdS + st * kPBytes), 16);
+      }
       auto issue_sdp = [&](int s) {
         const int st = s & 1;
-        const uint32_t sQ = smem_u32(smem + kOffQ + st * kQBytes);
-        const uint32_t sdO = smem_u32(smem + kOffdO + st * kQBytes);
         mbar_wait(&qdo_full[st], (s >> 1) & 1);
         tc_fence_after();
+        const uint32_t q_lo = st ? loQ[1] : loQ[0], do_lo = st ? lodO[1] : lodO[0];
 #pragma unroll
         for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ak = make_smem_desc_sw128(sK + dh * 16384 + ks * 32, 16, 1024);
-            const uint64_t bq = make_smem_desc_sw128(sQ + dh * 8192 + ks * 32, 16, 1024);
-            umma_ss<false, 1>(tmem_base + kColS, ak, bq, idesc_st, (dh | ks) != 0);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss<false, 1>(tmem_base + kColS, desc_join(loK + (dh * 16384 + ks * 32) / 16, kHi),
+                              desc_join(q_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
 #pragma unroll
         for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t av = make_smem_desc_sw128(sV + dh * 16384 + ks * 32, 16, 1024);
-            const uint64_t bo = make_smem_desc_sw128(sdO + dh * 8192 + ks * 32, 16, 1024);
-            umma_ss<false, 1>(tmem_base + kColdP, av, bo, idesc_st, (dh | ks) != 0);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss<false, 1>(tmem_base + kColdP, desc_join(loV + (dh * 16384 + ks * 32) / 16, kHi),
+                              desc_join(do_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
         umma_commit(sdp_full);
       };
       mbar_wait(kv_full, 0);
       issue_sdp(0);
       for (int s = 0; s < n_steps; ++s) {
         const int st = s & 1;
-        const uint32_t sQ = smem_u32(smem + kOffQ + st * kQBytes);
-        const uint32_t sdO = smem_u32(smem + kOffdO + st * kQBytes);
-        const uint32_t sP = smem_u32(smem + kOffP + st * kPBytes);
-        const uint32_t sdS = smem_u32(smem + kOffdS + st * kPBytes);
+        const uint32_t qmn_lo = st ? loQmn[1] : loQmn[0], domn_lo = st ? lodOmn[1] : lodOmn[0];
+        const uint32_t p_lo = st ? loP[1] : loP[0], ds_lo = st ? lodS[1] : lodS[0];
         // softmax-grad of step s done: S^T/dP^T columns are free and P^T/dS^T[st] are in smem
         mbar_wait(&pds_full[st], (s >> 1) & 1);
         if (s + 1 < n_steps) issue_sdp(s + 1);
-        mbar_wait(dq_empty, (s & 1) ^ 1);  // previous dQ^T drained from TMEM
+        mbar_wait(&dq_empty[st], ((s >> 1) & 1) ^ 1);  // dQ^T buffer st drained (step s-2)
         tc_fence_after();
         // dV += P^T dO ; dK += dS^T Q        (K dim = q, 64 -> 4 steps of 16)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ap = make_smem_desc_sw128(sP + ks * 32, 16, 1024);
-          const uint64_t bo = make_smem_desc_sw128(sdO + ks * 16 * 128, 8192, 1024);
-          umma_ss<false, 1>(tmem_base + kColdV, ap, bo, idesc_acc, (s | ks) != 0);
-        }
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss<false, 1>(tmem_base + kColdV, desc_join(p_lo + ks * 2, kHi), desc_join(domn_lo + ks * 128, kHi),
+                            idesc_acc, (s | ks) != 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = make_smem_desc_sw128(sdS + ks * 32, 16, 1024);
-          const uint64_t bq = make_smem_desc_sw128(sQ + ks * 16 * 128, 8192, 1024);
-          umma_ss<false, 1>(tmem_base + kColdK, ad, bq, idesc_acc, (s | ks) != 0);
-        }
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss<false, 1>(tmem_base + kColdK, desc_join(ds_lo + ks * 2, kHi), desc_join(qmn_lo + ks * 128, kHi),
+                            idesc_acc, (s | ks) != 0);
         // dQ^T = K^T dS^T   (M = d, N = q, K dim = kv, 128 -> 8 steps of 16)
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ak = make_smem_desc_sw128(sK + ks * 16 * 128, 16384, 1024);
-          const uint64_t bd = make_smem_desc_sw128(sdS + ks * 16 * 128, 16, 1024);
-          umma_ss<false, 1>(tmem_base + kColdQ, ak, bd, idesc_dq, ks != 0);
-        }
-        umma_commit(dq_full);
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ss<false, 1>(tmem_base + kColdQ + st * 64, desc_join(loKmn + ks * 128, kHi),
+                            desc_join(ds_lo + ks * 128, kHi), idesc_dq, ks != 0);
+        umma_commit(&dq_full[st]);
         umma_commit(&qdo_empty[st]);
         umma_commit(&pds_empty[st]);
       }
       umma_commit(acc_done);
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < 8) {
-    // ------------------------------------ softmax-grad threads (thread = kv row) ------------------------------------
-    const int t = threadIdx.x - 128;
-    const int ew = warp - 4;
-    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+  } else if (warp >= 4) {
+    // ------------------------------------ workers: softmax-grad (thread = kv row, 32 query columns) and
+    //                                      dQ^T drain (thread = head-dim element, 32 query rows) ------------------
+    const int wt = threadIdx.x - 128;           // 0..255
+    const int grp = (warp - 4) >> 2;            // query-column half handled by this warp
+    const int lq = warp & 3;                    // TMEM lane quarter (hardware: warp % 4)
+    const int t = lq * 32 + lane_id();          // kv row / head-dim element
+    const uint32_t lane_off = uint32_t(lq * 32) << 16;
     const int kv = kv0 + t;
-    for (int s = 0; s < n_steps; ++s) {
+    const uint32_t s_stat_u = smem_u32(s_stat);
+    float* stage = reinterpret_cast<float*>(smem + kOffdQ);
+
+    auto load_stat = [&](int s) -> float {     // lse (log2 units) for wt < 64, delta for 64 <= wt < 128
+      if (wt >= 128 || s >= n_steps) return 0.f;
+      const int hq = hk * G + s / steps_per_head;
+      const int qq = (i_start + s % steps_per_head) * kQ + (wt & 63);
+      const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
+      if (wt < 64) return (qq < p.S) ? p.lse[idx] * kLog2e : INFINITY;
+      return (qq < p.S) ? p.delta[idx] : 0.f;
+    };
+    auto drain = [&](int s) {
+      // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> one
+      // bulk reduce-add per 32-row half into dq_accum[b, hq, q0 + 32 grp : +32, :] (fp32 add performed at L2)
       const int st = s & 1;
       const int hq = hk * G + s / steps_per_head;
       const int q0 = (i_start + s % steps_per_head) * kQ;
-      const uint32_t sP = smem_u32(smem + kOffP + st * kPBytes), sdS = smem_u32(smem + kOffdS + st * kPBytes);
-      // stage lse (in log2 units) and delta of the 64 query rows
-      float* stat = s_stat + st * 2 * kQ;
-      {
-        const int qq = q0 + (t & 63);
-        const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
-        if (t < 64) stat[t] = (qq < p.S) ? p.lse[idx] * kLog2e : INFINITY;
-        else stat[t] = (qq < p.S) ? p.delta[idx] : 0.f;
+      mbar_wait(&dq_full[st], (s >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + kColdQ + st * 64 + grp * 32 + lane_off, v);
+      tmem_wait_ld_regs(v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&dq_empty[st]);
+      if (t == 0) tma_store_wait_read<0>();      // this group's previous bulk reduce has read its staging half
+      named_bar_sync(2 + grp, 128);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) stage[(grp * 32 + i) * kHD + t] = __uint_as_float(v[i]);
+      fence_proxy_async_smem();
+      named_bar_sync(2 + grp, 128);
+      if (t == 0) {
+        const int rows = min(32, p.S - (q0 + grp * 32));
+        if (rows > 0) {
+          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0 + grp * 32) * kHD;
+          bulk_reduce_add_f32(dst, stage + grp * 32 * kHD, (uint32_t)rows * kHD * 4);
+        }
+        tma_store_commit();
       }
-      named_bar_sync(1, 128);
+    };
+
+    float nxt = load_stat(0);
+    if (wt < 128) s_stat[wt] = nxt;
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s & 1;
+      const int q0 = (i_start + s % steps_per_head) * kQ;
+      const uint32_t sP = smem_u32(smem + kOffP + st * kPBytes), sdS = smem_u32(smem + kOffdS + st * kPBytes);
+      named_bar_sync(1, kWorkers);               // stats of step s visible; all workers finished step s-1
+      nxt = load_stat(s + 1);                    // prefetch next step's lse / delta (global)
+      const uint32_t stat_u = s_stat_u + st * (2 * kQ * 4) + grp * 32 * 4;
       const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0));
       mbar_wait(&pds_empty[st], ((s >> 1) & 1) ^ 1);  // P^T/dS^T[st] no longer read by the MMAs of step s-2
       mbar_wait(sdp_full, s & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tmem_base + kColS + lane_off + c * 32, sv);
-        tmem_ld_32x32(tmem_base + kColdP + lane_off + c * 32, dv);
+        tmem_ld_32x32(tmem_base + kColS + grp * 32 + lane_off, sv);
+        tmem_ld_32x32(tmem_base + kColdP + grp * 32 + lane_off, dv);
         tmem_wait_ld_regs(sv);
         tmem_wait_ld_regs(dv);
         uint32_t pr[16], dsr[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int qi = c * 32 + i;
-          float p0 = ex2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -stat[qi]));
-          float p1 = ex2(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -stat[qi + 1]));
-          if (!full_tile) {
-            const int qa = q0 + qi;
-            if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)))) p0 = 0.f;
-            if (!((kv < p.S) && ((kv < p.P) || (kv <= qa + 1)))) p1 = 0.f;
+        for (int i = 0; i < 32; i += 4) {
+          const float4 l4 = lds_f4(stat_u + i * 4);                 // lse2 of 4 query columns
+          const float4 d4 = lds_f4(stat_u + kQ * 4 + i * 4);        // delta
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pv[4], dsv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float pe = ex2(fmaf(__uint_as_float(sv[i + e]), p.scale_log2, -ls[e]));
+            if (!full_tile) {
+              const int qa = q0 + grp * 32 + i + e;
+              if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)))) pe = 0.f;
+            }
+            pv[e] = pe;
+            dsv[e] = pe * (__uint_as_float(dv[i + e]) - dl[e]) * p.scale;
           }
-          const float d0 = p0 * (__uint_as_float(dv[i]) - stat[kQ + qi]) * p.scale;
-          const float d1 = p1 * (__uint_as_float(dv[i + 1]) - stat[kQ + qi + 1]) * p.scale;
-          pr[i / 2] = pack_bf16(p0, p1);
-          dsr[i / 2] = pack_bf16(d0, d1);
+          pr[i / 2] = pack_bf16(pv[0], pv[1]);
+          pr[i / 2 + 1] = pack_bf16(pv[2], pv[3]);
+          dsr[i / 2] = pack_bf16(dsv[0], dsv[1]);
+          dsr[i / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
         }
-        // rows of 64 q values = 128 B = 8 chunks of 16 B, swizzled by (row & 7); this half = chunks 4c .. 4c+3
+        // rows of 64 q values = 128 B = 8 chunks of 16 B, swizzled by (row & 7); this warp: chunks 4 grp .. 4 grp + 3
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const uint32_t off = t * 128 + (((c * 4 + cc) ^ (t & 7)) << 4);
+          const uint32_t off = t * 128 + (((grp * 4 + cc) ^ (t & 7)) << 4);
           sts_v4(sP + off, pr[cc * 4], pr[cc * 4 + 1], pr[cc * 4 + 2], pr[cc * 4 + 3]);
           sts_v4(sdS + off, dsr[cc * 4], dsr[cc * 4 + 1], dsr[cc * 4 + 2], dsr[cc * 4 + 3]);
         }
@@ -558,20 +606,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&pds_full[st]);
+      if (wt < 128) s_stat[(st ^ 1) * 2 * kQ + wt] = nxt;   // stats of step s+1 (buffer last read in step s-1)
+      if (s > 0) drain(s - 1);                               // dQ^T of the previous step is complete by now
     }
-    // write dK, dV (thread = kv row)
+    drain(n_steps - 1);
+    if (t == 0) tma_store_wait<0>();  // all bulk reductions issued by this thread have completed
+    // write dV (group 0) / dK (group 1); thread = kv row
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const bool row_ok = kv < p.S;
-    __nv_bfloat16* dkrow = p.dk + ((int64_t)b * p.S + kv) * p.lddk + (int64_t)hk * kHD;
-    __nv_bfloat16* dvrow = p.dv + ((int64_t)b * p.S + kv) * p.lddv + (int64_t)hk * kHD;
+    __nv_bfloat16* drow = grp == 0 ? p.dv + ((int64_t)b * p.S + kv) * p.lddv + (int64_t)hk * kHD
+                                   : p.dk + ((int64_t)b * p.S + kv) * p.lddk + (int64_t)hk * kHD;
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (c < 4 ? kColdV : kColdK) + lane_off + (c & 3) * 32, v);
+      tmem_ld_32x32(tmem_base + (grp == 0 ? kColdV : kColdK) + lane_off + c * 32, v);
       tmem_wait_ld_regs(v);
       if (row_ok) {
-        __nv_bfloat16* dst = (c < 4 ? dvrow : dkrow) + (c & 3) * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 o4;
@@ -579,47 +630,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           o4.y = pack_bf16(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
           o4.z = pack_bf16(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
           o4.w = pack_bf16(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-          stg_v4(dst + i, o4);
+          stg_v4(drow + c * 32 + i, o4);
         }
       }
     }
     tc_fence_before();
-  } else if (warp >= 8) {
-    // ------------------------------------ dQ drain threads (thread = head-dim element d) ------------------------------------
-    // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> ONE bulk
-    // reduce-add of the tile into dq_accum[b, hq, q0:q0+64, :] (contiguous 32 KB, fp32 add performed at L2).
-    const int t = threadIdx.x - 256;
-    const uint32_t lane_off = uint32_t((warp - 8) * 32) << 16;
-    float* stage = reinterpret_cast<float*>(smem + kOffdQ);
-    for (int s = 0; s < n_steps; ++s) {
-      const int hq = hk * G + s / steps_per_head;
-      const int q0 = (i_start + s % steps_per_head) * kQ;
-      mbar_wait(dq_full, s & 1);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_base + kColdQ + lane_off, v0);
-      tmem_ld_32x32(tmem_base + kColdQ + lane_off + 32, v1);
-      tmem_wait_ld_regs(v0);
-      tmem_wait_ld_regs(v1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(dq_empty);  // TMEM columns free for the next dQ^T
-      if (t == 0) tma_store_wait_read<0>();       // previous bulk reduce finished reading the staging tile
-      named_bar_sync(2, 128);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) stage[i * kHD + t] = __uint_as_float(v0[i]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) stage[(32 + i) * kHD + t] = __uint_as_float(v1[i]);
-      fence_proxy_async_smem();
-      named_bar_sync(2, 128);
-      if (t == 0) {
-        const int rows = min(kQ, p.S - q0);
-        float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0) * kHD;
-        bulk_reduce_add_f32(dst, stage, (uint32_t)rows * kHD * 4);
-        tma_store_commit();
-      }
-    }
-    if (t == 0) tma_store_wait<0>();  // all bulk reductions of this CTA have completed
   }
 
   tc_fence_before();

@@ -256,6 +256,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// Split form for hot issue loops: hi word is constant per operand kind, lo word = (addr >> 4) | (lbo >> 4) << 16,
+// so stepping an operand costs one 32-bit add (byte offset >> 4).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // Instruction descriptor (upper 32 bits of idescE), dense, no negate, no saturate.
 //   c_fmt: 1 = F32, 2 = S32; ab_fmt: kind::f16 -> 0 F16 / 1 BF16, kind::i8 -> 0 U8 / 1 S8
 //   a_mn / b_mn: 1 = operand is MN-major in smem

@@ -25,7 +25,8 @@ constexpr int kBM = 128;          // rows of A per CTA
 constexpr int kBN = 256;          // accumulator columns per tile
 constexpr int kBKBytes = 128;     // one 128B swizzle row of K per stage
 constexpr int kMaxLoraRank = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int kEpiThreads = 256;
 constexpr int kGroupM = 8;        // m-tiles per scheduling group (L2 reuse of the B panel)
 
 struct GemmParams {
@@ -119,7 +120,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+      mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp of every CTA in the group
     }
     fence_mbar_init();
   }
@@ -196,8 +197,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const int ew = warp - 4;                 // TMEM lanes [32*ew, 32*ew+32)
-    const int et = threadIdx.x - 128;        // 0..127
+    const int ew = warp & 3;                 // TMEM lanes [32*ew, 32*ew+32) (hardware: warp % 4)
+    const int ch = (warp - 4) >> 2;          // column half of the tile handled by this warp: chunks 4*ch .. 4*ch+3
+    const int et = threadIdx.x - 128;        // 0..255
     const int R = p.lora_rank;
     constexpr int kRS = kRank > 0 ? kRank : 4;  // floats per staged lora_b row
     const uint32_t s_cs = smem_u32(s_colscale);
@@ -216,19 +218,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = row < p.M;
 
       // stage per-column data for this tile (previous tile's readers are done: barrier below)
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (has_cs) {
-        for (int i = et; i < kBN; i += 128)
+        for (int i = et; i < kBN; i += kEpiThreads)
           s_colscale[i] = (col0 + i < p.N) ? __bfloat162float(p.col_scale[col0 + i]) : 0.f;
       }
       if constexpr (kRank > 0) {
-        for (int i = et; i < kBN * kRank; i += 128) {
+        for (int i = et; i < kBN * kRank; i += kEpiThreads) {
           const int n = i / kRank, r = i % kRank;
           s_lorab[i] = (col0 + n < p.N && r < R) ? __bfloat162float(p.lora_b[(int64_t)(col0 + n) * R + r]) * p.lora_scale
                                                   : 0.f;
         }
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
 
       float rs = 1.f;
       if (p.row_scale != nullptr && row_ok) rs = __bfloat162float(p.row_scale[row]);
@@ -256,12 +258,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kBN;
-      const int n_chunks = min(kBN / 32, (p.N - col0 + 31) / 32);
+      const int n_chunks = min(ch * 4 + 4, min(kBN / 32, (p.N - col0 + 31) / 32));
 
       uint32_t v[2][32];
-      tmem_ld_32x32(taddr, v[0]);
+      if (ch * 4 < n_chunks) tmem_ld_32x32(taddr + ch * 4 * 32, v[0]);
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; c += 2) {
+      for (int c = ch * 4; c < n_chunks; c += 2) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int cc = c + half;
@@ -506,7 +508,9 @@ lora_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tmem_ld_32x32(tmem_base + (uint32_t(lq * 32) << 16), v);
       tmem_wait_ld_regs(v);
       if (row < P) {
-        for (int r = 0; r < R; ++r) atomicAdd(out + (int64_t)row * R + r, alpha * __uint_as_float(v[r]));
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r < R) atomicAdd(out + (int64_t)row * R + r, alpha * __uint_as_float(v[r]));
       }
     }
     tc_fence_before();
