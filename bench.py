@@ -222,6 +222,10 @@ def run_ours(args):
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
     clocks = sampler.stop() if rank == 0 else None
 
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}
@@ -271,6 +275,8 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_reference(args, steps=1, warmup=0)
     print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------ reference (CPU oracle port)
