@@ -46,7 +46,7 @@ class _KernelTiming:
 TIMING = _KernelTiming()
 
 
-def _call(lib, name: str, args: tuple, kclass: str, flops: float = 0.0, nbytes: float = 0.0):
+def _call(lib, name: str, args: tuple, kclass: str, flops: float = 0.0, nbytes: float = 0.0, shape=None):
     """Invoke one C-ABI entry point; raise on a non-zero return; optionally time it with CUDA events."""
     fn = getattr(lib, name)
     if TIMING.on:
@@ -55,6 +55,8 @@ def _call(lib, name: str, args: tuple, kclass: str, flops: float = 0.0, nbytes: 
         rc = fn(*args)
         e1.record()
         TIMING.records.append((kclass, e0, e1, flops, nbytes))
+        if shape is not None:
+            TIMING.records.append((f"{kclass}[M={shape[0]},N={shape[1]},K={shape[2]}]", e0, e1, flops, nbytes))
     else:
         rc = fn(*args)
     check(rc, name)
@@ -129,7 +131,7 @@ def int8_gemm_dequant(A: Tensor, W: Tensor, a_scale: Tensor, w_scale: Tensor, *,
     ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
     _call(lib, "llamax_int8_gemm_dequant",
           (_p(A), A.stride(0), _p(W), W.stride(0), _p(a_scale), _p(w_scale), _p(out), out.stride(0), M, N, K, ctypes.byref(ep) if ep is not None else None, st,),
-          "int8_gemm", 2.0 * M * N * K, 0.0)
+          "int8_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))
     return out
 
 
@@ -163,7 +165,7 @@ def bf16_gemm(A: Tensor, B: Tensor, *, col_scale: Tensor | None = None, round_be
     ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
     _call(lib, "llamax_bf16_gemm",
           (_p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), M, N, K, _p(col_scale), int(round_before_scale), ctypes.byref(ep) if ep is not None else None, st,),
-          "bf16_gemm", 2.0 * M * N * K, 0.0)
+          "bf16_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))
     return out
 
 
