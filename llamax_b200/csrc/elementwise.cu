@@ -17,12 +17,13 @@ struct RowCfg {
   int V;  // 16-byte vectors (8 bf16) held per thread: 1, 2, 4 or 8
 };
 
-static inline bool row_cfg(int64_t D, RowCfg& c) {
+static inline bool row_cfg(int64_t D, RowCfg& c, bool one_vec_per_thread = false) {
   if (D <= 0 || D % 8) return false;
   const int nvec = (int)(D / 8);
   // two 16-byte vectors per thread when the row allows it (measured on B200: 256 threads x 2 vectors beats
   // 512 x 1 for D = 4096 rows by ~25 %), at most 512 threads per row
   int threads = std::min(512, (((nvec + 1) / 2 + 31) / 32) * 32);
+  if (one_vec_per_thread) threads = std::min(512, ((nvec + 31) / 32) * 32);  // persistent kernels: more warps per CTA
   int v = (nvec + threads - 1) / threads;
   if (v > 8) return false;
   c.V = v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : 8;
@@ -536,7 +537,7 @@ int llamax_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void*
                        void* dw_partial, int32_t nparts, int64_t M, int64_t D, void* stream) {
   RowCfg c;
   if (!dy || !x || !w || !rstd || !dx) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: null pointer");
-  if (!row_cfg(D, c)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: D must be a multiple of 8 and <= 65536");
+  if (!row_cfg(D, c, true)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: D must be a multiple of 8 and <= 65536");
   if (nparts <= 0 || nparts > 4096) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: nparts out of range");
   LX_DISPATCH_V(c.V, rmsnorm_bwd_kernel<kV><<<nparts, c.threads, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, (const bf16*)x, (const bf16*)w, (const float*)rstd, (const bf16*)dres, (bf16*)dx,
