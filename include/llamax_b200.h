@@ -110,19 +110,22 @@ int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_
 
 /* ---- K8/K9: prefix-LM attention (modelling/llama.py:129-137) --------------------------------------
  * mask(q, kv) = (kv < prefix_len) | (q >= kv);  prefix_len = 0 is plain causal.
+ * Optional packed-sequence document-causal mask (train_metamathqa.py:67-70): doc_start / doc_end int32 [B, S] hold the
+ * first / last position of the document containing each position (documents are contiguous); visible pairs are
+ * additionally restricted to kv >= doc_start[q].  NULL = no document structure.
  * q bf16 [B,S,Hq,D] with row pitch ldq (elements between consecutive positions), k/v [B,S,Hkv,D] pitch
  * ldk/ldv, o [B,S,Hq,D] pitch ldo, lse fp32 [B,Hq,S] (natural-log-sum-exp of scaled scores).
  * GQA native: Hq % Hkv == 0, no K/V expansion.  D must be 128 (64 also supported).  scale = 1/sqrt(D). */
 int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
-                    int64_t prefix_len, float scale, void* stream);
+                    int64_t prefix_len, const void* doc_start, float scale, void* stream);
 /* dq/dk/dv bf16 with pitches lddq/lddk/lddv; dq_accum fp32 workspace [B,S,Hq,D] (zeroed by the call);
  * delta fp32 workspace [B,Hq,S]. */
 int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
                     int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
-                    int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len, float scale,
-                    void* stream);
+                    int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
+                    const void* doc_start, const void* doc_end, float scale, void* stream);
 
 /* ---- K6 backward: LoRA weight gradients (autograd of modelling/lora.py:43) ------------------------
  *   out[p, r] (fp32) = alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx;  Ht = H^T bf16 [R, M] pitch ldht

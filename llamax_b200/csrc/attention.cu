@@ -49,6 +49,7 @@ struct AttnFwdParams {
   float* lse;
   int B, S, Hq, Hkv, P;
   float scale_log2;  // softmax scale * log2(e)
+  const int32_t* doc_start;  // [B, S] first position of the document containing each position, or null
 };
 
 namespace fwd {
@@ -87,7 +88,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int hk = h / (p.Hq / p.Hkv);
   const int q0 = qt * kTile;
   const int kv_end = min(p.S, max(p.P, q0 + kTile));
-  const int n_kv = (kv_end + kTile - 1) / kTile;
+  // packed documents: keys before the start of the first row's document are never visible to this tile
+  const int j_begin = p.doc_start ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
+  const int n_kv = (kv_end + kTile - 1) / kTile - j_begin;  // number of visited kv tiles
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQ);
@@ -131,13 +134,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], kTileBytes);
         uint8_t* sk = smem + kOffK + st * kTileBytes;
-        tma_load_4d(sk, &tmK, &k_full[st], 0, hk, j * kTile, b);
-        tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, j * kTile, b);
+        tma_load_4d(sk, &tmK, &k_full[st], 0, hk, (j_begin + j) * kTile, b);
+        tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, (j_begin + j) * kTile, b);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], kTileBytes);
         uint8_t* sv = smem + kOffV + st * kTileBytes;
-        tma_load_4d(sv, &tmV, &v_full[st], 0, hk, j * kTile, b);
-        tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, j * kTile, b);
+        tma_load_4d(sv, &tmV, &v_full[st], 0, hk, (j_begin + j) * kTile, b);
+        tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, (j_begin + j) * kTile, b);
       }
     }
     __syncwarp();
@@ -193,11 +196,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int q = q0 + r;
     const uint32_t sP = smem_u32(smem + kOffP);
     float m_used = -INFINITY, l = 0.f;
+    const int ds_row = p.doc_start ? p.doc_start[(int64_t)b * p.S + min(q, p.S - 1)] : 0;
+    const int ds_tile = p.doc_start ? p.doc_start[(int64_t)b * p.S + min(q0 + kTile - 1, p.S - 1)] : 0;
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
-      const int kv0 = j * kTile;
+      const int kv0 = (j_begin + j) * kTile;
       // tile needs the element test unless every (q, kv) pair is visible and in range
-      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0));
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tmem_S + st * 128 + lane_off;
@@ -219,7 +224,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kv = kv0 + c * 32 + i;
-            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q));
+            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (kv >= ds_row);
             if (!ok) sv[c][i] = 0xff800000u;  // -inf
           }
       }
@@ -236,12 +241,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       uint32_t preg[64];
       float rowsum = 0.f;
+      // a row may see nothing in a visited tile (packed documents): keep the exponent finite so that exp2(-inf) = 0
+      const float m_exp = (m_used == -INFINITY) ? 0.f : m_used;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_used));      // -inf -> 0
-          const float p1 = ex2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_used));
+          const float p0 = ex2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_exp));      // -inf -> 0
+          const float p1 = ex2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_exp));
           rowsum += p0 + p1;
           preg[c * 16 + i / 2] = pack_bf16(p0, p1);
         }
@@ -321,6 +328,8 @@ struct AttnBwdParams {
   int64_t lddv;
   int B, S, Hq, Hkv, P;
   float scale, scale_log2;
+  const int32_t* doc_start;  // [B, S] or null (packed-sequence document-causal mask)
+  const int32_t* doc_end;    // [B, S] last position of the document containing each position
 };
 
 namespace bwd {
@@ -339,8 +348,8 @@ constexpr int kOffP = kOffdO + 2 * kQBytes;       // 2 buffers
 constexpr int kOffdS = kOffP + 2 * kPBytes;       // 2 buffers
 constexpr int kOffdQ = kOffdS + 2 * kPBytes;      // fp32 [64 q][128 d] staging for the bulk reduce-add
 constexpr int kdQBytes = kQ * kHD * 4;            // 32 KB
-constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta: 2 stages x 2 x 64 floats
-constexpr int kOffBar = kOffStat + 2 * 2 * kQ * 4;
+constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta / doc_start: 2 stages x 3 x 64 words
+constexpr int kOffBar = kOffStat + 2 * 3 * kQ * 4;
 // kv_full, qdo full/empty[2], sdp_full, pds full/empty[2], dq full/empty[2], acc_done
 constexpr int kNumBars = 1 + 4 + 1 + 4 + 4 + 1;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
@@ -375,7 +384,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int G = p.Hq / p.Hkv;
   const int nq_tiles = (p.S + kQ - 1) / kQ;
   const int i_start = (kv0 < p.P) ? 0 : kv0 / kQ;  // first query tile that sees this kv tile
-  const int steps_per_head = nq_tiles - i_start;
+  // packed documents: queries after the end of the last kv row's document never see this tile
+  const int i_end = p.doc_end ? min(nq_tiles, p.doc_end[(int64_t)b * p.S + min(kv0 + kKV - 1, p.S - 1)] / kQ + 1) : nq_tiles;
+  const int steps_per_head = i_end - i_start;
   const int n_steps = G * steps_per_head;
 
   if (warp == 0 && elect_one()) {
@@ -515,13 +526,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t s_stat_u = smem_u32(s_stat);
     float* stage = reinterpret_cast<float*>(smem + kOffdQ);
 
-    auto load_stat = [&](int s) -> float {     // lse (log2 units) for wt < 64, delta for 64 <= wt < 128
-      if (wt >= 128 || s >= n_steps) return 0.f;
+    // lse (log2 units) for wt < 64, delta for 64 <= wt < 128, document start (int bits) for 128 <= wt < 192
+    auto load_stat = [&](int s) -> float {
+      if (wt >= 192 || s >= n_steps) return 0.f;
       const int hq = hk * G + s / steps_per_head;
       const int qq = (i_start + s % steps_per_head) * kQ + (wt & 63);
       const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
       if (wt < 64) return (qq < p.S) ? p.lse[idx] * kLog2e : INFINITY;
-      return (qq < p.S) ? p.delta[idx] : 0.f;
+      if (wt < 128) return (qq < p.S) ? p.delta[idx] : 0.f;
+      return __int_as_float((p.doc_start && qq < p.S) ? p.doc_start[(int64_t)b * p.S + qq] : 0);
     };
     auto drain = [&](int s) {
       // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> one
@@ -554,15 +567,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
 
     float nxt = load_stat(0);
-    if (wt < 128) s_stat[wt] = nxt;
+    if (wt < 192) s_stat[wt] = nxt;
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
       const int q0 = (i_start + s % steps_per_head) * kQ;
       const uint32_t sP = smem_u32(smem + kOffP + st * kPBytes), sdS = smem_u32(smem + kOffdS + st * kPBytes);
       named_bar_sync(1, kWorkers);               // stats of step s visible; all workers finished step s-1
       nxt = load_stat(s + 1);                    // prefetch next step's lse / delta (global)
-      const uint32_t stat_u = s_stat_u + st * (2 * kQ * 4) + grp * 32 * 4;
-      const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0));
+      const uint32_t stat_u = s_stat_u + st * (3 * kQ * 4) + grp * 32 * 4;
+      const int ds_tile = p.doc_start ? p.doc_start[(int64_t)b * p.S + min(q0 + kQ - 1, p.S - 1)] : 0;
+      const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0)) &&
+                             (kv0 >= ds_tile);
       mbar_wait(&pds_empty[st], ((s >> 1) & 1) ^ 1);  // P^T/dS^T[st] no longer read by the MMAs of step s-2
       mbar_wait(sdp_full, s & 1);
       tc_fence_after();
@@ -578,13 +593,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float4 l4 = lds_f4(stat_u + i * 4);                 // lse2 of 4 query columns
           const float4 d4 = lds_f4(stat_u + kQ * 4 + i * 4);        // delta
           const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+          int dst4[4] = {0, 0, 0, 0};
+          if (!full_tile) {
+            const float4 s4 = lds_f4(stat_u + 2 * kQ * 4 + i * 4);  // document start of each query column
+            dst4[0] = __float_as_int(s4.x); dst4[1] = __float_as_int(s4.y);
+            dst4[2] = __float_as_int(s4.z); dst4[3] = __float_as_int(s4.w);
+          }
           float pv[4], dsv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float pe = ex2(fmaf(__uint_as_float(sv[i + e]), p.scale_log2, -ls[e]));
             if (!full_tile) {
               const int qa = q0 + grp * 32 + i + e;
-              if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)))) pe = 0.f;
+              if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (kv >= dst4[e]))) pe = 0.f;
             }
             pv[e] = pe;
             dsv[e] = pe * (__uint_as_float(dv[i + e]) - dl[e]) * p.scale;
@@ -606,7 +627,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&pds_full[st]);
-      if (wt < 128) s_stat[(st ^ 1) * 2 * kQ + wt] = nxt;   // stats of step s+1 (buffer last read in step s-1)
+      if (wt < 192) s_stat[(st ^ 1) * 3 * kQ + wt] = nxt;   // stats of step s+1 (buffer last read in step s-1)
       if (s > 0) drain(s - 1);                               // dQ^T of the previous step is complete by now
     }
     drain(n_steps - 1);
@@ -707,7 +728,7 @@ extern "C" {
 
 int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
-                    int64_t prefix_len, float scale, void* stream) {
+                    int64_t prefix_len, const void* doc_start, float scale, void* stream) {
   if (!q || !k || !v || !o || !lse) return set_error(LLAMAX_ERR_ARG, "attn_fwd: null pointer");
   int rc = check_attn_args(B, S, Hq, Hkv, D, prefix_len, "attn_fwd");
   if (rc) return rc;
@@ -729,6 +750,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.B = (int)B; p.S = (int)S; p.Hq = Hq; p.Hkv = Hkv;
   p.P = (int)std::min<int64_t>(prefix_len, S);
   p.scale_log2 = scale * kLog2e;
+  p.doc_start = (const int32_t*)doc_start;
   dim3 grid((unsigned)ceil_div(S, fwd::kTile), Hq, (unsigned)B);
   attn_fwd_kernel<<<grid, 256, fwd::kSmemBytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   LX_CHECK_LAUNCH("attn_fwd");
@@ -738,8 +760,10 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
 int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
                     int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
-                    int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len, float scale,
-                    void* stream) {
+                    int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
+                    const void* doc_start, const void* doc_end, float scale, void* stream) {
+  if ((doc_start == nullptr) != (doc_end == nullptr))
+    return set_error(LLAMAX_ERR_ARG, "attn_bwd: doc_start and doc_end go together");
   if (!q || !k || !v || !o || !lse || !dout || !dq || !dk || !dv || !dq_accum || !delta)
     return set_error(LLAMAX_ERR_ARG, "attn_bwd: null pointer");
   int rc = check_attn_args(B, S, Hq, Hkv, D, prefix_len, "attn_bwd");
@@ -778,6 +802,8 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.P = (int)std::min<int64_t>(prefix_len, S);
   p.scale = scale;
   p.scale_log2 = scale * kLog2e;
+  p.doc_start = (const int32_t*)doc_start;
+  p.doc_end = (const int32_t*)doc_end;
   dim3 grid((unsigned)ceil_div(S, bwd::kKV), Hkv, (unsigned)B);
   attn_bwd_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");

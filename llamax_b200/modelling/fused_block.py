@@ -141,7 +141,7 @@ class FusedDecoderBlock(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: Tensor, rope: Tensor, meta, *trainables):
-        layer, prefix_len = meta
+        layer, prefix_len, doc_start, doc_end = meta
         att, ff = layer.attention, layer.feed_forward
         B, S, Dm = x.shape
         M = B * S
@@ -165,7 +165,8 @@ class FusedDecoderBlock(torch.autograd.Function):
             r_off += spec.R
             _linear(spec, xn1, xq, xs, h, out=qkv[:, c0:c1])
         ops.rope_(qkv, rope, B, S, Hq + Hkv, D)
-        o, lse = ops.attn_fwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], B, S, Hq, Hkv, D, prefix_len)
+        o, lse = ops.attn_fwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], B, S, Hq, Hkv, D, prefix_len,
+                              doc_start=doc_start)
         oq = osc = None
         if so.dynamic:
             oq, osc = ops.rowquant_int8(o)
@@ -191,7 +192,7 @@ class FusedDecoderBlock(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout: Tensor):
-        layer, prefix_len = ctx.meta
+        layer, prefix_len, doc_start, doc_end = ctx.meta
         x2, xn1, rstd1, qkv, o, lse, x1, xn2, rstd2, ab, h_qkv, h_o, h_13, h_2, rope = ctx.saved_tensors
         att, ff = layer.attention, layer.feed_forward
         B, S, Dm = ctx.shape
@@ -238,7 +239,8 @@ class FusedDecoderBlock(torch.autograd.Function):
         rqkv = sq.R + sk.R + sv.R
         dqkv = torch.empty(M, nq + 2 * nk + rqkv, device=dout.device, dtype=torch.bfloat16)
         ops.attn_bwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], o, lse, do,
-                     dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len)
+                     dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len,
+                     doc_start=doc_start, doc_end=doc_end)
         ops.rope_(dqkv, rope, B, S, Hq + Hkv, D, inverse=True)
         dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, h_qkv)
         del dqkv

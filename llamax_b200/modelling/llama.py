@@ -53,6 +53,38 @@ class PrefixLM:
         return f"PrefixLM(prefix_len={self.prefix_len})"
 
 
+class DocumentCausal:
+    """Mask descriptor for packed sequences (train_metamathqa.py:51-83): tokens attend causally within their own
+    document. `doc_ids` int [B, S], non-decreasing along S (documents are contiguous)."""
+
+    prefix_len = 0
+
+    def __init__(self, doc_ids: Tensor):
+        if doc_ids.dim() == 1:
+            doc_ids = doc_ids[None]
+        self.doc_ids = doc_ids
+        self.doc_start, self.doc_end = ops.doc_bounds(doc_ids)
+
+    def __repr__(self):
+        return f"DocumentCausal(shape={tuple(self.doc_ids.shape)})"
+
+
+def document_block_mask(doc_ids: Tensor):
+    """A real FlexAttention BlockMask for the document-causal mask of the reference (train_metamathqa.py:67-71),
+    tagged with the document bounds so that this package's kernels accept it too."""
+    from torch.nn.attention.flex_attention import create_block_mask
+
+    ids = doc_ids.reshape(-1)
+
+    def mask_mod(b, h, q_idx, kv_idx):
+        return (ids[q_idx] == ids[kv_idx]) & (q_idx >= kv_idx)
+
+    bm = create_block_mask(mask_mod, None, None, ids.numel(), ids.numel(), device=ids.device)
+    bm.prefix_len = 0
+    bm.doc_start, bm.doc_end = ops.doc_bounds(ids[None])
+    return bm
+
+
 def prefix_lm_block_mask(prefix_len: int, seq_len: int, device="cuda"):
     """A real FlexAttention BlockMask for the prefix-LM mask, tagged with `.prefix_len` so that both this package
     and the reference's flex_attention branch (llama.py:129-132) accept it."""
@@ -64,6 +96,12 @@ def prefix_lm_block_mask(prefix_len: int, seq_len: int, device="cuda"):
     bm = create_block_mask(mask_mod, None, None, seq_len, seq_len, device=device)
     bm.prefix_len = int(prefix_len)
     return bm
+
+
+def _doc_bounds_of(block_mask):
+    """(doc_start, doc_end) int32 [B, S] of a document mask descriptor, or (None, None)."""
+    ds = getattr(block_mask, "doc_start", None)
+    return (ds, getattr(block_mask, "doc_end", None)) if ds is not None else (None, None)
 
 
 def _prefix_len_of(mask, block_mask, input_pos) -> int:
@@ -128,14 +166,15 @@ class _PrefixLMAttentionFn(torch.autograd.Function):
     """o = softmax(q k^T / sqrt(D) + mask) v on [B, S, H, D] tensors (GQA native)."""
 
     @staticmethod
-    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, prefix_len: int):
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, prefix_len: int, doc_start=None, doc_end=None):
         B, S, Hq, D = q.shape
         Hkv = k.shape[2]
         q2, k2, v2 = (t.reshape(B * S, -1) for t in (q, k, v))
         q2, k2, v2 = (t if t.stride(1) == 1 else t.contiguous() for t in (q2, k2, v2))
-        o, lse = ops.attn_fwd(q2, k2, v2, B, S, Hq, Hkv, D, prefix_len)
+        o, lse = ops.attn_fwd(q2, k2, v2, B, S, Hq, Hkv, D, prefix_len, doc_start=doc_start)
         ctx.save_for_backward(q2, k2, v2, o, lse)
         ctx.dims = (B, S, Hq, Hkv, D, prefix_len)
+        ctx.docs = (doc_start, doc_end)
         return o.view(B, S, Hq, D)
 
     @staticmethod
@@ -143,12 +182,13 @@ class _PrefixLMAttentionFn(torch.autograd.Function):
         q2, k2, v2, o, lse = ctx.saved_tensors
         B, S, Hq, Hkv, D, prefix_len = ctx.dims
         dq, dk, dv = torch.empty_like(q2), torch.empty_like(k2), torch.empty_like(v2)
-        ops.attn_bwd(q2, k2, v2, o, lse, do.reshape(B * S, Hq * D), dq, dk, dv, B, S, Hq, Hkv, D, prefix_len)
-        return dq.view(B, S, Hq, D), dk.view(B, S, Hkv, D), dv.view(B, S, Hkv, D), None
+        ops.attn_bwd(q2, k2, v2, o, lse, do.reshape(B * S, Hq * D), dq, dk, dv, B, S, Hq, Hkv, D, prefix_len,
+                     doc_start=ctx.docs[0], doc_end=ctx.docs[1])
+        return dq.view(B, S, Hq, D), dk.view(B, S, Hkv, D), dv.view(B, S, Hkv, D), None, None, None
 
 
-def prefix_lm_attention(q: Tensor, k: Tensor, v: Tensor, prefix_len: int = 0) -> Tensor:
-    return _PrefixLMAttentionFn.apply(q, k, v, prefix_len)
+def prefix_lm_attention(q: Tensor, k: Tensor, v: Tensor, prefix_len: int = 0, doc_start=None, doc_end=None) -> Tensor:
+    return _PrefixLMAttentionFn.apply(q, k, v, prefix_len, doc_start, doc_end)
 
 
 class Attention(nn.Module):
@@ -177,7 +217,7 @@ class Attention(nn.Module):
         k = self.wk(x).view(B, L, self.num_kv_heads, self.head_dim)
         v = self.wv(x).view(B, L, self.num_kv_heads, self.head_dim)
         q, k = apply_rope(q, rope), apply_rope(k, rope)
-        out = prefix_lm_attention(q, k, v, prefix_len)
+        out = prefix_lm_attention(q, k, v, prefix_len, *_doc_bounds_of(block_mask))
         return self.wo(out.reshape(B, L, self.num_heads * self.head_dim))
 
 
@@ -225,7 +265,8 @@ class TransformerLayer(nn.Module):
                 block_mask=None) -> Tensor:
         if fused_block_supported(self, x):
             prefix_len = _prefix_len_of(mask, block_mask, input_pos)
-            return FusedDecoderBlock.apply(x, rope, (self, prefix_len), *block_trainables(self))
+            return FusedDecoderBlock.apply(x, rope, (self, prefix_len, *_doc_bounds_of(block_mask)),
+                                           *block_trainables(self))
         # unfused composition (e.g. bf16 base weights): same math, module by module
         x = x + self.attention(self.attention_norm(x), rope, mask=mask, input_pos=input_pos, block_mask=block_mask)
         x = x + self.feed_forward(self.ffn_norm(x))

@@ -320,8 +320,21 @@ def _pairs(S: int, prefix_len: int) -> float:
     return S * P_ + (S - P_) * (S - P_ + 1) / 2
 
 
+def doc_bounds(doc_ids: Tensor):
+    """doc_ids int [B, S] (non-decreasing per row: packed documents) -> (doc_start, doc_end) int32 [B, S]."""
+    B, S = doc_ids.shape
+    idx = torch.arange(S, device=doc_ids.device).expand(B, S)
+    first = torch.ones_like(doc_ids, dtype=torch.bool)
+    first[:, 1:] = doc_ids[:, 1:] != doc_ids[:, :-1]
+    last = torch.ones_like(first)
+    last[:, :-1] = first[:, 1:]
+    start = torch.where(first, idx, torch.zeros_like(idx)).cummax(dim=1).values
+    end = torch.where(last, idx, torch.full_like(idx, S - 1)).flip(1).cummin(dim=1).values.flip(1)
+    return start.to(torch.int32).contiguous(), end.to(torch.int32).contiguous()
+
+
 def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, prefix_len: int,
-             scale: float | None = None):
+             scale: float | None = None, doc_start: Tensor | None = None):
     """q [B*S, Hq*D] / k, v [B*S, Hkv*D] row views (unit inner stride). Returns (o [B*S, Hq*D], lse [B,Hq,S])."""
     lib, st = _prep(q)
     for t in (q, k, v):
@@ -330,12 +343,13 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int,
     lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     scale = float(scale) if scale is not None else D ** -0.5
     _call(lib, "llamax_attn_fwd",
-          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), B, S, Hq, Hkv, D, int(prefix_len), scale, st,),
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), B, S, Hq, Hkv, D, int(prefix_len), _p(doc_start), scale, st,),
           "attn_fwd", 4.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return o, lse
 
 
-def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, scale=None):
+def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, scale=None, doc_start=None,
+             doc_end=None):
     """Writes dq/dk/dv (row views like q/k/v)."""
     lib, st = _prep(q)
     dout = _rows(dout)
@@ -343,6 +357,6 @@ def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, sc
     delta = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     scale = float(scale) if scale is not None else D ** -0.5
     _call(lib, "llamax_attn_bwd",
-          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len), scale, st,),
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len), _p(doc_start), _p(doc_end), scale, st,),
           "attn_bwd", 10.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return dq, dk, dv

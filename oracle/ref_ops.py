@@ -175,7 +175,14 @@ def prefix_lm_mask(L: int, prefix_len: int) -> Tensor:
     return (kv < prefix_len) | (q >= kv)
 
 
-def attention_ref(q: Tensor, k: Tensor, v: Tensor, prefix_len: int, dtype=torch.float32) -> Tensor:
+def document_causal_mask(doc_ids: Tensor) -> Tensor:
+    """[B, 1, S, S] mask of the packed-sequence trainer: same document and causal (train_metamathqa.py:67-70)."""
+    S = doc_ids.shape[-1]
+    same = doc_ids[:, :, None] == doc_ids[:, None, :]
+    return (same & torch.tril(torch.ones(S, S, dtype=torch.bool)))[:, None]
+
+
+def attention_ref(q: Tensor, k: Tensor, v: Tensor, prefix_len: int, dtype=torch.float32, doc_ids=None) -> Tensor:
     """q [B,Hq,S,D], k/v [B,Hkv,S,D] -> [B,Hq,S,D]; dense masked softmax evaluated in `dtype`."""
     B, Hq, S, D = q.shape
     rep = Hq // k.shape[1]
@@ -183,14 +190,15 @@ def attention_ref(q: Tensor, k: Tensor, v: Tensor, prefix_len: int, dtype=torch.
     kf = k.to(dtype).repeat_interleave(rep, dim=1)
     vf = v.to(dtype).repeat_interleave(rep, dim=1)
     s = (qf @ kf.transpose(-1, -2)) / math.sqrt(D)
-    s = s.masked_fill(~prefix_lm_mask(S, prefix_len), float("-inf"))
+    mask = prefix_lm_mask(S, prefix_len) if doc_ids is None else document_causal_mask(doc_ids)
+    s = s.masked_fill(~mask, float("-inf"))
     return torch.softmax(s, dim=-1) @ vf
 
 
-def attention_ref_grads(q, k, v, dout, prefix_len, dtype=torch.float64):
+def attention_ref_grads(q, k, v, dout, prefix_len, dtype=torch.float64, doc_ids=None):
     """(out, dq, dk, dv) via autograd on the dense formulation in `dtype`."""
     q_, k_, v_ = (t.detach().to(dtype).requires_grad_(True) for t in (q, k, v))
-    out = attention_ref(q_, k_, v_, prefix_len, dtype)
+    out = attention_ref(q_, k_, v_, prefix_len, dtype, doc_ids)
     out.backward(dout.to(dtype))
     return out.detach(), q_.grad, k_.grad, v_.grad
 
@@ -237,7 +245,7 @@ def lora_linear_ref(x, lw: LayerWeights, name: str, dynamic: bool):
 
 
 def transformer_layer_ref(x: Tensor, rope: Tensor, lw: LayerWeights, Hq: int, Hkv: int, D: int, prefix_len: int,
-                          dynamic: bool) -> Tensor:
+                          dynamic: bool, doc_ids: Tensor | None = None) -> Tensor:
     """Reference op sequence of TransformerLayer.forward (llama.py:163-174) in the input dtype (bf16)."""
     B, L, _ = x.shape
     h = rmsnorm_ref(x, lw.attention_norm)
@@ -247,7 +255,7 @@ def transformer_layer_ref(x: Tensor, rope: Tensor, lw: LayerWeights, Hq: int, Hk
     q = apply_rope(q, rope).transpose(1, 2)
     k = apply_rope(k, rope).transpose(1, 2)
     v = v.transpose(1, 2)
-    mask = prefix_lm_mask(L, prefix_len)
+    mask = prefix_lm_mask(L, prefix_len) if doc_ids is None else document_causal_mask(doc_ids)
     o = F.scaled_dot_product_attention(q, k, v, mask, 0.0, False, enable_gqa=True)
     o = o.transpose(1, 2).reshape(B, L, Hq * D)
     x = x + lora_linear_ref(o, lw, "wo", dynamic)

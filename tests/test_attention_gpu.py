@@ -70,3 +70,40 @@ def test_attention_properties_full_size(S, P):
     v3.mul_(2.0)
     o3, _ = ops.attn_fwd(*_split(g3, Hq, Hkv), B, S, Hq, Hkv, D, P)
     assert rel_err(o3, 2.0 * o.double()) < 1e-2
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,lengths", [
+    (1, 640, 4, 1, [100, 28, 300, 212]),          # documents crossing 128-tile borders, one exactly tile-aligned end
+    (1, 2048, 8, 2, [700, 1, 600, 747]),          # a 1-token document
+    (2, 384, 2, 1, [384]),                        # single document == plain causal
+    (1, 1000, 4, 2, [128, 128, 256, 488]),        # tile-aligned documents, ragged total
+])
+def test_document_causal_mask_fwd_bwd(B, S, Hq, Hkv, lengths):
+    """Packed-sequence document-causal mask of the reference trainer (train_metamathqa.py:51-83): fully masked tiles
+    are skipped (range from doc_start / doc_end), partial tiles use the per-row document start."""
+    assert sum(lengths) == S
+    doc_ids = torch.repeat_interleave(torch.arange(len(lengths)), torch.tensor(lengths))[None].expand(B, S).contiguous()
+    torch.manual_seed(S)
+    qkv = torch.randn(B * S, (Hq + 2 * Hkv) * D).bfloat16()
+    dout = torch.randn(B * S, Hq * D).bfloat16()
+    q, k, v = _split(qkv, Hq, Hkv)
+    to4 = lambda t, H: t.reshape(B, S, H, D).transpose(1, 2)
+    o_ref, dq_ref, dk_ref, dv_ref = R.attention_ref_grads(to4(q, Hq), to4(k, Hkv), to4(v, Hkv), to4(dout, Hq), 0,
+                                                          doc_ids=doc_ids)
+    ds, de = ops.doc_bounds(doc_ids.cuda())
+    starts = torch.tensor([0] + lengths[:-1]).cumsum(0)
+    assert torch.equal(ds[0].cpu(), torch.repeat_interleave(starts, torch.tensor(lengths)).int())
+    assert torch.equal(de[0].cpu(), torch.repeat_interleave(starts + torch.tensor(lengths) - 1, torch.tensor(lengths)).int())
+    g = qkv.cuda()
+    qc, kc, vc = _split(g, Hq, Hkv)
+    o, lse = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, 0, doc_start=ds)
+    assert rel_err(to4(o.cpu(), Hq), o_ref) <= 1e-2
+    dqkv = torch.zeros_like(g)
+    dq, dk, dv = _split(dqkv, Hq, Hkv)
+    ops.attn_bwd(qc, kc, vc, o, lse, dout.cuda(), dq, dk, dv, B, S, Hq, Hkv, D, 0, doc_start=ds, doc_end=de)
+    assert rel_err(to4(dq.cpu(), Hq), dq_ref) <= 1e-2
+    assert rel_err(to4(dk.cpu(), Hkv), dk_ref) <= 1e-2
+    assert rel_err(to4(dv.cpu(), Hkv), dv_ref) <= 1e-2
+    if len(lengths) == 1:  # identical to the plain causal path, bit for bit
+        o2, lse2 = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, 0)
+        assert torch.equal(o, o2) and torch.equal(lse, lse2)
