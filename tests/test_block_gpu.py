@@ -127,3 +127,27 @@ def test_fused_block_document_mask():
     x2[:, 392:] += 1.0
     out2 = layer(x2.cuda(), rope.cuda(), block_mask=DocumentCausal(doc_ids.cuda()))
     assert torch.equal(out2[:, :392], out[:, :392])
+
+
+def test_activation_checkpointing_matches_plain():
+    """LlamaConfig.activation_checkpointing (llama.py:209-212) wraps the fused block in torch checkpoint: same loss and
+    gradients as the plain run."""
+    from llamax_b200.modelling import PrefixLM
+
+    torch.manual_seed(13)
+    tokens = torch.randint(0, 1024, (2, 160)).cuda()
+    labels = torch.randint(0, 1024, (2, 160)).cuda()
+    results = []
+    for ckpt in (False, True):
+        model = build_tiny_llama(True, num_layers=2)
+        model.config = model.config._replace(activation_checkpointing=ckpt)
+        model = model.cuda()
+        model.build_cache()
+        model.tok_embeddings.requires_grad_(False)
+        model.output.requires_grad_(False)
+        loss = model(tokens, labels=labels, block_mask=PrefixLM(40))
+        loss.backward()
+        results.append((loss.item(), model.layers[0].attention.wq.lora_b.grad.clone(), model.layers[1].ffn_norm.weight.grad.clone()))
+    # fp32 reductions by atomics (loss sum, split-K LoRA gradients, dQ bulk-reduce) are order-dependent: compare closely
+    assert abs(results[0][0] - results[1][0]) <= 1e-5 * abs(results[0][0])
+    assert rel_err(results[1][1], results[0][1]) <= 2e-2 and rel_err(results[1][2], results[0][2]) <= 2e-2
