@@ -115,7 +115,8 @@ int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_
  * additionally restricted to kv >= doc_start[q].  NULL = no document structure.
  * q bf16 [B,S,Hq,D] with row pitch ldq (elements between consecutive positions), k/v [B,S,Hkv,D] pitch
  * ldk/ldv, o [B,S,Hq,D] pitch ldo, lse fp32 [B,Hq,S] (natural-log-sum-exp of scaled scores).
- * GQA native: Hq % Hkv == 0, no K/V expansion.  D must be 128 (64 also supported).  scale = 1/sqrt(D). */
+ * GQA native: Hq % Hkv == 0, no K/V expansion.  D = 128, or 64 (run as zero-padded 128-wide tiles: the TMA
+ * descriptor zero-fills the missing half, at half the tensor-core efficiency).  scale = 1/sqrt(D). */
 int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
                     int64_t prefix_len, const void* doc_start, float scale, void* stream);

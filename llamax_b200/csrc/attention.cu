@@ -48,6 +48,7 @@ struct AttnFwdParams {
   int64_t ldo;
   float* lse;
   int B, S, Hq, Hkv, P;
+  int D;             // real head dim (64 or 128); tiles are always 128 wide, TMA zero-fills columns >= D
   float scale_log2;  // softmax scale * log2(e)
   const int32_t* doc_start;  // [B, S] first position of the document containing each position, or null
 };
@@ -288,9 +289,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv_l = 1.f / l;
     const bool row_ok = q < p.S;
-    __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * kHD;
+    __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * p.D;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < p.D / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_O + lane_off + c * 32, v);
       tmem_wait_ld();
@@ -327,6 +328,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dv;
   int64_t lddv;
   int B, S, Hq, Hkv, P;
+  int D;  // real head dim (64 or 128)
   float scale, scale_log2;
   const int32_t* doc_start;  // [B, S] or null (packed-sequence document-causal mask)
   const int32_t* doc_end;    // [B, S] last position of the document containing each position
@@ -553,14 +555,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (t == 0) tma_store_wait_read<0>();      // this group's previous bulk reduce has read its staging half
       named_bar_sync(2 + grp, 128);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) stage[(grp * 32 + i) * kHD + t] = __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i)
+        if (t < p.D) stage[(grp * 32 + i) * p.D + t] = __uint_as_float(v[i]);
       fence_proxy_async_smem();
       named_bar_sync(2 + grp, 128);
       if (t == 0) {
         const int rows = min(32, p.S - (q0 + grp * 32));
         if (rows > 0) {
-          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0 + grp * 32) * kHD;
-          bulk_reduce_add_f32(dst, stage + grp * 32 * kHD, (uint32_t)rows * kHD * 4);
+          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0 + grp * 32) * p.D;
+          bulk_reduce_add_f32(dst, stage + grp * 32 * p.D, (uint32_t)rows * p.D * 4);
         }
         tma_store_commit();
       }
@@ -636,10 +639,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const bool row_ok = kv < p.S;
-    __nv_bfloat16* drow = grp == 0 ? p.dv + ((int64_t)b * p.S + kv) * p.lddv + (int64_t)hk * kHD
-                                   : p.dk + ((int64_t)b * p.S + kv) * p.lddk + (int64_t)hk * kHD;
+    __nv_bfloat16* drow = grp == 0 ? p.dv + ((int64_t)b * p.S + kv) * p.lddv + (int64_t)hk * p.D
+                                   : p.dk + ((int64_t)b * p.S + kv) * p.lddk + (int64_t)hk * p.D;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < p.D / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (grp == 0 ? kColdV : kColdK) + lane_off + c * 32, v);
       tmem_wait_ld_regs(v);
@@ -663,18 +666,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
-// delta[b,h,s] = sum_d dO * O  (one warp per (row, head): 128 elements = 32 lanes x 4)
+// delta[b,h,s] = sum_d dO * O  (one warp per (row, head); each lane D/32 elements)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ dout,
-                                  int64_t lddo, float* __restrict__ delta, int64_t rows, int S, int Hq) {
+                                  int64_t lddo, float* __restrict__ delta, int64_t rows, int S, int Hq, int D) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= rows * Hq) return;
   const int64_t row = w / Hq;
   const int h = (int)(w - row * Hq);
   const int lane = threadIdx.x & 31;
-  const uint2 a = *reinterpret_cast<const uint2*>(o + row * ldo + h * kHD + lane * 4);
-  const uint2 g = *reinterpret_cast<const uint2*>(dout + row * lddo + h * kHD + lane * 4);
-  float s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
-            bf16_hi(a.y) * bf16_hi(g.y);
+  float s;
+  if (D == 128) {
+    const uint2 a = *reinterpret_cast<const uint2*>(o + row * ldo + h * D + lane * 4);
+    const uint2 g = *reinterpret_cast<const uint2*>(dout + row * lddo + h * D + lane * 4);
+    s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+        bf16_hi(a.y) * bf16_hi(g.y);
+  } else {  // D == 64
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(o + row * ldo + h * D + lane * 2);
+    const uint32_t g = *reinterpret_cast<const uint32_t*>(dout + row * lddo + h * D + lane * 2);
+    s = bf16_lo(a) * bf16_lo(g) + bf16_hi(a) * bf16_hi(g);
+  }
   s = warp_sum(s);
   if (lane == 0) {
     const int64_t bb = row / S, ss = row - bb * S;
@@ -684,16 +694,16 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t l
 
 // dq_accum fp32 [B, Hq, S, D] -> dq bf16 [B*S, Hq*D] (row pitch lddq); one thread = 8 head-dim elements
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t lddq,
-                                       int64_t B, int S, int Hq) {
-  const int64_t total = B * Hq * (int64_t)S * (kHD / 8);
+                                       int64_t B, int S, int Hq, int D) {
+  const int64_t total = B * Hq * (int64_t)S * (D / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % (kHD / 8)) * 8;
-    int64_t r = i / (kHD / 8);        // (b * Hq + h) * S + s
+    const int c = (int)(i % (D / 8)) * 8;
+    int64_t r = i / (D / 8);          // (b * Hq + h) * S + s
     const int s_ = (int)(r % S);
     r /= S;
     const int h = (int)(r % Hq);
     const int64_t b = r / Hq;
-    const float* src = acc + (((b * Hq + h) * S + s_) * kHD + c);
+    const float* src = acc + (((b * Hq + h) * S + s_) * D + c);
     const float4 a = *reinterpret_cast<const float4*>(src);
     const float4 b4 = *reinterpret_cast<const float4*>(src + 4);
     uint4 o4;
@@ -701,19 +711,22 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloa
     o4.y = pack_bf16(a.z, a.w);
     o4.z = pack_bf16(b4.x, b4.y);
     o4.w = pack_bf16(b4.z, b4.w);
-    *reinterpret_cast<uint4*>(dq + (b * S + s_) * lddq + (int64_t)h * kHD + c) = o4;
+    *reinterpret_cast<uint4*>(dq + (b * S + s_) * lddq + (int64_t)h * D + c) = o4;
   }
 }
 
-static int make_head_tmap(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t S, int H, int box_rows) {
-  const int64_t dims[4] = {kHD, H, S, B};
-  const int64_t strides[3] = {kHD, ld, S * ld};
+// [B, S, H, D] view with row pitch ld; 64-column boxes. For D = 64 the second box of a 128-wide tile starts at
+// column 64 = out of bounds and is zero-filled by TMA, so the 128-wide kernels run unchanged on zero-padded heads.
+static int make_head_tmap(CUtensorMap* m, const void* ptr, int64_t ld, int64_t B, int64_t S, int H, int D,
+                          int box_rows) {
+  const int64_t dims[4] = {D, H, S, B};
+  const int64_t strides[3] = {D, ld, S * ld};
   const int box[4] = {64, 1, box_rows, 1};
   return make_tmap_4d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box);
 }
 
 static int check_attn_args(int64_t B, int64_t S, int Hq, int Hkv, int D, int64_t P, const char* who) {
-  if (D != kHD) return set_error(LLAMAX_ERR_ARG, "attention: head_dim must be 128");
+  if (D != 128 && D != 64) return set_error(LLAMAX_ERR_ARG, "attention: head_dim must be 64 or 128");
   if (B <= 0 || S <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv) return set_error(LLAMAX_ERR_ARG, "attention: bad B/S/H");
   if (P < 0) return set_error(LLAMAX_ERR_ARG, "attention: prefix_len < 0");
   (void)who;
@@ -734,9 +747,9 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if (rc) return rc;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return set_error(LLAMAX_ERR_ARG, "attn_fwd: pitches must be multiples of 8");
   CUtensorMap tq, tk, tv;
-  if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, fwd::kTile))) return rc;
-  if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, fwd::kTile))) return rc;
-  if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, fwd::kTile))) return rc;
+  if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, D, fwd::kTile))) return rc;
+  if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, D, fwd::kTile))) return rc;
+  if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, fwd::kTile))) return rc;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
@@ -749,6 +762,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.lse = (float*)lse;
   p.B = (int)B; p.S = (int)S; p.Hq = Hq; p.Hkv = Hkv;
   p.P = (int)std::min<int64_t>(prefix_len, S);
+  p.D = D;
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
   dim3 grid((unsigned)ceil_div(S, fwd::kTile), Hq, (unsigned)B);
@@ -772,20 +786,20 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
     return set_error(LLAMAX_ERR_ARG, "attn_bwd: pitches must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = B * S;
-  cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)rows * Hq * kHD * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)rows * Hq * D * sizeof(float), st);
   if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: memset");
   {
     const int64_t warps = rows * Hq;
     const int blocks = (int)ceil_div(warps * 32, 256);
     attn_delta_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
-                                              (float*)delta, rows, (int)S, Hq);
+                                              (float*)delta, rows, (int)S, Hq, D);
     LX_CHECK_LAUNCH("attn_bwd: delta");
   }
   CUtensorMap tq, tk, tv, tdo;
-  if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, bwd::kQ))) return rc;
-  if ((rc = make_head_tmap(&tdo, dout, lddo, B, S, Hq, bwd::kQ))) return rc;
-  if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, bwd::kKV))) return rc;
-  if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, bwd::kKV))) return rc;
+  if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, D, bwd::kQ))) return rc;
+  if ((rc = make_head_tmap(&tdo, dout, lddo, B, S, Hq, D, bwd::kQ))) return rc;
+  if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, D, bwd::kKV))) return rc;
+  if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, bwd::kKV))) return rc;
   static thread_local bool configured = false;
   if (!configured) {
     e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
@@ -800,6 +814,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.dv = (__nv_bfloat16*)dv; p.lddv = lddv;
   p.B = (int)B; p.S = (int)S; p.Hq = Hq; p.Hkv = Hkv;
   p.P = (int)std::min<int64_t>(prefix_len, S);
+  p.D = D;
   p.scale = scale;
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
@@ -808,9 +823,9 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   attn_bwd_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");
   {
-    const int64_t total = rows * (Hq * kHD / 8);
+    const int64_t total = rows * (Hq * D / 8);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq);
+    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq, D);
     LX_CHECK_LAUNCH("attn_bwd: dq convert");
   }
   return 0;

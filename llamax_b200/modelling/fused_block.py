@@ -267,7 +267,7 @@ def fused_block_supported(layer, x: Tensor) -> bool:
     att, ff = layer.attention, layer.feed_forward
     mods = (att.wq, att.wk, att.wv, att.wo, ff.w1, ff.w3, ff.w2)
     return (
-        x.is_cuda and x.dtype is torch.bfloat16 and att.kv_cache is None and att.head_dim == 128
+        x.is_cuda and x.dtype is torch.bfloat16 and att.kv_cache is None and att.head_dim in (64, 128)
         and all(isinstance(m.weight, Int8LinearWeight) and m.bias is None for m in mods)
         and all(getattr(m, "rank", 0) <= 16 and getattr(m, "rank", 0) % 8 == 0 for m in mods)
         and att.wq.weight.dynamic_int8_act == att.wk.weight.dynamic_int8_act == att.wv.weight.dynamic_int8_act

@@ -107,3 +107,26 @@ def test_document_causal_mask_fwd_bwd(B, S, Hq, Hkv, lengths):
     if len(lengths) == 1:  # identical to the plain causal path, bit for bit
         o2, lse2 = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, 0)
         assert torch.equal(o, o2) and torch.equal(lse, lse2)
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,P", [(2, 1024, 8, 2, 512), (1, 300, 8, 2, 0), (1, 129, 2, 1, 77)])
+def test_attention_head_dim_64(B, S, Hq, Hkv, P):
+    """head_dim 64 (BASELINE config 0: dim 512, GQA 8/2): same kernels on TMA-zero-padded 128-wide tiles."""
+    Dh = 64
+    torch.manual_seed(S)
+    qkv = torch.randn(B * S, (Hq + 2 * Hkv) * Dh).bfloat16()
+    dout = torch.randn(B * S, Hq * Dh).bfloat16()
+    sp = lambda t: (t[:, : Hq * Dh], t[:, Hq * Dh : (Hq + Hkv) * Dh], t[:, (Hq + Hkv) * Dh :])
+    q, k, v = sp(qkv)
+    to4 = lambda t, H: t.reshape(B, S, H, Dh).transpose(1, 2)
+    o_ref, dq_ref, dk_ref, dv_ref = R.attention_ref_grads(to4(q, Hq), to4(k, Hkv), to4(v, Hkv), to4(dout, Hq), P)
+    g = qkv.cuda()
+    qc, kc, vc = sp(g)
+    o, lse = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, Dh, P)
+    assert rel_err(to4(o.cpu(), Hq), o_ref) <= 1e-2
+    dqkv = torch.zeros_like(g)
+    dq, dk, dv = sp(dqkv)
+    ops.attn_bwd(qc, kc, vc, o, lse, dout.cuda(), dq, dk, dv, B, S, Hq, Hkv, Dh, P)
+    assert rel_err(to4(dq.cpu(), Hq), dq_ref) <= 1e-2
+    assert rel_err(to4(dk.cpu(), Hkv), dk_ref) <= 1e-2
+    assert rel_err(to4(dv.cpu(), Hkv), dv_ref) <= 1e-2

@@ -151,3 +151,61 @@ def test_activation_checkpointing_matches_plain():
     # fp32 reductions by atomics (loss sum, split-K LoRA gradients, dQ bulk-reduce) are order-dependent: compare closely
     assert abs(results[0][0] - results[1][0]) <= 1e-5 * abs(results[0][0])
     assert rel_err(results[1][1], results[0][1]) <= 2e-2 and rel_err(results[1][2], results[0][2]) <= 2e-2
+
+
+def test_config0_tiny_audio_prefix_lm():
+    """BASELINE.json configs[0] as stated: 4 layers, dim 512, GQA 8/2 (head_dim 64), audio Conv1D prefix, prefix-LM,
+    seq 1024 (512 audio-prefix positions from 10.24 s of audio + 512 text), batch 2; weight-only INT8 + LoRA r=8.
+    Loss and gradients (LoRA, conv stem) against the fp32 oracle composed from the same weights."""
+    from llamax_b200.modelling import AudioConfig, LlamaAudio, LlamaConfig, apply_linear_adapter_
+    from llamax_b200.subclasses import quantize_linear_
+
+    torch.manual_seed(0)
+    cfg = LlamaConfig(512, 4, 64, 8, 2, 1792, max_seq_len=1024, vocab_size=1024, rope_base=500000, is_llama3_1=True)
+    model = LlamaAudio(cfg, AudioConfig(n_mels=80)).bfloat16()
+    model.build_cache()
+    dynamic = False
+    quantize_linear_(model.layers, "int8", dynamic_int8_act=dynamic)
+    apply_linear_adapter_(model.layers, "lora", rank=8)
+    g = torch.Generator().manual_seed(1)
+    for m in model.modules():
+        if hasattr(m, "lora_b"):
+            m.lora_b.data.copy_((torch.randn(m.lora_b.shape, generator=g) * 0.02).bfloat16())
+    B, T = 2, 512
+    audio = torch.randn(B, 163840, generator=g)          # 10.24 s -> 1025 frames -> 1024 -> 512 prefix positions
+    tokens = torch.randint(0, 1024, (B, T), generator=g)
+    labels = torch.randint(0, 1024, (B, T), generator=g)
+
+    # oracle: the same front-end modules in fp32 on CPU, then the restated blocks, norm, head, CE
+    import copy
+
+    stem = copy.deepcopy(model.audio_embed).float()
+    mel = model.melspec(audio)[..., :-1].clip(1e-12).log10()
+    mel = (mel - mel.mean(2, keepdim=True)).bfloat16().float()
+    prefix = stem(mel).transpose(1, 2)
+    P = prefix.shape[1]
+    assert P == 512
+    x = torch.cat([prefix, model.tok_embeddings.weight.detach().float()[tokens]], 1)
+    rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[: P + T]
+    lws = [oracle_layer_weights(l, torch.float32) for l in model.layers]
+    for lw in lws:
+        x = R.transformer_layer_ref(x, rope, lw, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, P, dynamic)
+    x = R.rmsnorm_ref(x[:, P:], model.norm.weight.detach().float())
+    logits = x @ model.output.weight.detach().float().T
+    loss_ref = torch.nn.functional.cross_entropy(logits.reshape(-1, 1024), labels.reshape(-1))
+    loss_ref.backward()
+
+    model = model.cuda()
+    model.build_cache()
+    model.tok_embeddings.requires_grad_(False)
+    model.output.requires_grad_(False)
+    loss = model(audio.cuda(), tokens.cuda(), labels=labels.cuda(), prefix_lm=True)
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    errs = {
+        "wq0.lora_b": rel_err(model.layers[0].attention.wq.lora_b.grad, lws[0].lora_b["wq"].grad),
+        "w2_3.lora_a": rel_err(model.layers[3].feed_forward.w2.lora_a.grad, lws[3].lora_a["w2"].grad),
+        "conv2.weight": rel_err(model.audio_embed[2].weight.grad, stem[2].weight.grad),
+    }
+    print(loss.item(), loss_ref.item(), errs)
+    assert all(v <= 5e-2 for v in errs.values()), errs
