@@ -63,9 +63,15 @@ constexpr int kOffP = kOffV + 2 * kTileBytes;
 constexpr int kOffBar = kOffP + kTileBytes;
 constexpr int kNumBars = 1 + 4 + 4 + 4 + 2;       // q_full, k full/empty[2], v full/empty[2], s full/empty[2], p_full, pv_done
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+constexpr int kThreads = 256;                     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 softmax
 }  // namespace fwd
 
-__global__ void __launch_bounds__(256, 1)
+// kDocs: packed-document mask compiled in; kD: real head dim (64 runs on zero-padded 128-wide tiles).
+// (A variant with two softmax warpgroups per query tile — column halves, row maxima exchanged through smem — was
+// measured 10 % slower than this single-warpgroup version on B200: the extra 256-thread barrier per tile and the
+// doubled TMEM read contention cost more than the halved per-thread work saves.)
+template <bool kDocs, int kD>
+__global__ void __launch_bounds__(fwd::kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
   using namespace fwd;
@@ -90,7 +96,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q0 = qt * kTile;
   const int kv_end = min(p.S, max(p.P, q0 + kTile));
   // packed documents: keys before the start of the first row's document are never visible to this tile
-  const int j_begin = p.doc_start ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
+  const int j_begin = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
   const int n_kv = (kv_end + kTile - 1) / kTile - j_begin;  // number of visited kv tiles
 
   if (warp == 0 && elect_one()) {
@@ -197,8 +203,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int q = q0 + r;
     const uint32_t sP = smem_u32(smem + kOffP);
     float m_used = -INFINITY, l = 0.f;
-    const int ds_row = p.doc_start ? p.doc_start[(int64_t)b * p.S + min(q, p.S - 1)] : 0;
-    const int ds_tile = p.doc_start ? p.doc_start[(int64_t)b * p.S + min(q0 + kTile - 1, p.S - 1)] : 0;
+    const int ds_row = kDocs ? p.doc_start[(int64_t)b * p.S + min(q, p.S - 1)] : 0;
+    const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kTile - 1, p.S - 1)] : 0;
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       const int kv0 = (j_begin + j) * kTile;
@@ -225,7 +231,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kv = kv0 + c * 32 + i;
-            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (kv >= ds_row);
+            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
             if (!ok) sv[c][i] = 0xff800000u;  // -inf
           }
       }
@@ -289,9 +295,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv_l = 1.f / l;
     const bool row_ok = q < p.S;
-    __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * p.D;
+    __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * kD;
 #pragma unroll 1
-    for (int c = 0; c < p.D / 32; ++c) {
+    for (int c = 0; c < kD / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_O + lane_off + c * 32, v);
       tmem_wait_ld();
@@ -360,6 +366,7 @@ static_assert(kSmemBytes <= 232448, "attention backward shared memory budget");
 constexpr int kColdV = 0, kColdK = 128, kColS = 256, kColdP = 320, kColdQ = 384;
 }  // namespace bwd
 
+template <bool kDocs, int kD>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -387,7 +394,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nq_tiles = (p.S + kQ - 1) / kQ;
   const int i_start = (kv0 < p.P) ? 0 : kv0 / kQ;  // first query tile that sees this kv tile
   // packed documents: queries after the end of the last kv row's document never see this tile
-  const int i_end = p.doc_end ? min(nq_tiles, p.doc_end[(int64_t)b * p.S + min(kv0 + kKV - 1, p.S - 1)] / kQ + 1) : nq_tiles;
+  const int i_end = kDocs ? min(nq_tiles, p.doc_end[(int64_t)b * p.S + min(kv0 + kKV - 1, p.S - 1)] / kQ + 1) : nq_tiles;
   const int steps_per_head = i_end - i_start;
   const int n_steps = G * steps_per_head;
 
@@ -536,7 +543,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
       if (wt < 64) return (qq < p.S) ? p.lse[idx] * kLog2e : INFINITY;
       if (wt < 128) return (qq < p.S) ? p.delta[idx] : 0.f;
-      return __int_as_float((p.doc_start && qq < p.S) ? p.doc_start[(int64_t)b * p.S + qq] : 0);
+      return __int_as_float((kDocs && qq < p.S) ? p.doc_start[(int64_t)b * p.S + qq] : 0);
     };
     auto drain = [&](int s) {
       // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> one
@@ -556,14 +563,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(2 + grp, 128);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (t < p.D) stage[(grp * 32 + i) * p.D + t] = __uint_as_float(v[i]);
+        if (t < kD) stage[(grp * 32 + i) * kD + t] = __uint_as_float(v[i]);
       fence_proxy_async_smem();
       named_bar_sync(2 + grp, 128);
       if (t == 0) {
         const int rows = min(32, p.S - (q0 + grp * 32));
         if (rows > 0) {
-          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0 + grp * 32) * p.D;
-          bulk_reduce_add_f32(dst, stage + grp * 32 * p.D, (uint32_t)rows * p.D * 4);
+          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0 + grp * 32) * kD;
+          bulk_reduce_add_f32(dst, stage + grp * 32 * kD, (uint32_t)rows * kD * 4);
         }
         tma_store_commit();
       }
@@ -578,7 +585,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(1, kWorkers);               // stats of step s visible; all workers finished step s-1
       nxt = load_stat(s + 1);                    // prefetch next step's lse / delta (global)
       const uint32_t stat_u = s_stat_u + st * (3 * kQ * 4) + grp * 32 * 4;
-      const int ds_tile = p.doc_start ? p.doc_start[(int64_t)b * p.S + min(q0 + kQ - 1, p.S - 1)] : 0;
+      const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kQ - 1, p.S - 1)] : 0;
       const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0)) &&
                              (kv0 >= ds_tile);
       mbar_wait(&pds_empty[st], ((s >> 1) & 1) ^ 1);  // P^T/dS^T[st] no longer read by the MMAs of step s-2
@@ -597,7 +604,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float4 d4 = lds_f4(stat_u + kQ * 4 + i * 4);        // delta
           const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
           int dst4[4] = {0, 0, 0, 0};
-          if (!full_tile) {
+          if (kDocs && !full_tile) {
             const float4 s4 = lds_f4(stat_u + 2 * kQ * 4 + i * 4);  // document start of each query column
             dst4[0] = __float_as_int(s4.x); dst4[1] = __float_as_int(s4.y);
             dst4[2] = __float_as_int(s4.z); dst4[3] = __float_as_int(s4.w);
@@ -608,7 +615,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             float pe = ex2(fmaf(__uint_as_float(sv[i + e]), p.scale_log2, -ls[e]));
             if (!full_tile) {
               const int qa = q0 + grp * 32 + i + e;
-              if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (kv >= dst4[e]))) pe = 0.f;
+              if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (!kDocs || kv >= dst4[e]))) pe = 0.f;
             }
             pv[e] = pe;
             dsv[e] = pe * (__uint_as_float(dv[i + e]) - dl[e]) * p.scale;
@@ -639,10 +646,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const bool row_ok = kv < p.S;
-    __nv_bfloat16* drow = grp == 0 ? p.dv + ((int64_t)b * p.S + kv) * p.lddv + (int64_t)hk * p.D
-                                   : p.dk + ((int64_t)b * p.S + kv) * p.lddk + (int64_t)hk * p.D;
+    __nv_bfloat16* drow = grp == 0 ? p.dv + ((int64_t)b * p.S + kv) * p.lddv + (int64_t)hk * kD
+                                   : p.dk + ((int64_t)b * p.S + kv) * p.lddk + (int64_t)hk * kD;
 #pragma unroll 1
-    for (int c = 0; c < p.D / 32; ++c) {
+    for (int c = 0; c < kD / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (grp == 0 ? kColdV : kColdK) + lane_off + c * 32, v);
       tmem_wait_ld_regs(v);
@@ -667,8 +674,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // delta[b,h,s] = sum_d dO * O  (one warp per (row, head); each lane D/32 elements)
+template <int D>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ dout,
-                                  int64_t lddo, float* __restrict__ delta, int64_t rows, int S, int Hq, int D) {
+                                  int64_t lddo, float* __restrict__ delta, int64_t rows, int S, int Hq) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= rows * Hq) return;
   const int64_t row = w / Hq;
@@ -693,8 +701,9 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t l
 }
 
 // dq_accum fp32 [B, Hq, S, D] -> dq bf16 [B*S, Hq*D] (row pitch lddq); one thread = 8 head-dim elements
+template <int D>
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t lddq,
-                                       int64_t B, int S, int Hq, int D) {
+                                       int64_t B, int S, int Hq) {
   const int64_t total = B * Hq * (int64_t)S * (D / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % (D / 8)) * 8;
@@ -750,11 +759,14 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, D, fwd::kTile))) return rc;
   if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, D, fwd::kTile))) return rc;
   if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, fwd::kTile))) return rc;
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+  auto kern = doc_start ? (D == 128 ? attn_fwd_kernel<true, 128> : attn_fwd_kernel<true, 64>)
+                        : (D == 128 ? attn_fwd_kernel<false, 128> : attn_fwd_kernel<false, 64>);
+  static thread_local bool configured[4] = {false, false, false, false};
+  const int variant = (doc_start ? 2 : 0) + (D == 128 ? 1 : 0);
+  if (!configured[variant]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd: cudaFuncSetAttribute");
-    configured = true;
+    configured[variant] = true;
   }
   AttnFwdParams p;
   p.o = (__nv_bfloat16*)o;
@@ -766,7 +778,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
   dim3 grid((unsigned)ceil_div(S, fwd::kTile), Hq, (unsigned)B);
-  attn_fwd_kernel<<<grid, 256, fwd::kSmemBytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  kern<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   LX_CHECK_LAUNCH("attn_fwd");
   return 0;
 }
@@ -791,8 +803,12 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   {
     const int64_t warps = rows * Hq;
     const int blocks = (int)ceil_div(warps * 32, 256);
-    attn_delta_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
-                                              (float*)delta, rows, (int)S, Hq, D);
+    if (D == 128)
+      attn_delta_kernel<128><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
+                                                     (float*)delta, rows, (int)S, Hq);
+    else
+      attn_delta_kernel<64><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
+                                                    (float*)delta, rows, (int)S, Hq);
     LX_CHECK_LAUNCH("attn_bwd: delta");
   }
   CUtensorMap tq, tk, tv, tdo;
@@ -800,11 +816,14 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if ((rc = make_head_tmap(&tdo, dout, lddo, B, S, Hq, D, bwd::kQ))) return rc;
   if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, D, bwd::kKV))) return rc;
   if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, bwd::kKV))) return rc;
-  static thread_local bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+  auto kern = doc_start ? (D == 128 ? attn_bwd_kernel<true, 128> : attn_bwd_kernel<true, 64>)
+                        : (D == 128 ? attn_bwd_kernel<false, 128> : attn_bwd_kernel<false, 64>);
+  static thread_local bool configured[4] = {false, false, false, false};
+  const int variant = (doc_start ? 2 : 0) + (D == 128 ? 1 : 0);
+  if (!configured[variant]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: cudaFuncSetAttribute");
-    configured = true;
+    configured[variant] = true;
   }
   AttnBwdParams p;
   p.lse = (const float*)lse;
@@ -820,12 +839,15 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.doc_start = (const int32_t*)doc_start;
   p.doc_end = (const int32_t*)doc_end;
   dim3 grid((unsigned)ceil_div(S, bwd::kKV), Hkv, (unsigned)B);
-  attn_bwd_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");
   {
     const int64_t total = rows * (Hq * D / 8);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-    attn_dq_convert_kernel<<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq, D);
+    if (D == 128)
+      attn_dq_convert_kernel<128><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq);
+    else
+      attn_dq_convert_kernel<64><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq);
     LX_CHECK_LAUNCH("attn_bwd: dq convert");
   }
   return 0;
