@@ -99,8 +99,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Blocking wait with a watchdog: a protocol bug (or an unsupported shape) must surface as a launch failure that the
+// host reports, never as a kernel that spins forever. No kernel of this library runs longer than a few ms.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
+    if (global_timer_ns() - t0 > 10000000000ull) __trap();  // 10 s
   }
 }
 

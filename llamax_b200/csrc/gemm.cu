@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "host_utils.h"
 #include <algorithm>
+#include <cstdlib>
 
 #include "llamax_b200.h"
 
@@ -520,6 +521,138 @@ lora_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 1) tmem_dealloc<1>(tmem_base, 32);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny GEMM for the LoRA projections: C[M, N<=32] = A[M,K] * B[N,K]^T (bf16, fp32 accumulate).
+// HBM-bound on A: one CTA per 128 rows streams its rows once through an 8-stage TMA ring; UMMA 128 x 32 x 16
+// (the persistent 256-wide kernel would spend 8x the tensor time on zero columns).
+// ------------------------------------------------------------------------------------------------
+namespace sk {
+constexpr int kStages = 8;
+constexpr int kABytes = 128 * 128;     // [128 rows] x [64 bf16]
+constexpr int kBBytes = 32 * 128;      // [32 rows]  x [64 bf16]
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmem = kStages * kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
+}  // namespace sk
+
+__global__ void __launch_bounds__(192, 1)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   __nv_bfloat16* __restrict__ C, int64_t ldc, int M, int N, int K) {
+  using namespace sk;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* done_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 128;
+  const int num_kb = (K + 63) / 64;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_slot, 32);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStageBytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        tma_load_2d(sa, &tmA, &full_bar[stage], kb * 64, m0);
+        tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], kb * 64, 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(1, 1, 128, 32, 0, 0);
+      constexpr uint32_t kHi = desc_hi(1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t la = desc_lo(smem_u32(smem + stage * kStageBytes), 16);
+        const uint32_t lb = desc_lo(smem_u32(smem + stage * kStageBytes + kABytes), 16);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss<false, 1>(tmem_base, desc_join(la + ks * 2, kHi), desc_join(lb + ks * 2, kHi), idesc, (kb | ks) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    const int lq = warp & 3;  // warps 2..5 cover the four TMEM lane quarters
+    const int row = m0 + lq * 32 + lane_id();
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + (uint32_t(lq * 32) << 16), v);
+    tmem_wait_ld_regs(v);
+    if (row < M) {
+      __nv_bfloat16* dst = C + (int64_t)row * ldc;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j < N) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+          o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+          o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+          stg_v4(dst + j, o);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, 32);
+}
+
+static int launch_skinny(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int M, int N,
+                         int K, cudaStream_t stream) {
+  if ((lda * 2) % 16 || (ldb * 2) % 16 || (reinterpret_cast<uintptr_t>(A) % 16) || (reinterpret_cast<uintptr_t>(B) % 16))
+    return set_error(LLAMAX_ERR_ARG, "gemm: operand base / leading dimension must be 16-byte aligned");
+  if (N % 8 || ldc % 8 || (reinterpret_cast<uintptr_t>(C) % 16))
+    return set_error(LLAMAX_ERR_ARG, "gemm: N and ldc must be multiples of 8, C 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, 64, 32);
+  if (rc) return rc;
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "skinny gemm: cudaFuncSetAttribute");
+    configured = true;
+  }
+  skinny_gemm_kernel<<<(M + 127) / 128, 192, sk::kSmem, stream>>>(tmA, tmB, (__nv_bfloat16*)C, ldc, M, N, K);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "skinny gemm: launch");
+  return 0;
+}
+
 static int g_gemm_cg = 2;  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group
 
 }  // namespace lx
@@ -574,6 +707,11 @@ int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, voi
                      int64_t N, int64_t K, const void* col_scale, int round_before_scale,
                      const llamax_epilogue_t* epi, void* stream) {
   if (!A || !B || !C) return set_error(LLAMAX_ERR_ARG, "bf16_gemm: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(LLAMAX_ERR_ARG, "gemm: empty problem");
+  const bool plain = col_scale == nullptr && (epi == nullptr || (epi->lora_h == nullptr && epi->resid == nullptr));
+  static const bool no_skinny = getenv("LLAMAX_NO_SKINNY") != nullptr;  // A/B switch for benchmarking
+  if (plain && N <= 32 && !no_skinny)  // LoRA down / dh projections: HBM-bound skinny kernel
+    return launch_skinny(A, lda, B, ldb, C, ldc, (int)M, (int)N, (int)K, (cudaStream_t)stream);
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.C = C; p.ldc = ldc;
