@@ -72,17 +72,14 @@ __device__ __forceinline__ float block_reduce(float v, float* sm) {
   return r;
 }
 
-// rint(x / sc), bit-identical to the IEEE division of the reference, at the cost of one multiply in the common case:
-// x * (1/sc) differs from x / sc by < 2 ulp, which can only change the rounded integer when the quotient sits within
-// ~3e-5 of a half-integer; only then is the exact division evaluated.
-__device__ __forceinline__ int quant_code(float x, float sc, float inv) {
-  const float t = x * inv;
-  float r = rintf(t);
-  if (fabsf(fabsf(t - r) - 0.5f) < 3e-5f || !(fabsf(t) < 200.f)) r = rintf(x / sc);
-  return (int)r;
+// Row quantisation, bit-identical to the reference's IEEE division (subclasses/int8.py:10-16) at ~1 multiply per
+// element: x * (1/sc) differs from x / sc by < 2 ulp, which can only change the rounded integer when the quotient
+// sits within ~3e-5 of a half-integer. Each 8-element vector is rounded from the product; only if one of its elements
+// is that close to a tie is the whole vector redone with exact divisions (one rare branch per vector).
+__device__ __forceinline__ uint32_t pack4_s8(int q0, int q1, int q2, int q3) {
+  return __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
 }
 
-// quantise the (bf16-rounded) row held in registers; reference: subclasses/int8.py:10-16
 template <int kMaxV>
 __device__ __forceinline__ void quant_row_store(const float (&v)[kMaxV][8], int nvec, float amax, int8_t* qrow,
                                                 __nv_bfloat16* scale_out) {
@@ -93,14 +90,20 @@ __device__ __forceinline__ void quant_row_store(const float (&v)[kMaxV][8], int 
   for (int j = 0; j < kMaxV; ++j) {
     const int idx = threadIdx.x + j * blockDim.x;
     if (idx < nvec) {
-      uint32_t lo = 0, hi = 0;
+      float r[8];
+      bool near_tie = false;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int q0 = quant_code(v[j][e], sc, inv);
-        const int q1 = quant_code(v[j][4 + e], sc, inv);
-        lo |= (uint32_t)(q0 & 0xff) << (8 * e);
-        hi |= (uint32_t)(q1 & 0xff) << (8 * e);
+      for (int e = 0; e < 8; ++e) {
+        const float t = v[j][e] * inv;
+        r[e] = rintf(t);
+        near_tie |= fabsf(fabsf(t - r[e]) - 0.5f) < 3e-5f;
       }
+      if (near_tie) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = rintf(v[j][e] / sc);
+      }
+      const uint32_t lo = pack4_s8((int)r[0], (int)r[1], (int)r[2], (int)r[3]);
+      const uint32_t hi = pack4_s8((int)r[4], (int)r[5], (int)r[6], (int)r[7]);
       *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) = make_uint2(lo, hi);
     }
   }
