@@ -52,8 +52,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&r);
 }
+// fp32 -> nearest-even bf16 -> fp32, in integer arithmetic (ALU pipe). The cvt.rn.bf16.f32 instruction runs on the
+// 16-lane/clk conversion (XU) pipe, which made the fused norm / SwiGLU passes XU-bound instead of HBM-bound.
 __device__ __forceinline__ float round_bf16(float v) {
-  return __bfloat162float(__float2bfloat16_rn(v));
+  uint32_t u = __float_as_uint(v);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return __uint_as_float(u & 0xFFFF0000u);
+}
+// exact float of a signed byte held in the low 8 bits of w (any upper bits), without I2F (XU pipe):
+// 0x4B400000 | (b ^ 0x80) is the float 12582912 + (b ^ 0x80), and (b ^ 0x80) = b + 128 for b read as int8.
+__device__ __forceinline__ float s8_to_float(uint32_t w) {
+  return __uint_as_float(0x4B400000u | ((w & 0xFFu) ^ 0x80u)) - 12583040.0f;
 }
 
 // ----------------------------------------------------------------------------------------------

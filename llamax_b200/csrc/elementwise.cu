@@ -76,8 +76,12 @@ __device__ __forceinline__ float block_reduce(float v, float* sm) {
 // element: x * (1/sc) differs from x / sc by < 2 ulp, which can only change the rounded integer when the quotient
 // sits within ~3e-5 of a half-integer. Each 8-element vector is rounded from the product; only if one of its elements
 // is that close to a tie is the whole vector redone with exact divisions (one rare branch per vector).
-__device__ __forceinline__ uint32_t pack4_s8(int q0, int q1, int q2, int q3) {
-  return __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
+// Rounding without the conversion pipe: t + 1.5*2^23 rounds t to the nearest-even integer in the float's low mantissa
+// bits (|t| < 2^22); the low byte of that word is the two's-complement int8 code, and subtracting the constant gives
+// rint(t) back as a float. FRND / F2I (XU pipe, 16 lanes/clk) are not used.
+constexpr float kRoundMagic = 12582912.0f;  // 1.5 * 2^23
+__device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
 template <int kMaxV>
@@ -90,20 +94,21 @@ __device__ __forceinline__ void quant_row_store(const float (&v)[kMaxV][8], int 
   for (int j = 0; j < kMaxV; ++j) {
     const int idx = threadIdx.x + j * blockDim.x;
     if (idx < nvec) {
-      float r[8];
+      uint32_t w[8];
       bool near_tie = false;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float t = v[j][e] * inv;
-        r[e] = rintf(t);
-        near_tie |= fabsf(fabsf(t - r[e]) - 0.5f) < 3e-5f;
+        const float tm = __fadd_rn(t, kRoundMagic);
+        w[e] = __float_as_uint(tm);
+        near_tie |= fabsf(fabsf(t - __fsub_rn(tm, kRoundMagic)) - 0.5f) < 3e-5f;
       }
       if (near_tie) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) r[e] = rintf(v[j][e] / sc);
+        for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(__fadd_rn(v[j][e] / sc, kRoundMagic));
       }
-      const uint32_t lo = pack4_s8((int)r[0], (int)r[1], (int)r[2], (int)r[3]);
-      const uint32_t hi = pack4_s8((int)r[4], (int)r[5], (int)r[6], (int)r[7]);
+      const uint32_t lo = pack4_low_bytes(w[0], w[1], w[2], w[3]);
+      const uint32_t hi = pack4_low_bytes(w[4], w[5], w[6], w[7]);
       *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) = make_uint2(lo, hi);
     }
   }
@@ -370,7 +375,7 @@ __global__ void dequant_plain_kernel(const int8_t* __restrict__ w8, const __nv_b
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) f[q * 4 + e] = (float)(int8_t)((words[q] >> (8 * e)) & 0xff) * s;
+      for (int e = 0; e < 4; ++e) f[q * 4 + e] = s8_to_float(words[q] >> (8 * e)) * s;
     float lo[8], hi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { lo[e] = f[e]; hi[e] = f[8 + e]; }
@@ -395,7 +400,7 @@ dequant_transpose_kernel(const int8_t* __restrict__ w8, const __nv_bfloat16* __r
       for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          tile[kc + q * 4 + e][n] = __float2bfloat16_rn((float)(int8_t)((words[q] >> (8 * e)) & 0xff) * s);
+          tile[kc + q * 4 + e][n] = __float2bfloat16_rn(s8_to_float(words[q] >> (8 * e)) * s);
     } else {
 #pragma unroll
       for (int e = 0; e < 16; ++e) tile[kc + e][n] = __float2bfloat16_rn(0.f);
