@@ -36,7 +36,7 @@ def _compile(src, force):
     if not force and os.path.exists(obj):
         if os.path.getmtime(obj) >= max(os.path.getmtime(srcp), _newest_header_mtime()):
             return obj, False
-    cmd = [NVCC, *FLAGS, "-c", srcp, "-o", obj]
+    cmd = [NVCC, *FLAGS, *os.environ.get("LLAMAX_NVCC_FLAGS", "").split(), "-c", srcp, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

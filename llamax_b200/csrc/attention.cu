@@ -57,12 +57,10 @@ namespace fwd {
 constexpr int kTile = 128;
 constexpr int kTileBytes = kTile * kHD * 2;       // 32 KB: two 16 KB boxes of [128 rows x 128 B]
 constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kTileBytes;         // 2 stages
-constexpr int kOffV = kOffK + 2 * kTileBytes;     // 2 stages
-constexpr int kOffP = kOffV + 2 * kTileBytes;
-constexpr int kOffBar = kOffP + kTileBytes;
+constexpr int kOffK = kOffQ + kTileBytes;         // kNB stages of K, then kNB stages of V
 constexpr int kNumBars = 1 + 4 + 4 + 4 + 2;       // q_full, k full/empty[2], v full/empty[2], s full/empty[2], p_full, pv_done
-constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+constexpr int smem_bytes(int nb) { return kTileBytes * (1 + 2 * nb) + kNumBars * 8 + 16 + 1024; }
+constexpr int kNB = 2;                             // smem stages of K and V, TMEM score buffers
 constexpr int kThreads = 256;                     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 softmax
 }  // namespace fwd
 
@@ -70,6 +68,11 @@ constexpr int kThreads = 256;                     // warp0 TMA, warp1 MMA, warp2
 // (A variant with two softmax warpgroups per query tile — column halves, row maxima exchanged through smem — was
 // measured 10 % slower than this single-warpgroup version on B200: the extra 256-thread barrier per tile and the
 // doubled TMEM read contention cost more than the halved per-thread work saves.)
+// K/V are double-buffered in smem and S in TMEM (kNB = 2), one CTA per SM (160 KB smem, 512 TMEM columns).
+// P is handed to the PV MMA through TMEM: bf16 pairs written over the score columns just read, consumed by
+// tcgen05.mma with the A operand in TMEM (+9 % over staging P in 128B-swizzled smem).
+// Rejected after measurement: single buffers with two CTAs per SM and setmaxnreg register rebalancing (-12 %), and two
+// softmax warpgroups per query tile (-10 %).
 template <bool kDocs, int kD>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -77,6 +80,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   using namespace fwd;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kOffV = kOffK + kNB * kTileBytes;
+  constexpr int kOffBar = kOffV + kNB * kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
@@ -119,15 +124,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc<1>(tmem_slot, 512);
+    tmem_alloc<1>(tmem_slot, 256 * kNB);
     tmem_relinquish<1>();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 128 columns
+  const uint32_t tmem_S = tmem_base;              // kNB x 128 columns
+  const uint32_t tmem_O = tmem_base + kNB * 128;  // 128 columns
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
@@ -136,8 +141,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_4d(smem + kOffQ, &tmQ, q_full, 0, h, q0, b);
       tma_load_4d(smem + kOffQ + kTileBytes / 2, &tmQ, q_full, 64, h, q0, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = kNB == 2 ? (j & 1) : 0;
+        const uint32_t ph = (kNB == 2 ? (j >> 1) : j) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], kTileBytes);
         uint8_t* sk = smem + kOffK + st * kTileBytes;
@@ -157,11 +162,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
       constexpr uint32_t kHi = desc_hi(1024);
-      const uint32_t loQ = desc_lo(smem_u32(smem + kOffQ), 16), loP = desc_lo(smem_u32(smem + kOffP), 16);
+      const uint32_t loQ = desc_lo(smem_u32(smem + kOffQ), 16);
       const uint32_t loK0 = desc_lo(smem_u32(smem + kOffK), 16), loV0 = desc_lo(smem_u32(smem + kOffV), 16384);
       auto issue_s = [&](int j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = kNB == 2 ? (j & 1) : 0;
+        const uint32_t ph = (kNB == 2 ? (j >> 1) : j) & 1;
         mbar_wait(&k_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
@@ -178,20 +183,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_s(j + 1);
-        const int st = j & 1;
-        mbar_wait(&v_full[st], (j >> 1) & 1);
+        if (kNB == 2 && j + 1 < n_kv) issue_s(j + 1);  // next scores into the other TMEM buffer
+        const int st = kNB == 2 ? (j & 1) : 0;
+        mbar_wait(&v_full[st], (kNB == 2 ? (j >> 1) : j) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         const uint32_t loV = loV0 + st * (kTileBytes / 16);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss<false, 1>(tmem_O, desc_join(loP + kb * 1024 + ks * 2, kHi),
-                              desc_join(loV + (kb * 64 + ks * 16) * 8, kHi), idesc_pv, (j | kb | ks) != 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bd = desc_join(loV + (kb * 64 + ks * 16) * 8, kHi);
+            // A = P read from TMEM: bf16 pairs, 8 columns per 16-wide k-step, aliasing the score buffer
+            umma_ts_f16(tmem_O, tmem_S + st * 128 + (kb * 4 + ks) * 8, bd, idesc_pv, (j | kb | ks) != 0);
+          }
         umma_commit(pv_done);
         umma_commit(&v_empty[st]);
+        if (kNB == 1 && j + 1 < n_kv) issue_s(j + 1);  // single score buffer: free once PV_j (in order) consumed P_j
       }
     }
     __syncwarp();
@@ -201,16 +209,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int ew = warp - 4;
     const uint32_t lane_off = uint32_t(ew * 32) << 16;
     const int q = q0 + r;
-    const uint32_t sP = smem_u32(smem + kOffP);
     float m_used = -INFINITY, l = 0.f;
     const int ds_row = kDocs ? p.doc_start[(int64_t)b * p.S + min(q, p.S - 1)] : 0;
     const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kTile - 1, p.S - 1)] : 0;
     for (int j = 0; j < n_kv; ++j) {
-      const int st = j & 1;
+      const int st = kNB == 2 ? (j & 1) : 0;
       const int kv0 = (j_begin + j) * kTile;
       // tile needs the element test unless every (q, kv) pair is visible and in range
       const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
-      mbar_wait(&s_full[st], (j >> 1) & 1);
+      mbar_wait(&s_full[st], (kNB == 2 ? (j >> 1) : j) & 1);
       tc_fence_after();
       const uint32_t tS = tmem_S + st * 128 + lane_off;
       // single pass over TMEM: the whole score row (128 fp32) lives in registers
@@ -278,14 +285,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_wait_st();
         }
       }
-      // P (bf16) -> smem, K-major 128B-swizzled: [kv-half][row][8 x 16 B chunks, chunk ^= row & 7]
-#pragma unroll
-      for (int c16 = 0; c16 < 16; ++c16) {
-        const int kb = c16 >> 3, c = c16 & 7;
-        const uint32_t addr = sP + kb * 16384 + r * 128 + ((c ^ (r & 7)) << 4);
-        sts_v4(addr, preg[c16 * 4], preg[c16 * 4 + 1], preg[c16 * 4 + 2], preg[c16 * 4 + 3]);
+      {
+        // P (bf16 pairs) -> TMEM, over the first 64 columns of the score buffer this row was just read from
+        uint32_t(&p0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&preg[0]);
+        uint32_t(&p1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&preg[32]);
+        tmem_st_32x32(tS, p0);
+        tmem_st_32x32(tS + 32, p1);
+        tmem_wait_st();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(p_full);
@@ -319,7 +326,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 256 * kNB);
 }
 
 // ================================================================================================
@@ -761,10 +768,11 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, fwd::kTile))) return rc;
   auto kern = doc_start ? (D == 128 ? attn_fwd_kernel<true, 128> : attn_fwd_kernel<true, 64>)
                         : (D == 128 ? attn_fwd_kernel<false, 128> : attn_fwd_kernel<false, 64>);
-  static thread_local bool configured[4] = {false, false, false, false};
+  constexpr int smem_bytes = fwd::smem_bytes(fwd::kNB);
+  static thread_local bool configured[4] = {};
   const int variant = (doc_start ? 2 : 0) + (D == 128 ? 1 : 0);
   if (!configured[variant]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd: cudaFuncSetAttribute");
     configured[variant] = true;
   }
@@ -778,7 +786,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
   dim3 grid((unsigned)ceil_div(S, fwd::kTile), Hq, (unsigned)B);
-  kern<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  kern<<<grid, fwd::kThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   LX_CHECK_LAUNCH("attn_fwd");
   return 0;
 }
