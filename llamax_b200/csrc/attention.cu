@@ -7,13 +7,17 @@
 // projection output (no repeat_interleave, no transposes: TMA walks the strided layout). The mask is applied at
 // tile granularity: tiles that are fully masked are never visited, fully visible tiles skip the element test.
 //
+// Optional packed-sequence document mask: additionally kv >= doc_start[q] (tiles outside a row's document skipped).
+//
 // Forward  : CTA = (128 query rows, 1 query head). warp0 TMA, warp1 MMA issue, warps4-7 softmax (thread = row).
-//            S = Q K^T double-buffered in TMEM, P staged through smem (bf16), O accumulated in TMEM with lazy
+//            S = Q K^T double-buffered in TMEM, read once into registers; P (bf16 pairs) is written back over the
+//            score columns and consumed by the PV MMA straight from TMEM; O accumulates in TMEM with lazy
 //            rescaling; exp2-domain online softmax, LSE saved in natural log.
 // Backward : CTA = (128 kv rows, 1 kv head), loops over the group's query heads x 64-row query tiles.
 //            S^T = K Q^T and dP^T = V dO^T in TMEM (thread = kv row), P^T / dS^T staged through smem,
 //            dV += P^T dO and dK += dS^T Q accumulate in TMEM for the whole CTA lifetime,
-//            dQ^T = K^T dS^T is reduced into an fp32 buffer with coalesced red.global.add.
+//            dQ^T = K^T dS^T goes TMEM -> fp32 smem tile -> cp.reduce.async.bulk add into an fp32 buffer.
+// head_dim 128 natively; head_dim 64 runs on the same 128-wide tiles (TMA zero-fills the missing half).
 #include "common.cuh"
 #include "host_utils.h"
 #include "llamax_b200.h"
