@@ -10,7 +10,8 @@ import threading
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libllamax_b200.so")
+# LLAMAX_B200_LIB: load another build of the same library (tools/attn_trace.py uses an instrumented one)
+LIB_PATH = os.environ.get("LLAMAX_B200_LIB") or os.path.join(_HERE, "csrc", "libllamax_b200.so")
 
 P = c_void_p
 I64 = c_int64

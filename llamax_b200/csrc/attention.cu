@@ -18,6 +18,8 @@
 //            dV += P^T dO and dK += dS^T Q accumulate in TMEM for the whole CTA lifetime,
 //            dQ^T = K^T dS^T goes TMEM -> fp32 smem tile -> cp.reduce.async.bulk add into an fp32 buffer.
 // head_dim 128 natively; head_dim 64 runs on the same 128-wide tiles (TMA zero-fills the missing half).
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_utils.h"
 #include "llamax_b200.h"
@@ -33,6 +35,19 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+#ifdef LX_ATTN_TRACE
+// Debug build only (tools/attn_trace.py): SM-clock timestamps of one CTA's pipeline phases, 16 slots per step.
+__device__ long long* g_attn_trace = nullptr;
+#define LX_TR(on, s, slot)                                                        \
+  do {                                                                            \
+    if ((on) && g_attn_trace && (s) < 128) g_attn_trace[(s) * 32 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define LX_TR(on, s, slot) \
+  do {                     \
+  } while (0)
+#endif
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
@@ -99,6 +114,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int warp = threadIdx.x >> 5;
+#ifdef LX_ATTN_TRACE
+  const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 && (warp == 1 || warp == 4);
+#endif
   const int qt = gridDim.x - 1 - blockIdx.x;  // heaviest (largest q) tiles first
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.Hq / p.Hkv);
@@ -189,9 +207,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_kv; ++j) {
         if (kNB == 2 && j + 1 < n_kv) issue_s(j + 1);  // next scores into the other TMEM buffer
         const int st = kNB == 2 ? (j & 1) : 0;
+        LX_TR(tr_cta, j, 0);
         mbar_wait(&v_full[st], (kNB == 2 ? (j >> 1) : j) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
+        LX_TR(tr_cta, j, 1);
         const uint32_t loV = loV0 + st * (kTileBytes / 16);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
@@ -221,8 +241,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int kv0 = (j_begin + j) * kTile;
       // tile needs the element test unless every (q, kv) pair is visible and in range
       const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      LX_TR(tr_cta, j, 4);
       mbar_wait(&s_full[st], (kNB == 2 ? (j >> 1) : j) & 1);
       tc_fence_after();
+      LX_TR(tr_cta, j, 5);
       const uint32_t tS = tmem_S + st * 128 + lane_off;
       // single pass over TMEM: the whole score row (128 fp32) lives in registers
       uint32_t sv[4][32];
@@ -232,6 +254,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_wait_ld_regs(sv[1]);
       tmem_wait_ld_regs(sv[2]);
       tmem_wait_ld_regs(sv[3]);
+      LX_TR(tr_cta, j, 6);
       // S is in registers: release the TMEM buffer for the next QK^T right away
       tc_fence_before();
       __syncwarp();
@@ -272,10 +295,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
 
       l = l * alpha + rowsum;
+      LX_TR(tr_cta, j, 7);
 
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);  // O stable, P buffer free
         tc_fence_after();
+        LX_TR(tr_cta, j, 8);
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
@@ -297,6 +322,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st_32x32(tS + 32, p1);
         tmem_wait_st();
       }
+      LX_TR(tr_cta, j, 9);
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(p_full);
@@ -354,29 +380,39 @@ struct AttnBwdParams {
 namespace bwd {
 constexpr int kKV = 128;                          // kv rows per CTA
 constexpr int kQ = 64;                            // query rows per step
-constexpr int kThreads = 384;                     // warps 0-3 control, warps 4-11 workers (softmax-grad + dQ drain)
+// warpgroup 0: control (warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc); warpgroups 1-2: softmax-grad workers;
+// warpgroup 3: dQ drain (TMEM -> fp32 smem tile -> bulk reduce-add), off the workers' critical path
+constexpr int kThreads = 512;
 constexpr int kWorkers = 256;
+constexpr int kRegsCtrl = 64, kRegsWork = 176, kRegsDrain = 96;   // setmaxnreg: 64 + 2 * 176 + 96 = 4 * 128
 constexpr int kKVBytes = kKV * kHD * 2;           // 32 KB (2 boxes of [128 x 128 B])
 constexpr int kQBytes = kQ * kHD * 2;             // 16 KB (2 boxes of [64 x 128 B])
 constexpr int kPBytes = kKV * kQ * 2;             // 16 KB ([128 kv rows] x [64 q] bf16)
+constexpr int kStages = 3;                        // Q / dO tiles in flight: the TMA latency sits two steps ahead of its use
 constexpr int kOffK = 0;
 constexpr int kOffV = kOffK + kKVBytes;
-constexpr int kOffQ = kOffV + kKVBytes;           // 2 stages
-constexpr int kOffdO = kOffQ + 2 * kQBytes;       // 2 stages
-constexpr int kOffP = kOffdO + 2 * kQBytes;       // 2 buffers
-constexpr int kOffdS = kOffP + 2 * kPBytes;       // 2 buffers
+constexpr int kOffQ = kOffV + kKVBytes;           // kStages stages
+constexpr int kOffdO = kOffQ + kStages * kQBytes; // kStages stages
+constexpr int kOffdS = kOffdO + kStages * kQBytes;  // 2 buffers
 constexpr int kOffdQ = kOffdS + 2 * kPBytes;      // fp32 [64 q][128 d] staging for the bulk reduce-add
 constexpr int kdQBytes = kQ * kHD * 4;            // 32 KB
 constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta / doc_start: 2 stages x 3 x 64 words
 constexpr int kOffBar = kOffStat + 2 * 3 * kQ * 4;
-// kv_full, qdo full/empty[2], sdp_full, pds full/empty[2], dq full/empty[2], acc_done
-constexpr int kNumBars = 1 + 4 + 1 + 4 + 4 + 1;
+// kv_full, qdo full/empty[kStages], sdp full/empty, pds full/empty[2], dq full/empty, acc_done
+constexpr int kNumBars = 1 + 2 * kStages + 2 + 4 + 2 + 1;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "attention backward shared memory budget");
-// TMEM columns: dV, dK accumulators; S^T, dP^T; dQ^T double-buffered
-constexpr int kColdV = 0, kColdK = 128, kColS = 256, kColdP = 320, kColdQ = 384;
+// TMEM columns: dV, dK accumulators; S^T, dP^T; dQ^T; P^T as packed bf16 pairs (A operand of dV), double-buffered
+constexpr int kColdV = 0, kColdK = 128, kColS = 256, kColdP = 320, kColdQ = 384, kColP = 448;
 }  // namespace bwd
 
+// Pipeline (per step s = one 64-row query tile of one query head of the group):
+//   MMA   : [S^T, dP^T](s+1) is issued as soon as the workers hold S^T/dP^T(s) in registers (sdp_empty), so it runs
+//           under the workers' exp / dS arithmetic of step s; [dV, dK, dQ^T](s) follows when P^T/dS^T(s) are in smem.
+//   worker: TMEM -> registers, release, P^T = exp2(S^T - lse), dS^T = P^T (dP^T - delta) scale -> swizzled smem.
+//   drain : dQ^T(s) TMEM -> fp32 smem tile -> one cp.reduce.async.bulk add per step into dq_accum.
+// Measured with tools/attn_trace.py before this split (workers also drained, S^T/dP^T released only after the smem
+// stores, lse pre-scaled right at its global load): 3800 cycles per step against 1280 cycles of MMA work.
 template <bool kDocs, int kD>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -389,17 +425,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;
-  uint64_t* qdo_empty = bars + 3;
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* pds_full = bars + 6;
-  uint64_t* pds_empty = bars + 8;
-  uint64_t* dq_full = bars + 10;
-  uint64_t* dq_empty = bars + 12;
-  uint64_t* acc_done = bars + 14;
+  uint64_t* qdo_empty = qdo_full + kStages;
+  uint64_t* sdp_full = qdo_empty + kStages;
+  uint64_t* sdp_empty = sdp_full + 1;
+  uint64_t* pds_full = sdp_empty + 1;
+  uint64_t* pds_empty = pds_full + 2;
+  uint64_t* dq_full = pds_empty + 2;
+  uint64_t* dq_empty = dq_full + 1;
+  uint64_t* acc_done = dq_empty + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int warp = threadIdx.x >> 5;
   const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+#ifdef LX_ATTN_TRACE
+  const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 &&
+                      (warp == 1 || warp == 4 || warp == 12);
+#endif
   const int kv0 = jt * kKV;
   const int G = p.Hq / p.Hkv;
   const int nq_tiles = (p.S + kQ - 1) / kQ;
@@ -417,15 +458,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (warp == 1 && elect_one()) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&pds_full[i], 8);
       mbar_init(&pds_empty[i], 1);
-      mbar_init(&dq_full[i], 1);
-      mbar_init(&dq_empty[i], 8);
     }
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
     mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 8);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -438,221 +482,221 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------ TMA producer ------------------------------------
-    if (elect_one()) {
-      mbar_expect_tx(kv_full, 2 * kKVBytes);
-      tma_load_4d(smem + kOffK, &tmK, kv_full, 0, hk, kv0, b);
-      tma_load_4d(smem + kOffK + kKVBytes / 2, &tmK, kv_full, 64, hk, kv0, b);
-      tma_load_4d(smem + kOffV, &tmV, kv_full, 0, hk, kv0, b);
-      tma_load_4d(smem + kOffV + kKVBytes / 2, &tmV, kv_full, 64, hk, kv0, b);
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s & 1;
-        const int hq = hk * G + s / steps_per_head;
-        const int q0 = (i_start + s % steps_per_head) * kQ;
-        mbar_wait(&qdo_empty[st], ((s >> 1) & 1) ^ 1);
-        mbar_expect_tx(&qdo_full[st], 2 * kQBytes);
-        uint8_t* sq = smem + kOffQ + st * kQBytes;
-        uint8_t* sdo = smem + kOffdO + st * kQBytes;
-        tma_load_4d(sq, &tmQ, &qdo_full[st], 0, hq, q0, b);
-        tma_load_4d(sq + kQBytes / 2, &tmQ, &qdo_full[st], 64, hq, q0, b);
-        tma_load_4d(sdo, &tmdO, &qdo_full[st], 0, hq, q0, b);
-        tma_load_4d(sdo + kQBytes / 2, &tmdO, &qdo_full[st], 64, hq, q0, b);
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsCtrl>();
+    if (warp == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(kv_full, 2 * kKVBytes);
+        tma_load_4d(smem + kOffK, &tmK, kv_full, 0, hk, kv0, b);
+        tma_load_4d(smem + kOffK + kKVBytes / 2, &tmK, kv_full, 64, hk, kv0, b);
+        tma_load_4d(smem + kOffV, &tmV, kv_full, 0, hk, kv0, b);
+        tma_load_4d(smem + kOffV + kKVBytes / 2, &tmV, kv_full, 64, hk, kv0, b);
+        for (int s = 0, st = 0, ph = 0; s < n_steps; ++s) {
+          const int hq = hk * G + s / steps_per_head;
+          const int q0 = (i_start + s % steps_per_head) * kQ;
+          mbar_wait(&qdo_empty[st], ph ^ 1);
+          mbar_expect_tx(&qdo_full[st], 2 * kQBytes);
+          uint8_t* sq = smem + kOffQ + st * kQBytes;
+          uint8_t* sdo = smem + kOffdO + st * kQBytes;
+          tma_load_4d(sq, &tmQ, &qdo_full[st], 0, hq, q0, b);
+          tma_load_4d(sq + kQBytes / 2, &tmQ, &qdo_full[st], 64, hq, q0, b);
+          tma_load_4d(sdo, &tmdO, &qdo_full[st], 0, hq, q0, b);
+          tma_load_4d(sdo + kQBytes / 2, &tmdO, &qdo_full[st], 64, hq, q0, b);
+          if (++st == kStages) st = 0, ph ^= 1;
+        }
       }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------ MMA issuer ------------------------------------
-    // issue order per step s:  [S^T, dP^T](s+1)  then  [dV, dK, dQ^T](s)  so that the worker warps process step s+1
-    // while the three accumulation GEMMs of step s run.
-    if (elect_one()) {
-      constexpr uint32_t idesc_st = make_idesc(1, 1, 128, 64, 0, 0);    // S^T, dP^T : [kv x d] . [q x d]^T
-      constexpr uint32_t idesc_acc = make_idesc(1, 1, 128, 128, 0, 1);  // dV, dK    : [kv x q] . [q x d]   (B MN-major)
-      constexpr uint32_t idesc_dq = make_idesc(1, 1, 128, 64, 1, 1);    // dQ^T      : [kv x d]^T . [kv x q] (A, B MN-major)
-      constexpr uint32_t kHi = desc_hi(1024);
-      // descriptor low words (address >> 4 | LBO): K-major operands carry LBO 16 (unused), MN-major the atom stride
-      const uint32_t loK = desc_lo(smem_u32(smem + kOffK), 16), loV = desc_lo(smem_u32(smem + kOffV), 16);
-      const uint32_t loKmn = desc_lo(smem_u32(smem + kOffK), 16384);
-      uint32_t loQ[2], lodO[2], loQmn[2], lodOmn[2], loP[2], lodS[2];
+      __syncwarp();
+    } else if (warp == 1) {
+      // ------------------------------------ MMA issuer ------------------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_st = make_idesc(1, 1, 128, 64, 0, 0);    // S^T, dP^T : [kv x d] . [q x d]^T
+        constexpr uint32_t idesc_acc = make_idesc(1, 1, 128, 128, 0, 1);  // dV, dK    : [kv x q] . [q x d]   (B MN-major)
+        constexpr uint32_t idesc_dq = make_idesc(1, 1, 128, 64, 1, 1);    // dQ^T      : [kv x d]^T . [kv x q] (A, B MN-major)
+        constexpr uint32_t kHi = desc_hi(1024);
+        // descriptor low words (address >> 4 | LBO): K-major operands carry LBO 16 (unused), MN-major the atom stride
+        const uint32_t loK = desc_lo(smem_u32(smem + kOffK), 16), loV = desc_lo(smem_u32(smem + kOffV), 16);
+        const uint32_t loKmn = desc_lo(smem_u32(smem + kOffK), 16384);
+        // Q / dO stage g: K-major descriptors (S^T, dP^T) and MN-major ones (dK, dV) differ only in the LBO field
+        const uint32_t loQ0 = desc_lo(smem_u32(smem + kOffQ), 16), lodO0 = desc_lo(smem_u32(smem + kOffdO), 16);
+        const uint32_t loQmn0 = desc_lo(smem_u32(smem + kOffQ), 8192), lodOmn0 = desc_lo(smem_u32(smem + kOffdO), 8192);
+        const uint32_t lodS0 = desc_lo(smem_u32(smem + kOffdS), 16);
+        int g_sdp = 0, ph_sdp = 0;   // stage / phase of the next S^T, dP^T issue
+        auto issue_sdp = [&]() {
+          mbar_wait(&qdo_full[g_sdp], ph_sdp);
+          tc_fence_after();
+          const uint32_t q_lo = loQ0 + g_sdp * (kQBytes / 16), do_lo = lodO0 + g_sdp * (kQBytes / 16);
+          if (++g_sdp == kStages) g_sdp = 0, ph_sdp ^= 1;
 #pragma unroll
-      for (int st = 0; st < 2; ++st) {
-        loQ[st] = desc_lo(smem_u32(smem + kOffQ + st * kQBytes), 16);
-        lodO[st] = desc_lo(smem_u32(smem + kOffdO + st * kQBytes), 16);
-        loQmn[st] = desc_lo(smem_u32(smem + kOffQ + st * kQBytes), 8192);
-        lodOmn[st] = desc_lo(smem_u32(smem + kOffdO + st * kQBytes), 8192);
-        loP[st] = desc_lo(smem_u32(smem + kOffP + st * kPBytes), 16);
-        lodS[st] = desc_lo(smem_u32(smem + kOffdS + st * kPBytes), 16);
-      }
-      auto issue_sdp = [&](int s) {
-        const int st = s & 1;
-        mbar_wait(&qdo_full[st], (s >> 1) & 1);
-        tc_fence_after();
-        const uint32_t q_lo = st ? loQ[1] : loQ[0], do_lo = st ? lodO[1] : lodO[0];
+          for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
-        for (int dh = 0; dh < 2; ++dh)
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss<false, 1>(tmem_base + kColS, desc_join(loK + (dh * 16384 + ks * 32) / 16, kHi),
+                                desc_join(q_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
+#pragma unroll
+          for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss<false, 1>(tmem_base + kColdP, desc_join(loV + (dh * 16384 + ks * 32) / 16, kHi),
+                                desc_join(do_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
+          umma_commit(sdp_full);
+        };
+        mbar_wait(kv_full, 0);
+        issue_sdp();
+        for (int s = 0, g = 0; s < n_steps; ++s) {
+          const int st = s & 1;
+          const uint32_t qmn_lo = loQmn0 + g * (kQBytes / 16), domn_lo = lodOmn0 + g * (kQBytes / 16);
+          const uint32_t ds_lo = lodS0 + st * (kPBytes / 16);
+          LX_TR(tr_cta, s, 0);
+          if (s + 1 < n_steps) {
+            mbar_wait(sdp_empty, s & 1);   // S^T/dP^T(s) are in the workers' registers: the columns are free
+            issue_sdp();
+          }
+          LX_TR(tr_cta, s, 1);
+          mbar_wait(&pds_full[st], (s >> 1) & 1);        // P^T(s) is in TMEM, dS^T(s) in smem
+          tc_fence_after();
+          LX_TR(tr_cta, s, 2);
+          // dV += P^T dO (A = P^T straight from TMEM) ; dK += dS^T Q        (K dim = q, 64 -> 4 steps of 16)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_ss<false, 1>(tmem_base + kColS, desc_join(loK + (dh * 16384 + ks * 32) / 16, kHi),
-                              desc_join(q_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
-#pragma unroll
-        for (int dh = 0; dh < 2; ++dh)
+            umma_ts_f16(tmem_base + kColdV, tmem_base + kColP + st * 32 + ks * 8, desc_join(domn_lo + ks * 128, kHi),
+                        idesc_acc, (s | ks) != 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_ss<false, 1>(tmem_base + kColdP, desc_join(loV + (dh * 16384 + ks * 32) / 16, kHi),
-                              desc_join(do_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
-        umma_commit(sdp_full);
-      };
-      mbar_wait(kv_full, 0);
-      issue_sdp(0);
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s & 1;
-        const uint32_t qmn_lo = st ? loQmn[1] : loQmn[0], domn_lo = st ? lodOmn[1] : lodOmn[0];
-        const uint32_t p_lo = st ? loP[1] : loP[0], ds_lo = st ? lodS[1] : lodS[0];
-        // softmax-grad of step s done: S^T/dP^T columns are free and P^T/dS^T[st] are in smem
-        mbar_wait(&pds_full[st], (s >> 1) & 1);
-        if (s + 1 < n_steps) issue_sdp(s + 1);
-        mbar_wait(&dq_empty[st], ((s >> 1) & 1) ^ 1);  // dQ^T buffer st drained (step s-2)
-        tc_fence_after();
-        // dV += P^T dO ; dK += dS^T Q        (K dim = q, 64 -> 4 steps of 16)
+            umma_ss<false, 1>(tmem_base + kColdK, desc_join(ds_lo + ks * 2, kHi), desc_join(qmn_lo + ks * 128, kHi),
+                              idesc_acc, (s | ks) != 0);
+          // the drain warps hold dQ^T(s-1) in registers (dq_full(s-1) fired a whole [S^T,dP^T,dV,dK] ago)
+          mbar_wait(dq_empty, (s & 1) ^ 1);
+          tc_fence_after();
+          LX_TR(tr_cta, s, 3);
+          // dQ^T = K^T dS^T   (M = d, N = q, K dim = kv, 128 -> 8 steps of 16)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss<false, 1>(tmem_base + kColdV, desc_join(p_lo + ks * 2, kHi), desc_join(domn_lo + ks * 128, kHi),
-                            idesc_acc, (s | ks) != 0);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss<false, 1>(tmem_base + kColdK, desc_join(ds_lo + ks * 2, kHi), desc_join(qmn_lo + ks * 128, kHi),
-                            idesc_acc, (s | ks) != 0);
-        // dQ^T = K^T dS^T   (M = d, N = q, K dim = kv, 128 -> 8 steps of 16)
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ss<false, 1>(tmem_base + kColdQ + st * 64, desc_join(loKmn + ks * 128, kHi),
-                            desc_join(ds_lo + ks * 128, kHi), idesc_dq, ks != 0);
-        umma_commit(&dq_full[st]);
-        umma_commit(&qdo_empty[st]);
-        umma_commit(&pds_empty[st]);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss<false, 1>(tmem_base + kColdQ, desc_join(loKmn + ks * 128, kHi),
+                              desc_join(ds_lo + ks * 128, kHi), idesc_dq, ks != 0);
+          umma_commit(dq_full);
+          umma_commit(&qdo_empty[g]);
+          umma_commit(&pds_empty[st]);
+          if (++g == kStages) g = 0;
+        }
+        umma_commit(acc_done);
       }
-      umma_commit(acc_done);
+      __syncwarp();
     }
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ------------------------------------ workers: softmax-grad (thread = kv row, 32 query columns) and
-    //                                      dQ^T drain (thread = head-dim element, 32 query rows) ------------------
+  } else if (warp < 12) {
+    // ------------------------------------ workers: softmax-grad (thread = kv row, 32 query columns) ------------------
+    setmaxnreg_inc<kRegsWork>();
     const int wt = threadIdx.x - 128;           // 0..255
     const int grp = (warp - 4) >> 2;            // query-column half handled by this warp
     const int lq = warp & 3;                    // TMEM lane quarter (hardware: warp % 4)
-    const int t = lq * 32 + lane_id();          // kv row / head-dim element
+    const int t = lq * 32 + lane_id();          // kv row
     const uint32_t lane_off = uint32_t(lq * 32) << 16;
     const int kv = kv0 + t;
     const uint32_t s_stat_u = smem_u32(s_stat);
-    float* stage = reinterpret_cast<float*>(smem + kOffdQ);
 
-    // lse (log2 units) for wt < 64, delta for 64 <= wt < 128, document start (int bits) for 128 <= wt < 192
+    // lse for wt < 64 (scaled to log2 units when stored), delta (times the softmax scale) for 64 <= wt < 128, document start (int bits) for
+    // 128 <= wt < 192. Raw global loads only: nothing here may depend on the loaded value (it lands a step later).
     auto load_stat = [&](int s) -> float {
       if (wt >= 192 || s >= n_steps) return 0.f;
       const int hq = hk * G + s / steps_per_head;
       const int qq = (i_start + s % steps_per_head) * kQ + (wt & 63);
       const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
-      if (wt < 64) return (qq < p.S) ? p.lse[idx] * kLog2e : INFINITY;
+      if (wt < 64) return (qq < p.S) ? p.lse[idx] : INFINITY;
       if (wt < 128) return (qq < p.S) ? p.delta[idx] : 0.f;
       return __int_as_float((kDocs && qq < p.S) ? p.doc_start[(int64_t)b * p.S + qq] : 0);
     };
-    auto drain = [&](int s) {
-      // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> one
-      // bulk reduce-add per 32-row half into dq_accum[b, hq, q0 + 32 grp : +32, :] (fp32 add performed at L2)
-      const int st = s & 1;
-      const int hq = hk * G + s / steps_per_head;
-      const int q0 = (i_start + s % steps_per_head) * kQ;
-      mbar_wait(&dq_full[st], (s >> 1) & 1);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + kColdQ + st * 64 + grp * 32 + lane_off, v);
-      tmem_wait_ld_regs(v);
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&dq_empty[st]);
-      if (t == 0) tma_store_wait_read<0>();      // this group's previous bulk reduce has read its staging half
-      named_bar_sync(2 + grp, 128);
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (t < kD) stage[(grp * 32 + i) * kD + t] = __uint_as_float(v[i]);
-      fence_proxy_async_smem();
-      named_bar_sync(2 + grp, 128);
-      if (t == 0) {
-        const int rows = min(32, p.S - (q0 + grp * 32));
-        if (rows > 0) {
-          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0 + grp * 32) * kD;
-          bulk_reduce_add_f32(dst, stage + grp * 32 * kD, (uint32_t)rows * kD * 4);
-        }
-        tma_store_commit();
-      }
+    auto store_stat = [&](int buf, float v) {
+      if (wt < 64) s_stat[buf * 3 * kQ + wt] = v * kLog2e;
+      else if (wt < 128) s_stat[buf * 3 * kQ + wt] = v * p.scale;
+      else if (wt < 192) s_stat[buf * 3 * kQ + wt] = v;
     };
 
     float nxt = load_stat(0);
-    if (wt < 192) s_stat[wt] = nxt;
+    store_stat(0, nxt);
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
       const int q0 = (i_start + s % steps_per_head) * kQ;
-      const uint32_t sP = smem_u32(smem + kOffP + st * kPBytes), sdS = smem_u32(smem + kOffdS + st * kPBytes);
+      const uint32_t sdS = smem_u32(smem + kOffdS + st * kPBytes);
+      LX_TR(tr_cta, s, 4);
       named_bar_sync(1, kWorkers);               // stats of step s visible; all workers finished step s-1
+      LX_TR(tr_cta, s, 5);
       nxt = load_stat(s + 1);                    // prefetch next step's lse / delta (global)
       const uint32_t stat_u = s_stat_u + st * (3 * kQ * 4) + grp * 32 * 4;
       const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kQ - 1, p.S - 1)] : 0;
       const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0)) &&
                              (kv0 >= ds_tile);
-      mbar_wait(&pds_empty[st], ((s >> 1) & 1) ^ 1);  // P^T/dS^T[st] no longer read by the MMAs of step s-2
       mbar_wait(sdp_full, s & 1);
       tc_fence_after();
+      LX_TR(tr_cta, s, 6);
       {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + kColS + grp * 32 + lane_off, sv);
         tmem_ld_32x32(tmem_base + kColdP + grp * 32 + lane_off, dv);
         tmem_wait_ld_regs(sv);
         tmem_wait_ld_regs(dv);
+        // S^T / dP^T are in registers: let the MMA warp overwrite the columns with step s+1 right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(sdp_empty);
+        LX_TR(tr_cta, s, 7);
         uint32_t pr[16], dsr[16];
+        // The workers are issue-bound (two warps per scheduler): 5 instructions per element on fully visible tiles
+        // (FFMA, EX2, FFMA, FMUL, half a pack); the element test lives in a separate, uniformly branched copy.
+        auto block = [&](auto masked_tag) {
+          constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 l4 = lds_f4(stat_u + i * 4);                 // lse2 of 4 query columns
-          const float4 d4 = lds_f4(stat_u + kQ * 4 + i * 4);        // delta
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-          int dst4[4] = {0, 0, 0, 0};
-          if (kDocs && !full_tile) {
-            const float4 s4 = lds_f4(stat_u + 2 * kQ * 4 + i * 4);  // document start of each query column
-            dst4[0] = __float_as_int(s4.x); dst4[1] = __float_as_int(s4.y);
-            dst4[2] = __float_as_int(s4.z); dst4[3] = __float_as_int(s4.w);
-          }
-          float pv[4], dsv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float pe = ex2(fmaf(__uint_as_float(sv[i + e]), p.scale_log2, -ls[e]));
-            if (!full_tile) {
-              const int qa = q0 + grp * 32 + i + e;
-              if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (!kDocs || kv >= dst4[e]))) pe = 0.f;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 l4 = lds_f4(stat_u + i * 4);                 // lse2 of 4 query columns
+            const float4 d4 = lds_f4(stat_u + kQ * 4 + i * 4);        // delta * scale
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            int dst4[4] = {0, 0, 0, 0};
+            if (kDocs && kMasked) {
+              const float4 s4 = lds_f4(stat_u + 2 * kQ * 4 + i * 4);  // document start of each query column
+              dst4[0] = __float_as_int(s4.x); dst4[1] = __float_as_int(s4.y);
+              dst4[2] = __float_as_int(s4.z); dst4[3] = __float_as_int(s4.w);
             }
-            pv[e] = pe;
-            dsv[e] = pe * (__uint_as_float(dv[i + e]) - dl[e]) * p.scale;
+            float pv[4], dsv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float pe = ex2(fmaf(__uint_as_float(sv[i + e]), p.scale_log2, -ls[e]));
+              if (kMasked) {
+                const int qa = q0 + grp * 32 + i + e;
+                if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (!kDocs || kv >= dst4[e]))) pe = 0.f;
+              }
+              pv[e] = pe;
+              dsv[e] = pe * fmaf(__uint_as_float(dv[i + e]), p.scale, -dl[e]);
+            }
+            pr[i / 2] = pack_bf16(pv[0], pv[1]);
+            pr[i / 2 + 1] = pack_bf16(pv[2], pv[3]);
+            dsr[i / 2] = pack_bf16(dsv[0], dsv[1]);
+            dsr[i / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
           }
-          pr[i / 2] = pack_bf16(pv[0], pv[1]);
-          pr[i / 2 + 1] = pack_bf16(pv[2], pv[3]);
-          dsr[i / 2] = pack_bf16(dsv[0], dsv[1]);
-          dsr[i / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
-        }
-        // rows of 64 q values = 128 B = 8 chunks of 16 B, swizzled by (row & 7); this warp: chunks 4 grp .. 4 grp + 3
+        };
+        if (full_tile) block(std::false_type{});
+        else block(std::true_type{});
+        LX_TR(tr_cta, s, 16);
+        mbar_wait(&pds_empty[st], ((s >> 1) & 1) ^ 1);  // P^T/dS^T[st] no longer read by the MMAs of step s-2
+        tc_fence_after();
+        LX_TR(tr_cta, s, 17);
+        // P^T: bf16 pairs into this thread's TMEM lane, 16 columns = this warp's 32 query columns
+        tmem_st_32x16(tmem_base + kColP + st * 32 + grp * 16 + lane_off, pr);
+        // dS^T rows of 64 q values = 128 B = 8 chunks of 16 B, swizzled by (row & 7); this warp: chunks 4 grp .. 4 grp + 3
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const uint32_t off = t * 128 + (((grp * 4 + cc) ^ (t & 7)) << 4);
-          sts_v4(sP + off, pr[cc * 4], pr[cc * 4 + 1], pr[cc * 4 + 2], pr[cc * 4 + 3]);
           sts_v4(sdS + off, dsr[cc * 4], dsr[cc * 4 + 1], dsr[cc * 4 + 2], dsr[cc * 4 + 3]);
         }
+        LX_TR(tr_cta, s, 18);
+        tmem_wait_st();
       }
+      LX_TR(tr_cta, s, 8);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&pds_full[st]);
-      if (wt < 192) s_stat[(st ^ 1) * 3 * kQ + wt] = nxt;   // stats of step s+1 (buffer last read in step s-1)
-      if (s > 0) drain(s - 1);                               // dQ^T of the previous step is complete by now
+      LX_TR(tr_cta, s, 9);
+      store_stat(st ^ 1, nxt);                  // stats of step s+1 (buffer last read in step s-1)
     }
-    drain(n_steps - 1);
-    if (t == 0) tma_store_wait<0>();  // all bulk reductions issued by this thread have completed
     // write dV (group 0) / dK (group 1); thread = kv row
     mbar_wait(acc_done, 0);
     tc_fence_after();
@@ -677,6 +721,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     tc_fence_before();
+  } else {
+    // ------------------------------------ dQ drain (thread = head-dim element, all 64 query rows of the step) ----------
+    // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> one bulk
+    // reduce-add per step into dq_accum[b, hq, q0 : q0 + 64, :] (fp32 add performed at L2)
+    setmaxnreg_dec<kRegsDrain>();
+    const int lq = warp & 3;
+    const int t = lq * 32 + lane_id();          // head-dim element == TMEM lane
+    const uint32_t lane_off = uint32_t(lq * 32) << 16;
+    const bool leader = threadIdx.x == 384;
+    float* stage = reinterpret_cast<float*>(smem + kOffdQ);
+    for (int s = 0; s < n_steps; ++s) {
+      const int hq = hk * G + s / steps_per_head;
+      const int q0 = (i_start + s % steps_per_head) * kQ;
+      LX_TR(tr_cta, s, 10);
+      mbar_wait(dq_full, s & 1);
+      tc_fence_after();
+      LX_TR(tr_cta, s, 11);
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + kColdQ + lane_off, v0);
+      tmem_ld_32x32(tmem_base + kColdQ + 32 + lane_off, v1);
+      tmem_wait_ld_regs(v0);
+      tmem_wait_ld_regs(v1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(dq_empty);
+      LX_TR(tr_cta, s, 12);
+      if (leader) tma_store_wait_read<0>();      // the previous bulk reduce has read the staging tile
+      named_bar_sync(2, 128);
+      LX_TR(tr_cta, s, 13);
+      if (t < kD) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stage[i * kD + t] = __uint_as_float(v0[i]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stage[(32 + i) * kD + t] = __uint_as_float(v1[i]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (leader) {
+        const int rows = min(kQ, p.S - q0);
+        if (rows > 0) {
+          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0) * kD;
+          bulk_reduce_add_f32(dst, stage, (uint32_t)rows * kD * 4);
+        }
+        tma_store_commit();
+      }
+      LX_TR(tr_cta, s, 14);
+    }
+    if (leader) tma_store_wait<0>();  // all bulk reductions issued by this thread have completed
   }
 
   tc_fence_before();
@@ -758,6 +850,14 @@ static int check_attn_args(int64_t B, int64_t S, int Hq, int Hkv, int D, int64_t
 using namespace lx;
 
 extern "C" {
+
+#ifdef LX_ATTN_TRACE
+int llamax_debug_attn_trace(void* buf) {
+  long long* b = (long long*)buf;
+  cudaError_t e = cudaMemcpyToSymbol(g_attn_trace, &b, sizeof(b));
+  return e == cudaSuccess ? 0 : set_cuda_error(e, "debug_attn_trace");
+}
+#endif
 
 int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,

@@ -45,12 +45,29 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Warpgroup register re-allocation (every warp of the warpgroup executes it; counts are multiples of 8).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // bf16 helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&r);
+}
+// Two finite fp32 -> packed bf16 with round-half-away (differs from nearest-even only on exact ties): two integer adds
+// and a byte permute on the ALU pipe. The cvt-based pack_bf16 (F2FP) issues on the 16-lane/clk XU pipe, which it
+// shares with ex2: in the attention softmax loops that made XU, not the tensor pipe, the limiter
+// (tools/attn_trace.py: 1610 cycles per 128x128 tile = 128 ex2 + 64 F2FP per thread at 8 cycles each).
+__device__ __forceinline__ uint32_t pack_bf16_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 // fp32 -> nearest-even bf16 -> fp32, in integer arithmetic (ALU pipe). The cvt.rn.bf16.f32 instruction runs on the
 // 16-lane/clk conversion (XU) pipe, which made the fused norm / SwiGLU passes XU-bound instead of HBM-bound.
@@ -365,6 +382,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// registers -> TMEM: 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 

@@ -17,6 +17,8 @@ Data layout (M = B*S tokens):
 
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -35,6 +37,43 @@ def _get_scratch(device, numel: int) -> Tensor:
         buf = torch.empty(numel, device=device, dtype=torch.bfloat16)
         _scratch[device] = buf
     return buf
+
+
+# Resident backward operands. The grad_input GEMM consumes (scale * W)^T in bf16; the base weights are frozen, so on a
+# 180 GB B200 the 2 B/parameter operand (14 GB for the 8B model) is built once per layer and kept, instead of being
+# re-materialised from the int8 codes on every backward (224 de-quantisation launches, ~2 % of the step).
+# "auto": keep an operand only while at least _CACHE_HEADROOM bytes stay free on the device after allocating it
+# (checked at the first backward, i.e. at peak activation memory); "1": always; "0": never (shared scratch).
+_CACHE_MODE = os.environ.get("LLAMAX_WEIGHT_CACHE", "auto")
+_CACHE_HEADROOM = 24 << 30
+
+
+def set_weight_cache(mode: str) -> None:
+    global _CACHE_MODE
+    assert mode in ("auto", "0", "1")
+    _CACHE_MODE = mode
+
+
+def _operand(cache: dict | None, key: str, specs, rows: int, width: int, device):
+    """bf16 [rows, width] buffer for the backward operand of `specs`. Returns (buffer, frozen_part_is_valid)."""
+    numel = rows * width
+    if cache is not None and _CACHE_MODE != "0":
+        sig = tuple((s.w8.data_ptr(), s.w8._version, s.ws.data_ptr(), s.ws._version) for s in specs)
+        hit = cache.get(key)
+        if hit is not None and hit[0] == sig and hit[1].device == device:
+            return hit[1], True
+        if hit is not None and hit[1].device == device and hit[1].numel() == numel:
+            cache[key] = (sig, hit[1])   # weights were overwritten in place: rebuild into the same buffer
+            return hit[1], False
+        ok = _CACHE_MODE == "1"
+        if not ok:
+            free, _ = torch.cuda.mem_get_info(device)
+            ok = free - 2 * numel >= _CACHE_HEADROOM
+        if ok:
+            buf = torch.empty(rows, width, device=device, dtype=torch.bfloat16)
+            cache[key] = (sig, buf)
+            return buf, False
+    return _get_scratch(device, numel)[:numel].view(rows, width), False
 
 
 class LinearSpec:
@@ -80,7 +119,8 @@ def _linear(spec: LinearSpec, x_bf16, x_q8, x_qs, h, out=None, resid=None):
     return ops.bf16_gemm(x_bf16, wd, col_scale=spec.ws, round_before_scale=True, out=out, **ep)
 
 
-def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Tensor | None, need_dx=True):
+def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Tensor | None, need_dx=True,
+                    cache: dict | None = None, key: str = ""):
     """Backward of linears that share one input. dy_cat [M, n_total + r_total]: gradient blocks already written in
     the first n_total columns (block i = specs[i].N columns); the LoRA dh columns are filled here.
     Returns (dx [M,K], [(dA_i, dB_i) | None per spec])."""
@@ -89,12 +129,13 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Te
     r_total = sum(s.R for s in specs)
     width = n_total + r_total
     assert dy_cat.shape[1] == width
-    wt = _get_scratch(dy_cat.device, K * width)[: K * width].view(K, width)
+    wt, valid = _operand(cache, key, specs, K, width, dy_cat.device)
     n_off, r_off = 0, 0
     lora_grads = []
     for s in specs:
         dy_i = dy_cat[:, n_off : n_off + s.N]
-        ops.dequant_weight(s.w8, s.ws, transpose=True, apply_scale=True, out=wt[:, n_off : n_off + s.N])
+        if not valid:
+            ops.dequant_weight(s.w8, s.ws, transpose=True, apply_scale=True, out=wt[:, n_off : n_off + s.N])
         if s.R > 0:
             c0 = n_total + r_off
             # dh_i = scale * dy_i @ B_i    -> columns [c0, c0+R) of dy_cat
@@ -119,10 +160,17 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Te
     return dx, lora_grads
 
 
-def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, h: Tensor | None):
+def _single_operand(spec: LinearSpec, device, cache: dict | None, key: str) -> Tensor:
+    wt, valid = _operand(cache, key, (spec,), spec.K, spec.N, device)
+    if not valid:
+        ops.dequant_weight(spec.w8, spec.ws, transpose=True, apply_scale=True, out=wt)
+    return wt
+
+
+def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, h: Tensor | None, cache: dict | None = None,
+                     key: str = ""):
     """Backward of one linear whose incoming gradient buffer we do not own: LoRA term in the GEMM epilogue."""
-    wt = ops.dequant_weight(spec.w8, spec.ws, transpose=True, apply_scale=True,
-                            out=_get_scratch(dy.device, spec.N * spec.K)[: spec.N * spec.K].view(spec.K, spec.N))
+    wt = _single_operand(spec, dy.device, cache, key)
     if spec.R > 0:
         bt = (spec.lora_b.detach().t() * spec.lora_scale).contiguous()
         dh = ops.bf16_gemm(dy, bt)                                     # [M, R]
@@ -209,8 +257,8 @@ class FusedDecoderBlock(torch.autograd.Function):
         # --- w2 ---  (needs g = silu(a) * b only for dA of w2: re-materialised by the SwiGLU backward kernel)
         r13 = s1.R + s3.R
         dab = torch.empty(M, 2 * F_ + r13, device=dout.device, dtype=torch.bfloat16)
-        wt2 = ops.dequant_weight(s2.w8, s2.ws, transpose=True, apply_scale=True,
-                                 out=_get_scratch(dout.device, s2.N * s2.K)[: s2.N * s2.K].view(s2.K, s2.N))
+        cache = layer.__dict__.setdefault("_llamax_bwd_operands", {})
+        wt2 = _single_operand(s2, dout.device, cache, "w2")
         g2 = None
         if s2.R > 0:
             dh2 = ops.bf16_gemm(dout2, (s2.lora_b.detach().t() * s2.lora_scale).contiguous())
@@ -225,14 +273,14 @@ class FusedDecoderBlock(torch.autograd.Function):
         del dg, g
 
         # --- w1 | w3 ---
-        dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, h_13)
+        dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, h_13, cache=cache, key="w13")
         del dab
         want_dw_fn, want_dw_an = w_fn.requires_grad, w_an.requires_grad
         dx1, dw_fn = ops.rmsnorm_bwd(dxn2, x1, w_fn.detach(), rstd2, dout2, want_dw=want_dw_fn)
         del dxn2
 
         # --- wo ---
-        do, go = _single_backward(so, dx1, o, h_o)
+        do, go = _single_backward(so, dx1, o, h_o, cache=cache, key="wo")
 
         # --- attention ---
         nq, nk = Hq * D, Hkv * D
@@ -242,7 +290,7 @@ class FusedDecoderBlock(torch.autograd.Function):
                      dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len,
                      doc_start=doc_start, doc_end=doc_end)
         ops.rope_(dqkv, rope, B, S, Hq + Hkv, D, inverse=True)
-        dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, h_qkv)
+        dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, h_qkv, cache=cache, key="wqkv")
         del dqkv
         dx, dw_an = ops.rmsnorm_bwd(dxn1, x2, w_an.detach(), rstd1, dx1, want_dw=want_dw_an)
 
