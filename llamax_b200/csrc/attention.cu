@@ -117,8 +117,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #ifdef LX_ATTN_TRACE
   const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 && (warp == 1 || warp == 4);
 #endif
-  const int qt = gridDim.x - 1 - blockIdx.x;  // heaviest (largest q) tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
+  // grid = (query heads, batch, query tiles): the tile index is the slowest one and runs backwards, so CTAs are
+  // dispatched longest-first (the last query tile visits every kv tile); the 4 heads of a GQA group run together
+  const int qt = gridDim.z - 1 - blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y;
   const int hk = h / (p.Hq / p.Hkv);
   const int q0 = qt * kTile;
   const int kv_end = min(p.S, max(p.P, q0 + kTile));
@@ -379,40 +381,41 @@ struct AttnBwdParams {
 
 namespace bwd {
 constexpr int kKV = 128;                          // kv rows per CTA
-constexpr int kQ = 64;                            // query rows per step
+constexpr int kQ = 128;                           // query rows per step
 // warpgroup 0: control (warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc); warpgroups 1-2: softmax-grad workers;
-// warpgroup 3: dQ drain (TMEM -> fp32 smem tile -> bulk reduce-add), off the workers' critical path
+// warpgroup 3: dQ drain (TMEM -> fp32 smem tile -> bulk reduce-add)
 constexpr int kThreads = 512;
 constexpr int kWorkers = 256;
-constexpr int kRegsCtrl = 64, kRegsWork = 176, kRegsDrain = 96;   // setmaxnreg: 64 + 2 * 176 + 96 = 4 * 128
-constexpr int kKVBytes = kKV * kHD * 2;           // 32 KB (2 boxes of [128 x 128 B])
-constexpr int kQBytes = kQ * kHD * 2;             // 16 KB (2 boxes of [64 x 128 B])
-constexpr int kPBytes = kKV * kQ * 2;             // 16 KB ([128 kv rows] x [64 q] bf16)
-constexpr int kStages = 3;                        // Q / dO tiles in flight: the TMA latency sits two steps ahead of its use
+constexpr int kRegsCtrl = 64, kRegsWork = 144, kRegsDrain = 160;   // setmaxnreg: 64 + 2 * 144 + 160 = 4 * 128
+constexpr int kTileBytes = 128 * kHD * 2;         // 32 KB: two 16 KB boxes of [128 rows x 128 B]
 constexpr int kOffK = 0;
-constexpr int kOffV = kOffK + kKVBytes;
-constexpr int kOffQ = kOffV + kKVBytes;           // kStages stages
-constexpr int kOffdO = kOffQ + kStages * kQBytes; // kStages stages
-constexpr int kOffdS = kOffdO + kStages * kQBytes;  // 2 buffers
-constexpr int kOffdQ = kOffdS + 2 * kPBytes;      // fp32 [64 q][128 d] staging for the bulk reduce-add
-constexpr int kdQBytes = kQ * kHD * 4;            // 32 KB
-constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta / doc_start: 2 stages x 3 x 64 words
+constexpr int kOffV = kOffK + kTileBytes;
+constexpr int kOffQ = kOffV + kTileBytes;         // 2 stages (Q(s) lives from S^T(s) to dK(s), across S^T(s+1))
+constexpr int kOffdO = kOffQ + 2 * kTileBytes;    // 1 stage  (dO(s): dP^T(s) and dV(s) are adjacent in the MMA order)
+constexpr int kOffdS = kOffdO + kTileBytes;       // dS^T [128 kv][128 q] bf16: two boxes (q halves) of [128 x 128 B]
+constexpr int kOffdQ = kOffdS + kTileBytes;       // fp32 [32 q][128 d] staging for the bulk reduce-add
+constexpr int kStageRows = 32;
+constexpr int kdQBytes = kStageRows * kHD * 4;    // 16 KB
+constexpr int kOffStat = kOffdQ + kdQBytes;       // lse2 / delta*scale / doc_start: 2 buffers x 3 x 128 words
 constexpr int kOffBar = kOffStat + 2 * 3 * kQ * 4;
-// kv_full, qdo full/empty[kStages], sdp full/empty, pds full/empty[2], dq full/empty, acc_done
-constexpr int kNumBars = 1 + 2 * kStages + 2 + 4 + 2 + 1;
+// kv_full, q full/empty[2], do full/empty, s_full, p_full, dp_full, ds_full, dq full/empty, acc_done
+constexpr int kNumBars = 1 + 4 + 2 + 4 + 2 + 1;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "attention backward shared memory budget");
-// TMEM columns: dV, dK accumulators; S^T, dP^T; dQ^T; P^T as packed bf16 pairs (A operand of dV), double-buffered
-constexpr int kColdV = 0, kColdK = 128, kColS = 256, kColdP = 320, kColdQ = 384, kColP = 448;
+// TMEM columns: dV, dK accumulators; X = S^T, then P^T as bf16 pairs over the columns each warp read;
+// Y = dP^T, then dQ^T
+constexpr int kColdV = 0, kColdK = 128, kColX = 256, kColY = 384;
 }  // namespace bwd
 
-// Pipeline (per step s = one 64-row query tile of one query head of the group):
-//   MMA   : [S^T, dP^T](s+1) is issued as soon as the workers hold S^T/dP^T(s) in registers (sdp_empty), so it runs
-//           under the workers' exp / dS arithmetic of step s; [dV, dK, dQ^T](s) follows when P^T/dS^T(s) are in smem.
-//   worker: TMEM -> registers, release, P^T = exp2(S^T - lse), dS^T = P^T (dP^T - delta) scale -> swizzled smem.
-//   drain : dQ^T(s) TMEM -> fp32 smem tile -> one cp.reduce.async.bulk add per step into dq_accum.
-// Measured with tools/attn_trace.py before this split (workers also drained, S^T/dP^T released only after the smem
-// stores, lse pre-scaled right at its global load): 3800 cycles per step against 1280 cycles of MMA work.
+// Backward v5. Every tcgen05.mma of this kernel is 128 x 128 x 16: measured with tools/attn_trace.py, an SS-mode MMA with
+// M = 128 occupies the tensor pipe for >= 64 cycles whatever N is (the A-operand smem read), so the 64-query-row steps of
+// the previous version (N = 64 for S^T, dP^T, dQ^T) ran the pipe at half rate and were MMA-issue bound at ~2950 cycles
+// per 64 rows. With 128-row steps the five GEMMs need all 512 TMEM columns twice over, hence the aliasing:
+//   X: S^T(s) -> workers -> P^T(s) bf16 (A operand of dV, read straight from TMEM) -> S^T(s+1) once dV(s) has run
+//   Y: dP^T(s) -> workers -> dQ^T(s) -> drain warps -> dP^T(s+1)
+// MMA issue order per step:  dV(s), S^T(s+1) | dQ^T(s), dK(s) | dP^T(s+1)
+//   workers compute dS(s) under dV(s)/S^T(s+1), P(s+1) under dQ^T(s)/dK(s)/dP^T(s+1); the drain pulls dQ^T(s) into
+//   registers under dK(s), so the pipe only waits on semaphores that have normally fired already.
 template <bool kDocs, int kD>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -424,19 +427,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* s_stat = reinterpret_cast<float*>(smem + kOffStat);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* kv_full = bars;
-  uint64_t* qdo_full = bars + 1;
-  uint64_t* qdo_empty = qdo_full + kStages;
-  uint64_t* sdp_full = qdo_empty + kStages;
-  uint64_t* sdp_empty = sdp_full + 1;
-  uint64_t* pds_full = sdp_empty + 1;
-  uint64_t* pds_empty = pds_full + 2;
-  uint64_t* dq_full = pds_empty + 2;
-  uint64_t* dq_empty = dq_full + 1;
-  uint64_t* acc_done = dq_empty + 1;
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* do_full = bars + 5;
+  uint64_t* do_empty = bars + 6;
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* dp_full = bars + 9;
+  uint64_t* ds_full = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint64_t* dq_empty = bars + 12;
+  uint64_t* acc_done = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int warp = threadIdx.x >> 5;
-  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  // grid = (kv heads, batch, kv tiles): the kv tile is the slowest index, so CTAs are dispatched longest-first
+  // (tile 0 is visited by every query tile, the last tile only by the last one)
+  const int hk = blockIdx.x, b = blockIdx.y, jt = blockIdx.z;
 #ifdef LX_ATTN_TRACE
   const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 &&
                       (warp == 1 || warp == 4 || warp == 12);
@@ -458,18 +465,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (warp == 1 && elect_one()) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&qdo_full[i], 1);
-      mbar_init(&qdo_empty[i], 1);
-    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&pds_full[i], 8);
-      mbar_init(&pds_empty[i], 1);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
     }
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 8);
+    mbar_init(dp_full, 1);
+    mbar_init(ds_full, 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 4);
-    mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 8);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -487,104 +494,111 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (warp == 0) {
       // ------------------------------------ TMA producer ------------------------------------
       if (elect_one()) {
-        mbar_expect_tx(kv_full, 2 * kKVBytes);
+        mbar_expect_tx(kv_full, 2 * kTileBytes);
         tma_load_4d(smem + kOffK, &tmK, kv_full, 0, hk, kv0, b);
-        tma_load_4d(smem + kOffK + kKVBytes / 2, &tmK, kv_full, 64, hk, kv0, b);
+        tma_load_4d(smem + kOffK + kTileBytes / 2, &tmK, kv_full, 64, hk, kv0, b);
         tma_load_4d(smem + kOffV, &tmV, kv_full, 0, hk, kv0, b);
-        tma_load_4d(smem + kOffV + kKVBytes / 2, &tmV, kv_full, 64, hk, kv0, b);
-        for (int s = 0, st = 0, ph = 0; s < n_steps; ++s) {
+        tma_load_4d(smem + kOffV + kTileBytes / 2, &tmV, kv_full, 64, hk, kv0, b);
+        for (int s = 0; s < n_steps; ++s) {
+          const int st = s & 1;
           const int hq = hk * G + s / steps_per_head;
           const int q0 = (i_start + s % steps_per_head) * kQ;
-          mbar_wait(&qdo_empty[st], ph ^ 1);
-          mbar_expect_tx(&qdo_full[st], 2 * kQBytes);
-          uint8_t* sq = smem + kOffQ + st * kQBytes;
-          uint8_t* sdo = smem + kOffdO + st * kQBytes;
-          tma_load_4d(sq, &tmQ, &qdo_full[st], 0, hq, q0, b);
-          tma_load_4d(sq + kQBytes / 2, &tmQ, &qdo_full[st], 64, hq, q0, b);
-          tma_load_4d(sdo, &tmdO, &qdo_full[st], 0, hq, q0, b);
-          tma_load_4d(sdo + kQBytes / 2, &tmdO, &qdo_full[st], 64, hq, q0, b);
-          if (++st == kStages) st = 0, ph ^= 1;
+          mbar_wait(&q_empty[st], ((s >> 1) & 1) ^ 1);     // dK(s-2) has read Q[st]
+          mbar_expect_tx(&q_full[st], kTileBytes);
+          uint8_t* sq = smem + kOffQ + st * kTileBytes;
+          tma_load_4d(sq, &tmQ, &q_full[st], 0, hq, q0, b);
+          tma_load_4d(sq + kTileBytes / 2, &tmQ, &q_full[st], 64, hq, q0, b);
+          mbar_wait(do_empty, (s & 1) ^ 1);                // dV(s-1) has read dO
+          mbar_expect_tx(do_full, kTileBytes);
+          uint8_t* sdo = smem + kOffdO;
+          tma_load_4d(sdo, &tmdO, do_full, 0, hq, q0, b);
+          tma_load_4d(sdo + kTileBytes / 2, &tmdO, do_full, 64, hq, q0, b);
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       // ------------------------------------ MMA issuer ------------------------------------
       if (elect_one()) {
-        constexpr uint32_t idesc_st = make_idesc(1, 1, 128, 64, 0, 0);    // S^T, dP^T : [kv x d] . [q x d]^T
+        constexpr uint32_t idesc_st = make_idesc(1, 1, 128, 128, 0, 0);   // S^T, dP^T : [kv x d] . [q x d]^T
         constexpr uint32_t idesc_acc = make_idesc(1, 1, 128, 128, 0, 1);  // dV, dK    : [kv x q] . [q x d]   (B MN-major)
-        constexpr uint32_t idesc_dq = make_idesc(1, 1, 128, 64, 1, 1);    // dQ^T      : [kv x d]^T . [kv x q] (A, B MN-major)
+        constexpr uint32_t idesc_dq = make_idesc(1, 1, 128, 128, 1, 1);   // dQ^T      : [kv x d]^T . [kv x q] (A, B MN-major)
         constexpr uint32_t kHi = desc_hi(1024);
-        // descriptor low words (address >> 4 | LBO): K-major operands carry LBO 16 (unused), MN-major the atom stride
+        // descriptor low words (address >> 4 | LBO): K-major operands carry LBO 16 (unused), MN-major ones the stride
+        // between the two 64-element atoms of a 128-wide tile (= one 16 KB box)
         const uint32_t loK = desc_lo(smem_u32(smem + kOffK), 16), loV = desc_lo(smem_u32(smem + kOffV), 16);
         const uint32_t loKmn = desc_lo(smem_u32(smem + kOffK), 16384);
-        // Q / dO stage g: K-major descriptors (S^T, dP^T) and MN-major ones (dK, dV) differ only in the LBO field
-        const uint32_t loQ0 = desc_lo(smem_u32(smem + kOffQ), 16), lodO0 = desc_lo(smem_u32(smem + kOffdO), 16);
-        const uint32_t loQmn0 = desc_lo(smem_u32(smem + kOffQ), 8192), lodOmn0 = desc_lo(smem_u32(smem + kOffdO), 8192);
-        const uint32_t lodS0 = desc_lo(smem_u32(smem + kOffdS), 16);
-        int g_sdp = 0, ph_sdp = 0;   // stage / phase of the next S^T, dP^T issue
-        auto issue_sdp = [&]() {
-          mbar_wait(&qdo_full[g_sdp], ph_sdp);
-          tc_fence_after();
-          const uint32_t q_lo = loQ0 + g_sdp * (kQBytes / 16), do_lo = lodO0 + g_sdp * (kQBytes / 16);
-          if (++g_sdp == kStages) g_sdp = 0, ph_sdp ^= 1;
+        const uint32_t loQ0 = desc_lo(smem_u32(smem + kOffQ), 16), loQmn0 = desc_lo(smem_u32(smem + kOffQ), 16384);
+        const uint32_t lodO = desc_lo(smem_u32(smem + kOffdO), 16), lodOmn = desc_lo(smem_u32(smem + kOffdO), 16384);
+        const uint32_t lodS = desc_lo(smem_u32(smem + kOffdS), 16), lodSmn = desc_lo(smem_u32(smem + kOffdS), 16384);
+        const uint32_t tX = tmem_base + kColX, tY = tmem_base + kColY;
+        // [128 x 128] += A[128 x 128 (K-major, two 64-wide boxes)] . B[128 x 128 (K-major)]^T
+        auto mma_kk = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
           for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_ss<false, 1>(tmem_base + kColS, desc_join(loK + (dh * 16384 + ks * 32) / 16, kHi),
-                                desc_join(q_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
-#pragma unroll
-          for (int dh = 0; dh < 2; ++dh)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ss<false, 1>(tmem_base + kColdP, desc_join(loV + (dh * 16384 + ks * 32) / 16, kHi),
-                                desc_join(do_lo + (dh * 8192 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
-          umma_commit(sdp_full);
+              umma_ss<false, 1>(d, desc_join(a_lo + (dh * 16384 + ks * 32) / 16, kHi),
+                                desc_join(b_lo + (dh * 16384 + ks * 32) / 16, kHi), idesc_st, (dh | ks) != 0);
         };
         mbar_wait(kv_full, 0);
-        issue_sdp();
-        for (int s = 0, g = 0; s < n_steps; ++s) {
+        mbar_wait(&q_full[0], 0);
+        tc_fence_after();
+        mma_kk(tX, loK, loQ0);                       // S^T(0)
+        umma_commit(s_full);
+        mbar_wait(do_full, 0);
+        tc_fence_after();
+        mma_kk(tY, loV, lodO);                       // dP^T(0)
+        umma_commit(dp_full);
+        for (int s = 0; s < n_steps; ++s) {
           const int st = s & 1;
-          const uint32_t qmn_lo = loQmn0 + g * (kQBytes / 16), domn_lo = lodOmn0 + g * (kQBytes / 16);
-          const uint32_t ds_lo = lodS0 + st * (kPBytes / 16);
+          const uint32_t qmn_lo = loQmn0 + st * (kTileBytes / 16);
           LX_TR(tr_cta, s, 0);
-          if (s + 1 < n_steps) {
-            mbar_wait(sdp_empty, s & 1);   // S^T/dP^T(s) are in the workers' registers: the columns are free
-            issue_sdp();
-          }
+          mbar_wait(p_full, s & 1);                  // P^T(s) is in X
+          tc_fence_after();
           LX_TR(tr_cta, s, 1);
-          mbar_wait(&pds_full[st], (s >> 1) & 1);        // P^T(s) is in TMEM, dS^T(s) in smem
-          tc_fence_after();
-          LX_TR(tr_cta, s, 2);
-          // dV += P^T dO (A = P^T straight from TMEM) ; dK += dS^T Q        (K dim = q, 64 -> 4 steps of 16)
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ts_f16(tmem_base + kColdV, tmem_base + kColP + st * 32 + ks * 8, desc_join(domn_lo + ks * 128, kHi),
-                        idesc_acc, (s | ks) != 0);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss<false, 1>(tmem_base + kColdK, desc_join(ds_lo + ks * 2, kHi), desc_join(qmn_lo + ks * 128, kHi),
-                              idesc_acc, (s | ks) != 0);
-          // the drain warps hold dQ^T(s-1) in registers (dq_full(s-1) fired a whole [S^T,dP^T,dV,dK] ago)
-          mbar_wait(dq_empty, (s & 1) ^ 1);
-          tc_fence_after();
-          LX_TR(tr_cta, s, 3);
-          // dQ^T = K^T dS^T   (M = d, N = q, K dim = kv, 128 -> 8 steps of 16)
+          // dV += P^T dO   (A = P^T from TMEM: k-step ks covers queries 16 ks .. 16 ks + 15, written by worker group ks / 4)
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_ss<false, 1>(tmem_base + kColdQ, desc_join(loKmn + ks * 128, kHi),
-                              desc_join(ds_lo + ks * 128, kHi), idesc_dq, ks != 0);
+            umma_ts_f16(tmem_base + kColdV, tX + (ks >> 2) * 64 + (ks & 3) * 8, desc_join(lodOmn + ks * 128, kHi),
+                        idesc_acc, (s | ks) != 0);
+          umma_commit(do_empty);
+          if (s + 1 < n_steps) {
+            mbar_wait(&q_full[st ^ 1], ((s + 1) >> 1) & 1);
+            tc_fence_after();
+            mma_kk(tX, loK, loQ0 + (st ^ 1) * (kTileBytes / 16));   // S^T(s+1), in order behind dV(s)
+            umma_commit(s_full);
+          }
+          LX_TR(tr_cta, s, 2);
+          mbar_wait(ds_full, s & 1);                 // dS^T(s) is in smem, dP^T(s) has been read
+          tc_fence_after();
+          LX_TR(tr_cta, s, 3);
+          // dQ^T = K^T dS^T   (M = d, N = q, K dim = kv)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss<false, 1>(tY, desc_join(loKmn + ks * 128, kHi), desc_join(lodSmn + ks * 128, kHi), idesc_dq, ks != 0);
           umma_commit(dq_full);
-          umma_commit(&qdo_empty[g]);
-          umma_commit(&pds_empty[st]);
-          if (++g == kStages) g = 0;
+          // dK += dS^T Q      (K dim = q: boxes of 64 queries)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss<false, 1>(tmem_base + kColdK, desc_join(lodS + ((ks >> 2) * 16384 + (ks & 3) * 32) / 16, kHi),
+                              desc_join(qmn_lo + ks * 128, kHi), idesc_acc, (s | ks) != 0);
+          umma_commit(&q_empty[st]);
+          LX_TR(tr_cta, s, 4);
+          if (s + 1 < n_steps) {
+            mbar_wait(dq_empty, s & 1);              // the drain warps hold dQ^T(s) in registers
+            mbar_wait(do_full, (s + 1) & 1);
+            tc_fence_after();
+            mma_kk(tY, loV, lodO);                   // dP^T(s+1)
+            umma_commit(dp_full);
+          }
+          LX_TR(tr_cta, s, 5);
         }
         umma_commit(acc_done);
       }
       __syncwarp();
     }
   } else if (warp < 12) {
-    // ------------------------------------ workers: softmax-grad (thread = kv row, 32 query columns) ------------------
+    // ------------------------------------ workers: thread = kv row, 64 query columns ------------------------------------
     setmaxnreg_inc<kRegsWork>();
     const int wt = threadIdx.x - 128;           // 0..255
     const int grp = (warp - 4) >> 2;            // query-column half handled by this warp
@@ -593,109 +607,129 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_off = uint32_t(lq * 32) << 16;
     const int kv = kv0 + t;
     const uint32_t s_stat_u = smem_u32(s_stat);
+    const uint32_t tXw = tmem_base + kColX + grp * 64 + lane_off;
+    const uint32_t tYw = tmem_base + kColY + grp * 64 + lane_off;
+    const uint32_t sdS = smem_u32(smem + kOffdS) + grp * (kTileBytes / 2) + t * 128;
 
-    // lse for wt < 64 (scaled to log2 units when stored), delta (times the softmax scale) for 64 <= wt < 128, document start (int bits) for
-    // 128 <= wt < 192. Raw global loads only: nothing here may depend on the loaded value (it lands a step later).
-    auto load_stat = [&](int s) -> float {
-      if (wt >= 192 || s >= n_steps) return 0.f;
+    // stats of one step: lse (wt < 128; stored in log2 units), delta (wt >= 128; stored times the softmax scale) and,
+    // for packed documents, the document start of each query (loaded by wt < 128 as a second value).
+    // Raw global loads only: nothing may depend on the value before it is stored a step later.
+    auto load_stat = [&](int s, float& a, int& d) {
+      a = 0.f; d = 0;
+      if (s >= n_steps) return;
       const int hq = hk * G + s / steps_per_head;
-      const int qq = (i_start + s % steps_per_head) * kQ + (wt & 63);
+      const int qq = (i_start + s % steps_per_head) * kQ + (wt & 127);
       const int64_t idx = ((int64_t)b * p.Hq + hq) * p.S + qq;
-      if (wt < 64) return (qq < p.S) ? p.lse[idx] : INFINITY;
-      if (wt < 128) return (qq < p.S) ? p.delta[idx] : 0.f;
-      return __int_as_float((kDocs && qq < p.S) ? p.doc_start[(int64_t)b * p.S + qq] : 0);
+      if (wt < 128) {
+        a = (qq < p.S) ? p.lse[idx] : INFINITY;
+        if (kDocs) d = (qq < p.S) ? p.doc_start[(int64_t)b * p.S + qq] : 0;
+      } else {
+        a = (qq < p.S) ? p.delta[idx] : 0.f;
+      }
     };
-    auto store_stat = [&](int buf, float v) {
-      if (wt < 64) s_stat[buf * 3 * kQ + wt] = v * kLog2e;
-      else if (wt < 128) s_stat[buf * 3 * kQ + wt] = v * p.scale;
-      else if (wt < 192) s_stat[buf * 3 * kQ + wt] = v;
+    auto store_stat = [&](int buf, float a, int d) {
+      float* base = s_stat + buf * 3 * kQ;
+      if (wt < 128) {
+        base[wt] = a * kLog2e;
+        if (kDocs) base[2 * kQ + wt] = __int_as_float(d);
+      } else {
+        base[wt] = a * p.scale;                   // [kQ + (wt - 128)]
+      }
     };
 
-    float nxt = load_stat(0);
-    store_stat(0, nxt);
+    float nxt_a; int nxt_d;
+    load_stat(0, nxt_a, nxt_d);
+    store_stat(0, nxt_a, nxt_d);
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
       const int q0 = (i_start + s % steps_per_head) * kQ;
-      const uint32_t sdS = smem_u32(smem + kOffdS + st * kPBytes);
-      LX_TR(tr_cta, s, 4);
+      LX_TR(tr_cta, s, 6);
       named_bar_sync(1, kWorkers);               // stats of step s visible; all workers finished step s-1
-      LX_TR(tr_cta, s, 5);
-      nxt = load_stat(s + 1);                    // prefetch next step's lse / delta (global)
-      const uint32_t stat_u = s_stat_u + st * (3 * kQ * 4) + grp * 32 * 4;
+      load_stat(s + 1, nxt_a, nxt_d);            // prefetch next step's stats (global)
+      const uint32_t stat_u = s_stat_u + st * (3 * kQ * 4) + grp * 64 * 4;
       const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kQ - 1, p.S - 1)] : 0;
       const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0)) &&
                              (kv0 >= ds_tile);
-      mbar_wait(sdp_full, s & 1);
+      mbar_wait(s_full, s & 1);
       tc_fence_after();
-      LX_TR(tr_cta, s, 6);
+      LX_TR(tr_cta, s, 7);
+      uint32_t pr[32];                           // P^T of this row: 64 queries as bf16 pairs
       {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tmem_base + kColS + grp * 32 + lane_off, sv);
-        tmem_ld_32x32(tmem_base + kColdP + grp * 32 + lane_off, dv);
-        tmem_wait_ld_regs(sv);
-        tmem_wait_ld_regs(dv);
-        // S^T / dP^T are in registers: let the MMA warp overwrite the columns with step s+1 right away
-        tc_fence_before();
-        __syncwarp();
-        if (lane_id() == 0) mbar_arrive(sdp_empty);
-        LX_TR(tr_cta, s, 7);
-        uint32_t pr[16], dsr[16];
-        // The workers are issue-bound (two warps per scheduler): 5 instructions per element on fully visible tiles
-        // (FFMA, EX2, FFMA, FMUL, half a pack); the element test lives in a separate, uniformly branched copy.
+        uint32_t sv[2][32];
+        tmem_ld_32x32(tXw, sv[0]);
+        tmem_ld_32x32(tXw + 32, sv[1]);
+        tmem_wait_ld_regs(sv[0]);
+        tmem_wait_ld_regs(sv[1]);
+        LX_TR(tr_cta, s, 8);
         auto block = [&](auto masked_tag) {
           constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 l4 = lds_f4(stat_u + i * 4);                 // lse2 of 4 query columns
-            const float4 d4 = lds_f4(stat_u + kQ * 4 + i * 4);        // delta * scale
-            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-            int dst4[4] = {0, 0, 0, 0};
-            if (kDocs && kMasked) {
-              const float4 s4 = lds_f4(stat_u + 2 * kQ * 4 + i * 4);  // document start of each query column
-              dst4[0] = __float_as_int(s4.x); dst4[1] = __float_as_int(s4.y);
-              dst4[2] = __float_as_int(s4.z); dst4[3] = __float_as_int(s4.w);
-            }
-            float pv[4], dsv[4];
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float pe = ex2(fmaf(__uint_as_float(sv[i + e]), p.scale_log2, -ls[e]));
-              if (kMasked) {
-                const int qa = q0 + grp * 32 + i + e;
-                if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (!kDocs || kv >= dst4[e]))) pe = 0.f;
+            for (int i = 0; i < 32; i += 4) {
+              const float4 l4 = lds_f4(stat_u + (c * 32 + i) * 4);                 // lse2 of 4 query columns
+              const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+              int dst4[4] = {0, 0, 0, 0};
+              if (kDocs && kMasked) {
+                const float4 s4 = lds_f4(stat_u + 2 * kQ * 4 + (c * 32 + i) * 4);  // document start of each query column
+                dst4[0] = __float_as_int(s4.x); dst4[1] = __float_as_int(s4.y);
+                dst4[2] = __float_as_int(s4.z); dst4[3] = __float_as_int(s4.w);
               }
-              pv[e] = pe;
-              dsv[e] = pe * fmaf(__uint_as_float(dv[i + e]), p.scale, -dl[e]);
+              float pv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float pe = ex2(fmaf(__uint_as_float(sv[c][i + e]), p.scale_log2, -ls[e]));
+                if (kMasked) {
+                  const int qa = q0 + grp * 64 + c * 32 + i + e;
+                  if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (!kDocs || kv >= dst4[e]))) pe = 0.f;
+                }
+                pv[e] = pe;
+              }
+              pr[c * 16 + i / 2] = pack_bf16(pv[0], pv[1]);
+              pr[c * 16 + i / 2 + 1] = pack_bf16(pv[2], pv[3]);
             }
-            pr[i / 2] = pack_bf16(pv[0], pv[1]);
-            pr[i / 2 + 1] = pack_bf16(pv[2], pv[3]);
-            dsr[i / 2] = pack_bf16(dsv[0], dsv[1]);
-            dsr[i / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
-          }
         };
         if (full_tile) block(std::false_type{});
         else block(std::true_type{});
-        LX_TR(tr_cta, s, 16);
-        mbar_wait(&pds_empty[st], ((s >> 1) & 1) ^ 1);  // P^T/dS^T[st] no longer read by the MMAs of step s-2
-        tc_fence_after();
-        LX_TR(tr_cta, s, 17);
-        // P^T: bf16 pairs into this thread's TMEM lane, 16 columns = this warp's 32 query columns
-        tmem_st_32x16(tmem_base + kColP + st * 32 + grp * 16 + lane_off, pr);
-        // dS^T rows of 64 q values = 128 B = 8 chunks of 16 B, swizzled by (row & 7); this warp: chunks 4 grp .. 4 grp + 3
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const uint32_t off = t * 128 + (((grp * 4 + cc) ^ (t & 7)) << 4);
-          sts_v4(sdS + off, dsr[cc * 4], dsr[cc * 4 + 1], dsr[cc * 4 + 2], dsr[cc * 4 + 3]);
-        }
-        LX_TR(tr_cta, s, 18);
-        tmem_wait_st();
       }
-      LX_TR(tr_cta, s, 8);
+      // P^T -> the first 32 of the 64 X columns this warp has just read (no other warp touches them)
+      tmem_st_32x32(tXw, pr);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(p_full);
+      LX_TR(tr_cta, s, 9);
+
+      mbar_wait(dp_full, s & 1);                 // also: dQ^T(s-1), dK(s-1) have finished reading the dS^T tile
+      tc_fence_after();
+      LX_TR(tr_cta, s, 10);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t dv[32], dsr[16];
+        tmem_ld_32x32(tYw + c * 32, dv);
+        tmem_wait_ld_regs(dv);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 d4 = lds_f4(stat_u + kQ * 4 + (c * 32 + i) * 4);          // delta * scale
+          const uint32_t p01 = pr[c * 16 + i / 2], p23 = pr[c * 16 + i / 2 + 1];
+          const float ds0 = bf16_lo(p01) * fmaf(__uint_as_float(dv[i]), p.scale, -d4.x);
+          const float ds1 = bf16_hi(p01) * fmaf(__uint_as_float(dv[i + 1]), p.scale, -d4.y);
+          const float ds2 = bf16_lo(p23) * fmaf(__uint_as_float(dv[i + 2]), p.scale, -d4.z);
+          const float ds3 = bf16_hi(p23) * fmaf(__uint_as_float(dv[i + 3]), p.scale, -d4.w);
+          dsr[i / 2] = pack_bf16(ds0, ds1);
+          dsr[i / 2 + 1] = pack_bf16(ds2, ds3);
+        }
+        // box `grp` of the dS^T tile: row t = 128 B = 8 chunks of 16 B (8 queries), swizzled by (row & 7)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          sts_v4(sdS + (((c * 4 + cc) ^ (t & 7)) << 4), dsr[cc * 4], dsr[cc * 4 + 1], dsr[cc * 4 + 2], dsr[cc * 4 + 3]);
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&pds_full[st]);
-      LX_TR(tr_cta, s, 9);
-      store_stat(st ^ 1, nxt);                  // stats of step s+1 (buffer last read in step s-1)
+      if (lane_id() == 0) mbar_arrive(ds_full);
+      LX_TR(tr_cta, s, 11);
+      store_stat(st ^ 1, nxt_a, nxt_d);          // stats of step s+1 (buffer last read in step s-1)
     }
     // write dV (group 0) / dK (group 1); thread = kv row
     mbar_wait(acc_done, 0);
@@ -722,53 +756,43 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     tc_fence_before();
   } else {
-    // ------------------------------------ dQ drain (thread = head-dim element, all 64 query rows of the step) ----------
-    // TMEM dQ^T [d][q] -> fp32 smem tile [q][d] (a warp writes 128 contiguous bytes per q: conflict-free) -> one bulk
-    // reduce-add per step into dq_accum[b, hq, q0 : q0 + 64, :] (fp32 add performed at L2)
-    setmaxnreg_dec<kRegsDrain>();
+    // ------------------------------------ dQ drain (thread = head-dim element) ------------------------------------
+    // TMEM dQ^T [d][128 q] -> registers (Y is released at once) -> red.global.add into dq_accum[b, hq, q0 : q0 + 128, :]
+    setmaxnreg_inc<kRegsDrain>();
     const int lq = warp & 3;
     const int t = lq * 32 + lane_id();          // head-dim element == TMEM lane
     const uint32_t lane_off = uint32_t(lq * 32) << 16;
-    const bool leader = threadIdx.x == 384;
-    float* stage = reinterpret_cast<float*>(smem + kOffdQ);
     for (int s = 0; s < n_steps; ++s) {
       const int hq = hk * G + s / steps_per_head;
       const int q0 = (i_start + s % steps_per_head) * kQ;
-      LX_TR(tr_cta, s, 10);
+      LX_TR(tr_cta, s, 12);
       mbar_wait(dq_full, s & 1);
       tc_fence_after();
-      LX_TR(tr_cta, s, 11);
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_base + kColdQ + lane_off, v0);
-      tmem_ld_32x32(tmem_base + kColdQ + 32 + lane_off, v1);
-      tmem_wait_ld_regs(v0);
-      tmem_wait_ld_regs(v1);
+      LX_TR(tr_cta, s, 13);
+      uint32_t v[4][32];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tmem_ld_32x32(tmem_base + kColY + r * 32 + lane_off, v[r]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tmem_wait_ld_regs(v[r]);
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(dq_empty);
-      LX_TR(tr_cta, s, 12);
-      if (leader) tma_store_wait_read<0>();      // the previous bulk reduce has read the staging tile
-      named_bar_sync(2, 128);
-      LX_TR(tr_cta, s, 13);
-      if (t < kD) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) stage[i * kD + t] = __uint_as_float(v0[i]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) stage[(32 + i) * kD + t] = __uint_as_float(v1[i]);
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(2, 128);
-      if (leader) {
-        const int rows = min(kQ, p.S - q0);
-        if (rows > 0) {
-          float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0) * kD;
-          bulk_reduce_add_f32(dst, stage, (uint32_t)rows * kD * 4);
-        }
-        tma_store_commit();
-      }
       LX_TR(tr_cta, s, 14);
+      // fp32 adds performed at L2, straight from registers: a warp covers 32 consecutive head-dim elements of one
+      // query row per instruction (one 128-byte request). The kernel is shared-memory-bandwidth bound (MMA operand
+      // fetches, see tools/mma_bench.cu), so the former smem staging + cp.reduce.async.bulk cost 128 KB of smem
+      // traffic per step that this path does not.
+      if (t < kD) {
+        float* dst = p.dq_accum + (((int64_t)b * p.Hq + hq) * p.S + q0) * kD + t;
+        const int rows = min(kQ, p.S - q0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (r * 32 + i < rows) red_add_f32(dst + (r * 32 + i) * kD, __uint_as_float(v[r][i]));
+      }
+      LX_TR(tr_cta, s, 15);
     }
-    if (leader) tma_store_wait<0>();  // all bulk reductions issued by this thread have completed
   }
 
   tc_fence_before();
@@ -889,7 +913,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.D = D;
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
-  dim3 grid((unsigned)ceil_div(S, fwd::kTile), Hq, (unsigned)B);
+  dim3 grid(Hq, (unsigned)B, (unsigned)ceil_div(S, fwd::kTile));
   kern<<<grid, fwd::kThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   LX_CHECK_LAUNCH("attn_fwd");
   return 0;
@@ -950,7 +974,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
   p.doc_end = (const int32_t*)doc_end;
-  dim3 grid((unsigned)ceil_div(S, bwd::kKV), Hkv, (unsigned)B);
+  dim3 grid(Hkv, (unsigned)B, (unsigned)ceil_div(S, bwd::kKV));
   kern<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");
   {

@@ -394,6 +394,10 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // 16-byte global access helpers
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;

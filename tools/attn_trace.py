@@ -70,8 +70,8 @@ torch.cuda.synchronize()
 trace.zero_()
 ops.attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, P)
 torch.cuda.synchronize()
-show("backward (CTA kv-tile 0, kv head 0): worker warp 4, drain warp 12, mma thread",
-     [(4, "w:top"), (5, "w:bar"), (6, "w:sdp_full"), (7, "w:ld_done"), (16, "w:computed"), (17, "w:pds_emp"), (18, "w:st_iss"), (8, "w:sts_done"), (9, "w:arrived"),
-      (10, "d:top"), (11, "d:dq_full"), (12, "d:in_reg"), (13, "d:bar"), (14, "d:end"),
-      (0, "m:top"), (1, "m:sdp_iss"), (2, "m:pds_full"), (3, "m:dq_emp")],
-     40, 72)
+show("backward (CTA kv-tile 0, kv head 0): worker warp 4, drain warp 12, mma thread; step = 128 query rows",
+     [(6, "w:top"), (7, "w:s_full"), (8, "w:S_regs"), (9, "w:p_arr"), (10, "w:dp_full"), (11, "w:ds_arr"),
+      (12, "d:top"), (13, "d:dq_full"), (14, "d:in_reg"), (15, "d:end"),
+      (0, "m:top"), (1, "m:p_full"), (2, "m:dV,S"), (3, "m:ds_full"), (4, "m:dQ,dK"), (5, "m:dP")],
+     20, 44)
