@@ -121,12 +121,14 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
                     int64_t prefix_len, const void* doc_start, float scale, void* stream);
 /* dq/dk/dv bf16 with pitches lddq/lddk/lddv; dq_accum fp32 workspace [B,S,Hq,D] (zeroed by the call);
- * delta fp32 workspace [B,Hq,S]. */
+ * delta fp32 workspace [B,Hq,S]. rope_inverse: null, or the fp32 [>= S, D/2, 2] (cos, sin) table of K7: dq and dk then
+ * leave the call already rotated back through RoPE (the autograd of apply_rope, llama.py:63-73), which saves the
+ * separate in-place pass over the q|k gradient columns. */
 int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
                     int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
                     int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
-                    const void* doc_start, const void* doc_end, float scale, void* stream);
+                    const void* doc_start, const void* doc_end, float scale, const void* rope_inverse, void* stream);
 
 /* ---- K6 backward: LoRA weight gradients (autograd of modelling/lora.py:43) ------------------------
  *   out[p, r] (fp32) = alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx;  Ht = H^T bf16 [R, M] pitch ldht

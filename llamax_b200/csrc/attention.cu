@@ -271,11 +271,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (!ok) sv[c][i] = 0xff800000u;  // -inf
           }
       }
-      float mx = -INFINITY;
+      // four independent max chains (one per 32-column chunk): a single chain of 64 dependent FMNMX3 is ~300 cycles of
+      // pure latency for the one softmax warp a scheduler has
+      float mx4[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 4; ++c) {
+        mx4[c] = __uint_as_float(sv[c][0]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+        for (int i = 1; i < 32; ++i) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][i]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_tile = mx * p.scale_log2;
       float alpha = 1.f;
       if (m_tile > m_used + 8.f) {  // lazy rescale: only when the running max grows by more than 2^8
@@ -377,6 +382,7 @@ struct AttnBwdParams {
   float scale, scale_log2;
   const int32_t* doc_start;  // [B, S] or null (packed-sequence document-causal mask)
   const int32_t* doc_end;    // [B, S] last position of the document containing each position
+  const float* rope;         // null, or [>= S, D/2, 2] (cos, sin): dk (here) and dq (convert kernel) get the RoPE backward
 };
 
 namespace bwd {
@@ -742,6 +748,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (grp == 0 ? kColdV : kColdK) + lane_off + c * 32, v);
       tmem_wait_ld_regs(v);
+      if (row_ok && grp == 1 && p.rope != nullptr) {
+        // dK through the RoPE backward: (g0, g1) -> (g0 c + g1 s, g1 c - g0 s) per adjacent pair, position = kv row
+        const float4* cs = reinterpret_cast<const float4*>(p.rope + ((int64_t)kv * (kD / 2) + c * 16) * 2);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 t4 = cs[i / 4];   // (c0, s0, c1, s1)
+          const float g0 = __uint_as_float(v[i]), g1 = __uint_as_float(v[i + 1]);
+          const float g2 = __uint_as_float(v[i + 2]), g3 = __uint_as_float(v[i + 3]);
+          v[i] = __float_as_uint(g0 * t4.x + g1 * t4.y);
+          v[i + 1] = __float_as_uint(g1 * t4.x - g0 * t4.y);
+          v[i + 2] = __float_as_uint(g2 * t4.z + g3 * t4.w);
+          v[i + 3] = __float_as_uint(g3 * t4.z - g2 * t4.w);
+        }
+      }
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -830,7 +850,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t l
 // dq_accum fp32 [B, Hq, S, D] -> dq bf16 [B*S, Hq*D] (row pitch lddq); one thread = 8 head-dim elements
 template <int D>
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t lddq,
-                                       int64_t B, int S, int Hq) {
+                                       int64_t B, int S, int Hq, const float* __restrict__ rope) {
   const int64_t total = B * Hq * (int64_t)S * (D / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % (D / 8)) * 8;
@@ -840,8 +860,15 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloa
     const int h = (int)(r % Hq);
     const int64_t b = r / Hq;
     const float* src = acc + (((b * Hq + h) * S + s_) * D + c);
-    const float4 a = *reinterpret_cast<const float4*>(src);
-    const float4 b4 = *reinterpret_cast<const float4*>(src + 4);
+    float4 a = *reinterpret_cast<const float4*>(src);
+    float4 b4 = *reinterpret_cast<const float4*>(src + 4);
+    if (rope != nullptr) {  // RoPE backward on the fp32 sums (one rounding fewer than rotating the bf16 result)
+      const float4* cs = reinterpret_cast<const float4*>(rope + ((int64_t)s_ * (D / 2) + c / 2) * 2);
+      const float4 t0 = cs[0], t1 = cs[1];
+      a = make_float4(a.x * t0.x + a.y * t0.y, a.y * t0.x - a.x * t0.y, a.z * t0.z + a.w * t0.w, a.w * t0.z - a.z * t0.w);
+      b4 = make_float4(b4.x * t1.x + b4.y * t1.y, b4.y * t1.x - b4.x * t1.y, b4.z * t1.z + b4.w * t1.w,
+                       b4.w * t1.z - b4.z * t1.w);
+    }
     uint4 o4;
     o4.x = pack_bf16(a.x, a.y);
     o4.y = pack_bf16(a.z, a.w);
@@ -923,7 +950,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
                     int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
                     int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
-                    const void* doc_start, const void* doc_end, float scale, void* stream) {
+                    const void* doc_start, const void* doc_end, float scale, const void* rope_inverse, void* stream) {
   if ((doc_start == nullptr) != (doc_end == nullptr))
     return set_error(LLAMAX_ERR_ARG, "attn_bwd: doc_start and doc_end go together");
   if (!q || !k || !v || !o || !lse || !dout || !dq || !dk || !dv || !dq_accum || !delta)
@@ -974,6 +1001,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
   p.doc_end = (const int32_t*)doc_end;
+  p.rope = (const float*)rope_inverse;
   dim3 grid(Hkv, (unsigned)B, (unsigned)ceil_div(S, bwd::kKV));
   kern<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");
@@ -981,9 +1009,11 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
     const int64_t total = rows * (Hq * D / 8);
     const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
     if (D == 128)
-      attn_dq_convert_kernel<128><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq);
+      attn_dq_convert_kernel<128><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq,
+                                                             (const float*)rope_inverse);
     else
-      attn_dq_convert_kernel<64><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq);
+      attn_dq_convert_kernel<64><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq,
+                                                            (const float*)rope_inverse);
     LX_CHECK_LAUNCH("attn_bwd: dq convert");
   }
   return 0;

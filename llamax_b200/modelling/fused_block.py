@@ -288,8 +288,7 @@ class FusedDecoderBlock(torch.autograd.Function):
         dqkv = torch.empty(M, nq + 2 * nk + rqkv, device=dout.device, dtype=torch.bfloat16)
         ops.attn_bwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], o, lse, do,
                      dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len,
-                     doc_start=doc_start, doc_end=doc_end)
-        ops.rope_(dqkv, rope, B, S, Hq + Hkv, D, inverse=True)
+                     doc_start=doc_start, doc_end=doc_end, rope_inverse=rope)   # dq, dk come back un-rotated
         dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, h_qkv, cache=cache, key="wqkv")
         del dqkv
         dx, dw_an = ops.rmsnorm_bwd(dxn1, x2, w_an.detach(), rstd1, dx1, want_dw=want_dw_an)

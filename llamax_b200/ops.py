@@ -349,14 +349,18 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int,
 
 
 def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, scale=None, doc_start=None,
-             doc_end=None):
-    """Writes dq/dk/dv (row views like q/k/v)."""
+             doc_end=None, rope_inverse=None):
+    """Writes dq/dk/dv (row views like q/k/v). rope_inverse: fp32 [>= S, D/2, 2] table -> dq, dk come back already
+    rotated through the RoPE backward (no separate rope_(..., inverse=True) pass needed)."""
+    if rope_inverse is not None:
+        assert rope_inverse.dtype is torch.float32 and rope_inverse.is_contiguous()
+        assert rope_inverse.shape[0] >= S and rope_inverse.shape[1] == D // 2
     lib, st = _prep(q)
     dout = _rows(dout)
     dq_accum = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.float32)
     delta = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     scale = float(scale) if scale is not None else D ** -0.5
     _call(lib, "llamax_attn_bwd",
-          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len), _p(doc_start), _p(doc_end), scale, st,),
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len), _p(doc_start), _p(doc_end), scale, _p(rope_inverse), st,),
           "attn_bwd", 10.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return dq, dk, dv

@@ -130,3 +130,38 @@ def test_attention_head_dim_64(B, S, Hq, Hkv, P):
     assert rel_err(to4(dq.cpu(), Hq), dq_ref) <= 1e-2
     assert rel_err(to4(dk.cpu(), Hkv), dk_ref) <= 1e-2
     assert rel_err(to4(dv.cpu(), Hkv), dv_ref) <= 1e-2
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,P,Dh", [(2, 384, 8, 2, 100, 128), (1, 300, 4, 2, 0, 64)])
+def test_attention_bwd_fused_rope_backward(B, S, Hq, Hkv, P, Dh):
+    """attn_bwd(rope_inverse=table) == attn_bwd followed by the in-place inverse RoPE pass on the q|k gradients
+    (autograd of apply_rope, llama.py:63-73). The fused path rotates the fp32 sums, so it differs from the two-pass
+    result only by bf16 rounding; both are checked against the fp64 rotation of the oracle gradients."""
+    torch.manual_seed(5 + S)
+    nq, nk = Hq * Dh, Hkv * Dh
+    qkv = torch.randn(B * S, nq + 2 * nk).bfloat16()
+    dout = torch.randn(B * S, nq).bfloat16()
+    rope = R.build_rope(Dh, 512, 500000.0, True)[:S].contiguous()
+    to4 = lambda t, H: t.reshape(B, S, H, Dh).transpose(1, 2)
+    _, dq_ref, dk_ref, dv_ref = R.attention_ref_grads(to4(qkv[:, :nq], Hq), to4(qkv[:, nq:nq + nk], Hkv),
+                                                      to4(qkv[:, nq + nk:], Hkv), to4(dout, Hq), P)
+
+    def unrotate(g):  # [B,H,S,D] fp64 -> RoPE backward
+        g = g.double()
+        c, s = rope[:, :, 0].double(), rope[:, :, 1].double()  # [S, D/2]
+        g0, g1 = g[..., 0::2], g[..., 1::2]
+        return torch.stack((g0 * c + g1 * s, g1 * c - g0 * s), -1).flatten(-2)
+
+    g = qkv.cuda()
+    qc, kc, vc = g[:, :nq], g[:, nq:nq + nk], g[:, nq + nk:]
+    o, lse = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, Dh, P)
+    fused = torch.zeros_like(g)
+    ops.attn_bwd(qc, kc, vc, o, lse, dout.cuda(), fused[:, :nq], fused[:, nq:nq + nk], fused[:, nq + nk:], B, S, Hq, Hkv,
+                 Dh, P, rope_inverse=rope.cuda())
+    two = torch.zeros_like(g)
+    ops.attn_bwd(qc, kc, vc, o, lse, dout.cuda(), two[:, :nq], two[:, nq:nq + nk], two[:, nq + nk:], B, S, Hq, Hkv, Dh, P)
+    ops.rope_(two, rope.cuda(), B, S, Hq + Hkv, Dh, inverse=True)
+    assert torch.equal(fused[:, nq + nk:], two[:, nq + nk:])                     # dv untouched
+    assert rel_err(fused[:, :nq + nk].float().cpu(), two[:, :nq + nk].float().cpu()) <= 1e-2
+    assert rel_err(to4(fused[:, :nq].cpu(), Hq), unrotate(dq_ref)) <= 1e-2
+    assert rel_err(to4(fused[:, nq:nq + nk].cpu(), Hkv), unrotate(dk_ref)) <= 1e-2

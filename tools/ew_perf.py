@@ -1,0 +1,61 @@
+"""Isolated timing of the HBM-bound passes at the bench shapes (M = 16384 tokens, 8B dims): achieved GB/s against the
+algorithmic bytes of each pass. CUDA events, best of 7 after 2 warm-ups."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from llamax_b200 import ops
+
+torch.manual_seed(0)
+M, D, F, Hq, Hkv, hd, B, S = 16384, 4096, 14336, 32, 8, 128, 8, 2048
+dev = "cuda"
+
+
+def timeit(fn, n=7):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts)
+
+
+def report(name, ms, nbytes):
+    print(f"  {name:34s} {ms * 1e3:8.1f} us  {nbytes / ms / 1e6:7.0f} GB/s", flush=True)
+
+
+x = torch.randn(M, D, device=dev).bfloat16()
+dy = torch.randn(M, D, device=dev).bfloat16()
+res = torch.randn(M, D, device=dev).bfloat16()
+w = torch.ones(D, device=dev).bfloat16()
+xn, rstd, _, _ = ops.rmsnorm_fwd(x, w, 1e-5, quant=False)
+report("rmsnorm_fwd", timeit(lambda: ops.rmsnorm_fwd(x, w, 1e-5, quant=False)), 4.0 * M * D)
+report("rmsnorm_fwd + quant", timeit(lambda: ops.rmsnorm_fwd(x, w, 1e-5, quant=True)), 5.0 * M * D)
+report("rmsnorm_bwd (+resid, +dw)", timeit(lambda: ops.rmsnorm_bwd(dy, x, w, rstd, res, want_dw=True)), 8.0 * M * D)
+report("rowquant_int8", timeit(lambda: ops.rowquant_int8(x)), 3.0 * M * D)
+ab = torch.randn(M, 2 * F, device=dev).bfloat16()
+report("swiglu_fwd + quant + g", timeit(lambda: ops.swiglu_fwd(ab[:, :F], ab[:, F:], quant=True, want_g=True)), 7.0 * M * F)
+report("swiglu_fwd + quant", timeit(lambda: ops.swiglu_fwd(ab[:, :F], ab[:, F:], quant=True, want_g=False)), 5.0 * M * F)
+dg = torch.randn(M, F, device=dev).bfloat16()
+dab = torch.empty(M, 2 * F + 16, device=dev).bfloat16()
+report("swiglu_bwd (+g)", timeit(lambda: ops.swiglu_bwd(dg, ab[:, :F], ab[:, F:], want_g=True, out_ab=dab)), 12.0 * M * F)
+del dg, dab
+qkv = torch.randn(M, (Hq + 2 * Hkv) * hd, device=dev).bfloat16()
+from oracle import ref_ops as R  # rope table only (host-side constant)
+rope = R.build_rope(hd, 4096, 500000.0, True)[:S].to(dev)
+report("rope (q|k in place)", timeit(lambda: ops.rope_(qkv, rope, B, S, Hq + Hkv, hd)), 4.0 * M * (Hq + Hkv) * hd)
+h = torch.randn(M, 8, device=dev).bfloat16()
+report("lora_wgrad [M,F]^T [M,8]", timeit(lambda: ops.lora_wgrad(ab[:, :F], h, 1.0)), 2.0 * M * (F + 8))
+report("lora_wgrad [M,D]^T [M,8]", timeit(lambda: ops.lora_wgrad(x, h, 1.0)), 2.0 * M * (D + 8))
+a8 = torch.randn(8, D, device=dev).bfloat16()
+report("lora_down x[M,D] @ A^T[8,D]", timeit(lambda: ops.bf16_gemm(x, a8)), 2.0 * M * (D + 8))
+a8f = torch.randn(8, F, device=dev).bfloat16()
+g = ab[:, :F]
+report("lora_down g[M,F] @ A^T[8,F]", timeit(lambda: ops.bf16_gemm(g, a8f)), 2.0 * M * (F + 8))
+o = torch.randn(M, Hq * hd, device=dev).bfloat16()
+do = torch.randn(M, Hq * hd, device=dev).bfloat16()
+print("ok")
