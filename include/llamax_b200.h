@@ -137,6 +137,15 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
 int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, void* out, int64_t M, int64_t P,
                       int32_t R, float alpha, void* stream);
 
+/* Fused pair for one LoRA linear's backward (autograd of modelling/lora.py:43), ONE pass over dY [M,N] (pitch lddy):
+ *   dh [M,R] bf16 (pitch lddh) = dY . Bt^T            Bt = lora_scale * B^T, bf16 [R,N] pitch ldbt
+ *   dB [N,R] fp32 (zeroed by the call) = alpha * dY^T . h       Ht = h^T, bf16 [R,M] pitch ldht
+ * rank in {8,16,24,32}. dh_accum: fp32 workspace [M,R] (used when the column range is split across CTAs). */
+int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t ldbt, const void* Ht, int64_t ldht,
+                         void* dh, int64_t lddh, void* dh_accum, void* dB, int64_t M, int64_t N, int32_t R,
+                         float alpha, void* stream);
+
+
 /* ---- K12 (next row): cross-entropy over bf16 logits, forward + backward in place -------------------
  * F.cross_entropy(logits.float(), labels) (modelling/llama.py:216-218, audio.py:74-76), ignore_index = -100:
  *   loss_sum[0] += sum_rows (logsumexp(f32(logits[m,:])) - logits[m, label]);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "llamax_attn_bwd": [P, I64, P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, P, I64, P, P,
                         I64, I64, I32, I32, I32, I64, P, P, c_float, P, P],
     "llamax_lora_wgrad": [P, I64, P, I64, P, I64, I64, I32, c_float, P],
+    "llamax_lora_bwd_pair": [P, I64, P, I64, P, I64, P, I64, P, P, I64, I64, I32, c_float, P],
     "llamax_cross_entropy": [P, I64, P, P, P, I64, I64, c_int, P],
 }
 

@@ -398,6 +398,11 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// four consecutive fp32 adds as ONE L2 reduction (16-byte aligned address)
+__device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // 16-byte global access helpers
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;

@@ -653,6 +653,208 @@ static int launch_skinny(const void* A, int64_t lda, const void* B, int64_t ldb,
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused LoRA backward pair for one linear: ONE pass over dY [tokens, N] yields both
+//   dh [tokens, R] = dY . Bt^T          (Bt = scale * B^T, [R, N];  contraction over N)
+//   dB [N, R]     += alpha * dY^T . h   (Ht = h^T, [R, tokens];     contraction over tokens)
+// dY is the big operand (0.94 GB for the w1|w3 group at 16 k tokens); read separately by the skinny dh GEMM and by
+// lora_wgrad it was streamed from HBM twice. Here a CTA owns 128 tokens x a range of N and streams [128 x 128] tiles:
+// the tile is the K-major A operand of the dh MMA and, viewed MN-major, the A operand of the dB MMA (M = 128 columns
+// of N, K = the 128 tokens). dh accumulates in TMEM over the whole range; each tile's dB block [128 x R] is drained
+// from a double-buffered TMEM accumulator and reduced into dB with fp32 red.add. grid = (token blocks, N splits).
+// ------------------------------------------------------------------------------------------------
+namespace lp {
+constexpr int kStages = 5;
+constexpr int kABytes = 128 * 128 * 2;   // [128 tokens] x [128 columns] bf16 = two boxes of [128 x 128 B]
+constexpr int kBBytes = 32 * 128 * 2;    // [32 rank rows] x [128 columns]   = two boxes of [32 x 128 B]
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kHtBytes = 32 * 128 * 2;   // [32 rank rows] x [128 tokens]
+constexpr int kOffHt = kStages * kStageBytes;
+constexpr int kOffBar = kOffHt + kHtBytes;
+constexpr int kNumBars = 2 * kStages + 1 + 4 + 1;   // full/empty ring, ht_full, d2 full/empty[2], d1_done
+constexpr int kSmem = kOffBar + kNumBars * 8 + 16 + 1024;
+}  // namespace lp
+
+__global__ void __launch_bounds__(192, 1)
+lora_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmBt,
+                     const __grid_constant__ CUtensorMap tmHt, __nv_bfloat16* __restrict__ dh, int64_t lddh,
+                     float* __restrict__ dh_accum, float* __restrict__ dB, int M, int N, int R, int chunks_per_split,
+                     float alpha) {
+  using namespace lp;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* ht_full = empty_bar + kStages;
+  uint64_t* d2_full = ht_full + 1;
+  uint64_t* d2_empty = d2_full + 2;
+  uint64_t* d1_done = d2_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d1_done + 1);
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 128;
+  const int total_chunks = (N + 127) / 128;
+  const int c_begin = blockIdx.y * chunks_per_split;
+  const int num_c = min(chunks_per_split, total_chunks - c_begin);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmBt);
+    tma_prefetch_desc(&tmHt);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(ht_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d2_full[i], 1);
+      mbar_init(&d2_empty[i], 4);
+    }
+    mbar_init(d1_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_slot, 128);   // dh: columns 0..31; dB blocks: 32..63 and 64..95
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(ht_full, kHtBytes);
+      tma_load_2d(smem + kOffHt, &tmHt, ht_full, m0, 0);
+      tma_load_2d(smem + kOffHt + kHtBytes / 2, &tmHt, ht_full, m0 + 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < num_c; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStageBytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        const int n0 = (c_begin + c) * 128;
+        tma_load_2d(sa, &tmY, &full_bar[stage], n0, m0);
+        tma_load_2d(sa + kABytes / 2, &tmY, &full_bar[stage], n0 + 64, m0);
+        tma_load_2d(sa + kABytes, &tmBt, &full_bar[stage], n0, 0);
+        tma_load_2d(sa + kABytes + kBBytes / 2, &tmBt, &full_bar[stage], n0 + 64, 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_dh = make_idesc(1, 1, 128, 32, 0, 0);  // [tokens x n] . [r x n]^T
+      constexpr uint32_t idesc_db = make_idesc(1, 1, 128, 32, 1, 0);  // [tokens x n]^T (MN-major) . [r x tokens]^T
+      constexpr uint32_t kHi = desc_hi(1024);
+      const uint32_t loHt = desc_lo(smem_u32(smem + kOffHt), 16);
+      mbar_wait(ht_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < num_c; ++c) {
+        const int b = c & 1;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+        const uint32_t la = desc_lo(sa, 16), lamn = desc_lo(sa, 16384), lb = desc_lo(sa + kABytes, 16);
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss<false, 1>(tmem_base, desc_join(la + (bx * 16384 + ks * 32) / 16, kHi),
+                              desc_join(lb + (bx * 4096 + ks * 32) / 16, kHi), idesc_dh, (c | bx | ks) != 0);
+        mbar_wait(&d2_empty[b], ((c >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // 16 tokens per step
+          umma_ss<false, 1>(tmem_base + 32 + b * 32, desc_join(lamn + ks * 128, kHi),
+                            desc_join(loHt + ((ks >> 2) * 4096 + (ks & 3) * 32) / 16, kHi), idesc_db, ks != 0);
+        umma_commit(&d2_full[b]);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(d1_done);
+    }
+    __syncwarp();
+  } else {
+    // epilogue warps 2..5: TMEM lanes 32 * (warp % 4)
+    const int lq = warp & 3;
+    const int lrow = lq * 32 + lane_id();
+    const uint32_t lane_off = uint32_t(lq * 32) << 16;
+    for (int c = 0; c < num_c; ++c) {
+      const int b = c & 1;
+      mbar_wait(&d2_full[b], (c >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + 32 + b * 32 + lane_off, v);
+      tmem_wait_ld_regs(v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&d2_empty[b]);
+      const int n = (c_begin + c) * 128 + lrow;
+      if (n < N) {
+        float* dst = dB + (int64_t)n * R;   // R is a multiple of 8: rows are 32-byte aligned
+#pragma unroll
+        for (int r = 0; r < 32; r += 4)
+          if (r < R)
+            red_add_v4_f32(dst + r, alpha * __uint_as_float(v[r]), alpha * __uint_as_float(v[r + 1]),
+                           alpha * __uint_as_float(v[r + 2]), alpha * __uint_as_float(v[r + 3]));
+      }
+    }
+    if (num_c > 0) {
+      mbar_wait(d1_done, 0);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + lane_off, v);
+      tmem_wait_ld_regs(v);
+      const int row = m0 + lrow;
+      if (row < M) {
+        if (dh_accum != nullptr) {   // N is split across CTAs: fp32 partial sums, converted by lora_dh_convert_kernel
+#pragma unroll
+          for (int r = 0; r < 32; r += 4)
+            if (r < R)
+              red_add_v4_f32(dh_accum + (int64_t)row * R + r, __uint_as_float(v[r]), __uint_as_float(v[r + 1]),
+                             __uint_as_float(v[r + 2]), __uint_as_float(v[r + 3]));
+        } else {
+          __nv_bfloat16* dst = dh + (int64_t)row * lddh;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < R) {
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+              o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              stg_v4(dst + j, o);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, 128);
+}
+
+// fp32 [M, R] partial sums -> bf16 dh rows (pitch lddh); one thread per 8 values
+__global__ void lora_dh_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dh, int64_t lddh,
+                                       int64_t M, int R) {
+  const int per_row = R / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * per_row) return;
+  const int64_t row = i / per_row;
+  const int j = (int)(i - row * per_row) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(acc + row * R + j);
+  const float4 b = *reinterpret_cast<const float4*>(acc + row * R + j + 4);
+  uint4 o;
+  o.x = pack_bf16(a.x, a.y);
+  o.y = pack_bf16(a.z, a.w);
+  o.z = pack_bf16(b.x, b.y);
+  o.w = pack_bf16(b.z, b.w);
+  stg_v4(dh + row * lddh + j, o);
+}
+
 static int g_gemm_cg = 2;  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group
 
 }  // namespace lx
@@ -751,6 +953,56 @@ int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, 
   dim3 grid(p_tiles, splits);
   lora_wgrad_tc_kernel<<<grid, 192, wg::kSmem, st>>>(tmX, tmHt, (float*)out, (int)P, R, (int)M, k_per_split, alpha);
   LX_CHECK_LAUNCH("lora_wgrad");
+  return 0;
+}
+
+int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t ldbt, const void* Ht, int64_t ldht,
+                         void* dh, int64_t lddh, void* dh_accum, void* dB, int64_t M, int64_t N, int32_t R,
+                         float alpha, void* stream) {
+  if (!dY || !Bt || !Ht || !dh || !dh_accum || !dB) return set_error(LLAMAX_ERR_ARG, "lora_bwd_pair: null pointer");
+  if (R < 8 || R > 32 || R % 8) return set_error(LLAMAX_ERR_ARG, "lora_bwd_pair: rank must be 8, 16, 24 or 32");
+  if (M <= 0 || N <= 0) return set_error(LLAMAX_ERR_ARG, "lora_bwd_pair: empty problem");
+  if (lddy % 8 || ldbt % 8 || ldht % 8 || lddh % 8 || (reinterpret_cast<uintptr_t>(dY) % 16) ||
+      (reinterpret_cast<uintptr_t>(Bt) % 16) || (reinterpret_cast<uintptr_t>(Ht) % 16) ||
+      (reinterpret_cast<uintptr_t>(dh) % 16))
+    return set_error(LLAMAX_ERR_ARG, "lora_bwd_pair: operands must be 16-byte aligned with pitches multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m_blocks = (int)((M + 127) / 128);
+  const int total_chunks = (int)((N + 127) / 128);
+  // enough CTAs for ~2.5 waves; a split streams at least 8 tiles
+  int splits = std::max(1, std::min(total_chunks / 8, (5 * sm_count() / 2 + m_blocks - 1) / m_blocks));
+  int chunks_per_split = (total_chunks + splits - 1) / splits;
+  splits = (total_chunks + chunks_per_split - 1) / chunks_per_split;
+  cudaError_t e = cudaMemsetAsync(dB, 0, (size_t)N * R * sizeof(float), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "lora_bwd_pair: memset");
+  if (splits > 1) {
+    e = cudaMemsetAsync(dh_accum, 0, (size_t)M * R * sizeof(float), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "lora_bwd_pair: memset");
+  }
+  CUtensorMap tmY, tmBt, tmHt;
+  int rc = make_tmap_2d(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dY, N, M, lddy, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmBt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Bt, N, R, ldbt, 64, 32);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmHt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Ht, M, R, ldht, 64, 32);
+  if (rc) return rc;
+  static thread_local bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(lora_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lp::kSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "lora_bwd_pair: cudaFuncSetAttribute");
+    configured = true;
+  }
+  dim3 grid(m_blocks, splits);
+  lora_bwd_pair_kernel<<<grid, 192, lp::kSmem, st>>>(tmY, tmBt, tmHt, (__nv_bfloat16*)dh, lddh,
+                                                     splits > 1 ? (float*)dh_accum : nullptr, (float*)dB, (int)M, (int)N,
+                                                     R, chunks_per_split, alpha);
+  LX_CHECK_LAUNCH("lora_bwd_pair");
+  if (splits > 1) {
+    const int64_t n = M * (R / 8);
+    lora_dh_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)dh_accum, (__nv_bfloat16*)dh, lddh,
+                                                                        M, R);
+    LX_CHECK_LAUNCH("lora_bwd_pair: convert");
+  }
   return 0;
 }
 

@@ -46,6 +46,16 @@ def _get_scratch(device, numel: int) -> Tensor:
 # (checked at the first backward, i.e. at peak activation memory); "1": always; "0": never (shared scratch).
 _CACHE_MODE = os.environ.get("LLAMAX_WEIGHT_CACHE", "auto")
 _CACHE_HEADROOM = 24 << 30
+# A/B switch (benchmarking only): "0" restores the two-pass LoRA backward (skinny dh GEMM + lora_wgrad per linear)
+_LORA_PAIR = os.environ.get("LLAMAX_LORA_PAIR", "1") != "0"
+
+
+def _lora_dh_dB(dy: Tensor, bt: Tensor, h: Tensor, out_dh: Tensor, scale: float) -> Tensor:
+    """out_dh = dy @ bt^T (bt already carries the LoRA scale), returns dB = scale * dy^T h (fp32)."""
+    if _LORA_PAIR:
+        return ops.lora_bwd_pair(dy, bt, h, out_dh, scale)
+    ops.bf16_gemm(dy, bt, out=out_dh)
+    return ops.lora_wgrad(dy, h, scale)
 
 
 def set_weight_cache(mode: str) -> None:
@@ -138,12 +148,11 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Te
             ops.dequant_weight(s.w8, s.ws, transpose=True, apply_scale=True, out=wt[:, n_off : n_off + s.N])
         if s.R > 0:
             c0 = n_total + r_off
-            # dh_i = scale * dy_i @ B_i    -> columns [c0, c0+R) of dy_cat
+            # one pass over dy_i:  dh_i = scale * dy_i @ B_i -> columns [c0, c0+R) of dy_cat;  dB = scale * dy_i^T h_i
             bt = (s.lora_b.detach().t() * s.lora_scale).contiguous()
-            ops.bf16_gemm(dy_i, bt, out=dy_cat[:, c0 : c0 + s.R])
             wt[:, c0 : c0 + s.R].copy_(s.lora_a.detach().t())
             h_i = h_cat[:, r_off : r_off + s.R]
-            dB = ops.lora_wgrad(dy_i, h_i, s.lora_scale)  # [N, R] fp32
+            dB = _lora_dh_dB(dy_i, bt, h_i, dy_cat[:, c0 : c0 + s.R], s.lora_scale)  # [N, R] fp32
             lora_grads.append([None, dB.to(s.lora_b.dtype)])
             r_off += s.R
         else:
@@ -173,10 +182,10 @@ def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, h: Tensor | Non
     wt = _single_operand(spec, dy.device, cache, key)
     if spec.R > 0:
         bt = (spec.lora_b.detach().t() * spec.lora_scale).contiguous()
-        dh = ops.bf16_gemm(dy, bt)                                     # [M, R]
+        dh = torch.empty(dy.shape[0], spec.R, device=dy.device, dtype=torch.bfloat16)
+        dB = _lora_dh_dB(dy, bt, h, dh, spec.lora_scale).to(spec.lora_b.dtype)   # dh [M, R] and dB in one pass
         at = spec.lora_a.detach().t().contiguous()                     # [K, R]
         dx = ops.bf16_gemm(dy, wt, lora_h=dh, lora_b=at, lora_scale=1.0)
-        dB = ops.lora_wgrad(dy, h, spec.lora_scale).to(spec.lora_b.dtype)
         dA = ops.lora_wgrad(x_in, dh, 1.0).t().to(spec.lora_a.dtype).contiguous()
         return dx, (dA, dB)
     return ops.bf16_gemm(dy, wt), None
@@ -261,9 +270,10 @@ class FusedDecoderBlock(torch.autograd.Function):
         wt2 = _single_operand(s2, dout.device, cache, "w2")
         g2 = None
         if s2.R > 0:
-            dh2 = ops.bf16_gemm(dout2, (s2.lora_b.detach().t() * s2.lora_scale).contiguous())
+            dh2 = torch.empty(M, s2.R, device=dout.device, dtype=torch.bfloat16)
+            dB2 = _lora_dh_dB(dout2, (s2.lora_b.detach().t() * s2.lora_scale).contiguous(), h_2, dh2,
+                              s2.lora_scale).to(s2.lora_b.dtype)
             dg = ops.bf16_gemm(dout2, wt2, lora_h=dh2, lora_b=s2.lora_a.detach().t().contiguous(), lora_scale=1.0)
-            dB2 = ops.lora_wgrad(dout2, h_2, s2.lora_scale).to(s2.lora_b.dtype)
         else:
             dg = ops.bf16_gemm(dout2, wt2)
         _, _, g = ops.swiglu_bwd(dg, ab[:, :F_], ab[:, F_:], want_g=s2.R > 0, out_ab=dab)

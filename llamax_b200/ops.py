@@ -300,6 +300,26 @@ def lora_wgrad(X: Tensor, H: Tensor, alpha: float = 1.0) -> Tensor:
     return out
 
 
+def lora_bwd_pair(dY: Tensor, Bt: Tensor, H: Tensor, out_dh: Tensor, alpha: float = 1.0) -> Tensor:
+    """One pass over dY [M,N]: writes out_dh [M,R] = dY @ Bt^T (Bt = scale * B^T, [R,N]) and returns
+    dB [N,R] (fp32) = alpha * dY^T @ H. Replaces a skinny dh GEMM + lora_wgrad that each streamed dY from HBM."""
+    lib, st = _prep(dY)
+    assert dY.dtype is torch.bfloat16 and Bt.dtype is torch.bfloat16 and H.dtype is torch.bfloat16
+    assert dY.stride(1) == 1 and Bt.is_contiguous() and out_dh.stride(1) == 1 and out_dh.dtype is torch.bfloat16
+    M, N = dY.shape
+    R = H.shape[1]
+    assert Bt.shape == (R, N) and out_dh.shape == (M, R)
+    Mp = (M + 7) // 8 * 8
+    Ht = torch.zeros(R, Mp, device=dY.device, dtype=torch.bfloat16) if Mp != M else torch.empty(R, M, device=dY.device, dtype=torch.bfloat16)
+    Ht[:, :M].copy_(H.t())
+    dB = torch.empty(N, R, device=dY.device, dtype=torch.float32)
+    acc = torch.empty(M, R, device=dY.device, dtype=torch.float32)
+    _call(lib, "llamax_lora_bwd_pair",
+          (_p(dY), dY.stride(0), _p(Bt), Bt.stride(0), _p(Ht), Ht.stride(0), _p(out_dh), out_dh.stride(0), _p(acc), _p(dB), M, N, R, float(alpha), st),
+          "lora_wgrad", 4.0 * M * N * R, 2.0 * M * (N + 2 * R))
+    return dB
+
+
 def cross_entropy_(logits: Tensor, labels: Tensor, loss_sum: Tensor, inv_n: Tensor | None, write_grad: bool):
     """In place: accumulates sum of per-row CE into loss_sum (fp32 scalar tensor); if write_grad, overwrites logits
     with (softmax - onehot) * inv_n (rows with label -100 -> 0)."""

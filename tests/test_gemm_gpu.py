@@ -129,3 +129,20 @@ def test_bad_arguments_raise():
         ops.int8_gemm_s32(A, W)
     with pytest.raises(LlamaxError):
         ops.rowquant_int8(torch.zeros(4, 16, dtype=torch.bfloat16))  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("M,N,R", [(300, 264, 8), (1024, 4096, 16), (2048, 14336, 8), (129, 128, 24), (640, 1024, 32)])
+def test_lora_bwd_pair_matches_separate_products(M, N, R):
+    """Fused one-pass LoRA backward (dh = dY Bt^T and dB = alpha dY^T h) vs the fp32 products (autograd of
+    modelling/lora.py:43); covers the split-N path (fp32 dh partials) and ragged token / column tails."""
+    torch.manual_seed(M + N + R)
+    dy = torch.randn(M, N + 16, device="cuda").bfloat16()[:, :N]            # pitched view
+    bt = (torch.randn(R, N, device="cuda") * 0.1).bfloat16()
+    h = torch.randn(M, R + 8, device="cuda").bfloat16()[:, :R]
+    out = torch.zeros(M, R + 8, device="cuda", dtype=torch.bfloat16)
+    dB = ops.lora_bwd_pair(dy, bt, h, out[:, :R], 0.5)
+    dh_ref = dy.float() @ bt.float().t()
+    dB_ref = 0.5 * (dy.float().t() @ h.float())
+    assert rel_err(out[:, :R].float(), dh_ref) <= 1e-2
+    assert rel_err(dB, dB_ref) <= 1e-2
+    assert torch.count_nonzero(out[:, R:]) == 0                               # nothing written past the rank columns

@@ -56,6 +56,24 @@ report("lora_down x[M,D] @ A^T[8,D]", timeit(lambda: ops.bf16_gemm(x, a8)), 2.0 
 a8f = torch.randn(8, F, device=dev).bfloat16()
 g = ab[:, :F]
 report("lora_down g[M,F] @ A^T[8,F]", timeit(lambda: ops.bf16_gemm(g, a8f)), 2.0 * M * (F + 8))
+bt = torch.randn(8, F, device=dev).bfloat16()
+dh = torch.empty(M, 8, device=dev).bfloat16()
+report("lora_bwd_pair dY[M,F] (dh + dB)", timeit(lambda: ops.lora_bwd_pair(g, bt, h, dh, 1.0)), 2.0 * M * (F + 16))
+bt16 = torch.randn(16, 2 * F, device=dev).bfloat16()
+h16 = torch.randn(M, 16, device=dev).bfloat16()
+dh16 = torch.empty(M, 16, device=dev).bfloat16()
+report("lora_bwd_pair dY[M,2F] r16", timeit(lambda: ops.lora_bwd_pair(ab, bt16, h16, dh16, 1.0)), 2.0 * M * (2 * F + 32))
+btd = torch.randn(8, D, device=dev).bfloat16()
+report("lora_bwd_pair dY[M,D]", timeit(lambda: ops.lora_bwd_pair(x, btd, h, dh, 1.0)), 2.0 * M * (D + 16))
 o = torch.randn(M, Hq * hd, device=dev).bfloat16()
-do = torch.randn(M, Hq * hd, device=dev).bfloat16()
+dbt = torch.randn(8, F, device=dev).bfloat16()
+dh = torch.empty(M, 8, device=dev).bfloat16()
+report("lora_bwd_pair dY[M,F] (dh + dB)", timeit(lambda: ops.lora_bwd_pair(g, bt, h, dh, 1.0)), 2.0 * M * (F + 16))
+bt16 = torch.randn(16, 2 * F, device=dev).bfloat16()
+h16 = torch.randn(M, 16, device=dev).bfloat16()
+dh16 = torch.empty(M, 16, device=dev).bfloat16()
+report("lora_bwd_pair dY[M,2F] r16", timeit(lambda: ops.lora_bwd_pair(ab, bt16, h16, dh16, 1.0)), 2.0 * M * (2 * F + 32))
+btd = torch.randn(8, D, device=dev).bfloat16()
+report("lora_bwd_pair dY[M,D]", timeit(lambda: ops.lora_bwd_pair(x, btd, h, dh, 1.0)), 2.0 * M * (D + 16))
+o = torch.randn(M, Hq * hd, device=dev).bfloat16()
 print("ok")
