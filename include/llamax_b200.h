@@ -130,6 +130,23 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
                     const void* doc_start, const void* doc_end, float scale, const void* rope_inverse, void* stream);
 
+/* ---- LoRA bookkeeping: many small strided copies in ONE launch -----------------------------------------------
+ * The LoRA backward needs a few dozen tiny re-layouts per decoder block (scale * B^T, A^T into the grad_input operand,
+ * h^T, fp32 dA^T / dB -> bf16 parameter gradients; modelling/lora.py:43 under autograd). As separate elementwise
+ * launches they cost more than their bytes; this entry runs up to LLAMAX_MAX_COPY_JOBS of them in one grid.
+ *   dst[c, r] (transpose) or dst[r, c] = bf16( scale * src[r, c] ),   src bf16 or fp32 [rows, cols] with pitch src_ld */
+#define LLAMAX_MAX_COPY_JOBS 64
+typedef struct {
+  const void* src;
+  void* dst;          /* bf16 */
+  int64_t src_ld;     /* elements */
+  int64_t dst_ld;     /* elements */
+  int32_t rows, cols; /* of src */
+  float scale;
+  int32_t flags;      /* bit 0: src is fp32 (else bf16); bit 1: transpose */
+} llamax_copy_job_t;
+int llamax_batched_copy(const llamax_copy_job_t* jobs, int32_t n_jobs, void* stream);
+
 /* ---- K6 backward: LoRA weight gradients (autograd of modelling/lora.py:43) ------------------------
  *   out[p, r] (fp32) = alpha * sum_m X[m, p] * H[m, r]       X bf16 [M,P] pitch ldx;  Ht = H^T bf16 [R, M] pitch ldht
  * used for dB = scale * dY^T h and dA^T = x^T dh.  tcgen05 GEMM with X read as an MN-major operand (no transpose

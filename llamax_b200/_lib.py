@@ -34,6 +34,23 @@ class Epilogue(Structure):
 
 EP = POINTER(Epilogue)
 
+MAX_COPY_JOBS = 64
+
+
+class CopyJob(Structure):
+    """llamax_copy_job_t"""
+
+    _fields_ = [
+        ("src", P),
+        ("dst", P),
+        ("src_ld", I64),
+        ("dst_ld", I64),
+        ("rows", I32),
+        ("cols", I32),
+        ("scale", c_float),
+        ("flags", I32),
+    ]
+
 # name -> argtypes (every function returns int except llamax_last_error)
 SIGNATURES = {
     "llamax_version": [],
@@ -55,6 +72,7 @@ SIGNATURES = {
                         I64, I64, I32, I32, I32, I64, P, P, c_float, P, P],
     "llamax_lora_wgrad": [P, I64, P, I64, P, I64, I64, I32, c_float, P],
     "llamax_lora_bwd_pair": [P, I64, P, I64, P, I64, P, I64, P, P, I64, I64, I32, c_float, P],
+    "llamax_batched_copy": [POINTER(CopyJob), I32, P],
     "llamax_cross_entropy": [P, I64, P, P, P, I64, I64, c_int, P],
 }
 

@@ -511,6 +511,47 @@ cross_entropy_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, const int64
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched small copies (LoRA bookkeeping): job = blockIdx.y, 32 x 32 tiles through shared memory
+// ------------------------------------------------------------------------------------------------
+struct CopyJobs {
+  llamax_copy_job_t j[LLAMAX_MAX_COPY_JOBS];
+};
+
+__global__ void __launch_bounds__(256) batched_copy_kernel(const __grid_constant__ CopyJobs jobs) {
+  __shared__ float tile[32][33];
+  const llamax_copy_job_t& jb = jobs.j[blockIdx.y];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int tiles_c = (jb.cols + 31) / 32, tiles_r = (jb.rows + 31) / 32;
+  const bool f32 = jb.flags & 1, tr = jb.flags & 2;
+  for (int t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + ty + k * 8, c = c0 + tx;
+      float v = 0.f;
+      if (r < jb.rows && c < jb.cols) {
+        const int64_t off = (int64_t)r * jb.src_ld + c;
+        v = f32 ? static_cast<const float*>(jb.src)[off] : __bfloat162float(static_cast<const __nv_bfloat16*>(jb.src)[off]);
+      }
+      tile[ty + k * 8][tx] = v * jb.scale;
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(jb.dst);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (tr) {
+        const int c = c0 + ty + k * 8, r = r0 + tx;      // dst[c, r]
+        if (r < jb.rows && c < jb.cols) dst[(int64_t)c * jb.dst_ld + r] = __float2bfloat16_rn(tile[tx][ty + k * 8]);
+      } else {
+        const int r = r0 + ty + k * 8, c = c0 + tx;
+        if (r < jb.rows && c < jb.cols) dst[(int64_t)r * jb.dst_ld + c] = __float2bfloat16_rn(tile[ty + k * 8][tx]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace lx
 
 using namespace lx;
@@ -631,6 +672,23 @@ int llamax_cross_entropy(void* logits, int64_t ld, const void* labels, void* los
                                                                       (float*)loss_sum, (const float*)inv_n, (int)V,
                                                                       write_grad);
   LX_CHECK_LAUNCH("cross_entropy");
+  return 0;
+}
+
+int llamax_batched_copy(const llamax_copy_job_t* jobs, int32_t n_jobs, void* stream) {
+  if (n_jobs == 0) return 0;
+  if (!jobs || n_jobs < 0 || n_jobs > LLAMAX_MAX_COPY_JOBS) return set_error(LLAMAX_ERR_ARG, "batched_copy: bad job list");
+  CopyJobs cj;
+  int max_tiles = 1;
+  for (int i = 0; i < n_jobs; ++i) {
+    const llamax_copy_job_t& j = jobs[i];
+    if (!j.src || !j.dst || j.rows <= 0 || j.cols <= 0) return set_error(LLAMAX_ERR_ARG, "batched_copy: bad job");
+    cj.j[i] = j;
+    max_tiles = std::max(max_tiles, ((j.rows + 31) / 32) * ((j.cols + 31) / 32));
+  }
+  dim3 grid((unsigned)std::min(max_tiles, 64), (unsigned)n_jobs);
+  batched_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cj);
+  LX_CHECK_LAUNCH("batched_copy");
   return 0;
 }
 

@@ -50,14 +50,6 @@ _CACHE_HEADROOM = 24 << 30
 _LORA_PAIR = os.environ.get("LLAMAX_LORA_PAIR", "1") != "0"
 
 
-def _lora_dh_dB(dy: Tensor, bt: Tensor, h: Tensor, out_dh: Tensor, scale: float) -> Tensor:
-    """out_dh = dy @ bt^T (bt already carries the LoRA scale), returns dB = scale * dy^T h (fp32)."""
-    if _LORA_PAIR:
-        return ops.lora_bwd_pair(dy, bt, h, out_dh, scale)
-    ops.bf16_gemm(dy, bt, out=out_dh)
-    return ops.lora_wgrad(dy, h, scale)
-
-
 def set_weight_cache(mode: str) -> None:
     global _CACHE_MODE
     assert mode in ("auto", "0", "1")
@@ -65,16 +57,18 @@ def set_weight_cache(mode: str) -> None:
 
 
 def _operand(cache: dict | None, key: str, specs, rows: int, width: int, device):
-    """bf16 [rows, width] buffer for the backward operand of `specs`. Returns (buffer, frozen_part_is_valid)."""
+    """bf16 [rows, width] buffer for the backward operand of `specs`.
+    Returns (buffer, frozen_part_is_valid, resident): a resident buffer belongs to this layer alone (it can be
+    filled ahead of its use); a non-resident one is the shared scratch."""
     numel = rows * width
     if cache is not None and _CACHE_MODE != "0":
         sig = tuple((s.w8.data_ptr(), s.w8._version, s.ws.data_ptr(), s.ws._version) for s in specs)
         hit = cache.get(key)
         if hit is not None and hit[0] == sig and hit[1].device == device:
-            return hit[1], True
+            return hit[1], True, True
         if hit is not None and hit[1].device == device and hit[1].numel() == numel:
             cache[key] = (sig, hit[1])   # weights were overwritten in place: rebuild into the same buffer
-            return hit[1], False
+            return hit[1], False, True
         ok = _CACHE_MODE == "1"
         if not ok:
             free, _ = torch.cuda.mem_get_info(device)
@@ -82,8 +76,8 @@ def _operand(cache: dict | None, key: str, specs, rows: int, width: int, device)
         if ok:
             buf = torch.empty(rows, width, device=device, dtype=torch.bfloat16)
             cache[key] = (sig, buf)
-            return buf, False
-    return _get_scratch(device, numel)[:numel].view(rows, width), False
+            return buf, False, True
+    return _get_scratch(device, numel)[:numel].view(rows, width), False, False
 
 
 class LinearSpec:
@@ -129,31 +123,80 @@ def _linear(spec: LinearSpec, x_bf16, x_q8, x_qs, h, out=None, resid=None):
     return ops.bf16_gemm(x_bf16, wd, col_scale=spec.ws, round_before_scale=True, out=out, **ep)
 
 
-def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Tensor | None, need_dx=True,
-                    cache: dict | None = None, key: str = ""):
+class _GradSink:
+    """Collects the fp32 -> parameter-dtype conversions of the LoRA gradients (dA^T [K,R] -> dA [R,K], dB [N,R]) so that
+    they run as ONE batched launch at the end of the block's backward instead of 2-3 elementwise launches each."""
+
+    def __init__(self):
+        self.jobs = []
+
+    def emit(self, src_f32: Tensor, transpose: bool, dtype) -> Tensor:
+        if dtype is not torch.bfloat16:
+            return (src_f32.t() if transpose else src_f32).to(dtype).contiguous()
+        shape = (src_f32.shape[1], src_f32.shape[0]) if transpose else tuple(src_f32.shape)
+        dst = torch.empty(shape, device=src_f32.device, dtype=torch.bfloat16)
+        self.jobs.append((src_f32, dst, 1.0, transpose))
+        return dst
+
+    def flush(self):
+        ops.batched_copy(self.jobs)
+        self.jobs = []
+
+
+def _lora_prepare(items, M: int, device):
+    """items: (spec, h [M,R] view, a_dst | None). ONE batched launch builds, per adapter,
+    bt = scale * B^T [R,N] (operand of dh), A^T (into a_dst = its columns of a resident grad_input operand, else
+    into a fresh [K,R] buffer) and ht = h^T [R,M] (operand of dB). Returns {id(spec): (bt, at, ht)}."""
+    prep, jobs = {}, []
+    for s, h, a_dst in items:
+        if s.R == 0:
+            continue
+        bt = torch.empty(s.R, s.N, device=device, dtype=torch.bfloat16)
+        at = a_dst if a_dst is not None else torch.empty(s.K, s.R, device=device, dtype=torch.bfloat16)
+        ht = ops.transposed_rank_buffer(s.R, M, device)
+        jobs += [(s.lora_b.detach(), bt, s.lora_scale, True), (s.lora_a.detach(), at, 1.0, True), (h, ht, 1.0, True)]
+        prep[id(s)] = (bt, at, ht)
+    ops.batched_copy(jobs)
+    return prep
+
+
+def _lora_dh_dB(dy: Tensor, bt: Tensor, ht: Tensor, out_dh: Tensor, scale: float) -> Tensor:
+    """out_dh = dy @ bt^T (bt already carries the LoRA scale), returns dB = scale * dy^T h (fp32)."""
+    if _LORA_PAIR:
+        return ops.lora_bwd_pair(dy, bt, None, out_dh, scale, Ht=ht)
+    ops.bf16_gemm(dy, bt, out=out_dh)
+    return ops.lora_wgrad(dy, None, scale, Ht=ht)
+
+
+def _fill_operand(wt: Tensor, valid: bool, specs):
+    if valid:
+        return
+    n_off = 0
+    for s in specs:
+        ops.dequant_weight(s.w8, s.ws, transpose=True, apply_scale=True, out=wt[:, n_off : n_off + s.N])
+        n_off += s.N
+
+
+def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tensor, a_placed: bool, prep, sink,
+                    need_dx=True):
     """Backward of linears that share one input. dy_cat [M, n_total + r_total]: gradient blocks already written in
-    the first n_total columns (block i = specs[i].N columns); the LoRA dh columns are filled here.
+    the first n_total columns (block i = specs[i].N columns); the LoRA dh columns are filled here. wt: the
+    [K, n_total + r_total] grad_input operand (frozen part valid; A^T columns valid iff a_placed).
     Returns (dx [M,K], [(dA_i, dB_i) | None per spec])."""
-    M = dy_cat.shape[0]
-    K = specs[0].K
     r_total = sum(s.R for s in specs)
-    width = n_total + r_total
-    assert dy_cat.shape[1] == width
-    wt, valid = _operand(cache, key, specs, K, width, dy_cat.device)
+    assert dy_cat.shape[1] == n_total + r_total
     n_off, r_off = 0, 0
     lora_grads = []
     for s in specs:
         dy_i = dy_cat[:, n_off : n_off + s.N]
-        if not valid:
-            ops.dequant_weight(s.w8, s.ws, transpose=True, apply_scale=True, out=wt[:, n_off : n_off + s.N])
         if s.R > 0:
             c0 = n_total + r_off
+            bt, at, ht = prep[id(s)]
+            if not a_placed:
+                wt[:, c0 : c0 + s.R].copy_(at)
             # one pass over dy_i:  dh_i = scale * dy_i @ B_i -> columns [c0, c0+R) of dy_cat;  dB = scale * dy_i^T h_i
-            bt = (s.lora_b.detach().t() * s.lora_scale).contiguous()
-            wt[:, c0 : c0 + s.R].copy_(s.lora_a.detach().t())
-            h_i = h_cat[:, r_off : r_off + s.R]
-            dB = _lora_dh_dB(dy_i, bt, h_i, dy_cat[:, c0 : c0 + s.R], s.lora_scale)  # [N, R] fp32
-            lora_grads.append([None, dB.to(s.lora_b.dtype)])
+            dB = _lora_dh_dB(dy_i, bt, ht, dy_cat[:, c0 : c0 + s.R], s.lora_scale)  # [N, R] fp32
+            lora_grads.append([None, sink.emit(dB, False, s.lora_b.dtype)])
             r_off += s.R
         else:
             lora_grads.append(None)
@@ -163,30 +206,20 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, h_cat: Te
         r_off = 0
         for s, lg in zip(specs, lora_grads):
             if lg is not None:
-                lg[0] = dA_t[:, r_off : r_off + s.R].t().to(s.lora_a.dtype).contiguous()
+                lg[0] = sink.emit(dA_t[:, r_off : r_off + s.R], True, s.lora_a.dtype)
                 r_off += s.R
     dx = ops.bf16_gemm(dy_cat, wt) if need_dx else None
     return dx, lora_grads
 
 
-def _single_operand(spec: LinearSpec, device, cache: dict | None, key: str) -> Tensor:
-    wt, valid = _operand(cache, key, (spec,), spec.K, spec.N, device)
-    if not valid:
-        ops.dequant_weight(spec.w8, spec.ws, transpose=True, apply_scale=True, out=wt)
-    return wt
-
-
-def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, h: Tensor | None, cache: dict | None = None,
-                     key: str = ""):
+def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, wt: Tensor, prep, sink):
     """Backward of one linear whose incoming gradient buffer we do not own: LoRA term in the GEMM epilogue."""
-    wt = _single_operand(spec, dy.device, cache, key)
     if spec.R > 0:
-        bt = (spec.lora_b.detach().t() * spec.lora_scale).contiguous()
+        bt, at, ht = prep[id(spec)]
         dh = torch.empty(dy.shape[0], spec.R, device=dy.device, dtype=torch.bfloat16)
-        dB = _lora_dh_dB(dy, bt, h, dh, spec.lora_scale).to(spec.lora_b.dtype)   # dh [M, R] and dB in one pass
-        at = spec.lora_a.detach().t().contiguous()                     # [K, R]
+        dB = sink.emit(_lora_dh_dB(dy, bt, ht, dh, spec.lora_scale), False, spec.lora_b.dtype)  # dh, dB in one pass
         dx = ops.bf16_gemm(dy, wt, lora_h=dh, lora_b=at, lora_scale=1.0)
-        dA = ops.lora_wgrad(x_in, dh, 1.0).t().to(spec.lora_a.dtype).contiguous()
+        dA = sink.emit(ops.lora_wgrad(x_in, dh, 1.0), True, spec.lora_a.dtype)
         return dx, (dA, dB)
     return ops.bf16_gemm(dy, wt), None
 
@@ -263,45 +296,80 @@ class FusedDecoderBlock(torch.autograd.Function):
         if not dout2.is_contiguous():
             dout2 = dout2.contiguous()
 
-        # --- w2 ---  (needs g = silu(a) * b only for dA of w2: re-materialised by the SwiGLU backward kernel)
-        r13 = s1.R + s3.R
-        dab = torch.empty(M, 2 * F_ + r13, device=dout.device, dtype=torch.bfloat16)
+        dev = dout.device
+        nq, nk = Hq * D, Hkv * D
+        rqkv, r13 = sq.R + sk.R + sv.R, s1.R + s3.R
         cache = layer.__dict__.setdefault("_llamax_bwd_operands", {})
-        wt2 = _single_operand(s2, dout.device, cache, "w2")
+        shapes = {"w2": ((s2,), s2.K, s2.N), "w13": ((s1, s3), s1.K, 2 * F_ + r13), "wo": ((so,), so.K, so.N),
+                  "wqkv": ((sq, sk, sv), sq.K, nq + 2 * nk + rqkv)}
+        # grad_input operands (scale * W)^T | A^T: resident ones are fetched (and, the first time, built) up front so
+        # that the LoRA columns can be refreshed by the batched prepare below; the shared scratch is filled at its use
+        held = {}
+        for key, (specs, rows, width) in shapes.items():
+            wt, valid, resident = _operand(cache, key, specs, rows, width, dev)
+            if resident:
+                _fill_operand(wt, valid, specs)
+                held[key] = wt
+
+        def operand(key):
+            if key in held:
+                return held[key], True
+            specs, rows, width = shapes[key]
+            wt, valid, _ = _operand(cache, key, specs, rows, width, dev)
+            _fill_operand(wt, valid, specs)
+            return wt, False
+
+        def a_dst(key, n_total, r_off, R):
+            return held[key][:, n_total + r_off : n_total + r_off + R] if (key in held and R > 0) else None
+
+        sink = _GradSink()
+        prep = _lora_prepare((
+            (sq, h_qkv[:, : sq.R] if sq.R else None, a_dst("wqkv", nq + 2 * nk, 0, sq.R)),
+            (sk, h_qkv[:, sq.R : sq.R + sk.R] if sk.R else None, a_dst("wqkv", nq + 2 * nk, sq.R, sk.R)),
+            (sv, h_qkv[:, sq.R + sk.R :] if sv.R else None, a_dst("wqkv", nq + 2 * nk, sq.R + sk.R, sv.R)),
+            (so, h_o, None),
+            (s1, h_13[:, : s1.R] if s1.R else None, a_dst("w13", 2 * F_, 0, s1.R)),
+            (s3, h_13[:, s1.R :] if s3.R else None, a_dst("w13", 2 * F_, s1.R, s3.R)),
+            (s2, h_2, None)), M, dev)
+
+        # --- w2 ---  (needs g = silu(a) * b only for dA of w2: re-materialised by the SwiGLU backward kernel)
+        dab = torch.empty(M, 2 * F_ + r13, device=dev, dtype=torch.bfloat16)
+        wt2, _ = operand("w2")
         g2 = None
         if s2.R > 0:
-            dh2 = torch.empty(M, s2.R, device=dout.device, dtype=torch.bfloat16)
-            dB2 = _lora_dh_dB(dout2, (s2.lora_b.detach().t() * s2.lora_scale).contiguous(), h_2, dh2,
-                              s2.lora_scale).to(s2.lora_b.dtype)
-            dg = ops.bf16_gemm(dout2, wt2, lora_h=dh2, lora_b=s2.lora_a.detach().t().contiguous(), lora_scale=1.0)
+            bt2, at2, ht2 = prep[id(s2)]
+            dh2 = torch.empty(M, s2.R, device=dev, dtype=torch.bfloat16)
+            dB2 = sink.emit(_lora_dh_dB(dout2, bt2, ht2, dh2, s2.lora_scale), False, s2.lora_b.dtype)
+            dg = ops.bf16_gemm(dout2, wt2, lora_h=dh2, lora_b=at2, lora_scale=1.0)
         else:
             dg = ops.bf16_gemm(dout2, wt2)
         _, _, g = ops.swiglu_bwd(dg, ab[:, :F_], ab[:, F_:], want_g=s2.R > 0, out_ab=dab)
         if s2.R > 0:
-            dA2 = ops.lora_wgrad(g, dh2, 1.0).t().to(s2.lora_a.dtype).contiguous()
-            g2 = (dA2, dB2)
+            g2 = (sink.emit(ops.lora_wgrad(g, dh2, 1.0), True, s2.lora_a.dtype), dB2)
         del dg, g
 
         # --- w1 | w3 ---
-        dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, h_13, cache=cache, key="w13")
+        wt13, placed13 = operand("w13")
+        dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, wt13, placed13, prep, sink)
         del dab
         want_dw_fn, want_dw_an = w_fn.requires_grad, w_an.requires_grad
         dx1, dw_fn = ops.rmsnorm_bwd(dxn2, x1, w_fn.detach(), rstd2, dout2, want_dw=want_dw_fn)
         del dxn2
 
         # --- wo ---
-        do, go = _single_backward(so, dx1, o, h_o, cache=cache, key="wo")
+        wto, _ = operand("wo")
+        do, go = _single_backward(so, dx1, o, wto, prep, sink)
 
         # --- attention ---
-        nq, nk = Hq * D, Hkv * D
-        rqkv = sq.R + sk.R + sv.R
-        dqkv = torch.empty(M, nq + 2 * nk + rqkv, device=dout.device, dtype=torch.bfloat16)
+        dqkv = torch.empty(M, nq + 2 * nk + rqkv, device=dev, dtype=torch.bfloat16)
         ops.attn_bwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], o, lse, do,
                      dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len,
                      doc_start=doc_start, doc_end=doc_end, rope_inverse=rope)   # dq, dk come back un-rotated
-        dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, h_qkv, cache=cache, key="wqkv")
+        wtqkv, placedqkv = operand("wqkv")
+        dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, wtqkv, placedqkv, prep, sink)
         del dqkv
         dx, dw_an = ops.rmsnorm_bwd(dxn1, x2, w_an.detach(), rstd1, dx1, want_dw=want_dw_an)
+        sink.flush()   # fp32 dA^T / dB -> parameter-dtype gradients, one launch
 
         grads = [dw_an, dw_fn]
         for spec, g_ in zip((sq, sk, sv, so, s1, s3, s2), (*gqkv, go, *g13, g2)):

@@ -284,15 +284,26 @@ def rope_(x: Tensor, rope: Tensor, B: int, S: int, nheads: int, D: int, *, inver
     return x
 
 
-def lora_wgrad(X: Tensor, H: Tensor, alpha: float = 1.0) -> Tensor:
-    """out[P,R] (fp32) = alpha * X[M,P]^T @ H[M,R]  (tensor cores; X is consumed in place, H^T is a tiny copy)."""
-    lib, st = _prep(X)
-    assert X.dtype is torch.bfloat16 and H.dtype is torch.bfloat16 and X.stride(1) == 1
-    M, Pn = X.shape
-    R = H.shape[1]
+def transposed_rank_buffer(R: int, M: int, device) -> Tensor:
+    """[R, M] bf16 buffer for an H^T operand: row pitch padded to a multiple of 8 elements (TMA), pad zeroed."""
     Mp = (M + 7) // 8 * 8
-    Ht = torch.zeros(R, Mp, device=X.device, dtype=torch.bfloat16) if Mp != M else torch.empty(R, M, device=X.device, dtype=torch.bfloat16)
-    Ht[:, :M].copy_(H.t())
+    if Mp == M:
+        return torch.empty(R, M, device=device, dtype=torch.bfloat16)
+    return torch.zeros(R, Mp, device=device, dtype=torch.bfloat16)[:, :M]
+
+
+def lora_wgrad(X: Tensor, H: Tensor | None, alpha: float = 1.0, *, Ht: Tensor | None = None) -> Tensor:
+    """out[P,R] (fp32) = alpha * X[M,P]^T @ H[M,R]  (tensor cores; X is consumed in place). Pass Ht = H^T [R,M]
+    (from transposed_rank_buffer) when it already exists; otherwise it is made here (a tiny copy)."""
+    lib, st = _prep(X)
+    assert X.dtype is torch.bfloat16 and X.stride(1) == 1
+    M, Pn = X.shape
+    if Ht is None:
+        assert H.dtype is torch.bfloat16
+        Ht = transposed_rank_buffer(H.shape[1], M, X.device)
+        Ht.copy_(H.t())
+    R = Ht.shape[0]
+    assert Ht.dtype is torch.bfloat16 and Ht.shape[1] == M and Ht.stride(1) == 1
     out = torch.empty(Pn, R, device=X.device, dtype=torch.float32)
     _call(lib, "llamax_lora_wgrad",
           (_p(X), X.stride(0), _p(Ht), Ht.stride(0), _p(out), M, Pn, R, float(alpha), st),
@@ -300,24 +311,51 @@ def lora_wgrad(X: Tensor, H: Tensor, alpha: float = 1.0) -> Tensor:
     return out
 
 
-def lora_bwd_pair(dY: Tensor, Bt: Tensor, H: Tensor, out_dh: Tensor, alpha: float = 1.0) -> Tensor:
+def lora_bwd_pair(dY: Tensor, Bt: Tensor, H: Tensor | None, out_dh: Tensor, alpha: float = 1.0, *,
+                  Ht: Tensor | None = None) -> Tensor:
     """One pass over dY [M,N]: writes out_dh [M,R] = dY @ Bt^T (Bt = scale * B^T, [R,N]) and returns
     dB [N,R] (fp32) = alpha * dY^T @ H. Replaces a skinny dh GEMM + lora_wgrad that each streamed dY from HBM."""
     lib, st = _prep(dY)
-    assert dY.dtype is torch.bfloat16 and Bt.dtype is torch.bfloat16 and H.dtype is torch.bfloat16
-    assert dY.stride(1) == 1 and Bt.is_contiguous() and out_dh.stride(1) == 1 and out_dh.dtype is torch.bfloat16
+    assert dY.dtype is torch.bfloat16 and Bt.dtype is torch.bfloat16
+    assert dY.stride(1) == 1 and Bt.stride(1) == 1 and out_dh.stride(1) == 1 and out_dh.dtype is torch.bfloat16
     M, N = dY.shape
-    R = H.shape[1]
+    if Ht is None:
+        assert H.dtype is torch.bfloat16
+        Ht = transposed_rank_buffer(H.shape[1], M, dY.device)
+        Ht.copy_(H.t())
+    R = Ht.shape[0]
+    assert Ht.dtype is torch.bfloat16 and Ht.shape[1] == M and Ht.stride(1) == 1
     assert Bt.shape == (R, N) and out_dh.shape == (M, R)
-    Mp = (M + 7) // 8 * 8
-    Ht = torch.zeros(R, Mp, device=dY.device, dtype=torch.bfloat16) if Mp != M else torch.empty(R, M, device=dY.device, dtype=torch.bfloat16)
-    Ht[:, :M].copy_(H.t())
     dB = torch.empty(N, R, device=dY.device, dtype=torch.float32)
     acc = torch.empty(M, R, device=dY.device, dtype=torch.float32)
     _call(lib, "llamax_lora_bwd_pair",
           (_p(dY), dY.stride(0), _p(Bt), Bt.stride(0), _p(Ht), Ht.stride(0), _p(out_dh), out_dh.stride(0), _p(acc), _p(dB), M, N, R, float(alpha), st),
           "lora_wgrad", 4.0 * M * N * R, 2.0 * M * (N + 2 * R))
     return dB
+
+
+def batched_copy(jobs) -> None:
+    """jobs: iterable of (src, dst, scale, transpose). dst (bf16, 2-D, unit inner stride) receives
+    bf16(scale * src) or its transpose; src is a 2-D bf16 / fp32 tensor with unit inner stride. ONE launch per
+    64 jobs instead of one elementwise launch (or three) per job."""
+    jobs = list(jobs)
+    if not jobs:
+        return
+    lib, st = _prep(jobs[0][0])
+    for i0 in range(0, len(jobs), _lib.MAX_COPY_JOBS):
+        chunk = jobs[i0 : i0 + _lib.MAX_COPY_JOBS]
+        arr = (_lib.CopyJob * len(chunk))()
+        for k, (src, dst, scale, transpose) in enumerate(chunk):
+            assert src.dim() == 2 and dst.dim() == 2 and src.stride(1) == 1 and dst.stride(1) == 1
+            assert dst.dtype is torch.bfloat16 and src.dtype in (torch.bfloat16, torch.float32)
+            assert tuple(dst.shape) == ((src.shape[1], src.shape[0]) if transpose else tuple(src.shape))
+            j = arr[k]
+            j.src, j.dst = src.data_ptr(), dst.data_ptr()
+            j.src_ld, j.dst_ld = src.stride(0), dst.stride(0)
+            j.rows, j.cols = src.shape
+            j.scale = float(scale)
+            j.flags = (1 if src.dtype is torch.float32 else 0) | (2 if transpose else 0)
+        _call(lib, "llamax_batched_copy", (arr, len(chunk), st), "batched_copy", 0.0, 0.0)
 
 
 def cross_entropy_(logits: Tensor, labels: Tensor, loss_sum: Tensor, inv_n: Tensor | None, write_grad: bool):

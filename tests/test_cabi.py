@@ -38,6 +38,12 @@ def test_epilogue_struct_layout_matches_header():
     assert ctypes.sizeof(e) == 48 and e.lora_rank.offset == 24 and e.lora_scale.offset == 28 and e.resid.offset == 32
 
 
+def test_copy_job_struct_layout_matches_header():
+    j = _lib.CopyJob
+    assert [f[0] for f in j._fields_] == ["src", "dst", "src_ld", "dst_ld", "rows", "cols", "scale", "flags"]
+    assert ctypes.sizeof(j) == 48 and j.rows.offset == 32 and j.scale.offset == 40 and j.flags.offset == 44
+
+
 def test_argument_validation_without_gpu():
     """Entry points reject bad arguments before touching the device."""
     lib = _lib.load()

@@ -117,3 +117,30 @@ def test_cross_entropy_fwd_bwd(M, V):
     assert abs((loss_sum * inv_n).item() - ref.item()) <= 1e-4 * abs(ref.item())
     assert rel_err(lc, lf.grad) <= 1e-2
     assert (lc[::5] == 0).all()
+
+
+def test_batched_copy_jobs():
+    """llamax_batched_copy: mixed bf16 / fp32 sources, transposes, scales, pitched sources and destinations, ragged
+    tile edges — bit-exact against bf16(scale * src) (same single rounding)."""
+    torch.manual_seed(3)
+    dev = "cuda"
+    a = torch.randn(8, 4096, device=dev).bfloat16()                       # A [R,K] -> A^T into a pitched operand slice
+    wt = torch.zeros(4096, 6168, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(1000, 16, device=dev).bfloat16()                      # B [N,R] -> scale * B^T
+    bt = torch.empty(16, 1000, device=dev, dtype=torch.bfloat16)
+    h = torch.randn(300, 24, device=dev).bfloat16()[:, 8:16]              # strided h slice -> h^T with padded pitch
+    ht = ops.transposed_rank_buffer(8, 300, dev)
+    g = torch.randn(4096, 24, device=dev)                                 # fp32 dA^T slice -> bf16 dA
+    da = torch.empty(8, 4096, device=dev, dtype=torch.bfloat16)
+    f = torch.randn(333, 8, device=dev)                                   # fp32 dB -> bf16 dB
+    db = torch.empty(333, 8, device=dev, dtype=torch.bfloat16)
+    ops.batched_copy([(a, wt[:, 6144:6152], 1.0, True), (b, bt, 0.5, True), (h, ht, 1.0, True),
+                      (g[:, 16:24], da, 1.0, True), (f, db, 1.0, False)])
+    assert torch.equal(wt[:, 6144:6152], a.t()) and torch.count_nonzero(wt[:, :6144]) == 0
+    assert torch.equal(bt, (b.float() * 0.5).bfloat16().t())
+    assert torch.equal(ht, h.t())
+    assert torch.equal(da, g[:, 16:24].bfloat16().t())
+    assert torch.equal(db, f.bfloat16())
+    jobs = [(b, torch.empty(16, 1000, device=dev, dtype=torch.bfloat16), 1.0, True) for _ in range(70)]  # > 64 jobs
+    ops.batched_copy(jobs)
+    assert all(torch.equal(j[1], b.t()) for j in jobs)

@@ -41,8 +41,13 @@ for _ in range(reps):
     ab = torch.randn(M, 2 * F, device=dev).bfloat16()
     ops.lora_wgrad(ab[:, :F], h[:, :8], 1.0)
     x = torch.randn(M, D, device=dev).bfloat16()
-    ops.rmsnorm_fwd(x, torch.ones(D, device=dev).bfloat16(), 1e-5, quant=True)
+    w1 = torch.ones(D, device=dev).bfloat16()
+    xn, rstd, _, _ = ops.rmsnorm_fwd(x, w1, 1e-5, quant=True)
     ops.swiglu_fwd(ab[:, :F], ab[:, F:], quant=True, want_g=True)
+    # 9. fused LoRA backward pair (dh + dB in one pass over dY), 10. RMSNorm backward
+    bt = torch.randn(8, F, device=dev).bfloat16()
+    ops.lora_bwd_pair(ab[:, :F], bt, h[:, :8], torch.empty(M, 8, device=dev).bfloat16(), 1.0)
+    ops.rmsnorm_bwd(xn, x, w1, rstd, res, want_dw=True)
     del ab, qkv, dqkv
 torch.cuda.synchronize()
 print("ok")
