@@ -130,6 +130,20 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
                     const void* doc_start, const void* doc_end, float scale, const void* rope_inverse, void* stream);
 
+/* ---- audio stem (modelling/audio.py:26-31,51-60): Conv1d(k3,s1)+GELU, Conv1d(k3,s2)+GELU -------------------------
+ * The convolutions run on llamax_bf16_gemm: with channels-last activations padded by one zero row on each side of a
+ * batch slab, output row t of a k = 3 convolution is the dot product of the weights with 3C CONSECUTIVE elements
+ * starting at padded row stride*t, i.e. the im2col matrix is a view with OVERLAPPING rows (lda = stride * C < K = 3C)
+ * that TMA walks directly — no im2col copy. These entries are the elementwise ends of that GEMM:
+ *   gelu_bias_fwd: z (in place) = bf16(z + bias[col]); y = bf16(gelu_erf(z)); rows with (row % period) outside [lo, hi)
+ *                  are padding: z = y = 0.        gelu_bwd: dz = bf16(dy * gelu'(z)), 0 on padding rows.
+ *   conv_s2k3_col2im: dxp[b, i, :] = sum_{2t + j = i} dcol[b, t, j, :]  (dcol [B, Tp/2, 3, C], dxp [B, Tp, C]) */
+int llamax_gelu_bias_fwd(void* z, const void* bias, void* y, int64_t rows, int64_t C, int32_t period, int32_t lo,
+                         int32_t hi, void* stream);
+int llamax_gelu_bwd(const void* dy, const void* z, void* dz, int64_t rows, int64_t C, int32_t period, int32_t lo,
+                    int32_t hi, void* stream);
+int llamax_conv_s2k3_col2im(const void* dcol, void* dxp, int64_t B, int64_t Tp, int64_t C, void* stream);
+
 /* ---- LoRA bookkeeping: many small strided copies in ONE launch -----------------------------------------------
  * The LoRA backward needs a few dozen tiny re-layouts per decoder block (scale * B^T, A^T into the grad_input operand,
  * h^T, fp32 dA^T / dB -> bf16 parameter gradients; modelling/lora.py:43 under autograd). As separate elementwise

@@ -512,6 +512,96 @@ cross_entropy_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, const int64
 }
 
 // ------------------------------------------------------------------------------------------------
+// Audio stem (modelling/audio.py:26-31): bias + exact (erf) GELU around the conv-as-GEMM outputs, and the
+// overlap-add of the stride-2 k=3 convolution's input gradient. Rows are channels-last [batch * period, C];
+// rows whose index inside a batch slab (row % period) is not in [lo, hi) are padding and are written as zeros.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float z) {
+  const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+  return cdf + z * pdf;
+}
+
+// z (in place) = bf16(z + bias[col]);  y = bf16(gelu(z))
+__global__ void gelu_bias_fwd_kernel(__nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ bias,
+                                     __nv_bfloat16* __restrict__ y, int64_t rows, int nvec, int period, int lo, int hi) {
+  const int64_t total = rows * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nvec;
+    const int c = (int)(i - row * nvec) * 8;
+    const int rr = (int)(row % period);
+    float zf[8], bf[8], yf[8];
+    if (rr >= lo && rr < hi) {
+      unpack8(*reinterpret_cast<const uint4*>(z + row * (int64_t)nvec * 8 + c), zf);
+      unpack8(*reinterpret_cast<const uint4*>(bias + c), bf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        zf[e] = round_bf16(zf[e] + bf[e]);
+        yf[e] = gelu_erf(zf[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) zf[e] = yf[e] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(z + row * (int64_t)nvec * 8 + c) = pack8(zf);
+    *reinterpret_cast<uint4*>(y + row * (int64_t)nvec * 8 + c) = pack8(yf);
+  }
+}
+
+// dz = bf16(dy * gelu'(z)) on valid rows, 0 on padding rows (dz may alias dy)
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                                __nv_bfloat16* __restrict__ dz, int64_t rows, int nvec, int period, int lo, int hi) {
+  const int64_t total = rows * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nvec;
+    const int c = (int)(i - row * nvec) * 8;
+    const int rr = (int)(row % period);
+    float o[8];
+    if (rr >= lo && rr < hi) {
+      float g[8], zf[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + row * (int64_t)nvec * 8 + c), g);
+      unpack8(*reinterpret_cast<const uint4*>(z + row * (int64_t)nvec * 8 + c), zf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = g[e] * gelu_erf_grad(zf[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(dz + row * (int64_t)nvec * 8 + c) = pack8(o);
+  }
+}
+
+// Input gradient of Conv1d(k = 3, stride 2, pad 1) from the column gradient dcol [B, Tp/2, 3, C] (slab row t holds the
+// gradients of padded input rows 2t, 2t+1, 2t+2):  dxp[b, i] = sum over (t, j) with 2t + j = i.  dxp [B, Tp, C].
+__global__ void conv_s2k3_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dxp,
+                                        int64_t B, int Tp, int nvec) {
+  const int half = Tp / 2;                       // column-matrix rows per batch slab (the last one is padding)
+  const int64_t total = B * Tp * (int64_t)nvec;
+  const int64_t C = (int64_t)nvec * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 8;
+    const int64_t r = i / nvec;
+    const int ip = (int)(r % Tp);
+    const int64_t b = r / Tp;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int tt = ip - j;
+      if (tt >= 0 && (tt & 1) == 0 && (tt >> 1) < half - 1) {   // valid output rows: t < Tp/2 - 1
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(dcol + ((b * half + (tt >> 1)) * 3 + j) * C + c), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    }
+    *reinterpret_cast<uint4*>(dxp + r * C + c) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Batched small copies (LoRA bookkeeping): job = blockIdx.y, 32 x 32 tiles through shared memory
 // ------------------------------------------------------------------------------------------------
 struct CopyJobs {
@@ -689,6 +779,42 @@ int llamax_batched_copy(const llamax_copy_job_t* jobs, int32_t n_jobs, void* str
   dim3 grid((unsigned)std::min(max_tiles, 64), (unsigned)n_jobs);
   batched_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cj);
   LX_CHECK_LAUNCH("batched_copy");
+  return 0;
+}
+
+int llamax_gelu_bias_fwd(void* z, const void* bias, void* y, int64_t rows, int64_t C, int32_t period, int32_t lo,
+                         int32_t hi, void* stream) {
+  if (!z || !bias || !y) return set_error(LLAMAX_ERR_ARG, "gelu_bias_fwd: null pointer");
+  if (C % 8 || period <= 0 || lo < 0 || hi > period) return set_error(LLAMAX_ERR_ARG, "gelu_bias_fwd: bad shape");
+  if (rows == 0) return 0;
+  const int64_t total = rows * (C / 8);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  gelu_bias_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)z, (const bf16*)bias, (bf16*)y, rows, (int)(C / 8),
+                                                                 period, lo, hi);
+  LX_CHECK_LAUNCH("gelu_bias_fwd");
+  return 0;
+}
+
+int llamax_gelu_bwd(const void* dy, const void* z, void* dz, int64_t rows, int64_t C, int32_t period, int32_t lo,
+                    int32_t hi, void* stream) {
+  if (!dy || !z || !dz) return set_error(LLAMAX_ERR_ARG, "gelu_bwd: null pointer");
+  if (C % 8 || period <= 0 || lo < 0 || hi > period) return set_error(LLAMAX_ERR_ARG, "gelu_bwd: bad shape");
+  if (rows == 0) return 0;
+  const int64_t total = rows * (C / 8);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  gelu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)z, (bf16*)dz, rows, (int)(C / 8),
+                                                            period, lo, hi);
+  LX_CHECK_LAUNCH("gelu_bwd");
+  return 0;
+}
+
+int llamax_conv_s2k3_col2im(const void* dcol, void* dxp, int64_t B, int64_t Tp, int64_t C, void* stream) {
+  if (!dcol || !dxp) return set_error(LLAMAX_ERR_ARG, "conv_s2k3_col2im: null pointer");
+  if (C % 8 || Tp % 2 || Tp < 4 || B <= 0) return set_error(LLAMAX_ERR_ARG, "conv_s2k3_col2im: bad shape");
+  const int64_t total = B * Tp * (C / 8);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  conv_s2k3_col2im_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dcol, (bf16*)dxp, B, (int)Tp, (int)(C / 8));
+  LX_CHECK_LAUNCH("conv_s2k3_col2im");
   return 0;
 }
 

@@ -334,6 +334,37 @@ def lora_bwd_pair(dY: Tensor, Bt: Tensor, H: Tensor | None, out_dh: Tensor, alph
     return dB
 
 
+def gelu_bias_fwd_(z: Tensor, bias: Tensor, period: int, lo: int, hi: int) -> Tensor:
+    """In place z = bf16(z + bias); returns y = bf16(gelu_erf(z)). z: [rows, C] contiguous; rows whose index modulo
+    `period` is outside [lo, hi) are padding rows and come out as zeros in both."""
+    lib, st = _prep(z)
+    assert z.dtype is torch.bfloat16 and z.dim() == 2 and z.is_contiguous() and bias.dtype is torch.bfloat16
+    rows, C = z.shape
+    y = torch.empty_like(z)
+    _call(lib, "llamax_gelu_bias_fwd", (_p(z), _p(bias.contiguous()), _p(y), rows, C, period, lo, hi, st),
+          "gelu", 0.0, 6.0 * rows * C)
+    return y
+
+
+def gelu_bwd(dy: Tensor, z: Tensor, period: int, lo: int, hi: int, out: Tensor | None = None) -> Tensor:
+    """dz = bf16(dy * gelu_erf'(z)), zeros on padding rows."""
+    lib, st = _prep(z)
+    assert dy.dtype is torch.bfloat16 and dy.is_contiguous() and z.is_contiguous() and dy.shape == z.shape
+    rows, C = z.shape
+    dz = torch.empty_like(z) if out is None else out
+    _call(lib, "llamax_gelu_bwd", (_p(dy), _p(z), _p(dz), rows, C, period, lo, hi, st), "gelu", 0.0, 6.0 * rows * C)
+    return dz
+
+
+def conv_s2k3_col2im(dcol: Tensor, B: int, Tp: int, C: int) -> Tensor:
+    """dcol [B * Tp/2, 3C] (row t of a slab = gradients of padded input rows 2t..2t+2) -> dxp [B, Tp, C]."""
+    lib, st = _prep(dcol)
+    assert dcol.dtype is torch.bfloat16 and dcol.is_contiguous() and dcol.shape == (B * (Tp // 2), 3 * C)
+    dxp = torch.empty(B, Tp, C, device=dcol.device, dtype=torch.bfloat16)
+    _call(lib, "llamax_conv_s2k3_col2im", (_p(dcol), _p(dxp), B, Tp, C, st), "col2im", 0.0, 5.0 * B * Tp * C)
+    return dxp
+
+
 def batched_copy(jobs) -> None:
     """jobs: iterable of (src, dst, scale, transpose). dst (bf16, 2-D, unit inner stride) receives
     bf16(scale * src) or its transpose; src is a 2-D bf16 / fp32 tensor with unit inner stride. ONE launch per

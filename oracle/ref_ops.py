@@ -262,3 +262,11 @@ def transformer_layer_ref(x: Tensor, rope: Tensor, lw: LayerWeights, Hq: int, Hk
     h = rmsnorm_ref(x, lw.ffn_norm)
     g = swiglu_ref(lora_linear_ref(h, lw, "w1", dynamic), lora_linear_ref(h, lw, "w3", dynamic))
     return x + lora_linear_ref(g, lw, "w2", dynamic)
+
+
+def audio_stem_ref(mel: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+    """Whisper-style stem of LlamaAudio (modelling/audio.py:26-31 applied at :56-60), evaluated in the dtype of its
+    inputs: GELU(Conv1d(k3, s2, p1)(GELU(Conv1d(k3, s1, p1)(mel)))).transpose(1, 2).  mel [B, n_mels, T]."""
+    x = F.gelu(F.conv1d(mel, w1, b1, stride=1, padding=1))
+    x = F.gelu(F.conv1d(x, w2, b2, stride=2, padding=1))
+    return x.transpose(1, 2)

@@ -1,9 +1,9 @@
 #!/bin/bash
-# Same-box A/B of an environment switch:  tools/ab.sh VAR A_VALUE B_VALUE  (alternates A B A B, prints ms/step)
+# Same-box A/B of an environment switch:  [BENCH_ARGS=...] tools/ab.sh VAR A_VALUE B_VALUE  (alternates A B A B)
 VAR=$1; A=$2; B=$3
 for i in 1 2; do
   for v in "$A" "$B"; do
-    env $VAR=$v python bench.py --no-cpu-baseline --steps 4 2>/dev/null | python -c "
+    env $VAR=$v python bench.py --no-cpu-baseline --steps 4 $BENCH_ARGS 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 k=d['kernels']
