@@ -80,6 +80,11 @@ int llamax_dequant_weight(const void* w8, const void* scale, void* out, int64_t 
  *   s = amax(|x_f32|) / 127;  q = rint(x_f32 / max(s, 1e-12));  scale_out = bf16(s)        bit-exact */
 int llamax_rowquant_int8(const void* x, int64_t ldx, void* q8, void* scale_out, int64_t M, int64_t K,
                          void* stream);
+/* Same quantiser applied to x[m,c] * col_scale[c] (fp32 product; col_scale bf16 [K]). Used only by the OPT-IN,
+ * non-parity INT8 grad_input mode (the reference author's TODO at subclasses/int8.py:105): grad_output * weight_scale
+ * is quantised row-wise so that grad_input = q(dY * s) @ W_int8 runs on the int8 tensor path. */
+int llamax_rowquant_int8_colscale(const void* x, int64_t ldx, const void* col_scale, void* q8, void* scale_out,
+                                  int64_t M, int64_t K, void* stream);
 
 /* ---- K1: RMSNorm (nn.RMSNorm(eps) at modelling/llama.py:158,160,182) ------------------------------
  *   y = bf16( (x_f32 * rsqrt(mean(x_f32^2) + eps)) * w_f32 )

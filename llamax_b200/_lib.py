@@ -61,6 +61,7 @@ SIGNATURES = {
     "llamax_bf16_gemm": [P, I64, P, I64, P, I64, I64, I64, I64, P, c_int, EP, P],
     "llamax_dequant_weight": [P, P, P, I64, I64, I64, c_int, c_int, P],
     "llamax_rowquant_int8": [P, I64, P, P, I64, I64, P],
+    "llamax_rowquant_int8_colscale": [P, I64, P, P, P, I64, I64, P],
     "llamax_rmsnorm_fwd": [P, P, P, P, P, P, I64, I64, c_float, P],
     "llamax_rmsnorm_bwd": [P, P, P, P, P, P, P, I32, I64, I64, P],
     "llamax_reduce_partials": [P, P, I32, I64, P],

@@ -164,9 +164,12 @@ __global__ void rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __
 // ------------------------------------------------------------------------------------------------
 // row-wise int8 quantisation alone
 // ------------------------------------------------------------------------------------------------
-template <int kMaxV>
+// kColScale: quantise x[m, c] * col_scale[c] (fp32 product) instead of x — the opt-in INT8 grad_input path quantises
+// grad_output * weight_scale (subclasses/int8.py:127) row-wise in one pass.
+template <int kMaxV, bool kColScale = false>
 __global__ void rowquant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int8_t* __restrict__ q8,
-                                __nv_bfloat16* __restrict__ qscale, int K, int nvec) {
+                                __nv_bfloat16* __restrict__ qscale, int K, int nvec,
+                                const __nv_bfloat16* __restrict__ col_scale = nullptr) {
   __shared__ float sm[32];
   const int64_t row = blockIdx.x;
   const __nv_bfloat16* xr = x + row * ldx;
@@ -177,6 +180,12 @@ __global__ void rowquant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
     const int idx = threadIdx.x + j * blockDim.x;
     if (idx < nvec) {
       unpack8(ldg_nc_v4(xr + (int64_t)idx * 8), v[j]);
+      if (kColScale) {
+        float cs[8];
+        unpack8(*reinterpret_cast<const uint4*>(col_scale + (int64_t)idx * 8), cs);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] *= cs[e];
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[j][e]));
     }
@@ -815,6 +824,18 @@ int llamax_conv_s2k3_col2im(const void* dcol, void* dxp, int64_t B, int64_t Tp, 
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
   conv_s2k3_col2im_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dcol, (bf16*)dxp, B, (int)Tp, (int)(C / 8));
   LX_CHECK_LAUNCH("conv_s2k3_col2im");
+  return 0;
+}
+
+int llamax_rowquant_int8_colscale(const void* x, int64_t ldx, const void* col_scale, void* q8, void* scale_out,
+                                  int64_t M, int64_t K, void* stream) {
+  RowCfg c;
+  if (!x || !col_scale || !q8 || !scale_out) return set_error(LLAMAX_ERR_ARG, "rowquant_int8_colscale: null pointer");
+  if (!row_cfg(K, c) || ldx % 8) return set_error(LLAMAX_ERR_ARG, "rowquant_int8_colscale: K and ldx must be multiples of 8");
+  if (M == 0) return 0;
+  LX_DISPATCH_V(c.V, rowquant_kernel<kV, true><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, (int8_t*)q8, (bf16*)scale_out, (int)K, c.nvec, (const bf16*)col_scale));
+  LX_CHECK_LAUNCH("rowquant_int8_colscale");
   return 0;
 }
 

@@ -202,6 +202,21 @@ def rowquant_int8(x: Tensor):
     return q, s
 
 
+def rowquant_int8_colscale(x: Tensor, col_scale: Tensor):
+    """rowquant_int8 of x[m,c] * col_scale[c] (opt-in INT8 grad_input mode): returns (int8 [M,K], bf16 scale [M])."""
+    x2 = _rows(x)
+    lib, st = _prep(x2)
+    assert x2.dtype is torch.bfloat16 and col_scale.dtype is torch.bfloat16 and col_scale.is_contiguous()
+    M, K = x2.shape
+    assert col_scale.numel() == K
+    q = torch.empty(M, K, device=x.device, dtype=torch.int8)
+    s = torch.empty(M, device=x.device, dtype=torch.bfloat16)
+    _call(lib, "llamax_rowquant_int8_colscale",
+          (_p(x2), x2.stride(0), _p(col_scale), _p(q), _p(s), M, K, st,),
+          "rowquant", 0.0, 3.0 * M * K)
+    return q, s
+
+
 def rmsnorm_fwd(x: Tensor, w: Tensor, eps: float, *, quant: bool = False, want_y: bool = True):
     """Returns (y bf16 | None, rstd fp32 [M], q8 | None, qscale | None)."""
     x2 = _rows(x)

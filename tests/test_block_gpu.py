@@ -209,3 +209,23 @@ def test_config0_tiny_audio_prefix_lm():
     }
     print(loss.item(), loss_ref.item(), errs)
     assert all(v <= 5e-2 for v in errs.values()), errs
+
+
+def test_optin_int8_grad_input_is_close_but_not_parity():
+    """SURVEY section 8 row f4 (opt-in, NON-parity): grad_input = q_rowwise(dY * s_w) @ W_int8 on the int8 tensor path.
+    The forward is untouched (bit-identical output); gradients carry 8-bit row quantisation noise, so they are only
+    required to stay within 5e-2 of the fp32 oracle — looser than the 1e-2 parity bar, which is why the mode is off by
+    default and never used for the headline."""
+    import llamax_b200.modelling.fused_block as FB
+
+    base = _layer_case(True, 100)
+    FB.set_int8_grad_input(True)
+    try:
+        rep = _layer_case(True, 100)
+    finally:
+        FB.set_int8_grad_input(False)
+    print({k: (f"{rep[k][0]:.2e}", f"{base[k][0]:.2e}") for k in rep})
+    assert rep["out"][0] == base["out"][0]
+    for key, (err, _) in rep.items():
+        assert err <= 5e-2, f"{key}: {err:.3e}"
+    assert any(rep[k][0] != base[k][0] for k in ("dx", "a_wq", "an"))   # the mode really took the other path
