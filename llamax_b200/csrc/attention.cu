@@ -366,6 +366,319 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 2) tmem_dealloc<1>(tmem_base, 256 * kNB);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward, two query tiles per CTA ("ping-pong"). tools/attn_trace.py on the one-tile kernel above: the softmax
+// warpgroup needs ~2400 cycles per 128x128 tile (128 ex2 per thread on the 16-lane XU pipe = 1024, the max, TMEM
+// round-trips, barriers — one warp per scheduler, nothing to overlap with) against 1364 cycles of MMA work, and the
+// chain softmax(j) -> PV(j) is serial. Here a CTA owns TWO 128-row query tiles with one softmax warpgroup each: while
+// one group is in its exp phase the other waits for its MMAs, so XU pipe and tensor pipe are both kept busy and each
+// K/V tile is loaded once for 256 query rows.
+//   TMEM (512 columns): S0 | S1 (P written over the score columns read, A operand of PV from TMEM) | O0 | O1
+//   MMA issue order   : S0(j0), S1(j0);  then per kv tile j:  PV0(j), S0(j+1) | PV1(j), S1(j+1)
+// ------------------------------------------------------------------------------------------------
+namespace fwd2 {
+constexpr int kTile = 128;
+constexpr int kTileBytes = kTile * kHD * 2;        // 32 KB
+constexpr int kOffQ = 0;                           // 2 query tiles
+constexpr int kOffK = kOffQ + 2 * kTileBytes;      // 2 stages
+constexpr int kOffV = kOffK + 2 * kTileBytes;      // 2 stages
+constexpr int kOffBar = kOffV + 2 * kTileBytes;
+// q_full, k full/empty[2], v full/empty[2], s_full[2 tiles], p_full[2 tiles], pv_done[2 tiles]
+constexpr int kNumBars = 1 + 4 + 4 + 2 + 2 + 2;
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+constexpr int kThreads = 384;                      // warpgroup 0: TMA / MMA / TMEM alloc; warpgroups 1, 2: softmax of tile 0, 1
+constexpr int kRegsCtrl = 56, kRegsSoftmax = 224;  // 56 + 2 * 224 = 504 <= 512
+}  // namespace fwd2
+
+template <bool kDocs, int kD>
+__global__ void __launch_bounds__(fwd2::kThreads, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  using namespace fwd2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;     // [tile]
+  uint64_t* p_full = bars + 11;    // [tile]
+  uint64_t* pv_done = bars + 13;   // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+#ifdef LX_ATTN_TRACE
+  const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 && (warp == 1 || warp == 4);
+#endif
+  // grid = (query heads, batch, pairs of query tiles): pairs run backwards so CTAs are dispatched longest-first
+  const int pr = gridDim.z - 1 - blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hk = h / (p.Hq / p.Hkv);
+  // per-tile kv tile ranges [jb_x, je_x); a tile past the end of the sequence has an empty range
+  int jb_[2], je_[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const int q0 = (2 * pr + x) * kTile;
+    if (q0 < p.S) {
+      const int kv_end = min(p.S, max(p.P, q0 + kTile));
+      je_[x] = (kv_end + kTile - 1) / kTile;
+      jb_[x] = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
+    } else {
+      jb_[x] = je_[x] = 0;
+    }
+  }
+  const bool act1 = je_[1] > jb_[1];
+  const int jb = act1 ? min(jb_[0], jb_[1]) : jb_[0];
+  const int je = max(je_[0], je_[1]);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsCtrl>();
+    if (warp == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {   // rows past the end of the sequence are zero-filled
+          tma_load_4d(smem + kOffQ + x * kTileBytes, &tmQ, q_full, 0, h, (2 * pr + x) * kTile, b);
+          tma_load_4d(smem + kOffQ + x * kTileBytes + kTileBytes / 2, &tmQ, q_full, 64, h, (2 * pr + x) * kTile, b);
+        }
+        for (int j = jb; j < je; ++j) {
+          const int st = (j - jb) & 1;
+          const uint32_t ph = ((j - jb) >> 1) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], kTileBytes);
+          uint8_t* sk = smem + kOffK + st * kTileBytes;
+          tma_load_4d(sk, &tmK, &k_full[st], 0, hk, j * kTile, b);
+          tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, j * kTile, b);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], kTileBytes);
+          uint8_t* sv = smem + kOffV + st * kTileBytes;
+          tma_load_4d(sv, &tmV, &v_full[st], 0, hk, j * kTile, b);
+          tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, j * kTile, b);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ------------------------------------ MMA issuer ------------------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
+        constexpr uint32_t kHi = desc_hi(1024);
+        const uint32_t loQ0 = desc_lo(smem_u32(smem + kOffQ), 16);
+        const uint32_t loK0 = desc_lo(smem_u32(smem + kOffK), 16), loV0 = desc_lo(smem_u32(smem + kOffV), 16384);
+        auto active = [&](int x, int j) { return j >= jb_[x] && j < je_[x]; };
+        // S_x(j) = Q_x K(j)^T; releases K(j) if x is the last tile that reads it
+        auto issue_s = [&](int x, int j) {
+          const int st = (j - jb) & 1;
+          mbar_wait(&k_full[st], ((j - jb) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t loQ = loQ0 + x * (kTileBytes / 16), loK = loK0 + st * (kTileBytes / 16);
+#pragma unroll
+          for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss<false, 1>(tmem_base + x * 128, desc_join(loQ + dh * 1024 + ks * 2, kHi),
+                                desc_join(loK + dh * 1024 + ks * 2, kHi), idesc_s, (dh | ks) != 0);
+          umma_commit(&s_full[x]);
+          if (x == 1 || !active(1, j)) umma_commit(&k_empty[st]);
+        };
+        mbar_wait(q_full, 0);
+        int it[2] = {0, 0};   // iterations done per tile
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+          if (active(x, jb)) issue_s(x, jb);
+        for (int j = jb; j < je; ++j) {
+          const int st = (j - jb) & 1;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (!active(x, j)) continue;
+            if (j == jb_[x] && j != jb) issue_s(x, j);   // a tile whose document starts later than its partner's
+            if (x == 0) LX_TR(tr_cta, j, 0);
+            mbar_wait(&v_full[st], ((j - jb) >> 1) & 1);
+            mbar_wait(&p_full[x], it[x] & 1);
+            tc_fence_after();
+            if (x == 0) LX_TR(tr_cta, j, 1);
+            const uint32_t loV = loV0 + st * (kTileBytes / 16);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts_f16(tmem_base + 256 + x * 128, tmem_base + x * 128 + (kb * 4 + ks) * 8,
+                            desc_join(loV + (kb * 64 + ks * 16) * 8, kHi), idesc_pv, (it[x] | kb | ks) != 0);
+            umma_commit(&pv_done[x]);
+            if (x == 1 || !active(1, j)) umma_commit(&v_empty[st]);
+            ++it[x];
+            if (active(x, j + 1)) issue_s(x, j + 1);     // in order behind PV_x(j), which reads P from the same columns
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------ softmax / correction / epilogue: one warpgroup per query tile ------------
+    setmaxnreg_inc<kRegsSoftmax>();
+    const int x = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane_id();  // row in tile == TMEM lane
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const int q0 = (2 * pr + x) * kTile;
+    const int q = q0 + r;
+    const int jb_x = x ? jb_[1] : jb_[0], je_x = x ? je_[1] : je_[0];
+    const int n_kv = je_x - jb_x;
+    const uint32_t tS = tmem_base + x * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + x * 128 + lane_off;
+    float m_used = -INFINITY, l = 0.f;
+    const int ds_row = kDocs ? p.doc_start[(int64_t)b * p.S + min(q, p.S - 1)] : 0;
+    const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kTile - 1, p.S - 1)] : 0;
+    for (int i = 0; i < n_kv; ++i) {
+      const int kv0 = (jb_x + i) * kTile;
+      // tile needs the element test unless every (q, kv) pair is visible and in range
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      if (x == 0) LX_TR(tr_cta, jb_x + i, 4);
+      mbar_wait(&s_full[x], i & 1);
+      tc_fence_after();
+      if (x == 0) LX_TR(tr_cta, jb_x + i, 5);
+      // single pass over TMEM: the whole score row (128 fp32) lives in registers
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, sv[c]);
+      tmem_wait_ld_regs(sv[0]);
+      tmem_wait_ld_regs(sv[1]);
+      tmem_wait_ld_regs(sv[2]);
+      tmem_wait_ld_regs(sv[3]);
+      if (x == 0) LX_TR(tr_cta, jb_x + i, 6);
+      if (!full_tile) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int kv = kv0 + c * 32 + e;
+            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
+            if (!ok) sv[c][e] = 0xff800000u;  // -inf
+          }
+      }
+      float mx4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mx4[c] = __uint_as_float(sv[c][0]);
+#pragma unroll
+        for (int e = 1; e < 32; ++e) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][e]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_tile = mx * p.scale_log2;
+      float alpha = 1.f;
+      if (m_tile > m_used + 8.f) {  // lazy rescale: only when the running max grows by more than 2^8
+        alpha = ex2(m_used - m_tile);
+        m_used = m_tile;
+      }
+      uint32_t preg[64];
+      float rowsum = 0.f;
+      // a row may see nothing in a visited tile (packed documents): keep the exponent finite so that exp2(-inf) = 0
+      const float m_exp = (m_used == -INFINITY) ? 0.f : m_used;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(sv[c][e]), p.scale_log2, -m_exp));      // -inf -> 0
+          const float p1 = ex2(fmaf(__uint_as_float(sv[c][e + 1]), p.scale_log2, -m_exp));
+          rowsum += p0 + p1;
+          preg[c * 16 + e / 2] = pack_bf16(p0, p1);
+        }
+      l = l * alpha + rowsum;
+      if (x == 0) LX_TR(tr_cta, jb_x + i, 7);
+      if (i > 0) {
+        mbar_wait(&pv_done[x], (i - 1) & 1);  // O stable
+        tc_fence_after();
+        if (x == 0) LX_TR(tr_cta, jb_x + i, 8);
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st_32x32(tO + c * 32, v);
+          }
+          tmem_wait_st();
+        }
+      }
+      {
+        // P (bf16 pairs) -> TMEM, over the first 64 columns of the score tile this row was just read from
+        uint32_t(&p0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&preg[0]);
+        uint32_t(&p1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&preg[32]);
+        tmem_st_32x32(tS, p0);
+        tmem_st_32x32(tS + 32, p1);
+        tmem_wait_st();
+      }
+      if (x == 0) LX_TR(tr_cta, jb_x + i, 9);
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&p_full[x]);
+    }
+    // epilogue
+    if (n_kv > 0) {
+      mbar_wait(&pv_done[x], (n_kv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l;
+      const bool row_ok = q < p.S;
+      __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * kD;
+#pragma unroll 1
+      for (int c = 0; c < kD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + c * 32, v);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 o4;
+            o4.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+            o4.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+            o4.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+            o4.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+            stg_v4(orow + c * 32 + e, o4);
+          }
+        }
+      }
+      if (row_ok) p.lse[((int64_t)b * p.Hq + h) * p.S + q] = (m_used + log2f(l)) * kLn2;
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ================================================================================================
 // backward
 // ================================================================================================
@@ -921,11 +1234,18 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, D, fwd::kTile))) return rc;
   if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, D, fwd::kTile))) return rc;
   if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, fwd::kTile))) return rc;
-  auto kern = doc_start ? (D == 128 ? attn_fwd_kernel<true, 128> : attn_fwd_kernel<true, 64>)
-                        : (D == 128 ? attn_fwd_kernel<false, 128> : attn_fwd_kernel<false, 64>);
-  constexpr int smem_bytes = fwd::smem_bytes(fwd::kNB);
-  static thread_local bool configured[4] = {};
-  const int variant = (doc_start ? 2 : 0) + (D == 128 ? 1 : 0);
+  static const bool one_tile = [] {  // A/B switch: LLAMAX_ATTN_FWD_ONE_TILE=1 -> one query tile per CTA
+    const char* e = getenv("LLAMAX_ATTN_FWD_ONE_TILE");
+    return e != nullptr && e[0] == '1';
+  }();
+  auto kern1 = doc_start ? (D == 128 ? attn_fwd_kernel<true, 128> : attn_fwd_kernel<true, 64>)
+                         : (D == 128 ? attn_fwd_kernel<false, 128> : attn_fwd_kernel<false, 64>);
+  auto kern2 = doc_start ? (D == 128 ? attn_fwd2_kernel<true, 128> : attn_fwd2_kernel<true, 64>)
+                         : (D == 128 ? attn_fwd2_kernel<false, 128> : attn_fwd2_kernel<false, 64>);
+  auto kern = one_tile ? kern1 : kern2;
+  const int smem_bytes = one_tile ? fwd::smem_bytes(fwd::kNB) : fwd2::kSmemBytes;
+  static thread_local bool configured[8] = {};
+  const int variant = (doc_start ? 2 : 0) + (D == 128 ? 1 : 0) + (one_tile ? 4 : 0);
   if (!configured[variant]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd: cudaFuncSetAttribute");
@@ -940,8 +1260,9 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.D = D;
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
-  dim3 grid(Hq, (unsigned)B, (unsigned)ceil_div(S, fwd::kTile));
-  kern<<<grid, fwd::kThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  const unsigned q_tiles = (unsigned)ceil_div(S, fwd::kTile);
+  dim3 grid(Hq, (unsigned)B, one_tile ? q_tiles : (q_tiles + 1) / 2);
+  kern<<<grid, one_tile ? fwd::kThreads : fwd2::kThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   LX_CHECK_LAUNCH("attn_fwd");
   return 0;
 }
