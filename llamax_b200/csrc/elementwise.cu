@@ -785,7 +785,7 @@ int llamax_batched_copy(const llamax_copy_job_t* jobs, int32_t n_jobs, void* str
     cj.j[i] = j;
     max_tiles = std::max(max_tiles, ((j.rows + 31) / 32) * ((j.cols + 31) / 32));
   }
-  dim3 grid((unsigned)std::min(max_tiles, 64), (unsigned)n_jobs);
+  dim3 grid((unsigned)std::min(max_tiles, 512), (unsigned)n_jobs);   // tiny tiles: one per CTA where possible
   batched_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cj);
   LX_CHECK_LAUNCH("batched_copy");
   return 0;

