@@ -26,8 +26,8 @@ METRIC = "train tokens/s, Llama-3.1-8B INT8+LoRA prefix-LM"
 UNIT = "tokens/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r1_ncu_full_top_kernels.csv), keyed by GEMM shape
-NCU_TRAFFIC_BYTES = {"[M=16384,N=4096,K=28688]": 6990669000 + 135219712}  # algorithmic: 1.31 GB (A re-read per n-sweep)
+# (profiles/r1_ncu_full_hot_kernels.csv, kernel ID 0; earlier captures of the same kernel: 5.2-7.1 GB), keyed by GEMM shape
+NCU_TRAFFIC_BYTES = {"[M=16384,N=4096,K=28688]": 5247264000 + 131630000}  # algorithmic: 1.31 GB (A re-read per n-sweep)
 
 LLAMA8B = dict(embed_dim=4096, num_layers=32, head_dim=128, num_heads=32, num_kv_heads=8, intermediate_dim=14336,
                vocab_size=128256, rope_base=500000, is_llama3_1=True)

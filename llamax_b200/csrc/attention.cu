@@ -1133,28 +1133,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
-// delta[b,h,s] = sum_d dO * O  (one warp per (row, head); each lane D/32 elements)
+// delta[b,h,s] = sum_d dO * O. 16-byte loads: D / 8 lanes per (row, head), so a warp covers 2 (D = 128) or 4 (D = 64)
+// heads of one row; the 8-byte-per-lane version ran at half the HBM rate.
 template <int D>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ dout,
                                   int64_t lddo, float* __restrict__ delta, int64_t rows, int S, int Hq) {
+  constexpr int kLanes = D / 8;                 // lanes per head: 16 or 8
+  constexpr int kHeadsPerWarp = 32 / kLanes;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= rows * Hq) return;
-  const int64_t row = w / Hq;
-  const int h = (int)(w - row * Hq);
   const int lane = threadIdx.x & 31;
-  float s;
-  if (D == 128) {
-    const uint2 a = *reinterpret_cast<const uint2*>(o + row * ldo + h * D + lane * 4);
-    const uint2 g = *reinterpret_cast<const uint2*>(dout + row * lddo + h * D + lane * 4);
+  const int groups = (Hq + kHeadsPerWarp - 1) / kHeadsPerWarp;   // warps per row
+  if (w >= rows * groups) return;
+  const int64_t row = w / groups;
+  const int h = (int)(w - row * groups) * kHeadsPerWarp + lane / kLanes;
+  float s = 0.f;
+  if (h < Hq) {
+    const int c = h * D + (lane % kLanes) * 8;
+    const uint4 a = ldg_nc_v4(o + row * ldo + c);
+    const uint4 g = ldg_nc_v4(dout + row * lddo + c);
     s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
-        bf16_hi(a.y) * bf16_hi(g.y);
-  } else {  // D == 64
-    const uint32_t a = *reinterpret_cast<const uint32_t*>(o + row * ldo + h * D + lane * 2);
-    const uint32_t g = *reinterpret_cast<const uint32_t*>(dout + row * lddo + h * D + lane * 2);
-    s = bf16_lo(a) * bf16_lo(g) + bf16_hi(a) * bf16_hi(g);
+        bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+        bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
   }
-  s = warp_sum(s);
-  if (lane == 0) {
+#pragma unroll
+  for (int off = kLanes / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (h < Hq && (lane % kLanes) == 0) {
     const int64_t bb = row / S, ss = row - bb * S;
     delta[(bb * Hq + h) * S + ss] = s;
   }
@@ -1285,7 +1288,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)rows * Hq * D * sizeof(float), st);
   if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: memset");
   {
-    const int64_t warps = rows * Hq;
+    const int64_t warps = rows * ceil_div(Hq, 32 / (D / 8));
     const int blocks = (int)ceil_div(warps * 32, 256);
     if (D == 128)
       attn_delta_kernel<128><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
