@@ -275,8 +275,10 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": ("Llama-3.1-8B shape, frozen INT8 base + LoRA r=%d, %s, seq %d batch %d per GPU" %
                                 (args.rank, "MetaMathQA-shaped text SFT (causal)" if args.workload == "text"
-                                 else "LibriSpeech-shaped 30 s audio prefix (1500) + 256 text, prefix-LM", args.seq, args.batch)),
-                   "layers": args.layers, "global_batch": args.batch * world, "seq_len": args.seq,
+                                 else "LibriSpeech-shaped 30 s audio prefix (1500) + 256 text, prefix-LM",
+                                 args.seq if args.workload == "text" else positions // args.batch, args.batch)),
+                   "layers": args.layers, "global_batch": args.batch * world,
+                   "seq_len": args.seq if args.workload == "text" else positions // args.batch,
                    "int8_mode": "weight-only" if args.weight_only else "dynamic_int8_act", "parallelism": f"dp{world}",
                    **({"NON_PARITY_OPT_IN": "int8 grad_input (gradients quantised to 8 bit per row): not the reference's "
                                             "numerics, not a headline number"} if args.int8_grad_input else {}),

@@ -1,5 +1,5 @@
 """GPU bring-up checks, each run in its own subprocess with a timeout so that a hung kernel cannot take the
-whole call down.  Usage (on a GPU box):  python tools/gpu_check.py [name ...]   (no names = all)
+whole call down.  Usage (on a GPU box):  python tests/gpu_bringup_checks.py [name ...]   (no names = all)
 Results are appended to gpurun_out/gpu_check.log.
 """
 import os

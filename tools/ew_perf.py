@@ -45,8 +45,9 @@ dab = torch.empty(M, 2 * F + 16, device=dev).bfloat16()
 report("swiglu_bwd (+g)", timeit(lambda: ops.swiglu_bwd(dg, ab[:, :F], ab[:, F:], want_g=True, out_ab=dab)), 12.0 * M * F)
 del dg, dab
 qkv = torch.randn(M, (Hq + 2 * Hkv) * hd, device=dev).bfloat16()
-from oracle import ref_ops as R  # rope table only (host-side constant)
-rope = R.build_rope(hd, 4096, 500000.0, True)[:S].to(dev)
+from llamax_b200.modelling.llama import LlamaConfig, build_rope  # noqa: E402  (the product's own table builder)
+rope = build_rope(LlamaConfig(D, 1, hd, Hq, Hkv, F, max_seq_len=4096, vocab_size=1024, rope_base=500000,
+                              is_llama3_1=True))[:S].contiguous().to(dev)
 report("rope (q|k in place)", timeit(lambda: ops.rope_(qkv, rope, B, S, Hq + Hkv, hd)), 4.0 * M * (Hq + Hkv) * hd)
 h = torch.randn(M, 8, device=dev).bfloat16()
 report("lora_wgrad [M,F]^T [M,8]", timeit(lambda: ops.lora_wgrad(ab[:, :F], h, 1.0)), 2.0 * M * (F + 8))
