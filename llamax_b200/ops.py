@@ -319,6 +319,8 @@ def lora_wgrad(X: Tensor, H: Tensor | None, alpha: float = 1.0, *, Ht: Tensor | 
         Ht.copy_(H.t())
     R = Ht.shape[0]
     assert Ht.dtype is torch.bfloat16 and Ht.shape[1] == M and Ht.stride(1) == 1
+    if R > 32:   # the kernel's accumulator is 32 columns wide: wider rank groups (e.g. q|k|v at rank 16) go in chunks
+        return torch.cat([lora_wgrad(X, None, alpha, Ht=Ht[r0 : r0 + 32]) for r0 in range(0, R, 32)], 1)
     out = torch.empty(Pn, R, device=X.device, dtype=torch.float32)
     _call(lib, "llamax_lora_wgrad",
           (_p(X), X.stride(0), _p(Ht), Ht.stride(0), _p(out), M, Pn, R, float(alpha), st),
