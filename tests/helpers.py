@@ -18,8 +18,9 @@ def tiny_config(num_layers=2, max_seq_len=512):
                        rope_base=500000, is_llama3_1=True)
 
 
-def build_tiny_llama(dynamic: bool, num_layers=2, rank=8, seed=0, audio=False, max_seq_len=512):
-    """CPU-initialised (deterministic), quantised + LoRA'd model; caller moves it to CUDA."""
+def build_tiny_llama(dynamic: bool, num_layers=2, rank=8, seed=0, audio=False, max_seq_len=512, adapters="all"):
+    """CPU-initialised (deterministic), quantised + LoRA'd model; caller moves it to CUDA.
+    adapters: "all" | "attention" (LoRA on wq/wk/wv/wo only) | "none"."""
     from llamax_b200.modelling import AudioConfig, Llama, LlamaAudio, apply_linear_adapter_
     from llamax_b200.subclasses import quantize_linear_
 
@@ -28,7 +29,11 @@ def build_tiny_llama(dynamic: bool, num_layers=2, rank=8, seed=0, audio=False, m
     model = LlamaAudio(cfg, AudioConfig(n_mels=80)) if audio else Llama(cfg)
     model = model.bfloat16()
     quantize_linear_(model.layers, "int8", dynamic_int8_act=dynamic)
-    apply_linear_adapter_(model.layers, "lora", rank=rank)
+    if adapters == "all":
+        apply_linear_adapter_(model.layers, "lora", rank=rank)
+    elif adapters == "attention":
+        for layer in model.layers:
+            apply_linear_adapter_(layer.attention, "lora", rank=rank)
     g = torch.Generator().manual_seed(seed + 1)
     for m in model.modules():
         if hasattr(m, "lora_b"):  # zeros-init hides dA / dx_lora errors

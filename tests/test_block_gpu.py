@@ -14,8 +14,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-2
 
 
-def _layer_case(dynamic: bool, prefix_len: int, B=2, S=320, rank=8):
-    model = build_tiny_llama(dynamic, num_layers=1, rank=rank)
+def _layer_case(dynamic: bool, prefix_len: int, B=2, S=320, rank=8, adapters="all"):
+    model = build_tiny_llama(dynamic, num_layers=1, rank=rank, adapters=adapters)
     layer = model.layers[0]
     cfg = model.config
     rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:S]
@@ -41,6 +41,7 @@ def _layer_case(dynamic: bool, prefix_len: int, B=2, S=320, rank=8):
     out.backward(dout.cuda())
     att, ff = layer.attention, layer.feed_forward
     mods = dict(wq=att.wq, wk=att.wk, wv=att.wv, wo=att.wo, w1=ff.w1, w3=ff.w3, w2=ff.w2)
+    mods = {k: m for k, m in mods.items() if getattr(m, "rank", 0) > 0}
     ours = dict(out=out, dx=xc.grad, an=layer.attention_norm.weight.grad, fn=layer.ffn_norm.weight.grad,
                 **{f"a_{k}": m.lora_a.grad for k, m in mods.items()},
                 **{f"b_{k}": m.lora_b.grad for k, m in mods.items()})
@@ -286,5 +287,14 @@ def test_fused_block_lora_rank16():
     """rank 16 on all seven linears: the q|k|v group carries 48 LoRA columns (epilogue rank 16 per GEMM, dh columns
     K-concatenated into the grad_input GEMM, dA through the 32-column wgrad kernel in two chunks)."""
     report = _layer_case(True, 64, rank=16)
+    for key, (ours, ref_bf16) in report.items():
+        assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
+
+
+@pytest.mark.parametrize("adapters", ["attention", "none"])
+def test_fused_block_partial_or_no_adapters(adapters):
+    """LoRA only on the attention projections, or no adapters at all (frozen INT8 block, only the norms train)."""
+    report = _layer_case(True, 0, adapters=adapters)
+    assert ("a_w1" not in report) and (("a_wq" in report) == (adapters == "attention"))
     for key, (ours, ref_bf16) in report.items():
         assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
