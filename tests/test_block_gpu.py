@@ -298,3 +298,11 @@ def test_fused_block_partial_or_no_adapters(adapters):
     assert ("a_w1" not in report) and (("a_wq" in report) == (adapters == "attention"))
     for key, (ours, ref_bf16) in report.items():
         assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
+
+
+def test_fused_block_ragged_token_count():
+    """B*S = 301 tokens: not a multiple of any tile (128-row GEMM / attention tiles, 8-element TMA pitches of the
+    transposed LoRA operands)."""
+    report = _layer_case(True, 77, B=1, S=301)
+    for key, (ours, ref_bf16) in report.items():
+        assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
