@@ -176,10 +176,11 @@ int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, 
 /* Fused pair for one LoRA linear's backward (autograd of modelling/lora.py:43), ONE pass over dY [M,N] (pitch lddy):
  *   dh [M,R] bf16 (pitch lddh) = dY . Bt^T            Bt = lora_scale * B^T, bf16 [R,N] pitch ldbt
  *   dB [N,R] fp32 (zeroed by the call) = alpha * dY^T . h       Ht = h^T, bf16 [R,M] pitch ldht
- * rank in {8,16,24,32}. dh_accum: fp32 workspace [M,R] (used when the column range is split across CTAs). */
+ * rank in {8,16,24,32}. dh_accum: fp32 workspace [M,R] (used when the column range is split across CTAs).
+ * dht: NULL, or bf16 [R,M] (pitch lddht) that also receives dh^T — the H^T operand llamax_lora_wgrad needs for dA. */
 int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t ldbt, const void* Ht, int64_t ldht,
-                         void* dh, int64_t lddh, void* dh_accum, void* dB, int64_t M, int64_t N, int32_t R,
-                         float alpha, void* stream);
+                         void* dh, int64_t lddh, void* dht, int64_t lddht, void* dh_accum, void* dB, int64_t M,
+                         int64_t N, int32_t R, float alpha, void* stream);
 
 
 /* ---- K12 (next row): cross-entropy over bf16 logits, forward + backward in place -------------------

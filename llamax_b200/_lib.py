@@ -72,7 +72,7 @@ SIGNATURES = {
     "llamax_attn_bwd": [P, I64, P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, P, I64, P, P,
                         I64, I64, I32, I32, I32, I64, P, P, c_float, P, P],
     "llamax_lora_wgrad": [P, I64, P, I64, P, I64, I64, I32, c_float, P],
-    "llamax_lora_bwd_pair": [P, I64, P, I64, P, I64, P, I64, P, P, I64, I64, I32, c_float, P],
+    "llamax_lora_bwd_pair": [P, I64, P, I64, P, I64, P, I64, P, I64, P, P, I64, I64, I32, c_float, P],
     "llamax_gelu_bias_fwd": [P, P, P, I64, I64, I32, I32, I32, P],
     "llamax_gelu_bwd": [P, P, P, I64, I64, I32, I32, I32, P],
     "llamax_conv_s2k3_col2im": [P, P, I64, I64, I64, P],

@@ -678,8 +678,8 @@ constexpr int kSmem = kOffBar + kNumBars * 8 + 16 + 1024;
 __global__ void __launch_bounds__(192, 1)
 lora_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmBt,
                      const __grid_constant__ CUtensorMap tmHt, __nv_bfloat16* __restrict__ dh, int64_t lddh,
-                     float* __restrict__ dh_accum, float* __restrict__ dB, int M, int N, int R, int chunks_per_split,
-                     float alpha) {
+                     __nv_bfloat16* __restrict__ dht, int64_t lddht, float* __restrict__ dh_accum,
+                     float* __restrict__ dB, int M, int N, int R, int chunks_per_split, float alpha) {
   using namespace lp;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -827,6 +827,11 @@ lora_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
               stg_v4(dst + j, o);
             }
           }
+          if (dht != nullptr) {   // dh^T [R, M]: the operand of the dA weight gradient; 64 contiguous bytes per warp and r
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < R) dht[(int64_t)r * lddht + row] = __float2bfloat16_rn(__uint_as_float(v[r]));
+          }
         }
       }
     }
@@ -837,9 +842,9 @@ lora_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
   if (warp == 1) tmem_dealloc<1>(tmem_base, 128);
 }
 
-// fp32 [M, R] partial sums -> bf16 dh rows (pitch lddh); one thread per 8 values
+// fp32 [M, R] partial sums -> bf16 dh rows (pitch lddh) and, optionally, dh^T [R, M]; one thread per 8 values
 __global__ void lora_dh_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dh, int64_t lddh,
-                                       int64_t M, int R) {
+                                       __nv_bfloat16* __restrict__ dht, int64_t lddht, int64_t M, int R) {
   const int per_row = R / 8;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * per_row) return;
@@ -853,6 +858,11 @@ __global__ void lora_dh_convert_kernel(const float* __restrict__ acc, __nv_bfloa
   o.z = pack_bf16(b.x, b.y);
   o.w = pack_bf16(b.z, b.w);
   stg_v4(dh + row * lddh + j, o);
+  if (dht != nullptr) {
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dht[(int64_t)(j + k) * lddht + row] = __float2bfloat16_rn(f[k]);
+  }
 }
 
 static int g_gemm_cg = 2;  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group
@@ -957,8 +967,8 @@ int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, 
 }
 
 int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t ldbt, const void* Ht, int64_t ldht,
-                         void* dh, int64_t lddh, void* dh_accum, void* dB, int64_t M, int64_t N, int32_t R,
-                         float alpha, void* stream) {
+                         void* dh, int64_t lddh, void* dht, int64_t lddht, void* dh_accum, void* dB, int64_t M,
+                         int64_t N, int32_t R, float alpha, void* stream) {
   if (!dY || !Bt || !Ht || !dh || !dh_accum || !dB) return set_error(LLAMAX_ERR_ARG, "lora_bwd_pair: null pointer");
   if (R < 8 || R > 32 || R % 8) return set_error(LLAMAX_ERR_ARG, "lora_bwd_pair: rank must be 8, 16, 24 or 32");
   if (M <= 0 || N <= 0) return set_error(LLAMAX_ERR_ARG, "lora_bwd_pair: empty problem");
@@ -994,13 +1004,14 @@ int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t l
   }
   dim3 grid(m_blocks, splits);
   lora_bwd_pair_kernel<<<grid, 192, lp::kSmem, st>>>(tmY, tmBt, tmHt, (__nv_bfloat16*)dh, lddh,
+                                                     splits > 1 ? nullptr : (__nv_bfloat16*)dht, lddht,
                                                      splits > 1 ? (float*)dh_accum : nullptr, (float*)dB, (int)M, (int)N,
                                                      R, chunks_per_split, alpha);
   LX_CHECK_LAUNCH("lora_bwd_pair");
   if (splits > 1) {
     const int64_t n = M * (R / 8);
     lora_dh_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)dh_accum, (__nv_bfloat16*)dh, lddh,
-                                                                        M, R);
+                                                                        (__nv_bfloat16*)dht, lddht, M, R);
     LX_CHECK_LAUNCH("lora_bwd_pair: convert");
   }
   return 0;

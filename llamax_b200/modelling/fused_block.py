@@ -220,11 +220,13 @@ def _lora_prepare(items, M: int, device):
     return prep
 
 
-def _lora_dh_dB(dy: Tensor, bt: Tensor, ht: Tensor, out_dh: Tensor, scale: float) -> Tensor:
-    """out_dh = dy @ bt^T (bt already carries the LoRA scale), returns dB = scale * dy^T h (fp32)."""
+def _lora_dh_dB(dy: Tensor, bt: Tensor, ht: Tensor, out_dh: Tensor, scale: float, out_dht: Tensor) -> Tensor:
+    """out_dh = dy @ bt^T (bt already carries the LoRA scale), out_dht = out_dh^T (operand of the dA weight
+    gradient), returns dB = scale * dy^T h (fp32)."""
     if _LORA_PAIR:
-        return ops.lora_bwd_pair(dy, bt, None, out_dh, scale, Ht=ht)
+        return ops.lora_bwd_pair(dy, bt, None, out_dh, scale, Ht=ht, out_dht=out_dht)
     ops.bf16_gemm(dy, bt, out=out_dh)
+    out_dht.copy_(out_dh.t())
     return ops.lora_wgrad(dy, None, scale, Ht=ht)
 
 
@@ -260,6 +262,7 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tenso
     assert dy_cat.shape[1] == n_total + r_total
     n_off, r_off = 0, 0
     lora_grads = []
+    dht = ops.transposed_rank_buffer(r_total, dy_cat.shape[0], dy_cat.device) if r_total > 0 else None
     for s in specs:
         dy_i = dy_cat[:, n_off : n_off + s.N]
         if s.R > 0:
@@ -268,14 +271,14 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tenso
             if not a_placed and i8 is None:
                 wt[:, c0 : c0 + s.R].copy_(at)
             # one pass over dy_i:  dh_i = scale * dy_i @ B_i -> columns [c0, c0+R) of dy_cat;  dB = scale * dy_i^T h_i
-            dB = _lora_dh_dB(dy_i, bt, ht, dy_cat[:, c0 : c0 + s.R], s.lora_scale)  # [N, R] fp32
+            dB = _lora_dh_dB(dy_i, bt, ht, dy_cat[:, c0 : c0 + s.R], s.lora_scale, dht[r_off : r_off + s.R])  # [N, R] fp32
             lora_grads.append([None, sink.emit(dB, False, s.lora_b.dtype)])
             r_off += s.R
         else:
             lora_grads.append(None)
         n_off += s.N
     if r_total > 0:
-        dA_t = ops.lora_wgrad(x_in, dy_cat[:, n_total:], 1.0)  # [K, r_total] = x^T dh
+        dA_t = ops.lora_wgrad(x_in, None, 1.0, Ht=dht)  # [K, r_total] = x^T dh
         r_off = 0
         for s, lg in zip(specs, lora_grads):
             if lg is not None:
@@ -294,12 +297,13 @@ def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, wt: Tensor | No
     if spec.R > 0:
         bt, at, ht = prep[id(spec)]
         dh = torch.empty(dy.shape[0], spec.R, device=dy.device, dtype=torch.bfloat16)
-        dB = sink.emit(_lora_dh_dB(dy, bt, ht, dh, spec.lora_scale), False, spec.lora_b.dtype)  # dh, dB in one pass
+        dht = ops.transposed_rank_buffer(spec.R, dy.shape[0], dy.device)
+        dB = sink.emit(_lora_dh_dB(dy, bt, ht, dh, spec.lora_scale, dht), False, spec.lora_b.dtype)  # dh, dh^T, dB
         if i8 is not None:
             dx = _grad_input_i8(dy, i8[0], i8[1], dh, at)
         else:
             dx = ops.bf16_gemm(dy, wt, lora_h=dh, lora_b=at, lora_scale=1.0)
-        dA = sink.emit(ops.lora_wgrad(x_in, dh, 1.0), True, spec.lora_a.dtype)
+        dA = sink.emit(ops.lora_wgrad(x_in, None, 1.0, Ht=dht), True, spec.lora_a.dtype)
         return dx, (dA, dB)
     if i8 is not None:
         return _grad_input_i8(dy, i8[0], i8[1], None, None), None
@@ -438,7 +442,8 @@ class FusedDecoderBlock(torch.autograd.Function):
         if s2.R > 0:
             bt2, at2, ht2 = prep[id(s2)]
             dh2 = torch.empty(M, s2.R, device=dev, dtype=torch.bfloat16)
-            dB2 = sink.emit(_lora_dh_dB(dout2, bt2, ht2, dh2, s2.lora_scale), False, s2.lora_b.dtype)
+            dht2 = ops.transposed_rank_buffer(s2.R, M, dev)
+            dB2 = sink.emit(_lora_dh_dB(dout2, bt2, ht2, dh2, s2.lora_scale, dht2), False, s2.lora_b.dtype)
             if _INT8_GRAD:
                 dg = _grad_input_i8(dout2, i8["w2"][0], i8["w2"][1], dh2, at2)
             else:
@@ -449,7 +454,7 @@ class FusedDecoderBlock(torch.autograd.Function):
             dg = ops.bf16_gemm(dout2, wt2)
         _, _, g = ops.swiglu_bwd(dg, ab[:, :F_], ab[:, F_:], want_g=s2.R > 0, out_ab=dab)
         if s2.R > 0:
-            g2 = (sink.emit(ops.lora_wgrad(g, dh2, 1.0), True, s2.lora_a.dtype), dB2)
+            g2 = (sink.emit(ops.lora_wgrad(g, None, 1.0, Ht=dht2), True, s2.lora_a.dtype), dB2)
         del dg, g
 
         # --- w1 | w3 ---

@@ -329,7 +329,7 @@ def lora_wgrad(X: Tensor, H: Tensor | None, alpha: float = 1.0, *, Ht: Tensor | 
 
 
 def lora_bwd_pair(dY: Tensor, Bt: Tensor, H: Tensor | None, out_dh: Tensor, alpha: float = 1.0, *,
-                  Ht: Tensor | None = None) -> Tensor:
+                  Ht: Tensor | None = None, out_dht: Tensor | None = None) -> Tensor:
     """One pass over dY [M,N]: writes out_dh [M,R] = dY @ Bt^T (Bt = scale * B^T, [R,N]) and returns
     dB [N,R] (fp32) = alpha * dY^T @ H. Replaces a skinny dh GEMM + lora_wgrad that each streamed dY from HBM."""
     lib, st = _prep(dY)
@@ -343,10 +343,12 @@ def lora_bwd_pair(dY: Tensor, Bt: Tensor, H: Tensor | None, out_dh: Tensor, alph
     R = Ht.shape[0]
     assert Ht.dtype is torch.bfloat16 and Ht.shape[1] == M and Ht.stride(1) == 1
     assert Bt.shape == (R, N) and out_dh.shape == (M, R)
+    if out_dht is not None:   # also emit dh^T [R, M] (rows of a transposed_rank_buffer): the Ht operand of lora_wgrad
+        assert out_dht.dtype is torch.bfloat16 and out_dht.shape == (R, M) and out_dht.stride(1) == 1
     dB = torch.empty(N, R, device=dY.device, dtype=torch.float32)
     acc = torch.empty(M, R, device=dY.device, dtype=torch.float32)
     _call(lib, "llamax_lora_bwd_pair",
-          (_p(dY), dY.stride(0), _p(Bt), Bt.stride(0), _p(Ht), Ht.stride(0), _p(out_dh), out_dh.stride(0), _p(acc), _p(dB), M, N, R, float(alpha), st),
+          (_p(dY), dY.stride(0), _p(Bt), Bt.stride(0), _p(Ht), Ht.stride(0), _p(out_dh), out_dh.stride(0), _p(out_dht), out_dht.stride(0) if out_dht is not None else 0, _p(acc), _p(dB), M, N, R, float(alpha), st),
           "lora_wgrad", 4.0 * M * N * R, 2.0 * M * (N + 2 * R))
     return dB
 

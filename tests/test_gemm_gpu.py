@@ -140,7 +140,9 @@ def test_lora_bwd_pair_matches_separate_products(M, N, R):
     bt = (torch.randn(R, N, device="cuda") * 0.1).bfloat16()
     h = torch.randn(M, R + 8, device="cuda").bfloat16()[:, :R]
     out = torch.zeros(M, R + 8, device="cuda", dtype=torch.bfloat16)
-    dB = ops.lora_bwd_pair(dy, bt, h, out[:, :R], 0.5)
+    dht = ops.transposed_rank_buffer(R, M, "cuda")
+    dB = ops.lora_bwd_pair(dy, bt, h, out[:, :R], 0.5, out_dht=dht)
+    assert torch.equal(dht, out[:, :R].t())                                   # dh^T emitted by the same pass
     dh_ref = dy.float() @ bt.float().t()
     dB_ref = 0.5 * (dy.float().t() @ h.float())
     assert rel_err(out[:, :R].float(), dh_ref) <= 1e-2
