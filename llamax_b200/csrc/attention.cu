@@ -760,9 +760,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int warp = threadIdx.x >> 5;
-  // grid = (kv heads, batch, kv tiles): the kv tile is the slowest index, so CTAs are dispatched longest-first
-  // (tile 0 is visited by every query tile, the last tile only by the last one)
-  const int hk = blockIdx.x, b = blockIdx.y, jt = blockIdx.z;
+  // grid = (kv heads, kv tiles, batch): within a batch element CTAs are dispatched longest-first (tile 0 is visited by
+  // every query tile, the last tile only by the last one); batch elements follow one another so that the fp32 dQ
+  // accumulator being reduced into stays L2-resident (one element = 33 MB at 8B shape, S = 2048)
+  const int hk = blockIdx.x, jt = blockIdx.y, b = blockIdx.z;
 #ifdef LX_ATTN_TRACE
   const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 &&
                       (warp == 1 || warp == 4 || warp == 12);
@@ -1326,7 +1327,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.doc_start = (const int32_t*)doc_start;
   p.doc_end = (const int32_t*)doc_end;
   p.rope = (const float*)rope_inverse;
-  dim3 grid(Hkv, (unsigned)B, (unsigned)ceil_div(S, bwd::kKV));
+  dim3 grid(Hkv, (unsigned)ceil_div(S, bwd::kKV), (unsigned)B);
   kern<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");
   {
