@@ -225,11 +225,18 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.TIMING.enable()
+    # timed region: only the dominant kernel class (bf16 GEMM, a few hundred launches) carries CUDA-event pairs, so the
+    # instrumentation costs nothing measurable; the full per-kernel breakdown comes from a separate instrumented pass
+    ops.TIMING.enable(only={"bf16_gemm"})
     ms, loss_val = timed(args.steps, e2e=False)
-    kern = ops.TIMING.summary()            # per-kernel-class device time over the timed region
+    kern_dom = ops.TIMING.summary()        # bf16 GEMM launches of the timed region (roofline object)
     ops.TIMING.disable()
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
+    ops.TIMING.enable()
+    ms_prof, _ = timed(args.steps, e2e=False)
+    kern = ops.TIMING.summary()            # every library launch, by kernel class (events around each: ~2 % overhead)
+    ops.TIMING.disable()
+    kern.update({k: v for k, v in kern_dom.items()})   # the bf16 GEMM entries quoted are those of the timed region
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -292,6 +299,8 @@ def run_ours(args):
         "gpu_launches": sum(v["n"] * (4 if k == "attn_bwd" else 2 if k == "lora_wgrad" else 1) for k, v in kern.items()),
         "roofline": roof,
         "kernels": shares,
+        "kernels_note": "per-class device time from a separate fully instrumented pass of the same steps (%.2f ms/step); "
+                        "bf16_gemm and the roofline object are from the timed region itself" % (ms_prof / args.steps),
         "dp_payload_bytes": bucket.nbytes(),
     }
     if not args.no_cpu_baseline and world == 1:

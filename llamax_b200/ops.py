@@ -23,10 +23,12 @@ class _KernelTiming:
 
     def __init__(self):
         self.on = False
+        self.only = None
         self.records = []
 
-    def enable(self):
-        self.records, self.on = [], True
+    def enable(self, only=None):
+        """only: optional set of kernel classes to time (the others run without event records)."""
+        self.records, self.on, self.only = [], True, (set(only) if only else None)
 
     def disable(self):
         self.on = False
@@ -49,7 +51,7 @@ TIMING = _KernelTiming()
 def _call(lib, name: str, args: tuple, kclass: str, flops: float = 0.0, nbytes: float = 0.0, shape=None):
     """Invoke one C-ABI entry point; raise on a non-zero return; optionally time it with CUDA events."""
     fn = getattr(lib, name)
-    if TIMING.on:
+    if TIMING.on and (TIMING.only is None or kclass in TIMING.only):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
