@@ -68,6 +68,12 @@ int llamax_int8_gemm_s32(const void* A, int64_t lda, const void* B, int64_t ldb,
 int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
                      int64_t N, int64_t K, const void* col_scale, int round_before_scale,
                      const llamax_epilogue_t* epi, void* stream);
+/* Weight-gradient form: C[m,n] = bf16( sum_k At[k,m] * Bt[k,n] ), At bf16 [K,M] pitch ldat, Bt bf16 [K,N] pitch ldbt
+ * (M, N indices contiguous; M % 8 == 0, N % 8 == 0). Both tensors are consumed as stored (MN-major UMMA operands):
+ * dW[out,in] = dY[tokens,out]^T X[tokens,in] needs no transposed copies. Rows of Bt may overlap (pitch < N), which is
+ * how the audio stem's im2col view is read. Used for the conv-stem weight gradients and a trainable LM head. */
+int llamax_bf16_gemm_tn(const void* At, int64_t ldat, const void* Bt, int64_t ldbt, void* C, int64_t ldc, int64_t M,
+                        int64_t N, int64_t K, void* stream);
 
 /* De-quantise a frozen weight into a bf16 GEMM operand (scratch owned by the caller).
  *   transpose = 0: out[n,k] = bf16(w8[n,k]) (* scale[n] if apply_scale)          out [N,K], row pitch ldo

@@ -79,7 +79,10 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 }
 
 // kRank: compile-time LoRA rank of the epilogue (0 = none, 8, 16); runtime ranks are zero-padded up to it.
-template <bool kInt8, int CG, int kRank>
+// kMN: both operands are stored "transposed", A_t [K, M] and B_t [K, N] with the M / N index contiguous (the
+// weight-gradient form dW[out, in] = sum_tokens dY[token, out] * X[token, in] with tokens = K): the tiles are loaded as
+// [64 k] x [64 mn] boxes and fed to the UMMA as MN-major operands — no transposed copy of either tensor.
+template <bool kInt8, int CG, int kRank, bool kMN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<CG>;
@@ -149,7 +152,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          if constexpr (CG == 1) {
+          if constexpr (kMN) {
+            // boxes of [64 k rows] x [64 mn elements = 128 B]: inner coordinate = mn index, outer = k
+            constexpr int kBoxBytes = 64 * 128;
+            if constexpr (CG == 1) {
+              mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+#pragma unroll
+              for (int i = 0; i < kBM / 64; ++i)
+                tma_load_2d(sa + i * kBoxBytes, &tmA, &full_bar[stage], row_a + i * 64, kb * 64);
+#pragma unroll
+              for (int i = 0; i < kBN / 64; ++i)
+                tma_load_2d(sb + i * kBoxBytes, &tmB, &full_bar[stage], row_b + i * 64, kb * 64);
+            } else {
+              if (is_leader) mbar_expect_tx(&full_bar[stage], S::kStageBytes * 2);
+              const uint32_t bar_addr = full_addr + stage * 8;
+#pragma unroll
+              for (int i = 0; i < kBM / 64; ++i)
+                tma_load_2d_cg2(sa + i * kBoxBytes, &tmA, bar_addr, row_a + i * 64, kb * 64);
+#pragma unroll
+              for (int i = 0; i < kBN / CG / 64; ++i)
+                tma_load_2d_cg2(sb + i * kBoxBytes, &tmB, bar_addr, row_b + i * 64, kb * 64);
+            }
+          } else if constexpr (CG == 1) {
             mbar_expect_tx(&full_bar[stage], S::kStageBytes);
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * kElemPerRow, row_a);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * kElemPerRow, row_b);
@@ -167,7 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (is_leader && elect_one()) {
-      constexpr uint32_t idesc = kInt8 ? make_idesc(2, 1, kTileM, kBN) : make_idesc(1, 1, kTileM, kBN);
+      constexpr uint32_t idesc = kInt8 ? make_idesc(2, 1, kTileM, kBN)
+                                       : make_idesc(1, 1, kTileM, kBN, kMN ? 1 : 0, kMN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int local_tile = 0;
@@ -182,13 +207,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
-          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+          // K-major: 8-row atoms 1024 B apart, +32 B per k-step inside the swizzle atom (+2 in the addr >> 4 field);
+          // MN-major: 64-element mn atoms one 8 KB box apart (LBO), 8-k-row groups 1024 B apart, +16 k rows = 2048 B
+          const uint64_t adesc = make_smem_desc_sw128(sa, kMN ? 8192 : 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, kMN ? 8192 : 16, 1024);
+          constexpr int kStep = kMN ? 128 : 2;
 #pragma unroll
-          for (int k = 0; k < kBKBytes / 32; ++k) {
-            // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_ss<kInt8, CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < kBKBytes / 32; ++k)
+            umma_ss<kInt8, CG>(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb | k) != 0);
           if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -350,7 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <bool kInt8, int CG, int kRank>
+template <bool kInt8, int CG, int kRank, bool kMN = false>
 static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
   using S = GemmSmem<CG>;
@@ -369,12 +395,21 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
 
   CUtensorMap tmA, tmB;
   const CUtensorMapDataType dt = kInt8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  int rc = make_tmap_2d(&tmA, dt, esz, A, p.K, p.M, lda, elem_per_row, kBM);
-  if (rc) return rc;
-  rc = make_tmap_2d(&tmB, dt, esz, B, p.K, p.N, ldb, elem_per_row, kBN / CG);
-  if (rc) return rc;
+  int rc;
+  if constexpr (kMN) {   // A_t [K, M], B_t [K, N]: inner dimension = M / N, boxes [64 mn] x [64 k]
+    static_assert(!kInt8, "MN-major operands: bf16 only");
+    rc = make_tmap_2d(&tmA, dt, esz, A, p.M, p.K, lda, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB, dt, esz, B, p.N, p.K, ldb, 64, 64);
+    if (rc) return rc;
+  } else {
+    rc = make_tmap_2d(&tmA, dt, esz, A, p.K, p.M, lda, elem_per_row, kBM);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB, dt, esz, B, p.K, p.N, ldb, elem_per_row, kBN / CG);
+    if (rc) return rc;
+  }
 
-  auto kern = gemm_kernel<kInt8, CG, kRank>;
+  auto kern = gemm_kernel<kInt8, CG, kRank, kMN>;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -1015,6 +1050,18 @@ int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t l
     LX_CHECK_LAUNCH("lora_bwd_pair: convert");
   }
   return 0;
+}
+
+int llamax_bf16_gemm_tn(const void* At, int64_t ldat, const void* Bt, int64_t ldbt, void* C, int64_t ldc, int64_t M,
+                        int64_t N, int64_t K, void* stream) {
+  if (!At || !Bt || !C) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_tn: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(LLAMAX_ERR_ARG, "gemm: empty problem");
+  if (M % 8) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_tn: M must be a multiple of 8");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.C = C; p.ldc = ldc;
+  return g_gemm_cg == 2 ? launch_gemm_r<false, 2, 0, true>(At, ldat, Bt, ldbt, p, (cudaStream_t)stream)
+                        : launch_gemm_r<false, 1, 0, true>(At, ldat, Bt, ldbt, p, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -171,6 +171,23 @@ def bf16_gemm(A: Tensor, B: Tensor, *, col_scale: Tensor | None = None, round_be
     return out
 
 
+def bf16_gemm_tn(At: Tensor, Bt: Tensor, *, out: Tensor | None = None) -> Tensor:
+    """C[M,N] = At[K,M]^T @ Bt[K,N] (bf16 in/out, fp32 accumulate): the weight-gradient form, both operands consumed as
+    stored (rows = the contraction index; row pitches may be smaller than the row length, i.e. overlapping rows)."""
+    lib, st = _prep(At)
+    assert At.dtype is torch.bfloat16 and Bt.dtype is torch.bfloat16 and At.dim() == 2 and Bt.dim() == 2
+    assert At.stride(1) == 1 and Bt.stride(1) == 1 and At.shape[0] == Bt.shape[0]
+    K, M = At.shape
+    N = Bt.shape[1]
+    if out is None:
+        out = torch.empty(M, N, device=At.device, dtype=torch.bfloat16)
+    assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+    _call(lib, "llamax_bf16_gemm_tn",
+          (_p(At), At.stride(0), _p(Bt), Bt.stride(0), _p(out), out.stride(0), M, N, K, st,),
+          "bf16_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))
+    return out
+
+
 def dequant_weight(w8: Tensor, scale: Tensor | None, *, transpose: bool, apply_scale: bool,
                    out: Tensor | None = None) -> Tensor:
     lib, st = _prep(w8)

@@ -148,3 +148,29 @@ def test_lora_bwd_pair_matches_separate_products(M, N, R):
     assert rel_err(out[:, :R].float(), dh_ref) <= 1e-2
     assert rel_err(dB, dB_ref) <= 1e-2
     assert torch.count_nonzero(out[:, R:]) == 0                               # nothing written past the rank columns
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("K,M,N", [(64, 128, 256), (300, 264, 208), (1001, 512, 1536), (4096, 1024, 240), (130, 8, 8)])
+def test_bf16_gemm_tn_weight_gradient_form(cg, K, M, N):
+    """C = At^T Bt with both operands consumed as stored (MN-major UMMA operands), ragged K / M / N tails."""
+    ops.set_gemm_cta_group(cg)
+    try:
+        torch.manual_seed(K + M + N)
+        at = torch.randn(K, M + 8, device="cuda").bfloat16()[:, :M]      # pitched
+        bt = torch.randn(K, N, device="cuda").bfloat16()
+        out = ops.bf16_gemm_tn(at, bt)
+        assert rel_err(out, at.float().t() @ bt.float()) <= 1e-2
+    finally:
+        ops.set_gemm_cta_group(2)
+
+
+def test_bf16_gemm_tn_overlapping_rows():
+    """Bt as an im2col view with overlapping rows (row pitch 2C < row length 3C), the audio stem's dW form."""
+    torch.manual_seed(0)
+    C, rows = 64, 301
+    y = torch.randn(2 * rows + 4, C, device="cuda").bfloat16()
+    col = y.as_strided((rows, 3 * C), (2 * C, 1))
+    dz = torch.randn(rows, 128, device="cuda").bfloat16()
+    out = ops.bf16_gemm_tn(dz, col)
+    assert rel_err(out, dz.float().t() @ col.float()) <= 1e-2
