@@ -25,9 +25,6 @@ from .llama import Llama, LlamaConfig, PrefixLM
 _OWN_STEM = os.environ.get("LLAMAX_AUDIO_STEM", "1") != "0"
 
 
-def _pad8(n: int) -> int:
-    return (n + 7) // 8 * 8
-
 
 class AudioStemFn(torch.autograd.Function):
     """prefix [B, T/2, C] = GELU(Conv1d_k3s2(GELU(Conv1d_k3s1(mel)))) for mel [B, Cin, T] (T even), channels-last inside.
@@ -77,14 +74,9 @@ class AudioStemFn(torch.autograd.Function):
         dy2[:, : half - 1] = dout
         dz2 = ops.gelu_bwd(dy2.view(B * half, C), z2, half, 0, half - 1)
         db2 = dz2.sum(0, dtype=torch.float32).to(torch.bfloat16)
-        # dW2 [C, 3C] = dz2^T . im2col(y1): contraction over the (batch x time) rows -> both operands transposed copies
-        k2 = _pad8(M2)
-        dz2t = torch.zeros(C, k2, device=dev, dtype=torch.bfloat16)
-        dz2t[:, :M2] = dz2[:M2].t()
-        a2t = torch.zeros(3 * C, k2, device=dev, dtype=torch.bfloat16)
-        a2t[:, :M2] = y1.as_strided((M2, 3 * C), (2 * C, 1)).t()
-        dw2 = ops.bf16_gemm(dz2t, a2t).view(C, 3, C).permute(0, 2, 1).contiguous()
-        del dz2t, a2t
+        # dW2 [C, 3C] = dz2^T . im2col(y1): contraction over the (batch x time) rows; both operands are consumed as
+        # stored (MN-major UMMA operands), the im2col matrix again as the overlapping-row view of y1
+        dw2 = ops.bf16_gemm_tn(dz2[:M2], y1.as_strided((M2, 3 * C), (2 * C, 1))).view(C, 3, C).permute(0, 2, 1).contiguous()
         # input gradient of conv 2: column gradient, then overlap-add back onto the padded rows
         dcol = torch.zeros(B * half, 3 * C, device=dev, dtype=torch.bfloat16)
         ops.bf16_gemm(dz2[:M2], w2r.t().contiguous(), out=dcol[:M2])
@@ -92,12 +84,8 @@ class AudioStemFn(torch.autograd.Function):
         del dcol
         dz1 = ops.gelu_bwd(dy1p.view(B * Tp, C), z1, Tp, 1, T + 1)
         db1 = dz1.sum(0, dtype=torch.float32).to(torch.bfloat16)
-        k1 = _pad8(M1)
-        dz1t = torch.zeros(C, k1, device=dev, dtype=torch.bfloat16)
-        dz1t[:, :M1] = dz1[1 : 1 + M1].t()
-        a1t = torch.zeros(3 * Cin, k1, device=dev, dtype=torch.bfloat16)
-        a1t[:, :M1] = x0p.as_strided((M1, 3 * Cin), (Cin, 1)).t()
-        dw1 = ops.bf16_gemm(dz1t, a1t).view(C, 3, Cin).permute(0, 2, 1).contiguous()
+        dw1 = ops.bf16_gemm_tn(dz1[1 : 1 + M1], x0p.as_strided((M1, 3 * Cin), (Cin, 1)))
+        dw1 = dw1.view(C, 3, Cin).permute(0, 2, 1).contiguous()
         return None, dw1, db1, dw2, db2
 
 

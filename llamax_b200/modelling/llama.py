@@ -356,7 +356,7 @@ class _ChunkedLMLoss(torch.autograd.Function):
             if need_dx:
                 ops.bf16_gemm(logits, weight_t, out=dx[i : i + C])
             if need_dw:
-                dw += (logits.T @ xs).float()  # trainable head: library GEMM (contraction over tokens)
+                dw += ops.bf16_gemm_tn(logits, xs)  # trainable head: dW chunk = dlogits^T x, operands as stored
         ctx.save_for_backward(dx, dw)
         ctx.x_shape = x.shape
         ctx.w_dtype = weight.dtype

@@ -306,3 +306,31 @@ def test_fused_block_ragged_token_count():
     report = _layer_case(True, 77, B=1, S=301)
     for key, (ours, ref_bf16) in report.items():
         assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
+
+
+def test_trainable_lm_head_loss_and_weight_gradient():
+    """LM head + cross-entropy (llama.py:216-218) with a TRAINABLE head: loss, dx and dW (the dW chunks run on the
+    weight-gradient GEMM form, dlogits^T x with both operands as stored) against the fp32 evaluation. Ragged row count
+    (two chunks, the second partial), -100 labels."""
+    from llamax_b200.modelling.llama import _ChunkedLMLoss, chunked_lm_loss
+
+    torch.manual_seed(5)
+    M, D, V = 700, 256, 1032
+    x = (torch.randn(M, D) * 0.5).bfloat16()
+    w = (torch.randn(V, D) * 0.05).bfloat16()
+    labels = torch.randint(0, V, (M,))
+    labels[::7] = -100
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    loss_ref = torch.nn.functional.cross_entropy(xr @ wr.t(), labels)
+    loss_ref.backward()
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    old = _ChunkedLMLoss.CHUNK
+    _ChunkedLMLoss.CHUNK = 512
+    try:
+        loss = chunked_lm_loss(xc, wc, labels.cuda(), wc.detach().t().contiguous())
+        loss.backward()
+    finally:
+        _ChunkedLMLoss.CHUNK = old
+    assert abs(loss.item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
+    assert rel_err(xc.grad, xr.grad) <= TOL
+    assert rel_err(wc.grad, wr.grad) <= TOL
