@@ -68,6 +68,15 @@ int llamax_int8_gemm_s32(const void* A, int64_t lda, const void* B, int64_t ldb,
 int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
                      int64_t N, int64_t K, const void* col_scale, int round_before_scale,
                      const llamax_epilogue_t* epi, void* stream);
+/* grad_input GEMM of w2 with the SwiGLU backward as its epilogue (modelling/llama.py:152 differentiated):
+ *   dg[m,n] = bf16( sum_k A[m,k]*B[n,k] + lora term )            (never written)
+ *   da | db = swiglu_bwd(dg, a, b)   with a = ab[:, 0:N], b = ab[:, N:2N]  -> dab[:, 0:N] | dab[:, N:2N]
+ *   g       = bf16(silu(a)) * b      -> g [M,N] contiguous, optional (NULL = not needed)
+ * Same arithmetic as llamax_bf16_gemm followed by llamax_swiglu_bwd (identical results); N % 16 == 0,
+ * ld_ab / ld_dab multiples of 8 and >= 2N, pointers 16-byte aligned. epi: LoRA term only (no residual). */
+int llamax_bf16_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                                const llamax_epilogue_t* epi, const void* ab, int64_t ld_ab, void* dab, int64_t ld_dab,
+                                void* g, void* stream);
 /* Weight-gradient form: C[m,n] = bf16( sum_k At[k,m] * Bt[k,n] ), At bf16 [K,M] pitch ldat, Bt bf16 [K,N] pitch ldbt
  * (M, N indices contiguous; M % 8 == 0, N % 8 == 0). Both tensors are consumed as stored (MN-major UMMA operands):
  * dW[out,in] = dY[tokens,out]^T X[tokens,in] needs no transposed copies. Rows of Bt may overlap (pitch < N), which is

@@ -59,6 +59,7 @@ SIGNATURES = {
     "llamax_int8_gemm_dequant": [P, I64, P, I64, P, P, P, I64, I64, I64, I64, EP, P],
     "llamax_int8_gemm_s32": [P, I64, P, I64, P, I64, I64, I64, I64, P],
     "llamax_bf16_gemm": [P, I64, P, I64, P, I64, I64, I64, I64, P, c_int, EP, P],
+    "llamax_bf16_gemm_swiglu_bwd": [P, I64, P, I64, I64, I64, I64, EP, P, I64, P, I64, P, P],
     "llamax_bf16_gemm_tn": [P, I64, P, I64, P, I64, I64, I64, I64, P],
     "llamax_dequant_weight": [P, P, P, I64, I64, I64, c_int, c_int, P],
     "llamax_rowquant_int8": [P, I64, P, P, I64, I64, P],

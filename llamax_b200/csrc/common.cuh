@@ -416,4 +416,40 @@ __device__ __forceinline__ void stg_v4(void* p, const uint4& v) {
                : "memory");
 }
 
+// 32-byte global accesses (one full sector per thread; sm_100 LDG/STG.256). `wide` = the address is 32-byte aligned,
+// otherwise two 16-byte accesses.
+__device__ __forceinline__ void ldg_nc_32B(const void* p, uint32_t (&r)[8], bool wide) {
+  if (wide) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+  } else {
+    const uint4 lo = ldg_nc_v4(p), hi = ldg_nc_v4(static_cast<const uint8_t*>(p) + 16);
+    r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w; r[4] = hi.x; r[5] = hi.y; r[6] = hi.z; r[7] = hi.w;
+  }
+}
+__device__ __forceinline__ void stg_32B(void* p, const uint32_t (&r)[8], bool wide) {
+  if (wide) {
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  } else {
+    stg_v4(p, make_uint4(r[0], r[1], r[2], r[3]));
+    stg_v4(static_cast<uint8_t*>(p) + 16, make_uint4(r[4], r[5], r[6], r[7]));
+  }
+}
+
+
+// SwiGLU backward for one element (modelling/llama.py:143-152 differentiated, with the reference's bf16 roundings of
+// silu(a) and of dg*b): da, db and the re-materialised g = bf16(silu(a)) * b, all still fp32 (the caller rounds).
+// Shared by swiglu_bwd_kernel and the fused epilogue of the w2 grad_input GEMM so both give identical results.
+__device__ __forceinline__ void swiglu_bwd_elem(float dg, float a, float b, float& da, float& db, float& g) {
+  const float sig = __fdividef(1.0f, 1.0f + __expf(-a));
+  const float sl = round_bf16(a * sig);
+  db = dg * sl;
+  const float dsl = round_bf16(dg * b);
+  da = dsl * (sig * (1.0f + a * (1.0f - sig)));
+  g = sl * b;
+}
+
 }  // namespace lx

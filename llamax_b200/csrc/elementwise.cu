@@ -243,14 +243,7 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __
     unpack8(ldg_nc_v4(b + row * ld + c), bf);
     unpack8(ldg_nc_v4(dg + row * (int64_t)nvec * 8 + c), dgf);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float sig = __fdividef(1.0f, 1.0f + __expf(-af[e]));
-      const float sl = round_bf16(af[e] * sig);
-      ob[e] = dgf[e] * sl;
-      const float dsl = round_bf16(dgf[e] * bf[e]);
-      oa[e] = dsl * (sig * (1.0f + af[e] * (1.0f - sig)));
-      og[e] = sl * bf[e];
-    }
+    for (int e = 0; e < 8; ++e) swiglu_bwd_elem(dgf[e], af[e], bf[e], oa[e], ob[e], og[e]);
     *reinterpret_cast<uint4*>(da + row * ldd + c) = pack8(oa);
     *reinterpret_cast<uint4*>(db + row * ldd + c) = pack8(ob);
     if (g != nullptr) *reinterpret_cast<uint4*>(g + row * (int64_t)nvec * 8 + c) = pack8(og);

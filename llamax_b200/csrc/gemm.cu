@@ -44,6 +44,12 @@ struct GemmParams {
   const __nv_bfloat16* resid;
   int64_t ldr;
   int flags;  // 1: dump raw accumulator (int32 / fp32) to C; 2: round to bf16 before the column scale
+  // kSwi epilogue (SwiGLU backward fused behind the w2 grad_input GEMM): C is not written
+  const __nv_bfloat16* swi_ab;  // [M, 2N] pitch ld_ab: a = w1 x in columns [0, N), b = w3 x in [N, 2N)
+  int64_t ld_ab;
+  __nv_bfloat16* swi_dab;       // da -> columns [0, N), db -> [N, 2N), pitch ld_dab
+  int64_t ld_dab;
+  __nv_bfloat16* swi_g;         // optional g = bf16(silu(a)) * b, [M, N] contiguous
 };
 
 template <int CG>
@@ -82,7 +88,10 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 // kMN: both operands are stored "transposed", A_t [K, M] and B_t [K, N] with the M / N index contiguous (the
 // weight-gradient form dW[out, in] = sum_tokens dY[token, out] * X[token, in] with tokens = K): the tiles are loaded as
 // [64 k] x [64 mn] boxes and fed to the UMMA as MN-major operands — no transposed copy of either tensor.
-template <bool kInt8, int CG, int kRank, bool kMN = false>
+// kSwi: the accumulator (+ LoRA term) is d(loss)/d(g) of the SwiGLU (llama.py:152); the epilogue rounds it to bf16 as
+// the stand-alone GEMM would, then applies the SwiGLU backward to the thread's a / b columns and writes da | db (| g)
+// instead of dg: one [M, F] bf16 write + read and one launch less per block than GEMM -> swiglu_bwd_kernel.
+template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<CG>;
@@ -234,6 +243,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool dump = (p.flags & 1) != 0;
     const bool has_cs = p.col_scale != nullptr;
     const bool pre_round = (p.flags & 2) != 0;
+    // 32-byte accesses when every row start of ab / dab / g is 32-byte aligned (N % 16 == 0 is required by the host)
+    const bool swi_wide = kSwi && ((reinterpret_cast<uintptr_t>(p.swi_ab) | reinterpret_cast<uintptr_t>(p.swi_dab) |
+                                    reinterpret_cast<uintptr_t>(p.swi_g)) % 32 == 0) &&
+                          p.ld_ab % 16 == 0 && p.ld_dab % 16 == 0;
     int local_tile = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
       int tm, tn;
@@ -282,23 +295,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
 
+      const int n_chunks = min(ch * 4 + 4, min(kBN / 32, (p.N - col0 + 31) / 32));
+      // kSwi: this row's a / b values, 16 columns (32 B) per buffer, loaded one 16-column group ahead of their use
+      // (two epilogue warps per scheduler cannot hide a global-load latency by themselves); oda / odb / odg collect
+      // the packed results of a group for one 32 B store each.
+      uint32_t pa[2][8], pb[2][8], oda[8], odb[8], odg[8];
+      auto swi_load = [&](int c16, uint32_t(&da)[8], uint32_t(&db)[8]) {   // c16: first of 16 columns
+        if (row_ok && c16 < p.N) {
+          const __nv_bfloat16* ap = p.swi_ab + (int64_t)row * p.ld_ab + c16;
+          ldg_nc_32B(ap, da, swi_wide);
+          ldg_nc_32B(ap + p.N, db, swi_wide);
+        }
+      };
+      if constexpr (kSwi) {
+        if (ch * 4 < n_chunks) swi_load(col0 + ch * 4 * 32, pa[0], pb[0]);
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kBN;
-      const int n_chunks = min(ch * 4 + 4, min(kBN / 32, (p.N - col0 + 31) / 32));
 
-      uint32_t v[2][32];
-      if (ch * 4 < n_chunks) tmem_ld_32x32(taddr + ch * 4 * 32, v[0]);
+      // accumulator chunks: double-buffered (next chunk's tcgen05.ld in flight) except with the kSwi epilogue, whose
+      // per-chunk arithmetic dwarfs the TMEM latency and which needs the 32 registers for the a / b pipeline
+      constexpr int kVBufs = kSwi ? 1 : 2;
+      uint32_t v[kVBufs][32];
+      if constexpr (!kSwi) {
+        if (ch * 4 < n_chunks) tmem_ld_32x32(taddr + ch * 4 * 32, v[0]);
+      }
 #pragma unroll 1
       for (int c = ch * 4; c < n_chunks; c += 2) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int cc = c + half;
           if (cc >= n_chunks) break;
-          uint32_t(&vv)[32] = v[half];
-          tmem_wait_ld_regs(vv);
-          if (cc + 1 < n_chunks) tmem_ld_32x32(taddr + (cc + 1) * 32, v[half ^ 1]);  // prefetch next chunk
+          uint32_t(&vv)[32] = v[kSwi ? 0 : half];
           const int col = col0 + cc * 32;
+          if constexpr (kSwi) tmem_ld_32x32(taddr + cc * 32, vv);
+          tmem_wait_ld_regs(vv);
+          if constexpr (!kSwi) {
+            if (cc + 1 < n_chunks) tmem_ld_32x32(taddr + (cc + 1) * 32, v[half ^ 1]);  // prefetch next chunk
+          }
           if (dump) {
             if (row_ok) {
               uint32_t* dst = reinterpret_cast<uint32_t*>(p.C) + (int64_t)row * p.ldc + col;
@@ -342,7 +377,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               f[j] = a;
             }
-            if (row_ok && col + j8 < p.N) {
+            if constexpr (kSwi) {
+              // columns j8 .. j8+7 of the chunk: buffer (j8 >> 4) holds their a / b values; the other buffer is refilled
+              // with the next 16-column group (second half of this chunk, or first half of the next one) meanwhile
+              if (j8 == 0) swi_load(col + 16, pa[1], pb[1]);
+              if (j8 == 16 && cc + 1 < n_chunks) swi_load(col + 32, pa[0], pb[0]);
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const int w = ((j8 & 8) + j) >> 1;
+                const uint32_t ua = pa[j8 >> 4][w], ub = pb[j8 >> 4][w];
+                float da0, db0, g0, da1, db1, g1;
+                swiglu_bwd_elem(round_bf16(f[j]), bf16_lo(ua), bf16_lo(ub), da0, db0, g0);
+                swiglu_bwd_elem(round_bf16(f[j + 1]), bf16_hi(ua), bf16_hi(ub), da1, db1, g1);
+                oda[w] = pack_bf16(da0, da1);
+                odb[w] = pack_bf16(db0, db1);
+                odg[w] = pack_bf16(g0, g1);
+              }
+              if ((j8 & 8) && row_ok && col + (j8 & 16) < p.N) {
+                const int64_t c16 = col + (j8 & 16);
+                __nv_bfloat16* dp = p.swi_dab + (int64_t)row * p.ld_dab + c16;
+                stg_32B(dp, oda, swi_wide);
+                stg_32B(dp + p.N, odb, swi_wide);
+                if (p.swi_g != nullptr) stg_32B(p.swi_g + (int64_t)row * p.N + c16, odg, swi_wide);
+              }
+            } else if (row_ok && col + j8 < p.N) {
               if (rsd != nullptr) {
                 const uint4 r4 = *reinterpret_cast<const uint4*>(rsd + j8);
                 f[0] += bf16_lo(r4.x); f[1] += bf16_hi(r4.x);
@@ -376,7 +434,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <bool kInt8, int CG, int kRank, bool kMN = false>
+template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false>
 static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
   using S = GemmSmem<CG>;
@@ -409,7 +467,7 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
     if (rc) return rc;
   }
 
-  auto kern = gemm_kernel<kInt8, CG, kRank, kMN>;
+  auto kern = gemm_kernel<kInt8, CG, kRank, kMN, kSwi>;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -1050,6 +1108,35 @@ int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t l
     LX_CHECK_LAUNCH("lora_bwd_pair: convert");
   }
   return 0;
+}
+
+int llamax_bf16_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                                const llamax_epilogue_t* epi, const void* ab, int64_t ld_ab, void* dab, int64_t ld_dab,
+                                void* g, void* stream) {
+  if (!A || !B || !ab || !dab) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_swiglu_bwd: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(LLAMAX_ERR_ARG, "gemm: empty problem");
+  if (N % 16 || ld_ab % 8 || ld_dab % 8 || ld_ab < 2 * N || ld_dab < 2 * N)
+    return set_error(LLAMAX_ERR_ARG, "bf16_gemm_swiglu_bwd: N % 16 == 0 and pitches % 8 == 0, >= 2N required");
+  if ((reinterpret_cast<uintptr_t>(ab) | reinterpret_cast<uintptr_t>(dab) | reinterpret_cast<uintptr_t>(g)) % 16)
+    return set_error(LLAMAX_ERR_ARG, "bf16_gemm_swiglu_bwd: ab / dab / g must be 16-byte aligned");
+  if (epi != nullptr && epi->resid != nullptr)
+    return set_error(LLAMAX_ERR_ARG, "bf16_gemm_swiglu_bwd: no residual term in this epilogue");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  fill_epilogue(p, epi);
+  p.swi_ab = static_cast<const __nv_bfloat16*>(ab); p.ld_ab = ld_ab;
+  p.swi_dab = static_cast<__nv_bfloat16*>(dab); p.ld_dab = ld_dab;
+  p.swi_g = static_cast<__nv_bfloat16*>(g);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int r = p.lora_rank <= 0 ? 0 : p.lora_rank <= 8 ? 8 : 16;
+  if (g_gemm_cg == 2) {
+    if (r == 0) return launch_gemm_r<false, 2, 0, false, true>(A, lda, B, ldb, p, st);
+    if (r == 8) return launch_gemm_r<false, 2, 8, false, true>(A, lda, B, ldb, p, st);
+    return launch_gemm_r<false, 2, 16, false, true>(A, lda, B, ldb, p, st);
+  }
+  if (r == 0) return launch_gemm_r<false, 1, 0, false, true>(A, lda, B, ldb, p, st);
+  if (r == 8) return launch_gemm_r<false, 1, 8, false, true>(A, lda, B, ldb, p, st);
+  return launch_gemm_r<false, 1, 16, false, true>(A, lda, B, ldb, p, st);
 }
 
 int llamax_bf16_gemm_tn(const void* At, int64_t ldat, const void* Bt, int64_t ldbt, void* C, int64_t ldc, int64_t M,

@@ -55,6 +55,9 @@ _LORA_PAIR = os.environ.get("LLAMAX_LORA_PAIR", "1") != "0"
 # The gradient is quantised to 8 bits per row, so results differ from the reference beyond the parity tolerance;
 # default off, never used by bench.py's headline.
 _INT8_GRAD = os.environ.get("LLAMAX_INT8_GRAD_INPUT", "0") == "1"
+# A/B switch (benchmarking only): "0" runs the w2 grad_input GEMM and the SwiGLU backward as two launches (identical
+# results); default: SwiGLU backward as the GEMM's epilogue, the [M, F] gradient dg never exists in HBM
+_FUSE_SWIGLU_BWD = os.environ.get("LLAMAX_FUSE_SWIGLU_BWD", "1") != "0"
 _ones: dict = {}
 
 
@@ -439,23 +442,29 @@ class FusedDecoderBlock(torch.autograd.Function):
         dab = torch.empty(M, 2 * F_ + r13, device=dev, dtype=torch.bfloat16)
         wt2, _ = operand("w2")
         g2 = None
+        a_, b_ = ab[:, :F_], ab[:, F_:]
+        fuse = _FUSE_SWIGLU_BWD and not _INT8_GRAD and F_ % 16 == 0
+        dh2 = at2 = None
         if s2.R > 0:
             bt2, at2, ht2 = prep[id(s2)]
             dh2 = torch.empty(M, s2.R, device=dev, dtype=torch.bfloat16)
             dht2 = ops.transposed_rank_buffer(s2.R, M, dev)
             dB2 = sink.emit(_lora_dh_dB(dout2, bt2, ht2, dh2, s2.lora_scale, dht2), False, s2.lora_b.dtype)
+        if fuse:   # dg = dout2 @ (s W2) (+ dh2 @ A2) goes straight through the SwiGLU backward in the GEMM epilogue
+            _, _, g = ops.bf16_gemm_swiglu_bwd(dout2, wt2, a_, b_, out_ab=dab, want_g=s2.R > 0,
+                                               lora_h=dh2, lora_b=at2, lora_scale=1.0)
+        else:
             if _INT8_GRAD:
                 dg = _grad_input_i8(dout2, i8["w2"][0], i8["w2"][1], dh2, at2)
-            else:
+            elif s2.R > 0:
                 dg = ops.bf16_gemm(dout2, wt2, lora_h=dh2, lora_b=at2, lora_scale=1.0)
-        elif _INT8_GRAD:
-            dg = _grad_input_i8(dout2, i8["w2"][0], i8["w2"][1], None, None)
-        else:
-            dg = ops.bf16_gemm(dout2, wt2)
-        _, _, g = ops.swiglu_bwd(dg, ab[:, :F_], ab[:, F_:], want_g=s2.R > 0, out_ab=dab)
+            else:
+                dg = ops.bf16_gemm(dout2, wt2)
+            _, _, g = ops.swiglu_bwd(dg, a_, b_, want_g=s2.R > 0, out_ab=dab)
+            del dg
         if s2.R > 0:
             g2 = (sink.emit(ops.lora_wgrad(g, None, 1.0, Ht=dht2), True, s2.lora_a.dtype), dB2)
-        del dg, g
+        del g
 
         # --- w1 | w3 ---
         wt13, placed13 = operand("w13")

@@ -171,6 +171,28 @@ def bf16_gemm(A: Tensor, B: Tensor, *, col_scale: Tensor | None = None, round_be
     return out
 
 
+def bf16_gemm_swiglu_bwd(A: Tensor, B: Tensor, a: Tensor, b: Tensor, *, out_ab: Tensor, want_g: bool = False,
+                         lora_h=None, lora_b=None, lora_scale=1.0):
+    """swiglu_bwd(bf16(A[M,K] @ B[F,K]^T + LoRA term), a, b) with the SwiGLU backward as the GEMM's epilogue: the
+    [M, F] gradient dg is never written. a, b: the two F-wide column blocks of one [M, >= 2F] buffer; da | db go to the
+    first two F-wide column blocks of out_ab. Returns (da, db, g | None), identical to bf16_gemm -> swiglu_bwd."""
+    lib, st = _prep(A)
+    assert A.dtype is torch.bfloat16 and B.dtype is torch.bfloat16 and A.dim() == 2 and B.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
+    M, K = A.shape
+    F = B.shape[0]
+    assert a.shape == (M, F) and b.shape == (M, F) and a.stride(1) == 1 and a.stride(0) == b.stride(0)
+    assert b.data_ptr() == a.data_ptr() + 2 * F, "a | b must be adjacent column blocks of one buffer"
+    assert out_ab.dtype is torch.bfloat16 and out_ab.shape[0] == M and out_ab.shape[1] >= 2 * F and out_ab.stride(1) == 1
+    g = torch.empty(M, F, device=A.device, dtype=torch.bfloat16) if want_g else None
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, None)
+    _call(lib, "llamax_bf16_gemm_swiglu_bwd",
+          (_p(A), A.stride(0), _p(B), B.stride(0), M, F, K, ctypes.byref(ep) if ep is not None else None,
+           _p(a), a.stride(0), _p(out_ab), out_ab.stride(0), _p(g), st,),
+          "bf16_gemm", 2.0 * M * F * K, 0.0, shape=(M, F, K))
+    return out_ab[:, :F], out_ab[:, F : 2 * F], g
+
+
 def bf16_gemm_tn(At: Tensor, Bt: Tensor, *, out: Tensor | None = None) -> Tensor:
     """C[M,N] = At[K,M]^T @ Bt[K,N] (bf16 in/out, fp32 accumulate): the weight-gradient form, both operands consumed as
     stored (rows = the contraction index; row pitches may be smaller than the row length, i.e. overlapping rows)."""

@@ -174,3 +174,33 @@ def test_bf16_gemm_tn_overlapping_rows():
     dz = torch.randn(rows, 128, device="cuda").bfloat16()
     out = ops.bf16_gemm_tn(dz, col)
     assert rel_err(out, dz.float().t() @ col.float()) <= 1e-2
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,F,K,R,pad", [(256, 512, 128, 0, 0), (301, 1792, 520, 8, 16), (1000, 464, 264, 8, 8),
+                                         (130, 16, 64, 16, 16), (2048, 14336, 72, 8, 16)])
+def test_gemm_with_swiglu_backward_epilogue_equals_two_launches(cg, M, F, K, R, pad):
+    """The w2 grad_input GEMM with the SwiGLU backward as its epilogue (dg never written) must give exactly what
+    bf16_gemm -> swiglu_bwd gives: same bf16 rounding of dg, same element formulas. Ragged M, F tails inside a tile,
+    32-byte (pad 0 / 16) and 16-byte (pad 8) row alignment of the output, with and without the LoRA term and g."""
+    ops.set_gemm_cta_group(cg)
+    try:
+        torch.manual_seed(M + F + K + R)
+        dy = torch.randn(M, K, device="cuda").bfloat16()
+        wt = (torch.randn(F, K, device="cuda") * 0.05).bfloat16()
+        ab = torch.randn(M, 2 * F, device="cuda").bfloat16()
+        a, b = ab[:, :F], ab[:, F:]
+        lora = {}
+        if R:
+            lora = dict(lora_h=torch.randn(M, R, device="cuda").bfloat16(),
+                        lora_b=(torch.randn(F, R, device="cuda") * 0.1).bfloat16(), lora_scale=1.0)
+        dg = ops.bf16_gemm(dy, wt, **lora)
+        ref = torch.zeros(M, 2 * F + pad, device="cuda", dtype=torch.bfloat16)
+        _, _, g_ref = ops.swiglu_bwd(dg, a, b, want_g=True, out_ab=ref)
+        for want_g in (True, False):
+            out = torch.zeros(M, 2 * F + pad, device="cuda", dtype=torch.bfloat16)
+            da, db, g = ops.bf16_gemm_swiglu_bwd(dy, wt, a, b, out_ab=out, want_g=want_g, **lora)
+            assert torch.equal(out, ref)                      # da | db identical, pad columns untouched
+            assert (g is None) if not want_g else torch.equal(g, g_ref)
+    finally:
+        ops.set_gemm_cta_group(2)
