@@ -212,15 +212,18 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __n
   for (int j = 0; j < kMaxV; ++j) {
     const int idx = threadIdx.x + j * blockDim.x;
     if (idx < nvec) {
-      float af[8], bf[8];
-      unpack8(ldg_nc_v4(a + row * ld + (int64_t)idx * 8), af);
-      unpack8(ldg_nc_v4(b + row * ld + (int64_t)idx * 8), bf);
+      const uint4 ua = ldg_nc_v4(a + row * ld + (int64_t)idx * 8), ub = ldg_nc_v4(b + row * ld + (int64_t)idx * 8);
+      const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+      uint32_t wg[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        v[j][e] = round_bf16(round_bf16(silu_f(af[e])) * bf[e]);
-        amax = fmaxf(amax, fabsf(v[j][e]));
+      for (int e = 0; e < 4; ++e) {
+        // bf16(silu(a)) for two elements, then the bf16 product with b (exact product, one rounding)
+        wg[e] = mul_bf16x2(pack_bf16(silu_f(bf16_lo(wa[e])), silu_f(bf16_hi(wa[e]))), wb[e]);
+        v[j][2 * e] = bf16_lo(wg[e]);
+        v[j][2 * e + 1] = bf16_hi(wg[e]);
+        amax = fmaxf(amax, fmaxf(fabsf(v[j][2 * e]), fabsf(v[j][2 * e + 1])));
       }
-      if (g != nullptr) *reinterpret_cast<uint4*>(g + row * F + (int64_t)idx * 8) = pack8(v[j]);
+      if (g != nullptr) *reinterpret_cast<uint4*>(g + row * F + (int64_t)idx * 8) = make_uint4(wg[0], wg[1], wg[2], wg[3]);
     }
   }
   if (q8 != nullptr) {
@@ -238,15 +241,16 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / nvec;
     const int c = (int)(i - row * nvec) * 8;
-    float af[8], bf[8], dgf[8], oa[8], ob[8], og[8];
-    unpack8(ldg_nc_v4(a + row * ld + c), af);
-    unpack8(ldg_nc_v4(b + row * ld + c), bf);
-    unpack8(ldg_nc_v4(dg + row * (int64_t)nvec * 8 + c), dgf);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) swiglu_bwd_elem(dgf[e], af[e], bf[e], oa[e], ob[e], og[e]);
-    *reinterpret_cast<uint4*>(da + row * ldd + c) = pack8(oa);
-    *reinterpret_cast<uint4*>(db + row * ldd + c) = pack8(ob);
-    if (g != nullptr) *reinterpret_cast<uint4*>(g + row * (int64_t)nvec * 8 + c) = pack8(og);
+    const uint4 ua = ldg_nc_v4(a + row * ld + c), ub = ldg_nc_v4(b + row * ld + c);
+    const uint4 ud = ldg_nc_v4(dg + row * (int64_t)nvec * 8 + c);
+    uint4 oa, ob, og;
+    swiglu_bwd_pair(ud.x, ua.x, ub.x, oa.x, ob.x, og.x);
+    swiglu_bwd_pair(ud.y, ua.y, ub.y, oa.y, ob.y, og.y);
+    swiglu_bwd_pair(ud.z, ua.z, ub.z, oa.z, ob.z, og.z);
+    swiglu_bwd_pair(ud.w, ua.w, ub.w, oa.w, ob.w, og.w);
+    *reinterpret_cast<uint4*>(da + row * ldd + c) = oa;
+    *reinterpret_cast<uint4*>(db + row * ldd + c) = ob;
+    if (g != nullptr) *reinterpret_cast<uint4*>(g + row * (int64_t)nvec * 8 + c) = og;
   }
 }
 

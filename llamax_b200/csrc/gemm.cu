@@ -384,14 +384,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (j8 == 16 && cc + 1 < n_chunks) swi_load(col + 32, pa[0], pb[0]);
 #pragma unroll
               for (int j = 0; j < 8; j += 2) {
-                const int w = ((j8 & 8) + j) >> 1;
-                const uint32_t ua = pa[j8 >> 4][w], ub = pb[j8 >> 4][w];
-                float da0, db0, g0, da1, db1, g1;
-                swiglu_bwd_elem(round_bf16(f[j]), bf16_lo(ua), bf16_lo(ub), da0, db0, g0);
-                swiglu_bwd_elem(round_bf16(f[j + 1]), bf16_hi(ua), bf16_hi(ub), da1, db1, g1);
-                oda[w] = pack_bf16(da0, da1);
-                odb[w] = pack_bf16(db0, db1);
-                odg[w] = pack_bf16(g0, g1);
+                const int w = ((j8 & 8) + j) >> 1;   // dg pair rounded to bf16 exactly as the stand-alone GEMM stores it
+                swiglu_bwd_pair(pack_bf16(f[j], f[j + 1]), pa[j8 >> 4][w], pb[j8 >> 4][w], oda[w], odb[w], odg[w]);
               }
               if ((j8 & 8) && row_ok && col + (j8 & 16) < p.N) {
                 const int64_t c16 = col + (j8 & 16);
