@@ -7,6 +7,8 @@
 #include "host_utils.h"
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "llamax_b200.h"
 
 namespace lx {
@@ -22,7 +24,8 @@ static inline bool row_cfg(int64_t D, RowCfg& c, bool one_vec_per_thread = false
   const int nvec = (int)(D / 8);
   // two 16-byte vectors per thread when the row allows it (measured on B200: 256 threads x 2 vectors beats
   // 512 x 1 for D = 4096 rows by ~25 %), at most 512 threads per row
-  int threads = std::min(512, (((nvec + 1) / 2 + 31) / 32) * 32);
+  static const int vec_target = getenv("LLAMAX_ROW_VECS") ? std::max(1, atoi(getenv("LLAMAX_ROW_VECS"))) : 2;  // A/B only
+  int threads = std::min(512, (((nvec + vec_target - 1) / vec_target + 31) / 32) * 32);
   if (one_vec_per_thread) threads = std::min(512, ((nvec + 31) / 32) * 32);  // persistent kernels: more warps per CTA
   int v = (nvec + threads - 1) / threads;
   if (v > 8) return false;

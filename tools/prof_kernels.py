@@ -48,6 +48,11 @@ for _ in range(reps):
     bt = torch.randn(8, F, device=dev).bfloat16()
     ops.lora_bwd_pair(ab[:, :F], bt, h[:, :8], torch.empty(M, 8, device=dev).bfloat16(), 1.0)
     ops.rmsnorm_bwd(xn, x, w1, rstd, res, want_dw=True)
+    # 11. w2 grad_input GEMM [M, D + LoRA] -> [M, F] with the SwiGLU backward as its epilogue (dg never written)
+    wt2 = torch.randn(F, D, device=dev).bfloat16()
+    dab2 = torch.empty(M, 2 * F + 16, device=dev, dtype=torch.bfloat16)
+    ops.bf16_gemm_swiglu_bwd(x, wt2, ab[:, :F], ab[:, F:], out_ab=dab2, want_g=True, lora_h=h[:, :8], lora_b=lb)
+    del wt2, dab2
     del ab, qkv, dqkv
 torch.cuda.synchronize()
 print("ok")
