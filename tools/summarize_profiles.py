@@ -30,7 +30,7 @@ for r in rows[hi + 1:]:
 lx = sum(v[0] for k, v in agg.items() if "lx::" in k)
 out = [
     f"round 1 (final kernels of this round) — ncu launch list (gpu__time_duration.sum, --clock-control none) of",
-    "  python bench.py --layers 2 --steps 1 --warmup 3 --no-cpu-baseline   (5 optimizer steps: 3 warm-up + 1 timed + 1 e2e)",
+    "  python bench.py --layers 2 --steps 1 --warmup 3 --no-cpu-baseline   (6 optimizer steps: 3 warm-up + 1 timed + 1 instrumented + 1 e2e)",
     "per-launch times are cold-cache and serialised: compare SHARES, not absolutes. With 2 of 32 layers the",
     "per-step-constant LM head (8 bf16 GEMM launches + cross-entropy) and optimizer weigh 16x more than in the real step;",
     "the 32-layer shares measured live by bench.py (CUDA events) are in profiles/r1_bench_1gpu.json and DESIGN.md.",
