@@ -280,10 +280,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8 fwd (int32 acc) / bf16 bwd" if not args.weight_only else "bf16 (int8 weights)",
         "data": "synthetic",
-        "config": {"workload": ("Llama-3.1-8B shape, frozen INT8 base + LoRA r=%d, %s, seq %d batch %d per GPU" %
-                                (args.rank, "MetaMathQA-shaped text SFT (causal)" if args.workload == "text"
-                                 else "LibriSpeech-shaped 30 s audio prefix (1500) + 256 text, prefix-LM",
-                                 args.seq if args.workload == "text" else positions // args.batch, args.batch)),
+        "config": {"workload": workload_label(args, positions),
                    "layers": args.layers, "global_batch": args.batch * world,
                    "seq_len": args.seq if args.workload == "text" else positions // args.batch,
                    "int8_mode": "weight-only" if args.weight_only else "dynamic_int8_act", "parallelism": f"dp{world}",
@@ -308,6 +305,14 @@ def run_ours(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def workload_label(args, positions=None):
+    """`config.workload` of both arms (the reference arm times a bounded sample of the same workload)."""
+    seq = args.seq if args.workload == "text" else (positions // args.batch if positions else 1500 + 256)
+    return ("Llama-3.1-8B shape, frozen INT8 base + LoRA r=%d, %s, seq %d batch %d per GPU" %
+            (args.rank, "MetaMathQA-shaped text SFT (causal)" if args.workload == "text"
+             else "LibriSpeech-shaped 30 s audio prefix (1500) + 256 text, prefix-LM", seq, args.batch))
 
 
 # ------------------------------------------------------------------------------------------------ reference (CPU oracle port)
@@ -368,13 +373,16 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    base = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    base = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=1)  # first call pays thread-pool and allocator start-up
     wall = time.perf_counter() - t0
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * base["seconds_per_sample"] * 32, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16/int8 (CPU)",
            "data": "synthetic",
-           "config": {"workload": "Llama-3.1-8B shape, frozen INT8 base + LoRA r=%d, text SFT; bounded CPU sample" % args.rank},
+           "config": {"workload": workload_label(args), "layers": args.layers, "global_batch": args.batch,
+                      "seq_len": args.seq if args.workload == "text" else 1756,
+                      "int8_mode": "weight-only" if args.weight_only else "dynamic_int8_act", "parallelism": "cpu",
+                      "sample": "bounded: one decoder block + LM head on 1x512 positions per step, extrapolated to 32 blocks"},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(wall, 1)}
