@@ -301,7 +301,7 @@ def run_ours(args):
         "dp_payload_bytes": bucket.nbytes(),
     }
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_reference(args, steps=1, warmup=0)
+        out["cpu_baseline"] = cpu_reference(args, steps=1, warmup=1)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
