@@ -75,13 +75,15 @@ __device__ __forceinline__ float block_reduce(float v, float* sm) {
   return r;
 }
 
-// Row quantisation, bit-identical to the reference's IEEE division (subclasses/int8.py:10-16) at ~1 multiply per
-// element: x * (1/sc) differs from x / sc by < 2 ulp, which can only change the rounded integer when the quotient
-// sits within ~3e-5 of a half-integer. Each 8-element vector is rounded from the product; only if one of its elements
-// is that close to a tie is the whole vector redone with exact divisions (one rare branch per vector).
-// Rounding without the conversion pipe: t + 1.5*2^23 rounds t to the nearest-even integer in the float's low mantissa
-// bits (|t| < 2^22); the low byte of that word is the two's-complement int8 code, and subtracting the constant gives
-// rint(t) back as a float. FRND / F2I (XU pipe, 16 lanes/clk) are not used.
+// Row quantisation, bit-identical to the reference's IEEE division + round-half-even (subclasses/int8.py:10-16) at two
+// FMAs and one logic op per element: with inv = fl(1/sc), the exact quotient x/sc lies between x*inv_lo and x*inv_hi,
+// inv_lo/hi = inv * (1 -/+ 2^-21) (fl(1/sc) and the two products' roundings are each within 2^-24). Rounding to
+// integer is monotonic, so when both ends round to the same integer that integer is rint(fl(x/sc)) too; when they
+// differ (the quotient is within ~2^-20 relative of a half-integer: ~1e-4 of all elements) the whole 8-element vector
+// is redone with the reference's exact divisions (one rare branch per vector).
+// Rounding without the conversion pipe: fma(x, inv, 1.5*2^23) rounds x*inv ONCE, to the nearest-even integer held in
+// the float's low mantissa bits (|x*inv| < 2^22); the low byte of that word is the two's-complement int8 code.
+// FRND / F2I (XU pipe, 16 lanes/clk) are not used.
 constexpr float kRoundMagic = 12582912.0f;  // 1.5 * 2^23
 __device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
@@ -93,20 +95,19 @@ __device__ __forceinline__ void quant_row_store(const float (&v)[kMaxV][8], int 
   const float s = amax / 127.0f;
   const float sc = fmaxf(s, 1e-12f);
   const float inv = 1.0f / sc;
+  const float inv_lo = inv * (1.0f - 0x1p-21f), inv_hi = inv * (1.0f + 0x1p-21f);
 #pragma unroll
   for (int j = 0; j < kMaxV; ++j) {
     const int idx = threadIdx.x + j * blockDim.x;
     if (idx < nvec) {
       uint32_t w[8];
-      bool near_tie = false;
+      uint32_t differ = 0;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float t = v[j][e] * inv;
-        const float tm = __fadd_rn(t, kRoundMagic);
-        w[e] = __float_as_uint(tm);
-        near_tie |= fabsf(fabsf(t - __fsub_rn(tm, kRoundMagic)) - 0.5f) < 3e-5f;
+        w[e] = __float_as_uint(__fmaf_rn(v[j][e], inv_lo, kRoundMagic));
+        differ |= w[e] ^ __float_as_uint(__fmaf_rn(v[j][e], inv_hi, kRoundMagic));
       }
-      if (near_tie) {
+      if (differ) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(__fadd_rn(v[j][e] / sc, kRoundMagic));
       }
@@ -150,12 +151,15 @@ __global__ void rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __
     if (idx < nvec) {
       float wf[8];
       unpack8(*reinterpret_cast<const uint4*>(w + (int64_t)idx * 8), wf);
+      // round once with the packing conversion (needed for the y store anyway) and take the quantiser's input from
+      // the packed words: integer round_bf16 (4 ALU-pipe instructions per element) made this pass ALU-pipe bound
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        v[j][e] = round_bf16((v[j][e] * rstd) * wf[e]);
-        amax = fmaxf(amax, fabsf(v[j][e]));
-      }
-      if (y != nullptr) *reinterpret_cast<uint4*>(y + row * D + (int64_t)idx * 8) = pack8(v[j]);
+      for (int e = 0; e < 8; ++e) v[j][e] = (v[j][e] * rstd) * wf[e];
+      const uint4 yp = pack8(v[j]);
+      unpack8(yp, v[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[j][e]));
+      if (y != nullptr) *reinterpret_cast<uint4*>(y + row * D + (int64_t)idx * 8) = yp;
     }
   }
   if (q8 != nullptr) {
@@ -195,6 +199,132 @@ __global__ void rowquant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
   }
   amax = block_reduce<true>(amax, sm);
   quant_row_store(v, nvec, amax, q8 + row * K, qscale + row);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent "ring" variants of the row kernels.  One CTA per row exposes each row's global-load latency once per CTA
+// lifetime (load -> reduce -> scale -> reduce -> quantise -> store). Here a CTA walks rows r, r + grid, ... and keeps
+// the next kRingStages - 1 rows of its walk in flight as cp.async copies into a shared-memory ring. Every thread copies
+// exactly the 16-byte slots it later reads itself, so cp.async.wait_group is the only synchronisation the ring needs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRingStages = 3;
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Issue the copies of one row into ring stage `stage` (an empty group past the last row keeps the group count uniform)
+template <int kMaxV>
+__device__ __forceinline__ void ring_issue(uint4* ring, int slots, int stage, const __nv_bfloat16* xrow, bool valid,
+                                           int nvec) {
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) cp_async_16(ring + stage * slots + idx, xrow + (int64_t)idx * 8);
+    }
+  }
+  cp_async_commit();
+}
+
+template <int kMaxV>
+__global__ void rmsnorm_fwd_ring_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                        __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
+                                        int8_t* __restrict__ q8, __nv_bfloat16* __restrict__ qscale, int64_t M, int D,
+                                        int nvec, float eps) {
+  extern __shared__ uint4 ring[];
+  __shared__ float sm[32];
+  const int slots = blockDim.x * kMaxV;
+  uint4 wp[kMaxV];  // the norm weight, packed, for the CTA lifetime
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+    if (idx < nvec) wp[j] = *reinterpret_cast<const uint4*>(w + (int64_t)idx * 8);
+  }
+#pragma unroll
+  for (int s = 0; s < kRingStages; ++s) {
+    const int64_t r = blockIdx.x + (int64_t)s * gridDim.x;
+    ring_issue<kMaxV>(ring, slots, s, x + r * D, r < M, nvec);
+  }
+  int stage = 0;
+  for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+    cp_async_wait<kRingStages - 1>();
+    float v[kMaxV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        unpack8(ring[stage * slots + idx], v[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(v[j][e], v[j][e], ss);
+      }
+    }
+    const int64_t rnext = row + (int64_t)kRingStages * gridDim.x;   // refill the stage just consumed
+    ring_issue<kMaxV>(ring, slots, stage, x + rnext * D, rnext < M, nvec);
+    stage = stage + 1 == kRingStages ? 0 : stage + 1;
+    ss = block_reduce<false>(ss, sm);
+    const float rstd = 1.0f / sqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float wf[8];
+        unpack8(wp[j], wf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] = (v[j][e] * rstd) * wf[e];
+        const uint4 yp = pack8(v[j]);
+        unpack8(yp, v[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[j][e]));
+        if (y != nullptr) *reinterpret_cast<uint4*>(y + row * D + (int64_t)idx * 8) = yp;
+      }
+    }
+    if (q8 != nullptr) {
+      amax = block_reduce<true>(amax, sm);
+      quant_row_store(v, nvec, amax, q8 + row * D, qscale + row);
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int kMaxV>
+__global__ void rowquant_ring_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int8_t* __restrict__ q8,
+                                     __nv_bfloat16* __restrict__ qscale, int64_t M, int K, int nvec) {
+  extern __shared__ uint4 ring[];
+  __shared__ float sm[32];
+  const int slots = blockDim.x * kMaxV;
+#pragma unroll
+  for (int s = 0; s < kRingStages; ++s) {
+    const int64_t r = blockIdx.x + (int64_t)s * gridDim.x;
+    ring_issue<kMaxV>(ring, slots, s, x + r * ldx, r < M, nvec);
+  }
+  int stage = 0;
+  for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+    cp_async_wait<kRingStages - 1>();
+    float v[kMaxV][8];
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        unpack8(ring[stage * slots + idx], v[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[j][e]));
+      }
+    }
+    const int64_t rnext = row + (int64_t)kRingStages * gridDim.x;
+    ring_issue<kMaxV>(ring, slots, stage, x + rnext * ldx, rnext < M, nvec);
+    stage = stage + 1 == kRingStages ? 0 : stage + 1;
+    amax = block_reduce<true>(amax, sm);
+    quant_row_store(v, nvec, amax, q8 + row * K, qscale + row);
+  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -656,6 +786,30 @@ __global__ void __launch_bounds__(256) batched_copy_kernel(const __grid_constant
 using namespace lx;
 typedef __nv_bfloat16 bf16;
 
+// Ring (persistent, cp.async-prefetched) row kernels: used when the ring fits next to enough resident CTAs and there
+// are enough rows for the prefetch depth to matter. LLAMAX_ROW_RING=0 keeps the one-CTA-per-row kernels (A/B).
+static bool ring_cfg(const RowCfg& c, int64_t M, bool aligned, int& grid, int& smem) {
+  static const bool enabled = getenv("LLAMAX_ROW_RING") == nullptr || atoi(getenv("LLAMAX_ROW_RING")) != 0;
+  static const int per_sm_env = getenv("LLAMAX_ROW_RING_CTAS") ? atoi(getenv("LLAMAX_ROW_RING_CTAS")) : 0;
+  smem = kRingStages * c.threads * c.V * 16;
+  if (!enabled || !aligned || smem > 96 * 1024) return false;
+  const int by_smem = (200 * 1024) / (smem + 1024), by_threads = 2048 / c.threads;
+  int per_sm = std::max(1, std::min(by_smem, by_threads));
+  if (per_sm_env > 0) per_sm = std::min(per_sm, per_sm_env);
+  grid = sm_count() * per_sm;
+  if (M < (int64_t)grid * 2) return false;
+  return true;
+}
+#define LX_RING_SMEM(kern, smem, what)                                                                      \
+  do {                                                                                                      \
+    static thread_local int configured = 0;                                                                 \
+    if (configured < (smem)) {                                                                              \
+      cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));     \
+      if (e_ != cudaSuccess) return set_cuda_error(e_, what ": cudaFuncSetAttribute");                      \
+      configured = (smem);                                                                                  \
+    }                                                                                                       \
+  } while (0)
+
 extern "C" {
 
 int llamax_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, void* q8, void* qscale, int64_t M,
@@ -665,8 +819,17 @@ int llamax_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, void* 
   if ((q8 == nullptr) != (qscale == nullptr)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: q8 and qscale go together");
   if (!row_cfg(D, c)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: D must be a multiple of 8 and <= 65536");
   if (M == 0) return 0;
-  LX_DISPATCH_V(c.V, rmsnorm_fwd_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, (int)D, c.nvec, eps));
+  int ring_grid, ring_smem;
+  if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
+    LX_DISPATCH_V(c.V, {
+      LX_RING_SMEM(rmsnorm_fwd_ring_kernel<kV>, ring_smem, "rmsnorm_fwd");
+      rmsnorm_fwd_ring_kernel<kV><<<ring_grid, c.threads, ring_smem, (cudaStream_t)stream>>>(
+          (const bf16*)x, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, M, (int)D, c.nvec, eps);
+    });
+  } else {
+    LX_DISPATCH_V(c.V, rmsnorm_fwd_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, (int)D, c.nvec, eps));
+  }
   LX_CHECK_LAUNCH("rmsnorm_fwd");
   return 0;
 }
@@ -677,8 +840,17 @@ int llamax_rowquant_int8(const void* x, int64_t ldx, void* q8, void* scale_out, 
   if (!x || !q8 || !scale_out) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: null pointer");
   if (!row_cfg(K, c) || ldx % 8) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: K and ldx must be multiples of 8");
   if (M == 0) return 0;
-  LX_DISPATCH_V(c.V, rowquant_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, ldx, (int8_t*)q8, (bf16*)scale_out, (int)K, c.nvec));
+  int ring_grid, ring_smem;
+  if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
+    LX_DISPATCH_V(c.V, {
+      LX_RING_SMEM(rowquant_ring_kernel<kV>, ring_smem, "rowquant_int8");
+      rowquant_ring_kernel<kV><<<ring_grid, c.threads, ring_smem, (cudaStream_t)stream>>>(
+          (const bf16*)x, ldx, (int8_t*)q8, (bf16*)scale_out, M, (int)K, c.nvec);
+    });
+  } else {
+    LX_DISPATCH_V(c.V, rowquant_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, (int8_t*)q8, (bf16*)scale_out, (int)K, c.nvec));
+  }
   LX_CHECK_LAUNCH("rowquant_int8");
   return 0;
 }

@@ -23,6 +23,32 @@ def test_rowquant_bit_exact(M, K):
     assert torch.equal(q.cpu(), q_ref) and torch.equal(s.cpu(), s_ref)
 
 
+def test_rowquant_exact_ties_round_half_even():
+    """Quotients that sit exactly on half-integers (and one bf16 ulp either side): row maxima 127, 254 and 63.5 give
+    scales 1, 2 and 0.5, so x / scale = k + 0.5 exactly; torch.round is half-to-even. Also a row whose scale is not a
+    power of two, filled with the bf16 neighbours of every half-integer multiple of it."""
+    k = torch.arange(-127, 127, dtype=torch.float32) + 0.5            # 254 exact ties, all bf16-representable
+    rows = []
+    for s in (1.0, 2.0, 0.5):
+        r = torch.zeros(512)
+        r[:254] = k * s
+        r[254] = 127.0 * s                                            # pins the scale
+        rows.append(r)
+    s = 3.0 / 127.0
+    near = (k * s).bfloat16().float()
+    ulp = torch.maximum(near.abs(), torch.tensor(1e-3)) * 2.0 ** -8
+    r = torch.zeros(512)
+    r[:254] = near
+    r[254:508] = (near + ulp).bfloat16().float()
+    r[508] = 3.0
+    rows.append(r)
+    x = torch.stack(rows).bfloat16()
+    q_ref, s_ref = R.quantize_int8_rowwise(x)
+    assert q_ref[0, 0] == -126 and q_ref[0, 1] == -126 and q_ref[0, 127] == 0 and q_ref[0, 128] == 2   # half-to-even
+    q, sc = ops.rowquant_int8(x.cuda())
+    assert torch.equal(q.cpu(), q_ref) and torch.equal(sc.cpu(), s_ref)
+
+
 def test_rowquant_pitched_input():
     x = torch.randn(40, 1024).bfloat16()
     q, s = ops.rowquant_int8(x.cuda()[:, 256:768])

@@ -1,5 +1,5 @@
 """Isolated timing of the HBM-bound passes at the bench shapes (M = 16384 tokens, 8B dims): achieved GB/s against the
-algorithmic bytes of each pass. CUDA events, best of 7 after 2 warm-ups."""
+algorithmic bytes of each pass. CUDA events around a graph replay of 8 calls, best of 5."""
 import os
 import sys
 
@@ -13,14 +13,22 @@ M, D, F, Hq, Hkv, hd, B, S = 16384, 4096, 14336, 32, 8, 128, 8, 2048
 dev = "cuda"
 
 
-def timeit(fn, n=7):
-    for _ in range(2):
-        fn()
+def timeit(fn, n=5, reps=8):
+    """ms per call: `reps` calls captured in one CUDA graph and replayed (best of n). A Python call of these ops costs
+    30-60 us of host time (allocations, ctypes): timed one by one, every pass shorter than that reads as ~65 us."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     ts = []
     for _ in range(n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
     return min(ts)
 
 
