@@ -44,6 +44,7 @@ for _ in range(reps):
     w1 = torch.ones(D, device=dev).bfloat16()
     xn, rstd, _, _ = ops.rmsnorm_fwd(x, w1, 1e-5, quant=True)
     ops.swiglu_fwd(ab[:, :F], ab[:, F:], quant=True, want_g=True)
+    ops.rowquant_int8(x)                      # attention output -> wo operand
     # 9. fused LoRA backward pair (dh + dB in one pass over dY), 10. RMSNorm backward
     bt = torch.randn(8, F, device=dev).bfloat16()
     ops.lora_bwd_pair(ab[:, :F], bt, h[:, :8], torch.empty(M, 8, device=dev).bfloat16(), 1.0)
