@@ -1,0 +1,48 @@
+"""Attention forward (and backward) throughput at the bench shapes, graph-replayed: TFLOP/s over unmasked pairs.
+usage: [LLAMAX_B200_LIB=other.so] python tools/attn_fwd_perf.py [bwd]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from llamax_b200 import ops
+
+Hq, Hkv, D = 32, 8, 128
+with_bwd = len(sys.argv) > 1 and sys.argv[1] == "bwd"
+
+
+def timeit(fn, n=5, reps=6):
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
+    return min(ts)
+
+
+for B, S, P in ((8, 2048, 0), (2, 8192, 0), (8, 1756, 1500), (4, 4096, 1024)):
+    torch.manual_seed(0)
+    ld = (Hq + 2 * Hkv) * D
+    g = torch.randn(B * S, ld, device="cuda").bfloat16()
+    q, k, v = g[:, : Hq * D], g[:, Hq * D : (Hq + Hkv) * D], g[:, (Hq + Hkv) * D :]
+    pairs = S * P + (S - P) * (S - P + 1) / 2
+    fl = 4.0 * B * Hq * D * pairs
+    ms = timeit(lambda: ops.attn_fwd(q, k, v, B, S, Hq, Hkv, D, P))
+    line = f"B={B} S={S} P={P}: fwd {ms * 1e3:7.1f} us {fl / ms / 1e9:7.1f} TFLOP/s"
+    if with_bwd:
+        o, lse = ops.attn_fwd(q, k, v, B, S, Hq, Hkv, D, P)
+        dout = torch.randn(B * S, Hq * D, device="cuda").bfloat16()
+        dqkv = torch.empty_like(g)
+        dq, dk, dv = dqkv[:, : Hq * D], dqkv[:, Hq * D : (Hq + Hkv) * D], dqkv[:, (Hq + Hkv) * D :]
+        msb = timeit(lambda: ops.attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, P))
+        line += f" | bwd {msb * 1e3:7.1f} us {2.5 * fl / msb / 1e9:7.1f} TFLOP/s"
+    print(line, flush=True)
