@@ -7,11 +7,14 @@
 //                   replaces the Triton kernel of the reference (subclasses/int8_mm.py:50-118)
 //   kInt8 = false : bf16 x bf16 -> fp32 (tcgen05.mma.kind::f16); weight-only forward (subclasses/int8.py:118)
 //                   and grad_input (subclasses/int8.py:127) run on it with a de-quantised weight operand.
-// Fused epilogue options: LoRA up-projection (modelling/lora.py:43), residual add (modelling/llama.py:172-173).
+// Fused epilogue options: LoRA up-projection (modelling/lora.py:43), residual add (modelling/llama.py:172-173), and
+// (kSwi) the SwiGLU backward behind the w2 grad_input GEMM (modelling/llama.py:152 differentiated).
+// kMN: both operands stored [K, M] / [K, N] (weight-gradient form dW = dY^T X), consumed as MN-major UMMA operands.
 //
-// Structure (per CTA, 256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps4-7 = epilogue (TMEM -> registers -> global). smem ring of kStages {A,B} tiles with 128B swizzle,
-// two TMEM accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// Structure (per CTA, 384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warp3 idle,
+// warps4-11 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, one per column half of the
+// tile). smem ring of kStages {A,B} tiles with 128B swizzle, two TMEM accumulator stages (2 x 256 columns) so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 // CG = 2 runs CTA pairs (cta_group::2, UMMA 256 x 256): each CTA loads its 128 rows of A and half of B.
 #include "common.cuh"
 #include "host_utils.h"
