@@ -94,7 +94,10 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 // kSwi: the accumulator (+ LoRA term) is d(loss)/d(g) of the SwiGLU (llama.py:152); the epilogue rounds it to bf16 as
 // the stand-alone GEMM would, then applies the SwiGLU backward to the thread's a / b columns and writes da | db (| g)
 // instead of dg: one [M, F] bf16 write + read and one launch less per block than GEMM -> swiglu_bwd_kernel.
-template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false>
+// kRes: the residual term is read through the same one-group-ahead pipeline as kSwi's a / b (a 16-byte load per 8
+// columns issued right before its use exposed one global-load latency per 8 columns: +37..64 % kernel time on the
+// K = 4096 shapes, whose main loop is only ~16k cycles per tile). Requires resid != C.
+template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<CG>;
@@ -247,6 +250,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool has_cs = p.col_scale != nullptr;
     const bool pre_round = (p.flags & 2) != 0;
     // 32-byte accesses when every row start of ab / dab / g is 32-byte aligned (N % 16 == 0 is required by the host)
+    const bool res_wide = kRes && reinterpret_cast<uintptr_t>(p.resid) % 32 == 0 && p.ldr % 16 == 0;
     const bool swi_wide = kSwi && ((reinterpret_cast<uintptr_t>(p.swi_ab) | reinterpret_cast<uintptr_t>(p.swi_dab) |
                                     reinterpret_cast<uintptr_t>(p.swi_g)) % 32 == 0) &&
                           p.ld_ab % 16 == 0 && p.ld_dab % 16 == 0;
@@ -304,13 +308,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // the packed results of a group for one 32 B store each.
       uint32_t pa[2][8], pb[2][8], oda[8], odb[8], odg[8];
       auto swi_load = [&](int c16, uint32_t(&da)[8], uint32_t(&db)[8]) {   // c16: first of 16 columns
-        if (row_ok && c16 < p.N) {
-          const __nv_bfloat16* ap = p.swi_ab + (int64_t)row * p.ld_ab + c16;
-          ldg_nc_32B(ap, da, swi_wide);
-          ldg_nc_32B(ap + p.N, db, swi_wide);
+        if constexpr (kSwi) {
+          if (row_ok && c16 < p.N) {
+            const __nv_bfloat16* ap = p.swi_ab + (int64_t)row * p.ld_ab + c16;
+            ldg_nc_32B(ap, da, swi_wide);
+            ldg_nc_32B(ap + p.N, db, swi_wide);
+          }
+        } else if constexpr (kRes) {   // residual row segment (N % 8 == 0: the last group may be half a group)
+          if (row_ok && c16 < p.N) {
+            const __nv_bfloat16* rp = p.resid + (int64_t)row * p.ldr + c16;
+            if (c16 + 16 <= p.N) {
+              ldg_nc_32B(rp, da, res_wide);
+            } else {
+              const uint4 lo = ldg_nc_v4(rp);
+              da[0] = lo.x; da[1] = lo.y; da[2] = lo.z; da[3] = lo.w;
+            }
+          }
         }
       };
-      if constexpr (kSwi) {
+      if constexpr (kSwi || kRes) {
         if (ch * 4 < n_chunks) swi_load(col0 + ch * 4 * 32, pa[0], pb[0]);
       }
       mbar_wait(&tfull_bar[as], aphase);
@@ -319,9 +335,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       // accumulator chunks: double-buffered (next chunk's tcgen05.ld in flight) except with the kSwi epilogue, whose
       // per-chunk arithmetic dwarfs the TMEM latency and which needs the 32 registers for the a / b pipeline
-      constexpr int kVBufs = kSwi ? 1 : 2;
+      constexpr bool kSide = kSwi || kRes;   // epilogues with a pipelined side input
+      constexpr int kVBufs = kSide ? 1 : 2;
       uint32_t v[kVBufs][32];
-      if constexpr (!kSwi) {
+      if constexpr (!kSide) {
         if (ch * 4 < n_chunks) tmem_ld_32x32(taddr + ch * 4 * 32, v[0]);
       }
 #pragma unroll 1
@@ -330,11 +347,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int half = 0; half < 2; ++half) {
           const int cc = c + half;
           if (cc >= n_chunks) break;
-          uint32_t(&vv)[32] = v[kSwi ? 0 : half];
+          uint32_t(&vv)[32] = v[kSide ? 0 : half];
           const int col = col0 + cc * 32;
-          if constexpr (kSwi) tmem_ld_32x32(taddr + cc * 32, vv);
+          if constexpr (kSide) tmem_ld_32x32(taddr + cc * 32, vv);
           tmem_wait_ld_regs(vv);
-          if constexpr (!kSwi) {
+          if constexpr (!kSide) {
             if (cc + 1 < n_chunks) tmem_ld_32x32(taddr + (cc + 1) * 32, v[half ^ 1]);  // prefetch next chunk
           }
           if (dump) {
@@ -397,6 +414,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 stg_32B(dp + p.N, odb, swi_wide);
                 if (p.swi_g != nullptr) stg_32B(p.swi_g + (int64_t)row * p.N + c16, odg, swi_wide);
               }
+            } else if constexpr (kRes) {
+              if (j8 == 0) swi_load(col + 16, pa[1], pb[1]);
+              if (j8 == 16 && cc + 1 < n_chunks) swi_load(col + 32, pa[0], pb[0]);
+              if (row_ok && col + j8 < p.N) {
+                const uint32_t* r4 = &pa[j8 >> 4][(j8 & 8) >> 1];
+                uint4 o;
+                o.x = pack_bf16(f[0] + bf16_lo(r4[0]), f[1] + bf16_hi(r4[0]));
+                o.y = pack_bf16(f[2] + bf16_lo(r4[1]), f[3] + bf16_hi(r4[1]));
+                o.z = pack_bf16(f[4] + bf16_lo(r4[2]), f[5] + bf16_hi(r4[2]));
+                o.w = pack_bf16(f[6] + bf16_lo(r4[3]), f[7] + bf16_hi(r4[3]));
+                stg_v4(dst + j8, o);
+              }
             } else if (row_ok && col + j8 < p.N) {
               if (rsd != nullptr) {
                 const uint4 r4 = *reinterpret_cast<const uint4*>(rsd + j8);
@@ -431,7 +460,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false>
+template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false>
 static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
   using S = GemmSmem<CG>;
@@ -464,7 +493,7 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
     if (rc) return rc;
   }
 
-  auto kern = gemm_kernel<kInt8, CG, kRank, kMN, kSwi>;
+  auto kern = gemm_kernel<kInt8, CG, kRank, kMN, kSwi, kRes>;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -496,6 +525,17 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
 template <bool kInt8, int CG>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
+  if constexpr (kInt8) {
+    // forward projections with the residual connection (wo, w2): pipelined residual reads; needs resid != C and a
+    // 16-byte aligned residual (rows start on 16-byte boundaries when ldr % 8 == 0)
+    static const bool no_res = getenv("LLAMAX_NO_RES_PIPE") != nullptr;   // A/B switch for benchmarking
+    if (!no_res && p.resid != nullptr && (p.flags & 1) == 0 && static_cast<const void*>(p.resid) != p.C &&
+        reinterpret_cast<uintptr_t>(p.resid) % 16 == 0 && p.ldr % 8 == 0) {
+      if (p.lora_rank <= 0) return launch_gemm_r<kInt8, CG, 0, false, false, true>(A, lda, B, ldb, p, stream);
+      if (p.lora_rank <= 8) return launch_gemm_r<kInt8, CG, 8, false, false, true>(A, lda, B, ldb, p, stream);
+      return launch_gemm_r<kInt8, CG, 16, false, false, true>(A, lda, B, ldb, p, stream);
+    }
+  }
   if (p.lora_rank <= 0) return launch_gemm_r<kInt8, CG, 0>(A, lda, B, ldb, p, stream);
   if (p.lora_rank <= 8) return launch_gemm_r<kInt8, CG, 8>(A, lda, B, ldb, p, stream);
   return launch_gemm_r<kInt8, CG, 16>(A, lda, B, ldb, p, stream);

@@ -204,3 +204,31 @@ def test_gemm_with_swiglu_backward_epilogue_equals_two_launches(cg, M, F, K, R, 
             assert (g is None) if not want_g else torch.equal(g, g_ref)
     finally:
         ops.set_gemm_cta_group(2)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K,Rk,in_place", [(300, 512, 256, 0, False), (515, 1032, 4096, 8, False),
+                                               (128, 4096, 512, 16, False), (260, 520, 128, 8, True)])
+def test_int8_residual_epilogue_pipelined_reads(cg, M, N, K, Rk, in_place):
+    """wo / w2 forward form: dequant + LoRA + residual (llama.py:172-173). The residual is read one 16-column group
+    ahead (32-byte loads when rows are 32-byte aligned, else 16-byte; half a group at an N % 16 == 8 tail); an in-place
+    call (resid is out) takes the unpipelined path. fp32 reference, same tolerance as the other dequantised outputs."""
+    ops.set_gemm_cta_group(cg)
+    try:
+        g = torch.Generator().manual_seed(M + N + K + Rk)
+        A, W = _rand_i8(M, K, gen=g), _rand_i8(N, K, gen=g)
+        sa, sw = (torch.rand(M, generator=g) * 0.1).bfloat16(), (torch.rand(N, generator=g) * 0.01).bfloat16()
+        res = torch.randn(M, N, generator=g).bfloat16()
+        kw, lora_ref = {}, 0.0
+        if Rk:
+            h, lb = torch.randn(M, Rk, generator=g).bfloat16(), (torch.randn(N, Rk, generator=g) * 0.1).bfloat16()
+            kw = dict(lora_h=h.cuda(), lora_b=lb.cuda(), lora_scale=1.0)
+            lora_ref = h.float() @ lb.float().T
+        ref = ((A.int() @ W.int().T).float() * sa.float()[:, None]) * sw.float()[None, :] + lora_ref + res.float()
+        r = res.cuda()
+        out = ops.int8_gemm_dequant(A.cuda(), W.cuda(), sa.cuda(), sw.cuda(), resid=r, out=r if in_place else None, **kw)
+        assert rel_err(out, ref) <= 5e-3
+        if not in_place:
+            assert torch.equal(r.cpu(), res)                   # the residual itself is untouched
+    finally:
+        ops.set_gemm_cta_group(2)
