@@ -254,6 +254,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool swi_wide = kSwi && ((reinterpret_cast<uintptr_t>(p.swi_ab) | reinterpret_cast<uintptr_t>(p.swi_dab) |
                                     reinterpret_cast<uintptr_t>(p.swi_g)) % 32 == 0) &&
                           p.ld_ab % 16 == 0 && p.ld_dab % 16 == 0;
+    // INT8 forward GEMMs: the per-tile operands of the epilogue (column scale and LoRA-B row of the thread's column,
+    // row scale and LoRA-h row of the thread's row) are fetched one tile ahead into registers. Fetched at the top of
+    // the tile, their global-load latency sat on the epilogue's critical path before every tile — which IS the kernel's
+    // critical path at K = 4096 (~16k cycles of main loop per tile): the "+LoRA" cost of those shapes.
+    static_assert(kBN == kEpiThreads, "one staged column per epilogue thread");
+    constexpr bool kPipeStage = kInt8;
+    constexpr int kRV = kRank > 0 ? kRank / 8 : 1;
+    const bool fast_stage = kPipeStage && !dump &&
+                            (kRank == 0 || (R == kRank && reinterpret_cast<uintptr_t>(p.lora_b) % 16 == 0 &&
+                                            reinterpret_cast<uintptr_t>(p.lora_h) % 16 == 0 && p.ldh % 8 == 0));
+    uint32_t ncs = 0;
+    float nrs = 1.f;
+    uint4 nlb[kRV], nh[kRV];
+    auto stage_fetch = [&](int t) {
+      if (t >= num_tiles) return;
+      int fm, fn;
+      tile_coords(t, num_m, num_n, fm, fn);
+      const int n = fn * kBN + et;
+      const int frow = fm * kTileM + cta_rank * kBM + ew * 32 + lane_id();
+      ncs = (has_cs && n < p.N) ? (uint32_t) * reinterpret_cast<const uint16_t*>(p.col_scale + n) : 0u;
+      nrs = (p.row_scale != nullptr && frow < p.M) ? __bfloat162float(p.row_scale[frow]) : 1.f;
+      if constexpr (kRank > 0) {
+#pragma unroll
+        for (int r8 = 0; r8 < kRV; ++r8) {
+          nlb[r8] = n < p.N ? ldg_nc_v4(p.lora_b + (int64_t)n * kRank + r8 * 8) : make_uint4(0, 0, 0, 0);
+          nh[r8] = frow < p.M ? ldg_nc_v4(p.lora_h + (int64_t)frow * p.ldh + r8 * 8) : make_uint4(0, 0, 0, 0);
+        }
+      }
+    };
+    if (fast_stage) stage_fetch(cluster_id);
     int local_tile = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
       int tm, tn;
@@ -266,26 +296,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       // stage per-column data for this tile (previous tile's readers are done: barrier below)
       named_bar_sync(1, kEpiThreads);
-      if (has_cs) {
-        for (int i = et; i < kBN; i += kEpiThreads)
-          s_colscale[i] = (col0 + i < p.N) ? __bfloat162float(p.col_scale[col0 + i]) : 0.f;
-      }
-      if constexpr (kRank > 0) {
-        for (int i = et; i < kBN * kRank; i += kEpiThreads) {
-          const int n = i / kRank, r = i % kRank;
-          s_lorab[i] = (col0 + n < p.N && r < R) ? __bfloat162float(p.lora_b[(int64_t)(col0 + n) * R + r]) * p.lora_scale
-                                                  : 0.f;
+      if (fast_stage) {
+        if (has_cs) s_colscale[et] = bf16_lo(ncs);
+        if constexpr (kRank > 0) {
+#pragma unroll
+          for (int r8 = 0; r8 < kRV; ++r8) {
+            float* d = s_lorab + et * kRank + r8 * 8;
+            const uint4 u = nlb[r8];
+            d[0] = bf16_lo(u.x) * p.lora_scale; d[1] = bf16_hi(u.x) * p.lora_scale;
+            d[2] = bf16_lo(u.y) * p.lora_scale; d[3] = bf16_hi(u.y) * p.lora_scale;
+            d[4] = bf16_lo(u.z) * p.lora_scale; d[5] = bf16_hi(u.z) * p.lora_scale;
+            d[6] = bf16_lo(u.w) * p.lora_scale; d[7] = bf16_hi(u.w) * p.lora_scale;
+          }
+        }
+      } else {
+        if (has_cs) {
+          for (int i = et; i < kBN; i += kEpiThreads)
+            s_colscale[i] = (col0 + i < p.N) ? __bfloat162float(p.col_scale[col0 + i]) : 0.f;
+        }
+        if constexpr (kRank > 0) {
+          for (int i = et; i < kBN * kRank; i += kEpiThreads) {
+            const int n = i / kRank, r = i % kRank;
+            s_lorab[i] = (col0 + n < p.N && r < R)
+                             ? __bfloat162float(p.lora_b[(int64_t)(col0 + n) * R + r]) * p.lora_scale : 0.f;
+          }
         }
       }
       named_bar_sync(1, kEpiThreads);
 
       float rs = 1.f;
-      if (p.row_scale != nullptr && row_ok) rs = __bfloat162float(p.row_scale[row]);
       float h[kRS];
 #pragma unroll
       for (int r = 0; r < kRS; ++r) h[r] = 0.f;
+      if (fast_stage) {
+        rs = nrs;
+        if constexpr (kRank > 0) {
+#pragma unroll
+          for (int r8 = 0; r8 < kRV; ++r8) {
+            const uint4 u = nh[r8];
+            const int r = r8 * 8;
+            h[r + 0] = bf16_lo(u.x); h[r + 1] = bf16_hi(u.x); h[r + 2] = bf16_lo(u.y); h[r + 3] = bf16_hi(u.y);
+            h[r + 4] = bf16_lo(u.z); h[r + 5] = bf16_hi(u.z); h[r + 6] = bf16_lo(u.w); h[r + 7] = bf16_hi(u.w);
+          }
+        }
+        stage_fetch(tile + num_clusters);   // in flight during this tile's epilogue
+      } else if (p.row_scale != nullptr && row_ok) {
+        rs = __bfloat162float(p.row_scale[row]);
+      }
       if constexpr (kRank > 0) {
-        if (row_ok) {
+        if (row_ok && !fast_stage) {
           const __nv_bfloat16* hp = p.lora_h + (int64_t)row * p.ldh;
           if (R == kRank) {  // 16-byte vector loads (h rows are 16-byte aligned for rank 8 / 16)
 #pragma unroll
@@ -335,7 +394,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       // accumulator chunks: double-buffered (next chunk's tcgen05.ld in flight) except with the kSwi epilogue, whose
       // per-chunk arithmetic dwarfs the TMEM latency and which needs the 32 registers for the a / b pipeline
-      constexpr bool kSide = kSwi || kRes;   // epilogues with a pipelined side input
+      constexpr bool kSide = kSwi || kRes || (kPipeStage && kRank > 0);   // pipelined side inputs need the registers
       constexpr int kVBufs = kSide ? 1 : 2;
       uint32_t v[kVBufs][32];
       if constexpr (!kSide) {
