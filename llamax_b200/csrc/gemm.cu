@@ -259,7 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // the tile, their global-load latency sat on the epilogue's critical path before every tile — which IS the kernel's
     // critical path at K = 4096 (~16k cycles of main loop per tile): the "+LoRA" cost of those shapes.
     static_assert(kBN == kEpiThreads, "one staged column per epilogue thread");
-    constexpr bool kPipeStage = kInt8;
+    constexpr bool kPipeStage = kInt8 || kSwi;
     constexpr int kRV = kRank > 0 ? kRank / 8 : 1;
     const bool fast_stage = kPipeStage && !dump &&
                             (kRank == 0 || (R == kRank && reinterpret_cast<uintptr_t>(p.lora_b) % 16 == 0 &&
