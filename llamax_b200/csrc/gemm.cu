@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "host_utils.h"
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "llamax_b200.h"
@@ -1145,10 +1146,27 @@ int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, 
     configured = true;
   }
   const int p_tiles = (int)((P + 127) / 128);
+  // Token splits: one CTA per SM is resident (147 KB ring), so the kernel lasts waves x (tokens per split + a fixed
+  // fill/drain cost of ~5 stages). Pick the split count that minimises that: "just enough CTAs to cover the SMs" left a
+  // nearly empty second wave (P = 4096: 32 tiles x 5 splits = 160 CTAs on 148 SMs; 9 splits = 288 CTAs, two full waves
+  // of half the length). LLAMAX_WGRAD_SPLITS_OLD=1 keeps the old rule (A/B).
+  static const bool old_rule = getenv("LLAMAX_WGRAD_SPLITS_OLD") != nullptr;
   int splits = std::max(1, std::min(32, (sm_count() + p_tiles - 1) / p_tiles));
   int k_per_split = (int)((M + splits - 1) / splits);
   k_per_split = ((k_per_split + 63) / 64) * 64;
   splits = (int)((M + k_per_split - 1) / k_per_split);
+  if (!old_rule && p_tiles * 2 <= sm_count()) {   // wide outputs (P = 14336) stream at HBM rate either way: 79 vs 81 us
+    int64_t best_cost = INT64_MAX;
+    for (int s = 1; s <= 32; ++s) {
+      int kp = (int)((M + s - 1) / s);
+      kp = ((kp + 63) / 64) * 64;
+      const int s_eff = (int)((M + kp - 1) / kp);
+      if (s_eff != s) continue;
+      const int64_t waves = ((int64_t)p_tiles * s + sm_count() - 1) / sm_count();
+      const int64_t cost = waves * (kp + 320);
+      if (cost < best_cost) { best_cost = cost; splits = s; k_per_split = kp; }
+    }
+  }
   dim3 grid(p_tiles, splits);
   lora_wgrad_tc_kernel<<<grid, 192, wg::kSmem, st>>>(tmX, tmHt, (float*)out, (int)P, R, (int)M, k_per_split, alpha);
   LX_CHECK_LAUNCH("lora_wgrad");
