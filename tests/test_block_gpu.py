@@ -334,3 +334,61 @@ def test_trainable_lm_head_loss_and_weight_gradient():
     assert abs(loss.item() - loss_ref.item()) <= 1e-2 * abs(loss_ref.item())
     assert rel_err(xc.grad, xr.grad) <= TOL
     assert rel_err(wc.grad, wr.grad) <= TOL
+
+
+def test_training_trajectory_follows_oracle():
+    """Six optimisation steps on a fixed batch (2-layer model, prefix-LM, dynamic INT8 + LoRA): the product path's loss
+    trajectory must follow the oracle's (same update rule on both sides: a sign-free normalised gradient step on the
+    LoRA matrices and norm weights), step by step within 5e-3 (measured: 3e-4), and the loss must go down. Catches anything a single
+    forward/backward cannot: gradients written to the wrong parameter, stale cached operands after an update (the
+    resident (scale*W)^T | A^T buffers of the block backward), accumulation across steps."""
+    from llamax_b200.modelling import PrefixLM
+
+    dynamic, P, B, S, steps, lr = True, 48, 2, 160, 6, 0.05
+    model = build_tiny_llama(dynamic, num_layers=2)
+    cfg = model.config
+    torch.manual_seed(9)
+    tokens = torch.randint(0, cfg.vocab_size, (B, S))
+    labels = torch.randint(0, cfg.vocab_size, (B, S))
+    labels[:, :P] = -100
+    rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:S]
+    lws = [oracle_layer_weights(l, torch.float32) for l in model.layers]
+    emb = model.tok_embeddings.weight.detach().float()
+    w_norm, w_out = model.norm.weight.detach().float(), model.output.weight.detach().float()
+
+    def update(params):
+        with torch.no_grad():
+            for p_ in params:
+                if p_.grad is not None:
+                    p_ -= (lr * p_.grad.float() / p_.grad.float().abs().max().clamp_min(1e-12)).to(p_.dtype)
+                    p_.grad = None
+
+    ref_params = [t for lw in lws for t in (*lw.lora_a.values(), *lw.lora_b.values(), lw.attention_norm, lw.ffn_norm)]
+    ref_losses = []
+    for _ in range(steps):
+        x = emb[tokens]
+        for lw in lws:
+            x = R.transformer_layer_ref(x, rope, lw, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, P, dynamic)
+        logits = R.rmsnorm_ref(x, w_norm) @ w_out.T
+        loss = torch.nn.functional.cross_entropy(logits.view(-1, cfg.vocab_size), labels.view(-1))
+        loss.backward()
+        ref_losses.append(loss.item())
+        update(ref_params)
+
+    model = model.cuda()
+    model.build_cache()
+    for m in (model.tok_embeddings, model.output, model.norm):
+        m.requires_grad_(False)
+    params = [p_ for p_ in model.parameters() if p_.requires_grad]
+    assert len(params) == len(ref_params)
+    losses = []
+    tk, lb = tokens.cuda(), labels.cuda()
+    for _ in range(steps):
+        loss = model(tk, labels=lb, block_mask=PrefixLM(P))
+        loss.backward()
+        losses.append(loss.item())
+        update(params)
+    print("loss trajectory ours", [f"{v:.4f}" for v in losses], "oracle", [f"{v:.4f}" for v in ref_losses])
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 5e-3 * abs(b), (losses, ref_losses)
+    assert losses[-1] < losses[0] - 0.05 and ref_losses[-1] < ref_losses[0] - 0.05
