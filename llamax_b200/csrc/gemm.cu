@@ -32,7 +32,7 @@ constexpr int kBKBytes = 128;     // one 128B swizzle row of K per stage
 constexpr int kMaxLoraRank = 16;
 constexpr int kGemmThreads = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int kEpiThreads = 256;
-constexpr int kGroupM = 8;        // m-tiles per scheduling group (L2 reuse of the B panel)
+constexpr int kGroupM = 8;        // tiles of the shorter dimension per scheduling group (L2 reuse of the operand panels)
 
 struct GemmParams {
   int M, N, K;
@@ -54,6 +54,7 @@ struct GemmParams {
   __nv_bfloat16* swi_dab;       // da -> columns [0, N), db -> [N, 2N), pitch ld_dab
   int64_t ld_dab;
   __nv_bfloat16* swi_g;         // optional g = bf16(silu(a)) * b, [M, N] contiguous
+  int group;                    // tile-order group (set by the launcher, see tile_coords)
 };
 
 template <int CG>
@@ -67,14 +68,31 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kAuxBytes + kBarBytes + 1024;  // + align slack
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& tm, int& tn) {
-  const int per_group = kGroupM * num_n;
-  const int g = tile / per_group;
-  const int first_m = g * kGroupM;
-  const int gsize = min(num_m - first_m, kGroupM);
-  const int r = tile - g * per_group;
-  tm = first_m + r % gsize;
-  tn = r / gsize;
+// Tile order. One wave = `clusters` consecutive tiles (74 CTA pairs), and the operand panels a wave touches should stay
+// as few as possible: a group takes kGroupM tiles of one dimension and sweeps the other dimension completely, fastest
+// index inside the group, so a wave covers ~8 x 9.25 tiles = 17.25 live panels — except where it straddles two groups.
+// Groups therefore run along the LONGER dimension (fewer, longer groups): with 64 x 16 tiles (M = 16384, N = 4096),
+// groups of 8 m-tiles x 16 n-tiles (128 tiles, 1.7 waves) keep 21.7 panels live on average, groups of 8 n-tiles x 64
+// m-tiles (512 tiles, 6.9 waves) 18.3. group > 0: m-groups sweeping n; group < 0: n-groups sweeping m.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group, int& tm, int& tn) {
+  if (group > 0) {
+    const int per_group = group * num_n;
+    const int g = tile / per_group;
+    const int first_m = g * group;
+    const int gsize = min(num_m - first_m, group);
+    const int r = tile - g * per_group;
+    tm = first_m + r % gsize;
+    tn = r / gsize;
+  } else {
+    const int gn = -group;
+    const int per_group = gn * num_m;
+    const int g = tile / per_group;
+    const int first_n = g * gn;
+    const int gsize = min(num_n - first_n, gn);
+    const int r = tile - g * per_group;
+    tn = first_n + r % gsize;
+    tm = r / gsize;
+  }
 }
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -161,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t full_addr = CG == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int tm, tn;
-        tile_coords(tile, num_m, num_n, tm, tn);
+        tile_coords(tile, num_m, num_n, p.group, tm, tn);
         const int row_a = tm * kTileM + cta_rank * kBM;
         const int row_b = tn * kBN + cta_rank * (kBN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -271,7 +289,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     auto stage_fetch = [&](int t) {
       if (t >= num_tiles) return;
       int fm, fn;
-      tile_coords(t, num_m, num_n, fm, fn);
+      tile_coords(t, num_m, num_n, p.group, fm, fn);
       const int n = fn * kBN + et;
       const int frow = fm * kTileM + cta_rank * kBM + ew * 32 + lane_id();
       ncs = (has_cs && n < p.N) ? (uint32_t) * reinterpret_cast<const uint16_t*>(p.col_scale + n) : 0u;
@@ -288,7 +306,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int local_tile = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
       int tm, tn;
-      tile_coords(tile, num_m, num_n, tm, tn);
+      tile_coords(tile, num_m, num_n, p.group, tm, tn);
       const int as = local_tile & 1;
       const uint32_t aphase = (local_tile >> 1) & 1;
       const int row = tm * kTileM + cta_rank * kBM + ew * 32 + lane_id();
@@ -565,6 +583,12 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
   int clusters = num_sms / CG;
   if (clusters > num_tiles) clusters = num_tiles;
 
+  GemmParams pp = p;
+  {
+    static const int forced = getenv("LLAMAX_GEMM_GROUP") ? atoi(getenv("LLAMAX_GEMM_GROUP")) : 0;   // A/B switch
+    const int num_m = (p.M + kBM * CG - 1) / (kBM * CG), num_n = (p.N + kBN - 1) / kBN;
+    pp.group = forced != 0 ? forced : (num_m >= num_n ? -kGroupM : kGroupM);
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(kGemmThreads);
@@ -577,7 +601,7 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, pp);
   if (e != cudaSuccess) return set_cuda_error(e, "gemm: launch");
   return 0;
 }
