@@ -56,3 +56,23 @@ def test_argument_validation_without_gpu():
     p = ctypes.cast(buf, ctypes.c_void_p)
     rc = lib.llamax_attn_fwd(p, 64, p, 64, p, 64, p, 64, p, 1, 16, 2, 1, 32, 0, None, 1.0, None)
     assert rc == -1 and b"head_dim" in lib.llamax_last_error()
+
+
+def test_new_gemm_entry_points_validate_arguments_without_gpu():
+    """bf16_gemm_tn / bf16_gemm_swiglu_bwd reject null pointers and unsupported shapes before any launch."""
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.llamax_bf16_gemm_tn(None, 8, p, 8, p, 8, 8, 8, 8, None) == -1
+    assert b"null" in lib.llamax_last_error()
+    assert lib.llamax_bf16_gemm_tn(p, 8, p, 8, p, 8, 12, 8, 8, None) == -1          # M % 8 != 0
+    assert b"multiple of 8" in lib.llamax_last_error()
+    # fused SwiGLU-backward epilogue: N % 16, pitches >= 2N, 16-byte alignment
+    assert lib.llamax_bf16_gemm_swiglu_bwd(p, 64, p, 64, 16, 24, 64, None, p, 48, p, 48, None, None) == -1
+    assert b"N % 16" in lib.llamax_last_error()
+    assert lib.llamax_bf16_gemm_swiglu_bwd(p, 64, p, 64, 16, 32, 64, None, p, 48, p, 64, None, None) == -1   # ld_ab < 2N
+    assert lib.llamax_bf16_gemm_swiglu_bwd(p, 64, p, 64, 16, 32, 64, None, None, 64, p, 64, None, None) == -1
+    assert b"null" in lib.llamax_last_error()
+    mis = ctypes.c_void_p(p.value + 2)
+    assert lib.llamax_bf16_gemm_swiglu_bwd(p, 64, p, 64, 16, 32, 64, None, mis, 64, p, 64, None, None) == -1
+    assert b"aligned" in lib.llamax_last_error()
