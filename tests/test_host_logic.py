@@ -125,3 +125,22 @@ def test_config_fields_match_reference():
                                    "intermediate_dim", "max_seq_len", "vocab_size", "attn_dropout", "rope_base",
                                    "is_llama3_1", "activation_checkpointing")
     assert AudioConfig()._asdict() == dict(sample_rate=16000, n_fft=512, win_length=400, hop_length=160, n_mels=128)
+
+
+def test_gemm_tile_order_model_is_a_bijection():
+    """tools/tile_order_model.py restates csrc/gemm.cu's tile_coords (both group orientations): every tile of a ragged
+    grid is visited exactly once, and the orientation the launcher picks keeps no more panels live than the other."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "tile_order_model.py")
+    spec = importlib.util.spec_from_file_location("tile_order_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for nm, nn in [(64, 16), (64, 56), (55, 16), (3, 5), (1, 1), (7, 501), (64, 4), (9, 9)]:
+        for g in (8, -8, 3, -3):
+            seen = {mod.coords(t, nm, nn, g) for t in range(nm * nn)}
+            assert seen == {(a, b) for a in range(nm) for b in range(nn)}, (nm, nn, g)
+    for nm, nn in [(64, 16), (55, 16), (32, 501), (64, 24)]:
+        pick = -8 if nm >= nn else 8
+        assert mod.live_panels(nm, nn, pick) <= mod.live_panels(nm, nn, -pick) + 1e-9
