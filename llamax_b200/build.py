@@ -61,5 +61,33 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+REFERENCE_SRC = os.environ.get("LLAMAX_REFERENCE", "/root/reference")
+REFERENCE_DST = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+
+
+def install_reference(verbose: bool = True) -> str | None:
+    """Install the UNMODIFIED reference into the git-ignored `baseline/_ref` (it travels to the GPU box with the
+    snapshot) so that `bench.py --impl reference` and tools/incumbents.py can run the reference's own code there.
+    `pip install --target baseline/_ref /root/reference` fails (the reference has no package metadata: a flat layout
+    with two top-level packages and a pyproject that only configures formatters), so the install is what pip would
+    have done for a pure-Python project: its two packages, byte for byte. No-op where /root/reference is absent."""
+    import filecmp
+    import shutil
+
+    if not os.path.isdir(REFERENCE_SRC):
+        return REFERENCE_DST if os.path.isdir(os.path.join(REFERENCE_DST, "modelling")) else None
+    for pkg in ("modelling", "subclasses"):
+        src, dst = os.path.join(REFERENCE_SRC, pkg), os.path.join(REFERENCE_DST, pkg)
+        same = os.path.isdir(dst) and not filecmp.dircmp(src, dst, ignore=["__pycache__"]).diff_files \
+            and not filecmp.dircmp(src, dst, ignore=["__pycache__"]).left_only
+        if not same:
+            shutil.rmtree(dst, ignore_errors=True)
+            shutil.copytree(src, dst, ignore=shutil.ignore_patterns("__pycache__"))
+            if verbose:
+                print(f"[llamax_b200] installed reference package {pkg} -> {dst}")
+    return REFERENCE_DST
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    install_reference()

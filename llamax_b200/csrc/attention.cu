@@ -1248,13 +1248,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                          : (D == 128 ? attn_fwd2_kernel<false, 128> : attn_fwd2_kernel<false, 64>);
   auto kern = one_tile ? kern1 : kern2;
   const int smem_bytes = one_tile ? fwd::smem_bytes(fwd::kNB) : fwd2::kSmemBytes;
-  static thread_local bool configured[8] = {};
-  const int variant = (doc_start ? 2 : 0) + (D == 128 ? 1 : 0) + (one_tile ? 4 : 0);
-  if (!configured[variant]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return set_cuda_error(e, "attn_fwd: cudaFuncSetAttribute");
-    configured[variant] = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem_bytes, "attn_fwd: cudaFuncSetAttribute"))) return rc;
   AttnFwdParams p;
   p.o = (__nv_bfloat16*)o;
   p.ldo = ldo;
@@ -1306,13 +1300,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, bwd::kKV))) return rc;
   auto kern = doc_start ? (D == 128 ? attn_bwd_kernel<true, 128> : attn_bwd_kernel<true, 64>)
                         : (D == 128 ? attn_bwd_kernel<false, 128> : attn_bwd_kernel<false, 64>);
-  static thread_local bool configured[4] = {false, false, false, false};
-  const int variant = (doc_start ? 2 : 0) + (D == 128 ? 1 : 0);
-  if (!configured[variant]) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
-    if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: cudaFuncSetAttribute");
-    configured[variant] = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), bwd::kSmemBytes, "attn_bwd: cudaFuncSetAttribute"))) return rc;
   AttnBwdParams p;
   p.lse = (const float*)lse;
   p.delta = (const float*)delta;

@@ -802,12 +802,8 @@ static bool ring_cfg(const RowCfg& c, int64_t M, bool aligned, int& grid, int& s
 }
 #define LX_RING_SMEM(kern, smem, what)                                                                      \
   do {                                                                                                      \
-    static thread_local int configured = 0;                                                                 \
-    if (configured < (smem)) {                                                                              \
-      cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));     \
-      if (e_ != cudaSuccess) return set_cuda_error(e_, what ": cudaFuncSetAttribute");                      \
-      configured = (smem);                                                                                  \
-    }                                                                                                       \
+    int rc_ = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (smem), what ": cudaFuncSetAttribute");  \
+    if (rc_) return rc_;                                                                                    \
   } while (0)
 
 extern "C" {

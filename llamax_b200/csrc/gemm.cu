@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "host_utils.h"
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 
@@ -572,12 +573,7 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
   }
 
   auto kern = gemm_kernel<kInt8, CG, kRank, kMN, kSwi, kRes>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
-    if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute");
-    configured = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::kTotal, "gemm: cudaFuncSetAttribute"))) return rc;
   const int num_sms = sm_count();
   const int num_tiles = ((p.M + kBM * CG - 1) / (kBM * CG)) * ((p.N + kBN - 1) / kBN);
   int clusters = num_sms / CG;
@@ -855,12 +851,8 @@ static int launch_skinny(const void* A, int64_t lda, const void* B, int64_t ldb,
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, 64, 32);
   if (rc) return rc;
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmem);
-    if (e != cudaSuccess) return set_cuda_error(e, "skinny gemm: cudaFuncSetAttribute");
-    configured = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(skinny_gemm_kernel), sk::kSmem, "skinny gemm: cudaFuncSetAttribute")))
+    return rc;
   skinny_gemm_kernel<<<(M + 127) / 128, 192, sk::kSmem, stream>>>(tmA, tmB, (__nv_bfloat16*)C, ldc, M, N, K);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "skinny gemm: launch");
@@ -1079,7 +1071,7 @@ __global__ void lora_dh_convert_kernel(const float* __restrict__ acc, __nv_bfloa
   }
 }
 
-static int g_gemm_cg = 2;  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group
+static std::atomic<int> g_gemm_cg{2};  // CTA-group size used by the GEMMs (1 or 2); see llamax_set_gemm_cta_group
 
 }  // namespace lx
 
@@ -1163,12 +1155,8 @@ int llamax_lora_wgrad(const void* X, int64_t ldx, const void* Ht, int64_t ldht, 
   if (rc) return rc;
   rc = make_tmap_2d(&tmHt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Ht, M, R, ldht, 64, 32);
   if (rc) return rc;
-  static thread_local bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(lora_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmem);
-    if (e != cudaSuccess) return set_cuda_error(e, "lora_wgrad: cudaFuncSetAttribute");
-    configured = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(lora_wgrad_tc_kernel), wg::kSmem, "lora_wgrad: cudaFuncSetAttribute")))
+    return rc;
   const int p_tiles = (int)((P + 127) / 128);
   // Token splits: one CTA per SM is resident (147 KB ring), so the kernel lasts waves x (tokens per split + a fixed
   // fill/drain cost of ~5 stages). Pick the split count that minimises that: "just enough CTAs to cover the SMs" left a
@@ -1227,12 +1215,8 @@ int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t l
   if (rc) return rc;
   rc = make_tmap_2d(&tmHt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Ht, M, R, ldht, 64, 32);
   if (rc) return rc;
-  static thread_local bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(lora_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lp::kSmem);
-    if (e != cudaSuccess) return set_cuda_error(e, "lora_bwd_pair: cudaFuncSetAttribute");
-    configured = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(lora_bwd_pair_kernel), lp::kSmem, "lora_bwd_pair: cudaFuncSetAttribute")))
+    return rc;
   dim3 grid(m_blocks, splits);
   lora_bwd_pair_kernel<<<grid, 192, lp::kSmem, st>>>(tmY, tmBt, tmHt, (__nv_bfloat16*)dh, lddh,
                                                      splits > 1 ? nullptr : (__nv_bfloat16*)dht, lddht,

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "llamax_b200.h"
 
@@ -32,6 +33,50 @@ int sm_count() {
   return cached;
 }
 
+int ensure_dyn_smem(const void* kernel, int bytes, const char* who) {
+  struct Done { int dev; const void* kernel; int bytes; };
+  static thread_local std::vector<Done> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& d : done)
+    if (d.dev == dev && d.kernel == kernel) {
+      if (d.bytes >= bytes) return 0;
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) return set_cuda_error(e, who);
+      d.bytes = bytes;
+      return 0;
+    }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_cuda_error(e, who);
+  done.push_back({dev, kernel, bytes});
+  return 0;
+}
+
+// Encoded tensor maps are memoised per thread (direct-mapped, keyed by every argument of the encode call): a training
+// step re-issues the same few hundred (pointer, shape) combinations — the caching allocator hands the same blocks back
+// step after step — so ~600 driver encodes per step become table hits. A tensor map holds no state beyond its arguments,
+// so a stale hit is impossible: equal key = equal descriptor.
+struct TmapKey {
+  const void* ptr;
+  int64_t d[4], s[3];
+  int box[4];
+  int dt, esz, rank;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int kTmapSlots = 1024;
+static TmapSlot* tmap_slot(const TmapKey& k) {
+  static thread_local std::vector<TmapSlot> table(kTmapSlots);
+  uint64_t h = 1469598103934665603ull;
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+  for (size_t i = 0; i < sizeof(TmapKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return &table[h % kTmapSlots];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -53,6 +98,15 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* 
                  int64_t ld, int box_inner, int box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(LLAMAX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.d[0] = inner; key.d[1] = outer; key.s[0] = ld; key.box[0] = box_inner; key.box[1] = box_outer;
+  key.dt = (int)dt; key.esz = esz; key.rank = 2;
+  TmapSlot* slot = tmap_slot(key);
+  if (slot->valid && slot->key == key) {
+    *map = slot->map;
+    return 0;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
@@ -65,6 +119,9 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* 
              (int)r, (long long)inner, (long long)outer, (long long)ld);
     return set_error(LLAMAX_ERR_CUDA, buf);
   }
+  slot->key = key;
+  slot->map = *map;
+  slot->valid = true;
   return 0;
 }
 
@@ -72,6 +129,16 @@ int make_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* 
                  const int64_t strides_[3], const int box_[4]) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(LLAMAX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.dt = (int)dt; key.esz = esz; key.rank = 4;
+  for (int i = 0; i < 4; ++i) { key.d[i] = dims_[i]; key.box[i] = box_[i]; }
+  for (int i = 0; i < 3; ++i) key.s[i] = strides_[i];
+  TmapSlot* slot = tmap_slot(key);
+  if (slot->valid && slot->key == key) {
+    *map = slot->map;
+    return 0;
+  }
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < 4; ++i) {
@@ -86,6 +153,9 @@ int make_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* 
     snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(4d) failed: CUresult %d", (int)r);
     return set_error(LLAMAX_ERR_CUDA, buf);
   }
+  slot->key = key;
+  slot->map = *map;
+  slot->valid = true;
   return 0;
 }
 

@@ -19,6 +19,11 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* 
 int make_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* ptr, const int64_t dims[4],
                  const int64_t strides[3], const int box[4]);
 
+// One-time cudaFuncSetAttribute(MaxDynamicSharedMemorySize) per (device, kernel): the attribute is per device, so the
+// "already configured" memo is keyed by the current device ordinal (a per-thread flag alone left the first launch on a
+// second GPU of the same thread with the 48 KB default).
+int ensure_dyn_smem(const void* kernel, int bytes, const char* who);
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace lx

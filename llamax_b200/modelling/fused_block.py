@@ -125,7 +125,7 @@ def _operand(cache: dict | None, key: str, specs, rows: int, width: int, device)
     filled ahead of its use); a non-resident one is the shared scratch."""
     numel = rows * width
     if cache is not None and _CACHE_MODE != "0":
-        sig = tuple((s.w8.data_ptr(), s.w8._version, s.ws.data_ptr(), s.ws._version) for s in specs)
+        sig = (rows, width) + tuple((s.w8.data_ptr(), s.w8._version, s.ws.data_ptr(), s.ws._version) for s in specs)
         hit = cache.get(key)
         if hit is not None and hit[0] == sig and hit[1].device == device:
             return hit[1], True, True
@@ -362,6 +362,10 @@ class FusedDecoderBlock(torch.autograd.Function):
 
         ctx.meta = meta
         ctx.shape = (B, S, Dm)
+        # backward() re-reads the live parameters (LoRA A / B, norm weights, int8 codes / scales) instead of saving them:
+        # remember their versions so that an in-place update between forward and backward raises, as autograd's own
+        # saved-tensor check would, instead of silently mixing two parameter states
+        ctx.versions = _param_versions(layer)
         ctx.recompute_ffn = _RECOMPUTE == "ffn"
         if ctx.recompute_ffn:   # xn2, rstd2 and ab are rebuilt from x1 in backward
             ctx.save_for_backward(x2, xn1, rstd1, qkv, o, lse, x1, h_qkv, h_o, h_13, h_2, rope)
@@ -373,6 +377,9 @@ class FusedDecoderBlock(torch.autograd.Function):
     def backward(ctx, dout: Tensor):
         layer, prefix_len, doc_start, doc_end = ctx.meta
         att, ff = layer.attention, layer.feed_forward
+        if _param_versions(layer) != ctx.versions:
+            raise RuntimeError("FusedDecoderBlock: a parameter of this block (LoRA A/B, norm weight or int8 weight) was "
+                               "modified in place between forward and backward; its gradient would mix two states")
         if ctx.recompute_ffn:
             x2, xn1, rstd1, qkv, o, lse, x1, h_qkv, h_o, h_13, h_2, rope = ctx.saved_tensors
             s1_, s3_ = LinearSpec(ff.w1), LinearSpec(ff.w3)
@@ -497,6 +504,16 @@ class FusedDecoderBlock(torch.autograd.Function):
         return (dx.view(B, S, Dm), None, None, *grads)
 
 
+def _param_versions(layer):
+    att, ff = layer.attention, layer.feed_forward
+    v = [layer.attention_norm.weight._version, layer.ffn_norm.weight._version]
+    for m in (att.wq, att.wk, att.wv, att.wo, ff.w1, ff.w3, ff.w2):
+        v += [m.weight.int_data._version, m.weight.scale._version]
+        if getattr(m, "rank", 0) > 0:
+            v += [m.lora_a._version, m.lora_b._version]
+    return tuple(v)
+
+
 def block_trainables(layer):
     """Tensors passed to FusedDecoderBlock.apply after `meta`, in the order backward() returns their gradients."""
     att, ff = layer.attention, layer.feed_forward
@@ -512,6 +529,7 @@ def fused_block_supported(layer, x: Tensor) -> bool:
     mods = (att.wq, att.wk, att.wv, att.wo, ff.w1, ff.w3, ff.w2)
     return (
         x.is_cuda and x.dtype is torch.bfloat16 and att.kv_cache is None and att.head_dim in (64, 128)
+        and not (layer.training and att.attn_dropout > 0)   # falls through to Attention.forward, which raises
         and all(isinstance(m.weight, Int8LinearWeight) and m.bias is None for m in mods)
         and all(getattr(m, "rank", 0) <= 16 and getattr(m, "rank", 0) % 8 == 0 for m in mods)
         and att.wq.weight.dynamic_int8_act == att.wk.weight.dynamic_int8_act == att.wv.weight.dynamic_int8_act

@@ -273,6 +273,36 @@ class TransformerLayer(nn.Module):
         return x
 
 
+class _RMSNormFn(torch.autograd.Function):
+    """nn.RMSNorm (llama.py:182, the final norm) on this package's kernels: fp32 statistics, one rounding."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, eps: float):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y, rstd, _, _ = ops.rmsnorm_fwd(x2, w.detach(), eps)
+        ctx.save_for_backward(x2, w, rstd)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x2, w, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx, dw = ops.rmsnorm_bwd(dy2, x2, w.detach(), rstd, None, want_dw=ctx.needs_input_grad[1])
+        return dx.view(dy.shape), (dw.to(w.dtype) if dw is not None else None), None
+
+
+def rms_norm(norm: nn.RMSNorm, x: Tensor) -> Tensor:
+    w = norm.weight
+    if (x.is_cuda and x.dtype is torch.bfloat16 and w is not None and w.dtype is torch.bfloat16
+            and len(norm.normalized_shape) == 1 and x.shape[-1] % 8 == 0):
+        return _RMSNormFn.apply(x, w, norm.eps if norm.eps is not None else torch.finfo(torch.float32).eps)
+    return norm(x)
+
+
 class Llama(nn.Module):
     def __init__(self, config: LlamaConfig) -> None:
         super().__init__()
@@ -300,10 +330,19 @@ class Llama(nn.Module):
         return x
 
     def _head(self, x: Tensor, labels: Tensor | None) -> Tensor:
-        x = self.norm(x)
+        x = rms_norm(self.norm, x)
         if labels is None:
             return self.output(x)
-        return chunked_lm_loss(x, self.output.weight, labels, self._output_weight_t(x))
+        out = self.output
+        w = out.weight
+        # chunked fast path only for a plain frozen-or-trainable bf16 head: `type(...) is nn.Linear` excludes LoRALinear
+        # (whose adapter term the loss must see, llama.py:216 computes self.output(...)), a bias or a quantised weight
+        fast = (type(out) is nn.Linear and out.bias is None and type(w) is nn.Parameter and w.is_cuda
+                and w.dtype is torch.bfloat16 and x.is_cuda and x.dtype is torch.bfloat16 and w.shape[0] % 8 == 0)
+        if not fast:
+            logits = out(x)
+            return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), labels.view(-1))
+        return chunked_lm_loss(x, w, labels, self._output_weight_t(x))
 
     def _output_weight_t(self, x: Tensor):
         """W_out^T [embed, vocab] as the grad_input GEMM operand; cached while the weight is unchanged."""
@@ -349,6 +388,8 @@ class _ChunkedLMLoss(torch.autograd.Function):
         dx = torch.empty_like(x2) if need_dx else None
         dw = torch.zeros_like(weight, dtype=torch.float32) if need_dw else None
         wd = weight.detach()
+        if need_dx and weight_t is None:
+            weight_t = wd.t().contiguous()
         C = _ChunkedLMLoss.CHUNK
         buf = torch.empty(min(C, x2.shape[0]), wd.shape[0], device=x.device, dtype=torch.bfloat16)
         for i in range(0, x2.shape[0], C):
@@ -375,7 +416,8 @@ class _ChunkedLMLoss(torch.autograd.Function):
 def chunked_lm_loss(x: Tensor, weight: Tensor, labels: Tensor, weight_t: Tensor | None = None) -> Tensor:
     from ..subclasses.int8 import Int8LinearWeight
 
-    if isinstance(weight, Int8LinearWeight) or not x.is_cuda or x.dtype is not torch.bfloat16 or weight.shape[0] % 8:
+    if (isinstance(weight, Int8LinearWeight) or not x.is_cuda or x.dtype is not torch.bfloat16
+            or weight.dtype is not torch.bfloat16 or weight.shape[0] % 8):
         logits = F.linear(x, weight)  # quantised / odd head: module path + library cross-entropy
         return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), labels.view(-1))
     return _ChunkedLMLoss.apply(x, weight, labels, weight_t)

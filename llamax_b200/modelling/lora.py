@@ -81,7 +81,7 @@ class LoRALinear(nn.Linear):
         return f"{super().extra_repr()}, rank={self.rank}, alpha={self.alpha}"
 
     def forward(self, x: Tensor):
-        fused = (self.rank > 0 and self.rank % 4 == 0 and self.rank <= 16 and self.bias is None
+        fused = (self.rank > 0 and self.rank % 8 == 0 and self.rank <= 16 and self.bias is None
                  and isinstance(self.weight, Int8LinearWeight) and x.is_cuda)
         if fused:
             return _LoRAInt8Linear.apply(x, self.weight, self.lora_a, self.lora_b, self.scale)

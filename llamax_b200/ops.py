@@ -70,9 +70,9 @@ def _prep(t: Tensor):
         raise _lib.LlamaxError("llamax_b200 ops need CUDA tensors: there is no CPU implementation of this path")
     lib = _lib.load()
     dev = t.device.index
-    if getattr(_tls, "dev", None) != dev:
-        check(lib.llamax_set_device(dev), "llamax_set_device")
-        _tls.dev = dev
+    # always (re)select: torch.cuda.set_device / device guards on this thread may have changed the runtime's current
+    # device since the last call, and a per-thread memo of "the device I selected last" cannot see that
+    check(lib.llamax_set_device(dev), "llamax_set_device")
     return lib, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
