@@ -679,6 +679,668 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward v3: two query tiles per CTA as above, but every score row is shared by TWO threads (column halves), i.e. four
+// softmax warpgroups per CTA. Measured (tools/xu_bench.cu, profiles/r2_xu_bench.txt): one warp issues a MUFU.EX2 at most
+// every 8 cycles, while two warps on the same scheduler together reach one per ~5.5 cycles — a thread-per-row softmax is
+// bound by its own 128 dependent-free ex2 (>= 1024 cycles per tile) no matter how idle the XU pipe is, and that softmax
+// sits on the serial chain S(j) -> softmax(j) -> PV(j) -> S(j+1) of its tile (P aliases S in TMEM, so the chain cannot
+// be broken), which is what paces the kernel: 4250 cycles per pair of tiles against 2728 cycles of MMA work.
+// With 64 columns per thread the per-warp ex2 floor halves, four warps per scheduler fill the XU pipe, the O rescale and
+// the epilogue split by head-dim halves, and PV starts on the first 64 kv columns while the second half is still in exp.
+//   row maxima / row sums of the two halves are exchanged through shared memory (double-buffered slots, one 64-thread
+//   named barrier per lane quarter and tile); both halves take identical rescale decisions (same inputs).
+//   TMEM (512 columns): S0 | S1 | O0 | O1; P half h (bf16 pairs, 32 columns) is written over the first 32 columns of
+//   the 64 score columns its own warpgroup has just read.
+// ------------------------------------------------------------------------------------------------
+namespace fwd3 {
+constexpr int kTile = 128;
+constexpr int kTileBytes = kTile * kHD * 2;        // 32 KB
+constexpr int kOffQ = 0;                           // 2 query tiles
+constexpr int kOffK = kOffQ + 2 * kTileBytes;      // 2 stages
+constexpr int kOffV = kOffK + 2 * kTileBytes;      // 2 stages
+constexpr int kOffStat = kOffV + 2 * kTileBytes;   // exchange slots: [2 buffers][2 tiles][2 halves][128 rows] fp32
+constexpr int kStatBytes = 2 * 2 * 2 * kTile * 4;
+constexpr int kOffBar = kOffStat + kStatBytes;
+// q_full, k full/empty[2], v full/empty[2], s_full[2 tiles], p_full[2 tiles][2 halves], pv_done[2 tiles]
+constexpr int kNumBars = 1 + 4 + 4 + 2 + 4 + 2;
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+// warps 0-15: four softmax warpgroups (tile 0 halves 0, 1; tile 1 halves 0, 1); warp 16: TMA producer + TMEM allocator;
+// warp 17: MMA issuer. 18 warps get 112 registers each straight from the launch (65536 / 576 = 113): no setmaxnreg —
+// it can only trade registers inside the CTA's launch allocation, and 640 threads would start at 96 registers with
+// nothing to take the 16 extra per softmax thread from but a 32-register control warpgroup (measured: spills around
+// every MMA group of the issuer).
+constexpr int kThreads = 576;
+static_assert(kSmemBytes <= 232448, "attention forward shared memory budget");
+}  // namespace fwd3
+
+template <bool kDocs, int kD>
+__global__ void __launch_bounds__(fwd3::kThreads, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  using namespace fwd3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_stat = reinterpret_cast<float*>(smem + kOffStat);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;     // [tile]
+  uint64_t* p_full = bars + 11;    // [tile * 2 + half]
+  uint64_t* pv_done = bars + 15;   // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  // grid = (query heads, batch, pairs of query tiles): pairs run backwards so CTAs are dispatched longest-first
+  const int pr = gridDim.z - 1 - blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hk = h / (p.Hq / p.Hkv);
+  // per-tile kv tile ranges [jb_x, je_x); a tile past the end of the sequence has an empty range
+  int jb_[2], je_[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const int q0 = (2 * pr + x) * kTile;
+    if (q0 < p.S) {
+      const int kv_end = min(p.S, max(p.P, q0 + kTile));
+      je_[x] = (kv_end + kTile - 1) / kTile;
+      jb_[x] = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
+    } else {
+      jb_[x] = je_[x] = 0;
+    }
+  }
+  const bool act1 = je_[1] > jb_[1];
+  const int jb = act1 ? min(jb_[0], jb_[1]) : jb_[0];
+  const int je = max(je_[0], je_[1]);
+
+  if (warp == 16 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 17 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
+    fence_mbar_init();
+  }
+  if (warp == 16) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 16) {
+    if (warp == 16) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {   // rows past the end of the sequence are zero-filled
+          tma_load_4d(smem + kOffQ + x * kTileBytes, &tmQ, q_full, 0, h, (2 * pr + x) * kTile, b);
+          tma_load_4d(smem + kOffQ + x * kTileBytes + kTileBytes / 2, &tmQ, q_full, 64, h, (2 * pr + x) * kTile, b);
+        }
+        for (int j = jb; j < je; ++j) {
+          const int st = (j - jb) & 1;
+          const uint32_t ph = ((j - jb) >> 1) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], kTileBytes);
+          uint8_t* sk = smem + kOffK + st * kTileBytes;
+          tma_load_4d(sk, &tmK, &k_full[st], 0, hk, j * kTile, b);
+          tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, j * kTile, b);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], kTileBytes);
+          uint8_t* sv = smem + kOffV + st * kTileBytes;
+          tma_load_4d(sv, &tmV, &v_full[st], 0, hk, j * kTile, b);
+          tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, j * kTile, b);
+        }
+      }
+      __syncwarp();
+    } else {
+      // ------------------------------------ MMA issuer ------------------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
+        constexpr uint32_t kHi = desc_hi(1024);
+        const uint32_t loQ0 = desc_lo(smem_u32(smem + kOffQ), 16);
+        const uint32_t loK0 = desc_lo(smem_u32(smem + kOffK), 16), loV0 = desc_lo(smem_u32(smem + kOffV), 16384);
+        auto active = [&](int x, int j) { return j >= jb_[x] && j < je_[x]; };
+        // S_x(j) = Q_x K(j)^T; releases K(j) if x is the last tile that reads it
+        auto issue_s = [&](int x, int j) {
+          const int st = (j - jb) & 1;
+          mbar_wait(&k_full[st], ((j - jb) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t loQ = loQ0 + x * (kTileBytes / 16), loK = loK0 + st * (kTileBytes / 16);
+#pragma unroll
+          for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss<false, 1>(tmem_base + x * 128, desc_join(loQ + dh * 1024 + ks * 2, kHi),
+                                desc_join(loK + dh * 1024 + ks * 2, kHi), idesc_s, (dh | ks) != 0);
+          umma_commit(&s_full[x]);
+          if (x == 1 || !active(1, j)) umma_commit(&k_empty[st]);
+        };
+        mbar_wait(q_full, 0);
+        int it[2] = {0, 0};   // iterations done per tile
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+          if (active(x, jb)) issue_s(x, jb);
+        for (int j = jb; j < je; ++j) {
+          const int st = (j - jb) & 1;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (!active(x, j)) continue;
+            if (j == jb_[x] && j != jb) issue_s(x, j);   // a tile whose document starts later than its partner's
+            mbar_wait(&v_full[st], ((j - jb) >> 1) & 1);
+            const uint32_t loV = loV0 + st * (kTileBytes / 16);
+            // O_x += P_x V in two halves of the kv range: half hh of P comes from warpgroup hh of the tile and lives in
+            // the first 32 columns of that warpgroup's 64 score columns
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              mbar_wait(&p_full[x * 2 + hh], it[x] & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts_f16(tmem_base + 256 + x * 128, tmem_base + x * 128 + hh * 64 + ks * 8,
+                            desc_join(loV + (hh * 64 + ks * 16) * 8, kHi), idesc_pv, (it[x] | hh | ks) != 0);
+            }
+            umma_commit(&pv_done[x]);
+            if (x == 1 || !active(1, j)) umma_commit(&v_empty[st]);
+            ++it[x];
+            if (active(x, j + 1)) issue_s(x, j + 1);     // in order behind PV_x(j), which reads P from the same columns
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------ softmax / correction / epilogue: two warpgroups per query tile ------------
+    const int wg = warp >> 2;           // 0..3
+    const int x = wg >> 1;              // query tile
+    const int hf = wg & 1;              // column half (scores: kv columns; O / epilogue: head-dim columns)
+    const int ew = warp & 3;            // TMEM lane quarter (hardware: warp % 4)
+    const int r = ew * 32 + lane_id();  // row in tile == TMEM lane
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const int q0 = (2 * pr + x) * kTile;
+    const int q = q0 + r;
+    const int jb_x = x ? jb_[1] : jb_[0], je_x = x ? je_[1] : je_[0];
+    const int n_kv = je_x - jb_x;
+    const uint32_t tS = tmem_base + x * 128 + hf * 64 + lane_off;         // my 64 score columns (P over the first 32)
+    const uint32_t tO = tmem_base + 256 + x * 128 + hf * 64 + lane_off;   // my 64 O columns
+    const uint32_t bar_id = 1 + x * 4 + ew;                               // the 64 threads that share my 32 rows
+    float* my_slot = s_stat + (x * 2 + hf) * kTile + r;                   // + buffer * 4 * kTile
+    float* peer_slot = s_stat + (x * 2 + (hf ^ 1)) * kTile + r;
+    float m_used = -INFINITY, l = 0.f;
+    const int ds_row = kDocs ? p.doc_start[(int64_t)b * p.S + min(q, p.S - 1)] : 0;
+    const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kTile - 1, p.S - 1)] : 0;
+    for (int i = 0; i < n_kv; ++i) {
+      const int kv0 = (jb_x + i) * kTile;
+      // tile needs the element test unless every (q, kv) pair is visible and in range
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      mbar_wait(&s_full[x], i & 1);
+      tc_fence_after();
+      uint32_t sv[2][32];
+      tmem_ld_32x32(tS, sv[0]);
+      tmem_ld_32x32(tS + 32, sv[1]);
+      tmem_wait_ld_regs(sv[0]);
+      tmem_wait_ld_regs(sv[1]);
+      if (!full_tile) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int kv = kv0 + hf * 64 + c * 32 + e;
+            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
+            if (!ok) sv[c][e] = 0xff800000u;  // -inf
+          }
+      }
+      float mx4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mx4[c] = __uint_as_float(sv[c >> 1][(c & 1) * 16]);
+#pragma unroll
+        for (int e = 1; e < 16; ++e) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c >> 1][(c & 1) * 16 + e]));
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // row maximum over both column halves (double-buffered slot: the peer reads slot i & 1 after barrier i, my next
+      // write to it is after barrier i + 1)
+      my_slot[(i & 1) * 4 * kTile] = mx;
+      named_bar_sync(bar_id, 64);
+      mx = fmaxf(mx, peer_slot[(i & 1) * 4 * kTile]);
+      const float m_tile = mx * p.scale_log2;
+      float alpha = 1.f;
+      if (m_tile > m_used + 8.f) {  // lazy rescale: only when the running max grows by more than 2^8
+        alpha = ex2(m_used - m_tile);
+        m_used = m_tile;
+      }
+      uint32_t preg[32];
+      float rs0 = 0.f, rs1 = 0.f;
+      // a row may see nothing in a visited tile (packed documents): keep the exponent finite so that exp2(-inf) = 0
+      const float m_exp = (m_used == -INFINITY) ? 0.f : m_used;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(sv[c][e]), p.scale_log2, -m_exp));      // -inf -> 0
+          const float p1 = ex2(fmaf(__uint_as_float(sv[c][e + 1]), p.scale_log2, -m_exp));
+          rs0 += p0;
+          rs1 += p1;
+          preg[c * 16 + e / 2] = pack_bf16(p0, p1);
+        }
+      l = l * alpha + (rs0 + rs1);
+      if (i > 0) {
+        mbar_wait(&pv_done[x], (i - 1) & 1);  // O stable
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {   // the peer warp sees the same maxima: same decision
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st_32x32(tO + c * 32, v);
+          }
+          tmem_wait_st();
+        }
+      }
+      tmem_st_32x32(tS, preg);   // P half (bf16 pairs) over the first 32 of my 64 score columns
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&p_full[x * 2 + hf]);
+    }
+    // epilogue: row sum over both halves, then my 64 head-dim columns of O
+    if (n_kv > 0) {
+      float* eslot = s_stat + (n_kv & 1) * 4 * kTile;   // the buffer the last iteration did NOT use
+      eslot[(x * 2 + hf) * kTile + r] = l;
+      named_bar_sync(bar_id, 64);
+      l += eslot[(x * 2 + (hf ^ 1)) * kTile + r];
+      mbar_wait(&pv_done[x], (n_kv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l;
+      const bool row_ok = q < p.S;
+      __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * kD + hf * 64;
+      if (hf * 64 < kD) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + c * 32, v);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              uint4 o4;
+              o4.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+              o4.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+              o4.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+              o4.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+              stg_v4(orow + c * 32 + e, o4);
+            }
+          }
+        }
+      }
+      if (row_ok && hf == 0) p.lse[((int64_t)b * p.Hq + h) * p.S + q] = (m_used + log2f(l)) * kLn2;
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward v4: the v2 structure (two query tiles per CTA, one softmax warpgroup per tile, thread = row) with the serial
+// chain of a tile cut where it can be:  S(j) -> softmax(j) -> PV(j) -> S(j+1)  cannot be broken (P aliases S in TMEM, 512
+// columns are S0 | S1 | O0 | O1), and that chain — not a pipe — paces v2: 1364 cycles of the tile's own MMAs + ~2500 of
+// softmax latency + hand-offs = the measured ~4250 cycles per pair of tiles, with the tensor pipe busy 64 % of the time.
+//   * P is handed over in FOUR 32-column chunks, each with its own mbarrier: the two PV MMAs of a chunk run while the
+//     softmax warpgroup is in the exponentials of the next chunks, so of PV only the last chunk's MMAs stay on the chain;
+//   * one MMA-issuing warp PER TILE: with chunked hand-offs a single issuer thread would sit in tile 0's chunk waits
+//     while tile 1's chunks are ready (head-of-line blocking); the K / V stages are released by BOTH issuers (count 2);
+//   * the per-step wait on pv_done is gone: S(j) is issued behind PV(j-1) by the same thread, so s_full(j) implies it.
+// ------------------------------------------------------------------------------------------------
+namespace fwd4 {
+constexpr int kTile = 128;
+constexpr int kTileBytes = kTile * kHD * 2;        // 32 KB
+constexpr int kOffQ = 0;                           // 2 query tiles
+constexpr int kOffK = kOffQ + 2 * kTileBytes;      // 2 stages
+constexpr int kOffV = kOffK + 2 * kTileBytes;      // 2 stages
+constexpr int kOffBar = kOffV + 2 * kTileBytes;
+// q_full, k full/empty[2], v full/empty[2], s_full[2 tiles], p_chunk[2 tiles][4], pv_done[2 tiles], xu_tok[2 tiles]
+constexpr int kNumBars = 1 + 4 + 4 + 2 + 8 + 2 + 2;
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+constexpr int kThreads = 384;                      // warp 0 TMA, warps 1-2 MMA issue (tile 0, 1), warp 3 TMEM alloc; warpgroups 1, 2: softmax
+constexpr int kRegsCtrl = 56, kRegsSoftmax = 224;  // 128 * 56 + 256 * 224 = 384 * 168
+}  // namespace fwd4
+
+template <bool kDocs, int kD, bool kAluPack, bool kStagger>
+__global__ void __launch_bounds__(fwd4::kThreads, 1)
+attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  using namespace fwd4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;     // [tile]
+  uint64_t* p_chunk = bars + 11;   // [tile * 4 + chunk]
+  uint64_t* pv_done = bars + 19;   // [tile]
+  uint64_t* xu_tok = bars + 21;    // [tile]: "tile x may run its next exp phase" (arrived on by the OTHER tile's 4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+#ifdef LX_ATTN_TRACE
+  const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 &&
+                      (warp == 1 || warp == 2 || warp == 4 || warp == 8);
+#endif
+  // grid = (query heads, batch, pairs of query tiles): pairs run backwards so CTAs are dispatched longest-first
+  const int pr = gridDim.z - 1 - blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hk = h / (p.Hq / p.Hkv);
+  // per-tile kv tile ranges [jb_x, je_x); a tile past the end of the sequence has an empty range
+  int jb_[2], je_[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const int q0 = (2 * pr + x) * kTile;
+    if (q0 < p.S) {
+      const int kv_end = min(p.S, max(p.P, q0 + kTile));
+      je_[x] = (kv_end + kTile - 1) / kTile;
+      jb_[x] = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
+    } else {
+      jb_[x] = je_[x] = 0;
+    }
+  }
+  const bool act1 = je_[1] > jb_[1];
+  const int jb = act1 ? min(jb_[0], jb_[1]) : jb_[0];
+  const int je = max(je_[0], je_[1]);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 2);   // one commit from each tile's issuer
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 2);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&p_chunk[i], 4);
+    for (int i = 0; i < 2; ++i) mbar_init(&xu_tok[i], 4);
+    fence_mbar_init();
+  }
+  if (warp == 3) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsCtrl>();
+    if (warp == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {   // rows past the end of the sequence are zero-filled
+          tma_load_4d(smem + kOffQ + x * kTileBytes, &tmQ, q_full, 0, h, (2 * pr + x) * kTile, b);
+          tma_load_4d(smem + kOffQ + x * kTileBytes + kTileBytes / 2, &tmQ, q_full, 64, h, (2 * pr + x) * kTile, b);
+        }
+        for (int j = jb; j < je; ++j) {
+          const int st = (j - jb) & 1;
+          const uint32_t ph = ((j - jb) >> 1) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], kTileBytes);
+          uint8_t* sk = smem + kOffK + st * kTileBytes;
+          tma_load_4d(sk, &tmK, &k_full[st], 0, hk, j * kTile, b);
+          tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, j * kTile, b);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], kTileBytes);
+          uint8_t* sv = smem + kOffV + st * kTileBytes;
+          tma_load_4d(sv, &tmV, &v_full[st], 0, hk, j * kTile, b);
+          tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, j * kTile, b);
+        }
+      }
+      __syncwarp();
+    } else if (warp <= 2) {
+      // ------------------------------------ MMA issuer of tile x ------------------------------------
+      // Walks EVERY kv tile of the CTA's range, also those its own query tile does not visit (causal: the first tile of a
+      // pair skips the last kv tile; packed documents: later start): there it only waits for the stage and releases it,
+      // so the K / V barriers always see two arrivals and neither issuer can run a stage ahead of the other.
+      const int x = warp - 1;
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
+        constexpr uint32_t kHi = desc_hi(1024);
+        const uint32_t loQ = desc_lo(smem_u32(smem + kOffQ), 16) + x * (kTileBytes / 16);
+        const uint32_t loK0 = desc_lo(smem_u32(smem + kOffK), 16), loV0 = desc_lo(smem_u32(smem + kOffV), 16384);
+        const int jb_x = x ? jb_[1] : jb_[0], je_x = x ? je_[1] : je_[0];
+        const uint32_t tSx = tmem_base + x * 128, tOx = tmem_base + 256 + x * 128;
+        auto issue_s = [&](int j) {
+          const int st = (j - jb) & 1;
+          mbar_wait(&k_full[st], ((j - jb) >> 1) & 1);
+          if (j >= jb_x && j < je_x) {
+            tc_fence_after();
+            const uint32_t loK = loK0 + st * (kTileBytes / 16);
+#pragma unroll
+            for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ss<false, 1>(tSx, desc_join(loQ + dh * 1024 + ks * 2, kHi), desc_join(loK + dh * 1024 + ks * 2, kHi),
+                                  idesc_s, (dh | ks) != 0);
+            umma_commit(&s_full[x]);
+          }
+          umma_commit(&k_empty[st]);
+        };
+        mbar_wait(q_full, 0);
+        int it = 0;   // PV steps done
+        issue_s(jb);
+        for (int j = jb; j < je; ++j) {
+          const int st = (j - jb) & 1;
+          mbar_wait(&v_full[st], ((j - jb) >> 1) & 1);
+          if (j >= jb_x && j < je_x) {
+            const uint32_t loV = loV0 + st * (kTileBytes / 16);
+            LX_TR(tr_cta, j, x * 16 + 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              mbar_wait(&p_chunk[x * 4 + c], it & 1);
+              tc_fence_after();
+              if (c == 0) LX_TR(tr_cta, j, x * 16 + 1);
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int ks = c * 2 + k2;   // 16 kv rows per MMA: P columns 8 ks .. 8 ks + 7, V rows 16 ks .. 16 ks + 15
+                umma_ts_f16(tOx, tSx + ks * 8, desc_join(loV + ((ks >> 2) * 64 + (ks & 3) * 16) * 8, kHi), idesc_pv,
+                            (it | ks) != 0);
+              }
+            }
+            umma_commit(&pv_done[x]);
+            LX_TR(tr_cta, j, x * 16 + 2);
+            ++it;
+          }
+          umma_commit(&v_empty[st]);
+          if (j + 1 < je) issue_s(j + 1);   // in order behind PV_x(j), which reads P from the same columns
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------ softmax / correction / epilogue: one warpgroup per query tile ------------
+    setmaxnreg_inc<kRegsSoftmax>();
+    const int x = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane_id();  // row in tile == TMEM lane
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const int q0 = (2 * pr + x) * kTile;
+    const int q = q0 + r;
+    const int jb_x = x ? jb_[1] : jb_[0], je_x = x ? je_[1] : je_[0];
+    const int n_kv = je_x - jb_x;
+    const uint32_t tS = tmem_base + x * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + x * 128 + lane_off;
+    float m_used = -INFINITY, l = 0.f;
+    const int ds_row = kDocs ? p.doc_start[(int64_t)b * p.S + min(q, p.S - 1)] : 0;
+    const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kTile - 1, p.S - 1)] : 0;
+    for (int i = 0; i < n_kv; ++i) {
+      const int kv0 = (jb_x + i) * kTile;
+      // tile needs the element test unless every (q, kv) pair is visible and in range
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      LX_TR(tr_cta, jb_x + i, x * 16 + 4);
+      mbar_wait(&s_full[x], i & 1);   // also: PV(i-1) has completed (same issuing thread, in order): O is stable
+      tc_fence_after();
+      LX_TR(tr_cta, jb_x + i, x * 16 + 5);
+      // single pass over TMEM: the whole score row (128 fp32) lives in registers
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, sv[c]);
+      tmem_wait_ld_regs(sv[0]);
+      tmem_wait_ld_regs(sv[1]);
+      tmem_wait_ld_regs(sv[2]);
+      tmem_wait_ld_regs(sv[3]);
+      LX_TR(tr_cta, jb_x + i, x * 16 + 6);
+      if (!full_tile) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int kv = kv0 + c * 32 + e;
+            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
+            if (!ok) sv[c][e] = 0xff800000u;  // -inf
+          }
+      }
+      float mx4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mx4[c] = __uint_as_float(sv[c][0]);
+#pragma unroll
+        for (int e = 1; e < 32; ++e) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][e]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_tile = mx * p.scale_log2;
+      float alpha = 1.f;
+      if (m_tile > m_used + 8.f) {  // lazy rescale: only when the running max grows by more than 2^8
+        alpha = ex2(m_used - m_tile);
+        m_used = m_tile;
+      }
+      if (i > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st_32x32(tO + c * 32, v);
+        }
+        tmem_wait_st();
+      }
+      LX_TR(tr_cta, jb_x + i, x * 16 + 7);
+      // The exponentials of the two tiles share the XU pipe (16 ex2 / clk / SM = 8 cycles per warp instruction per
+      // scheduler). tools/attn_trace.py: left alone, the two tiles drift INTO phase within two steps, whatever their initial
+      // offset — both sit in their exp phase together (~2200 cycles each instead of ~1100 alone) and then both sit in
+      // their XU-idle part together (wait for S, TMEM load, row max: ~1700 cycles): ~3900 cycles per step. A token makes
+      // the exp phases mutually exclusive and strictly alternating, t0(0) t1(0) t0(1) t1(1) ..., so that one tile's
+      // XU-idle part hides under the other's exponentials. Without packed documents both tiles start at kv tile 0 and
+      // tile 1 has at least as many steps as tile 0, so the chain of waits is acyclic; with packed documents a tile may
+      // start several kv tiles after its partner and the token could wait on a K / V stage that waits on the token: off.
+      if (kStagger && !kDocs) {
+        // tile 1's exp i follows tile 0's exp i (if tile 0 has one); tile 0's exp i follows tile 1's exp i - 1 (if any)
+        if (x == 1 ? (i < je_[0] - jb_[0]) : (i > 0 && i - 1 < je_[1] - jb_[1])) mbar_wait(&xu_tok[x], (x == 1 ? i : i - 1) & 1);
+      }
+      float m_exp = (m_used == -INFINITY) ? 0.f : m_used;
+      asm volatile("" : "+f"(m_exp));   // pins the exponentials behind the wait (they are pure: ptxas hoists them otherwise)
+      // (a row may see nothing in a visited tile (packed documents): m_exp keeps the exponent finite, exp2(-inf) = 0)
+      float rs0 = 0.f, rs1 = 0.f;
+      // chunk c: exponentials of kv columns 32 c .. 32 c + 31 -> 16 bf16 pairs -> P columns 16 c .. 16 c + 15 (over score
+      // columns this thread holds in registers). The store of chunk c completes under the exponentials of chunk c + 1.
+      uint32_t pc[2][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(sv[c][e]), p.scale_log2, -m_exp));      // -inf -> 0
+          const float p1 = ex2(fmaf(__uint_as_float(sv[c][e + 1]), p.scale_log2, -m_exp));
+          rs0 += p0;
+          rs1 += p1;
+          pc[c & 1][e / 2] = kAluPack ? pack_bf16_alu(p0, p1) : pack_bf16(p0, p1);
+        }
+        if (c > 0) {   // chunk c - 1 is in TMEM: hand it to the issuer
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(&p_chunk[x * 4 + c - 1]);
+          if (c == 1) LX_TR(tr_cta, jb_x + i, x * 16 + 8);
+        }
+        tmem_st_32x16(tS + c * 16, pc[c & 1]);
+      }
+      if (kStagger && !kDocs) {   // exponentials done: the other tile may start its own
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&xu_tok[x ^ 1]);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&p_chunk[x * 4 + 3]);
+      LX_TR(tr_cta, jb_x + i, x * 16 + 9);
+      l = l * alpha + (rs0 + rs1);
+    }
+    // epilogue
+    if (n_kv > 0) {
+      mbar_wait(&pv_done[x], (n_kv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l;
+      const bool row_ok = q < p.S;
+      __nv_bfloat16* orow = p.o + ((int64_t)b * p.S + q) * p.ldo + (int64_t)h * kD;
+#pragma unroll 1
+      for (int c = 0; c < kD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + c * 32, v);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 o4;
+            o4.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+            o4.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+            o4.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+            o4.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+            stg_v4(orow + c * 32 + e, o4);
+          }
+        }
+      }
+      if (row_ok) p.lse[((int64_t)b * p.Hq + h) * p.S + q] = (m_used + log2f(l)) * kLn2;
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ================================================================================================
 // backward
 // ================================================================================================
@@ -1238,16 +1900,39 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if ((rc = make_head_tmap(&tq, q, ldq, B, S, Hq, D, fwd::kTile))) return rc;
   if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, D, fwd::kTile))) return rc;
   if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, fwd::kTile))) return rc;
-  static const bool one_tile = [] {  // A/B switch: LLAMAX_ATTN_FWD_ONE_TILE=1 -> one query tile per CTA
-    const char* e = getenv("LLAMAX_ATTN_FWD_ONE_TILE");
-    return e != nullptr && e[0] == '1';
+  // A/B switch: LLAMAX_ATTN_FWD = 1 (one query tile per CTA), 2 (two tiles, thread per row, one issuer), 3 (two tiles,
+  // two threads per row), 4 (default: two tiles, thread per row, chunked P hand-off, one issuer per tile)
+  static const int version = [] {
+    const char* e = getenv("LLAMAX_ATTN_FWD");
+    if (getenv("LLAMAX_ATTN_FWD_ONE_TILE") && getenv("LLAMAX_ATTN_FWD_ONE_TILE")[0] == '1') return 1;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 4;
   }();
+  // packed documents: v4's XU token is off there (see the kernel) and without it v4 loses to v2 -> v2
+  const int version_eff = (version == 4 && doc_start != nullptr) ? 2 : version;
+  const bool one_tile = version_eff == 1;
   auto kern1 = doc_start ? (D == 128 ? attn_fwd_kernel<true, 128> : attn_fwd_kernel<true, 64>)
                          : (D == 128 ? attn_fwd_kernel<false, 128> : attn_fwd_kernel<false, 64>);
   auto kern2 = doc_start ? (D == 128 ? attn_fwd2_kernel<true, 128> : attn_fwd2_kernel<true, 64>)
                          : (D == 128 ? attn_fwd2_kernel<false, 128> : attn_fwd2_kernel<false, 64>);
-  auto kern = one_tile ? kern1 : kern2;
-  const int smem_bytes = one_tile ? fwd::smem_bytes(fwd::kNB) : fwd2::kSmemBytes;
+  auto kern3 = doc_start ? (D == 128 ? attn_fwd3_kernel<true, 128> : attn_fwd3_kernel<true, 64>)
+                         : (D == 128 ? attn_fwd3_kernel<false, 128> : attn_fwd3_kernel<false, 64>);
+  static const bool alu_pack = getenv("LLAMAX_ATTN_ALU_PACK") && getenv("LLAMAX_ATTN_ALU_PACK")[0] == '1';
+  static const bool stagger = !(getenv("LLAMAX_ATTN_STAGGER") && getenv("LLAMAX_ATTN_STAGGER")[0] == '0');
+  auto pick4 = [&](auto docs_tag, auto d_tag) {
+    constexpr bool kDc = decltype(docs_tag)::value;
+    constexpr int kDd = decltype(d_tag)::value;
+    return alu_pack ? (stagger ? attn_fwd4_kernel<kDc, kDd, true, true> : attn_fwd4_kernel<kDc, kDd, true, false>)
+                    : (stagger ? attn_fwd4_kernel<kDc, kDd, false, true> : attn_fwd4_kernel<kDc, kDd, false, false>);
+  };
+  auto kern4 = doc_start ? (D == 128 ? pick4(std::true_type{}, std::integral_constant<int, 128>{})
+                                     : pick4(std::true_type{}, std::integral_constant<int, 64>{}))
+                         : (D == 128 ? pick4(std::false_type{}, std::integral_constant<int, 128>{})
+                                     : pick4(std::false_type{}, std::integral_constant<int, 64>{}));
+  auto kern = version_eff == 1 ? kern1 : version_eff == 2 ? kern2 : version_eff == 3 ? kern3 : kern4;
+  const int smem_bytes = version_eff == 1 ? fwd::smem_bytes(fwd::kNB) : version_eff == 2 ? fwd2::kSmemBytes
+                         : version_eff == 3 ? fwd3::kSmemBytes : fwd4::kSmemBytes;
+  const int threads = version_eff == 1 ? fwd::kThreads : version_eff == 2 ? fwd2::kThreads
+                      : version_eff == 3 ? fwd3::kThreads : fwd4::kThreads;
   if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem_bytes, "attn_fwd: cudaFuncSetAttribute"))) return rc;
   AttnFwdParams p;
   p.o = (__nv_bfloat16*)o;
@@ -1260,7 +1945,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.doc_start = (const int32_t*)doc_start;
   const unsigned q_tiles = (unsigned)ceil_div(S, fwd::kTile);
   dim3 grid(Hq, (unsigned)B, one_tile ? q_tiles : (q_tiles + 1) / 2);
-  kern<<<grid, one_tile ? fwd::kThreads : fwd2::kThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   LX_CHECK_LAUNCH("attn_fwd");
   return 0;
 }

@@ -30,6 +30,20 @@ EPS = 1e-5
 _scratch: dict = {}
 
 
+def _pitch(width: int) -> int:
+    """Row pitch (elements) for a bf16 GEMM operand of `width` columns: the next multiple of 64 elements = 128 bytes.
+    The grad_input operands are [.., sum N + sum R] wide (6168, 28688 at 8B shape with rank 8): with the natural pitch
+    every row starts 48 (or 32) bytes off a 128-byte line, so each 128-byte TMA box row straddles two lines and, at 48,
+    five 32-byte sectors instead of four — measured in-step: 861 TFLOP/s on [16384, 4096, K=6168] against 1227 on
+    K=28688 and 1145 on K=4096 (profiles/r2_bench_1gpu_start.json)."""
+    return (width + 63) // 64 * 64
+
+
+def _padded_empty(rows: int, width: int, device) -> Tensor:
+    """[rows, width] bf16 view of a buffer whose row pitch is _pitch(width)."""
+    return torch.empty(rows, _pitch(width), device=device, dtype=torch.bfloat16)[:, :width]
+
+
 def _get_scratch(device, numel: int) -> Tensor:
     """One growing bf16 scratch per device for de-quantised weight operands (re-used by every layer)."""
     buf = _scratch.get(device)
@@ -123,13 +137,13 @@ def _operand(cache: dict | None, key: str, specs, rows: int, width: int, device)
     """bf16 [rows, width] buffer for the backward operand of `specs`.
     Returns (buffer, frozen_part_is_valid, resident): a resident buffer belongs to this layer alone (it can be
     filled ahead of its use); a non-resident one is the shared scratch."""
-    numel = rows * width
+    numel = rows * _pitch(width)
     if cache is not None and _CACHE_MODE != "0":
         sig = (rows, width) + tuple((s.w8.data_ptr(), s.w8._version, s.ws.data_ptr(), s.ws._version) for s in specs)
         hit = cache.get(key)
         if hit is not None and hit[0] == sig and hit[1].device == device:
             return hit[1], True, True
-        if hit is not None and hit[1].device == device and hit[1].numel() == numel:
+        if hit is not None and hit[1].device == device and tuple(hit[1].shape) == (rows, width):
             cache[key] = (sig, hit[1])   # weights were overwritten in place: rebuild into the same buffer
             return hit[1], False, True
         ok = _CACHE_MODE == "1"
@@ -137,10 +151,10 @@ def _operand(cache: dict | None, key: str, specs, rows: int, width: int, device)
             free, _ = torch.cuda.mem_get_info(device)
             ok = free - 2 * numel >= _CACHE_HEADROOM
         if ok:
-            buf = torch.empty(rows, width, device=device, dtype=torch.bfloat16)
+            buf = _padded_empty(rows, width, device)
             cache[key] = (sig, buf)
             return buf, False, True
-    return _get_scratch(device, numel)[:numel].view(rows, width), False, False
+    return _get_scratch(device, numel)[:numel].view(rows, _pitch(width))[:, :width], False, False
 
 
 class LinearSpec:
@@ -446,7 +460,7 @@ class FusedDecoderBlock(torch.autograd.Function):
             (s2, h_2, None)), M, dev)
 
         # --- w2 ---  (needs g = silu(a) * b only for dA of w2: re-materialised by the SwiGLU backward kernel)
-        dab = torch.empty(M, 2 * F_ + r13, device=dev, dtype=torch.bfloat16)
+        dab = _padded_empty(M, 2 * F_ + r13, dev)
         wt2, _ = operand("w2")
         g2 = None
         a_, b_ = ab[:, :F_], ab[:, F_:]
@@ -486,7 +500,7 @@ class FusedDecoderBlock(torch.autograd.Function):
         do, go = _single_backward(so, dx1, o, wto, prep, sink, i8=i8.get("wo"))
 
         # --- attention ---
-        dqkv = torch.empty(M, nq + 2 * nk + rqkv, device=dev, dtype=torch.bfloat16)
+        dqkv = _padded_empty(M, nq + 2 * nk + rqkv, dev)
         ops.attn_bwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], o, lse, do,
                      dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len,
                      doc_start=doc_start, doc_end=doc_end, rope_inverse=rope)   # dq, dk come back un-rotated

@@ -8,8 +8,39 @@ import torch
 
 from llamax_b200 import ops
 
+import threading
+import time
+
+import pynvml
+
 Hq, Hkv, D = 32, 8, 128
 with_bwd = len(sys.argv) > 1 and sys.argv[1] == "bwd"
+pynvml.nvmlInit()
+_h = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+
+class Clocks:
+    """SM clock / power samples (NVML, every ~5 ms) while a timed loop runs."""
+
+    def __enter__(self):
+        self.s, self.p, self.on = [], [], True
+        self.t = threading.Thread(target=self.run, daemon=True)
+        self.t.start()
+        return self
+
+    def run(self):
+        while self.on:
+            self.s.append(pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM))
+            self.p.append(pynvml.nvmlDeviceGetPowerUsage(_h) / 1e3)
+            time.sleep(0.005)
+
+    def __exit__(self, *a):
+        self.on = False
+        self.t.join()
+
+    def summary(self):
+        s = sorted(self.s)
+        return f"SM {s[len(s) // 2]} MHz, {max(self.p):.0f} W" if s else "no samples"
 
 
 def timeit(fn, n=5, reps=6):
@@ -26,7 +57,17 @@ def timeit(fn, n=5, reps=6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) / reps)
+    global last_clocks
+    with Clocks() as c:   # clocks under a sustained loop of the same graph (~0.3 s)
+        t0 = time.time()
+        while time.time() - t0 < 0.3:
+            g.replay()
+        torch.cuda.synchronize()
+    last_clocks = c.summary()
     return min(ts)
+
+
+last_clocks = ""
 
 
 for B, S, P in ((8, 2048, 0), (2, 8192, 0), (8, 1756, 1500), (4, 4096, 1024)):
@@ -37,12 +78,12 @@ for B, S, P in ((8, 2048, 0), (2, 8192, 0), (8, 1756, 1500), (4, 4096, 1024)):
     pairs = S * P + (S - P) * (S - P + 1) / 2
     fl = 4.0 * B * Hq * D * pairs
     ms = timeit(lambda: ops.attn_fwd(q, k, v, B, S, Hq, Hkv, D, P))
-    line = f"B={B} S={S} P={P}: fwd {ms * 1e3:7.1f} us {fl / ms / 1e9:7.1f} TFLOP/s"
+    line = f"B={B} S={S} P={P}: fwd {ms * 1e3:7.1f} us {fl / ms / 1e9:7.1f} TFLOP/s [{last_clocks}]"
     if with_bwd:
         o, lse = ops.attn_fwd(q, k, v, B, S, Hq, Hkv, D, P)
         dout = torch.randn(B * S, Hq * D, device="cuda").bfloat16()
         dqkv = torch.empty_like(g)
         dq, dk, dv = dqkv[:, : Hq * D], dqkv[:, Hq * D : (Hq + Hkv) * D], dqkv[:, (Hq + Hkv) * D :]
         msb = timeit(lambda: ops.attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, P))
-        line += f" | bwd {msb * 1e3:7.1f} us {2.5 * fl / msb / 1e9:7.1f} TFLOP/s"
+        line += f" | bwd {msb * 1e3:7.1f} us {2.5 * fl / msb / 1e9:7.1f} TFLOP/s [{last_clocks}]"
     print(line, flush=True)

@@ -1,0 +1,10 @@
+export WD=llamax_b200/csrc/libllamax_b200_wd.so
+LLAMAX_B200_LIB=$WD timeout 300 python -m pytest tests/test_attention_gpu.py -x -q > gpurun_out/r2_attn_wd.log 2>&1; rc=$?; echo "attn wd rc=$rc"; tail -3 gpurun_out/r2_attn_wd.log
+if [ $rc -ne 0 ]; then exit 1; fi
+LLAMAX_ATTN_ALU_PACK=1 timeout 300 python -m pytest tests/test_attention_gpu.py -x -q 2>&1 | tail -2
+echo "== v2"; LLAMAX_ATTN_FWD=2 timeout 120 python tools/attn_fwd_perf.py
+echo "== v4 stagger"; timeout 120 python tools/attn_fwd_perf.py
+echo "== v4 stagger alu"; LLAMAX_ATTN_ALU_PACK=1 timeout 120 python tools/attn_fwd_perf.py
+echo "== v4 nostagger"; LLAMAX_ATTN_STAGGER=0 timeout 120 python tools/attn_fwd_perf.py
+echo "== v4 nostagger alu"; LLAMAX_ATTN_STAGGER=0 LLAMAX_ATTN_ALU_PACK=1 timeout 120 python tools/attn_fwd_perf.py
+timeout 120 python tools/attn_trace.py fwd > gpurun_out/r2_trace_v4s.log 2>&1; cat gpurun_out/r2_trace_v4s.log
