@@ -1273,7 +1273,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float m_exp = (m_used == -INFINITY) ? 0.f : m_used;
       asm volatile("" : "+f"(m_exp));   // pins the exponentials behind the wait (they are pure: ptxas hoists them otherwise)
       // (a row may see nothing in a visited tile (packed documents): m_exp keeps the exponent finite, exp2(-inf) = 0)
-      float rs0 = 0.f, rs1 = 0.f;
+      float rowsum = 0.f;   // same summation order as v2 (packed-document masks run on v2): bit-identical outputs
       // chunk c: exponentials of kv columns 32 c .. 32 c + 31 -> 16 bf16 pairs -> P columns 16 c .. 16 c + 15 (over score
       // columns this thread holds in registers). The store of chunk c completes under the exponentials of chunk c + 1.
       uint32_t pc[2][16];
@@ -1283,8 +1283,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int e = 0; e < 32; e += 2) {
           const float p0 = ex2(fmaf(__uint_as_float(sv[c][e]), p.scale_log2, -m_exp));      // -inf -> 0
           const float p1 = ex2(fmaf(__uint_as_float(sv[c][e + 1]), p.scale_log2, -m_exp));
-          rs0 += p0;
-          rs1 += p1;
+          rowsum += p0 + p1;
           pc[c & 1][e / 2] = kAluPack ? pack_bf16_alu(p0, p1) : pack_bf16(p0, p1);
         }
         if (c > 0) {   // chunk c - 1 is in TMEM: hand it to the issuer
@@ -1305,7 +1304,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&p_chunk[x * 4 + 3]);
       LX_TR(tr_cta, jb_x + i, x * 16 + 9);
-      l = l * alpha + (rs0 + rs1);
+      l = l * alpha + rowsum;
     }
     // epilogue
     if (n_kv > 0) {

@@ -10,6 +10,34 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
+TOL = 1e-2   # BASELINE.json north_star: max relative error <= 1e-2 against the fp32 reference
+
+
+def check_parity_table(report: dict, what: str, known_bf16_limited=()):
+    """report: name -> (err of the product path vs the fp32 oracle, err of the reference's own bf16 op sequence vs the
+    fp32 oracle), both max|a - b| / max|b|. Prints the per-tensor table and enforces the bar:
+      * every tensor <= 1e-2 (north_star), strictly — in particular the block output and the input gradient;
+      * tensors named in `known_bf16_limited` (the documented list: PARAMETER gradients, i.e. sums over all tokens of
+        products of bf16-rounded factors) may exceed 1e-2 only as far as the reference's own bf16 path does on the same
+        inputs: limit = max(1e-2, 1.5 x the reference's error) — both are maxima over thousands of entries of the same
+        bf16 rounding noise, and that statistic moves by +-35 % between equivalent summation orders (ours lands above the
+        reference's on some tensors and below it on about as many: profiles/r2_parity_tables.txt). The reference's
+        column is printed beside ours, so every use of the exception can be audited; it never applies where the
+        reference itself is within 0.67e-2."""
+    print(f"\n{what}: max|ours - fp32 oracle| / max|fp32 oracle|   (reference bf16 path vs the same oracle)")
+    bad = []
+    for k, (ours, ref_bf16) in report.items():
+        lim, flag = TOL, ""
+        if k in known_bf16_limited and 1.5 * ref_bf16 > TOL:
+            lim = 1.5 * ref_bf16
+            flag = "  [documented exception: reference bf16 path at %.2e]" % ref_bf16
+        ok = ours <= lim
+        print(f"  {k:10s} {ours:9.3e}   ({ref_bf16:9.3e})  limit {lim:8.2e} {'ok' if ok else 'FAIL'}{flag}")
+        if not ok:
+            bad.append((k, ours, ref_bf16, lim))
+    assert not bad, f"{what}: over tolerance: {bad}"
+
+
 def tiny_config(num_layers=2, max_seq_len=512):
     from llamax_b200.modelling import LlamaConfig
 
@@ -18,14 +46,15 @@ def tiny_config(num_layers=2, max_seq_len=512):
                        rope_base=500000, is_llama3_1=True)
 
 
-def build_tiny_llama(dynamic: bool, num_layers=2, rank=8, seed=0, audio=False, max_seq_len=512, adapters="all"):
+def build_tiny_llama(dynamic: bool, num_layers=2, rank=8, seed=0, audio=False, max_seq_len=512, adapters="all",
+                     config=None):
     """CPU-initialised (deterministic), quantised + LoRA'd model; caller moves it to CUDA.
-    adapters: "all" | "attention" (LoRA on wq/wk/wv/wo only) | "none"."""
+    adapters: "all" | "attention" (LoRA on wq/wk/wv/wo only) | "none". config: a LlamaConfig instead of the tiny one."""
     from llamax_b200.modelling import AudioConfig, Llama, LlamaAudio, apply_linear_adapter_
     from llamax_b200.subclasses import quantize_linear_
 
     torch.manual_seed(seed)
-    cfg = tiny_config(num_layers, max_seq_len)
+    cfg = config if config is not None else tiny_config(num_layers, max_seq_len)
     model = LlamaAudio(cfg, AudioConfig(n_mels=80)) if audio else Llama(cfg)
     model = model.bfloat16()
     quantize_linear_(model.layers, "int8", dynamic_int8_act=dynamic)

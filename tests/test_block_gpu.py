@@ -8,14 +8,21 @@ import pytest
 import torch
 
 from oracle import ref_ops as R
-from tests.helpers import build_tiny_llama, oracle_layer_weights, rel_err
+from tests.helpers import TOL, build_tiny_llama, check_parity_table, oracle_layer_weights, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-2
+
+# Documented exceptions to the strict 1e-2 bar: the PARAMETER gradients (LoRA A / B, RMSNorm weights) — sums over all
+# tokens of products of bf16-rounded factors, on which the REFERENCE's own bf16 op sequence, evaluated on CPU on the same
+# inputs, is itself 0.7 - 1.5e-2 away from its fp32 evaluation (tables in profiles/r2_parity_tables.txt). Block output and
+# input gradient are NOT on the list: strict 1e-2. check_parity_table holds a listed tensor to max(1e-2, 1.5 x the
+# reference's error in the same run).
+KNOWN_BF16_LIMITED = ("a_wq", "a_wk", "a_wv", "a_wo", "a_w1", "a_w3", "a_w2", "an", "fn", "b_wq", "b_wk", "b_wv",
+                      "b_wo", "b_w1", "b_w3", "b_w2")
 
 
-def _layer_case(dynamic: bool, prefix_len: int, B=2, S=320, rank=8, adapters="all"):
-    model = build_tiny_llama(dynamic, num_layers=1, rank=rank, adapters=adapters)
+def _layer_case(dynamic: bool, prefix_len: int, B=2, S=320, rank=8, adapters="all", config=None):
+    model = build_tiny_llama(dynamic, num_layers=1, rank=rank, adapters=adapters, config=config)
     layer = model.layers[0]
     cfg = model.config
     rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:S]
@@ -56,10 +63,41 @@ def _layer_case(dynamic: bool, prefix_len: int, B=2, S=320, rank=8, adapters="al
 @pytest.mark.parametrize("prefix_len", [0, 100])
 def test_fused_block_matches_oracle(dynamic, prefix_len):
     report = _layer_case(dynamic, prefix_len)
-    print({k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in report.items()})
-    for key, (ours, ref_bf16) in report.items():
-        # within the stated tolerance, or at least as close to fp32 as the reference's own bf16 path is
-        assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
+    check_parity_table(report, f"fused block dim 512, dynamic={dynamic}, P={prefix_len}", KNOWN_BF16_LIMITED)
+
+
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_fused_block_8b_shape_matches_oracle(dynamic):
+    """ONE decoder block at the Llama-3.1-8B shape (D 4096, F 14336, 32 / 8 heads x 128, LoRA r = 8), 512 positions, prefix
+    300, both INT8 modes, against the CPU oracle (fp32 evaluation of the reference op sequence): every output and
+    gradient within the strict bar."""
+    from llamax_b200.modelling import LlamaConfig
+
+    cfg = LlamaConfig(4096, 1, 128, 32, 8, 14336, max_seq_len=512, vocab_size=1024, rope_base=500000, is_llama3_1=True)
+    report = _layer_case(dynamic, 300, B=1, S=512, config=cfg)
+    check_parity_table(report, f"fused block 8B shape, dynamic={dynamic}, P=300, S=512", KNOWN_BF16_LIMITED)
+
+
+def test_int8_codes_at_8b_width_are_bit_exact():
+    """The int8 activation codes entering the frozen projections at D = 4096 / F = 14336: codes and scales produced by the
+    fused RMSNorm / SwiGLU passes equal quantize_int8_rowwise (int8.py:10-16) of the bf16 tensor the same pass writes,
+    bit for bit, and that bf16 tensor differs from the oracle's by at most 1 bf16 ulp on < 0.1 % of the elements."""
+    from llamax_b200 import ops
+
+    torch.manual_seed(21)
+    M, D, F_ = 512, 4096, 14336
+    x = (torch.randn(M, D) * 1.7).bfloat16()
+    w = (1 + 0.1 * torch.randn(D)).bfloat16()
+    y, rstd, q8, qs = ops.rmsnorm_fwd(x.cuda(), w.cuda(), 1e-5, quant=True)
+    q_ref, s_ref = R.quantize_int8_rowwise(y.cpu())
+    assert torch.equal(q8.cpu(), q_ref) and torch.equal(qs.cpu(), s_ref.reshape(-1))
+    y_ref = R.rmsnorm_ref(x, w)
+    diff = (y.cpu().view(torch.int16).int() - y_ref.view(torch.int16).int()).abs()
+    assert diff.max() <= 1 and (diff != 0).float().mean() < 1e-3
+    ab = torch.randn(M, 2 * F_).bfloat16().cuda()
+    g, gq, gs = ops.swiglu_fwd(ab[:, :F_], ab[:, F_:], quant=True, want_g=True)
+    q_ref, s_ref = R.quantize_int8_rowwise(g.cpu())
+    assert torch.equal(gq.cpu(), q_ref) and torch.equal(gs.cpu(), s_ref.reshape(-1))
 
 
 def test_tiny_model_loss_and_grads():
@@ -287,8 +325,7 @@ def test_fused_block_lora_rank16():
     """rank 16 on all seven linears: the q|k|v group carries 48 LoRA columns (epilogue rank 16 per GEMM, dh columns
     K-concatenated into the grad_input GEMM, dA through the 32-column wgrad kernel in two chunks)."""
     report = _layer_case(True, 64, rank=16)
-    for key, (ours, ref_bf16) in report.items():
-        assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
+    check_parity_table(report, "fused block dim 512, rank 16, P=64", KNOWN_BF16_LIMITED)
 
 
 @pytest.mark.parametrize("adapters", ["attention", "none"])
@@ -296,16 +333,14 @@ def test_fused_block_partial_or_no_adapters(adapters):
     """LoRA only on the attention projections, or no adapters at all (frozen INT8 block, only the norms train)."""
     report = _layer_case(True, 0, adapters=adapters)
     assert ("a_w1" not in report) and (("a_wq" in report) == (adapters == "attention"))
-    for key, (ours, ref_bf16) in report.items():
-        assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
+    check_parity_table(report, "fused block dim 512 (True, 0, adapters=adapters)", KNOWN_BF16_LIMITED)
 
 
 def test_fused_block_ragged_token_count():
     """B*S = 301 tokens: not a multiple of any tile (128-row GEMM / attention tiles, 8-element TMA pitches of the
     transposed LoRA operands)."""
     report = _layer_case(True, 77, B=1, S=301)
-    for key, (ours, ref_bf16) in report.items():
-        assert ours <= max(TOL, 1.5 * ref_bf16), f"{key}: ours {ours:.3e} vs bf16 reference {ref_bf16:.3e}"
+    check_parity_table(report, "fused block dim 512 (True, 77, B=1, S=301)", KNOWN_BF16_LIMITED)
 
 
 def test_trainable_lm_head_loss_and_weight_gradient():
