@@ -622,6 +622,220 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wide bf16 GEMM for long contractions: C[M,N] = A[M,K] * B[N,K]^T, plain bf16 store, CTA pairs, 512 x 256 output per
+// visit (two 256 x 256 cta_group::2 accumulators that share the B tile).
+//
+// Why a second tile shape. The w1|w3 grad_input GEMM [16384, 4096, K = 28688] is the largest kernel of the step. Measured
+// against cuBLAS on the same box (tools/gemm_vs_cublas.py, profiles/r2_gemm_vs_cublas.txt; `ncu --set full`): the 256 x 256
+// kernel above keeps the tensor pipe as busy per cycle as cuBLAS' nvjet 256x256 2-CTA kernel (96 % vs 95 %), but at the
+// 1 kW cap it runs at 1.22 GHz against 1.40 GHz — it spends its power budget on data movement: 7.8 GB of DRAM reads per
+// launch against 3.4 GB (1.3 GB algorithmic) and 30.1 GB against 22.6 GB from L2 into the SMs. Both follow from the tile:
+// a CTA pair that owns 512 x 256 outputs per visit loads 48 KB per CTA and k-block for twice the MMA work of 32 KB, and a
+// wave of 74 pairs touches ~17 x 512-row / 256-column operand panels instead of ~17 x 256 / 256.
+// Price: both TMEM accumulator buffers belong to one visit, so the epilogue of a visit is only half hidden (the first
+// k-block's MMAs into accumulator 0 run while accumulator 1 is still being drained). Used only where the main loop of a
+// visit is >= 128 k-blocks (K >= 8192): there the exposed part is < 2 %.
+// ------------------------------------------------------------------------------------------------
+namespace wd {
+constexpr int kStages = 4;
+constexpr int kABytes = 256 * 128;   // [256 rows] x [64 bf16]: rows 0..127 feed accumulator 0, rows 128..255 accumulator 1
+constexpr int kBBytes = 128 * 128;   // this CTA's half of the [256 x 64] B tile
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmem = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+}  // namespace wd
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 __nv_bfloat16* __restrict__ C, int64_t ldc, int M, int N, int K, int group) {
+  using namespace wd;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = cta_rank == 0;
+  const int num_m = (M + 511) / 512;
+  const int num_n = (N + kBN - 1) / kBN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + 63) / 64;
+  const int cluster_id = blockIdx.x / 2;
+  const int num_clusters = gridDim.x / 2;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);  // one arrive per epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(tmem_slot, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_addr = mapa_u32(smem_u32(&full_bar[0]), 0);
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int tm, tn;
+        tile_coords(tile, num_m, num_n, group, tm, tn);
+        const int row_a = tm * 512 + cta_rank * 256;
+        const int row_b = tn * kBN + cta_rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          if (is_leader) mbar_expect_tx(&full_bar[stage], kStageBytes * 2);
+          const uint32_t bar_addr = full_addr + stage * 8;
+          tma_load_2d_cg2(sa, &tmA, bar_addr, kb * 64, row_a);
+          tma_load_2d_cg2(sa + kABytes, &tmB, bar_addr, kb * 64, row_b);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(1, 1, 256, kBN);
+      constexpr uint32_t kHi = desc_hi(1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int visit = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++visit) {
+        const uint32_t aphase = visit & 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (kb == 0) mbar_wait(&tempty_bar[0], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t la0 = desc_lo(sa, 16), la1 = desc_lo(sa + 128 * 128, 16), lb = desc_lo(sa + kABytes, 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss<false, 2>(tmem_base, desc_join(la0 + 2 * k, kHi), desc_join(lb + 2 * k, kHi), idesc, (kb | k) != 0);
+          if (kb == 0) {   // accumulator 1 may still be draining: its first MMAs go behind accumulator 0's
+            mbar_wait(&tempty_bar[1], aphase ^ 1);
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss<false, 2>(tmem_base + kBN, desc_join(la1 + 2 * k, kHi), desc_join(lb + 2 * k, kHi), idesc, (kb | k) != 0);
+          umma_commit_cg2(&empty_bar[stage], 3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_cg2(&tfull_bar[0], 3);
+        umma_commit_cg2(&tfull_bar[1], 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int ew = warp & 3;                 // TMEM lanes [32*ew, 32*ew+32)
+    const int ch = (warp - 4) >> 2;          // column half of the accumulator handled by this warp
+    int visit = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++visit) {
+      int tm, tn;
+      tile_coords(tile, num_m, num_n, group, tm, tn);
+      const int col0 = tn * kBN;
+      const int n_chunks = min(ch * 4 + 4, min(kBN / 32, (N - col0 + 31) / 32));
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+        const int row = tm * 512 + cta_rank * 256 + a * 128 + ew * 32 + lane_id();
+        const bool row_ok = row < M;
+        mbar_wait(&tfull_bar[a], visit & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + a * kBN;
+        uint32_t v[2][32];
+        if (ch * 4 < n_chunks) tmem_ld_32x32(taddr + ch * 4 * 32, v[0]);
+#pragma unroll 1
+        for (int c = ch * 4; c < n_chunks; c += 2) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cc = c + half;
+            if (cc >= n_chunks) break;
+            uint32_t(&vv)[32] = v[half];
+            tmem_wait_ld_regs(vv);
+            if (cc + 1 < n_chunks) tmem_ld_32x32(taddr + (cc + 1) * 32, v[half ^ 1]);
+            const int col = col0 + cc * 32;
+            if (row_ok) {
+              __nv_bfloat16* dst = C + (int64_t)row * ldc + col;
+#pragma unroll
+              for (int j8 = 0; j8 < 32; j8 += 8) {
+                if (col + j8 < N) {
+                  uint4 o;
+                  o.x = pack_bf16(__uint_as_float(vv[j8 + 0]), __uint_as_float(vv[j8 + 1]));
+                  o.y = pack_bf16(__uint_as_float(vv[j8 + 2]), __uint_as_float(vv[j8 + 3]));
+                  o.z = pack_bf16(__uint_as_float(vv[j8 + 4]), __uint_as_float(vv[j8 + 5]));
+                  o.w = pack_bf16(__uint_as_float(vv[j8 + 6]), __uint_as_float(vv[j8 + 7]));
+                  stg_v4(dst + j8, o);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive_cluster(&tempty_bar[a], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+
+static int launch_gemm_wide(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int M, int N,
+                            int K, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, 64, 256);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, 64, 128);
+  if (rc) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_wide_kernel), wd::kSmem, "wide gemm: cudaFuncSetAttribute")))
+    return rc;
+  const int num_m = (M + 511) / 512, num_n = (N + kBN - 1) / kBN;
+  int clusters = std::min(sm_count() / 2, num_m * num_n);
+  static const int forced = getenv("LLAMAX_GEMM_GROUP") ? atoi(getenv("LLAMAX_GEMM_GROUP")) : 0;   // A/B switch
+  const int group = forced != 0 ? forced : (num_m >= num_n ? -kGroupM : kGroupM);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = wd::kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wide_kernel, tmA, tmB, (__nv_bfloat16*)C, ldc, M, N, K, group);
+  if (e != cudaSuccess) return set_cuda_error(e, "wide gemm: launch");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LoRA weight gradient on tensor cores:  out[p, r] += alpha * sum_m X[m, p] * H[m, r]
 //   = GEMM with M' = P (128 per CTA), N' = 32 (rank zero-padded), K' = tokens.
 // A' = X^T is read straight from X [tokens, P] as an MN-major operand (64-column boxes, like V in attention),
@@ -1130,6 +1344,12 @@ int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   static const bool no_skinny = getenv("LLAMAX_NO_SKINNY") != nullptr;  // A/B switch for benchmarking
   if (plain && N <= 32 && !no_skinny)  // LoRA down / dh projections: HBM-bound skinny kernel
     return launch_skinny(A, lda, B, ldb, C, ldc, (int)M, (int)N, (int)K, (cudaStream_t)stream);
+  // long contractions without an epilogue (w1|w3 grad_input, LM-head grad_input): 512 x 256 outputs per CTA-pair visit
+  static const bool no_wide = getenv("LLAMAX_GEMM_WIDE") != nullptr && getenv("LLAMAX_GEMM_WIDE")[0] == '0';  // A/B switch
+  if (plain && !no_wide && g_gemm_cg == 2 && K >= 8192 && M >= 1024 && N >= 256 && N % 8 == 0 && ldc % 8 == 0 &&
+      lda % 8 == 0 && ldb % 8 == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(C) % 16 == 0)
+    return launch_gemm_wide(A, lda, B, ldb, C, ldc, (int)M, (int)N, (int)K, (cudaStream_t)stream);
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.C = C; p.ldc = ldc;

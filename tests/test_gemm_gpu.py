@@ -232,3 +232,25 @@ def test_int8_residual_epilogue_pipelined_reads(cg, M, N, K, Rk, in_place):
             assert torch.equal(r.cpu(), res)                   # the residual itself is untouched
     finally:
         ops.set_gemm_cta_group(2)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 256, 8192), (1100, 264, 8200), (2048, 1024, 12288), (3000, 520, 8256)])
+def test_bf16_gemm_wide_tile_path(M, N, K):
+    """Long contractions (K >= 8192, M >= 1024, no epilogue) run on gemm_wide_kernel: 512 x 256 outputs per CTA-pair visit,
+    two accumulators sharing the B tile. Against fp32 matmul of the same bf16 operands, ragged M / N / K included, with
+    padded (128-byte) and natural operand pitches; and against the 256 x 256 kernel forced by a pitched C with an epilogue
+    residual of zeros (same k order -> identical bits)."""
+    torch.manual_seed(M + N)
+    Kp = (K + 63) // 64 * 64
+    a = (torch.randn(M, Kp, device="cuda") * 0.5).bfloat16()[:, :K]
+    b = (torch.randn(N, K, device="cuda") * 0.5).bfloat16()
+    c = ops.bf16_gemm(a, b)
+    ref = a.float() @ b.float().t()
+    assert rel_err(c, ref) <= 4e-3
+    # the 256 x 256 kernel (an epilogue term disables the wide path): accumulation order over k is the same
+    c2 = ops.bf16_gemm(a, b, resid=torch.zeros(M, N, device="cuda", dtype=torch.bfloat16))
+    assert torch.equal(c, c2)
+    # rows / columns beyond the problem are never written
+    out = torch.full((M + 8, N + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.bf16_gemm(a, b, out=out[:M, :N])
+    assert torch.equal(out[:M, :N], c) and bool((out[M:] == 7).all()) and bool((out[:, N:] == 7).all())
