@@ -402,7 +402,9 @@ def run_ours(args):
         dom = bf16_shapes[0]
         raw = kern_dom["bf16_gemm" + dom["shape"]]
         what = "grad_input of w1|w3" if "N=4096,K=28" in dom["shape"] else "largest bf16 GEMM of the step"
-        key = "gemm_kernel<bf16,cta_group::%d>%s" % (args.cta_group, dom["shape"])
+        kdim = int(dom["shape"].split("K=")[1].rstrip("]"))
+        wide = kdim >= 8192 and args.cta_group == 2 and os.environ.get("LLAMAX_GEMM_WIDE", "1") != "0"
+        key = ("gemm_wide_kernel<bf16,cta_group::2,512x256>%s" if wide else "gemm_kernel<bf16,cta_group::%d>%%s" % args.cta_group) % dom["shape"]
         tr = load_ncu_traffic(key)
         cls = kern_dom["bf16_gemm"]
         roof = {"kernel": "%s (%s)" % (key, what), "bound": "tensor", "achieved": dom["achieved"], "peak": peak_tf,

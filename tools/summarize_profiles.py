@@ -29,11 +29,11 @@ for r in rows[hi + 1:]:
     n += 1
 lx = sum(v[0] for k, v in agg.items() if "lx::" in k)
 out = [
-    f"round 1 (final kernels of this round) — ncu launch list (gpu__time_duration.sum, --clock-control none) of",
+    f"{tag} (final kernels of this round) — ncu launch list (gpu__time_duration.sum, --clock-control none) of",
     "  python bench.py --layers 2 --steps 1 --warmup 3 --no-cpu-baseline   (6 optimizer steps: 3 warm-up + 1 timed + 1 instrumented + 1 e2e)",
     "per-launch times are cold-cache and serialised: compare SHARES, not absolutes. With 2 of 32 layers the",
     "per-step-constant LM head (8 bf16 GEMM launches + cross-entropy) and optimizer weigh 16x more than in the real step;",
-    "the 32-layer shares measured live by bench.py (CUDA events) are in profiles/r1_bench_1gpu.json and DESIGN.md.",
+    f"the 32-layer shares measured live by bench.py (CUDA events) are in profiles/{tag}_bench_1gpu.json and DESIGN.md.",
     f"total {tot:.1f} ms over {n} launches; llamax_b200 kernels (lx::*) = {100 * lx / tot:.1f} % of device time",
     "",
 ]
@@ -60,3 +60,27 @@ for r in rr[2:]:
 csv.writer(open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_hot_kernels.csv"), "w")).writerows(tab)
 for r in tab:
     print(r[:9])
+
+
+# dram traffic of the dominant kernel for bench.py's roofline.traffic (keyed by kernel + shape; tools/prof_kernels.py
+# launches the bf16 grad_input GEMM [M=16384, N=4096, K=28688] first)
+import json
+
+git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+traffic = {}
+hn = tab[0]
+for r in tab[2:]:
+    name = r[hn.index("Kernel Name")]
+    if "gemm_wide_kernel" in name or name.startswith("void gemm_kernel<0, 2, 0, 0, 0, 0>") or "lx::gemm_kernel<0, 2, 0, 0, 0, 0>" in name:
+        rd, wr = float(r[hn.index("dram__bytes_read.sum")]), float(r[hn.index("dram__bytes_write.sum")])
+        unit_r, unit_w = tab[1][hn.index("dram__bytes_read.sum")], tab[1][hn.index("dram__bytes_write.sum")]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        nbytes = rd * scale[unit_r] + wr * scale[unit_w]
+        kname = "gemm_wide_kernel<bf16,cta_group::2,512x256>" if "wide" in name else "gemm_kernel<bf16,cta_group::2>"
+        traffic[kname + "[M=16384,N=4096,K=28688]"] = {
+            "bytes": int(nbytes), "git": git, "source": f"profiles/{tag}_ncu_full_hot_kernels.csv ID {r[0]} (dram__bytes_read.sum + dram__bytes_write.sum, one launch, ncu --set full)",
+            "algorithmic_bytes": int(2 * (16384 * 28688 + 4096 * 28688 + 16384 * 4096)),
+            "l2_hit_pct": float(r[hn.index("lts__t_sector_hit_rate.pct")])}
+        break
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+print(traffic)
