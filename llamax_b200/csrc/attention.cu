@@ -262,14 +262,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&s_empty[st]);
       if (!full_tile) {
+        // the visible keys of a row are ONE interval of the tile's columns, [lo, lo + width): the prefix-LM mask keeps
+        // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
+        // compare against a per-row constant and a select per element instead of three compares
+        const int lo = kDocs ? ds_row - kv0 : 0;
+        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kv = kv0 + c * 32 + i;
-            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
-            if (!ok) sv[c][i] = 0xff800000u;  // -inf
-          }
+          for (int i = 0; i < 32; ++i)
+            if ((uint32_t)(c * 32 + i - lo) >= width) sv[c][i] = 0xff800000u;  // -inf
       }
       // four independent max chains (one per 32-column chunk): a single chain of 64 dependent FMNMX3 is ~300 cycles of
       // pure latency for the one softmax warp a scheduler has
@@ -577,14 +579,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_wait_ld_regs(sv[3]);
       if (x == 0) LX_TR(tr_cta, jb_x + i, 6);
       if (!full_tile) {
+        // the visible keys of a row are ONE interval of the tile's columns, [lo, lo + width): the prefix-LM mask keeps
+        // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
+        // compare against a per-row constant and a select per element instead of three compares
+        const int lo = kDocs ? ds_row - kv0 : 0;
+        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int kv = kv0 + c * 32 + e;
-            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
-            if (!ok) sv[c][e] = 0xff800000u;  // -inf
-          }
+          for (int e = 0; e < 32; ++e)
+            if ((uint32_t)(c * 32 + e - lo) >= width) sv[c][e] = 0xff800000u;  // -inf
       }
       float mx4[4];
 #pragma unroll
@@ -897,14 +901,16 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_wait_ld_regs(sv[0]);
       tmem_wait_ld_regs(sv[1]);
       if (!full_tile) {
+        // the visible keys of a row are ONE interval of the tile's columns, [lo, lo + width): the prefix-LM mask keeps
+        // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
+        // compare against a per-row constant and a select per element instead of three compares
+        const int lo = kDocs ? ds_row - kv0 : 0;
+        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int kv = kv0 + hf * 64 + c * 32 + e;
-            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
-            if (!ok) sv[c][e] = 0xff800000u;  // -inf
-          }
+          for (int e = 0; e < 32; ++e)
+            if ((uint32_t)(hf * 64 + c * 32 + e - lo) >= width) sv[c][e] = 0xff800000u;  // -inf
       }
       float mx4[4];
 #pragma unroll
@@ -1222,14 +1228,16 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_wait_ld_regs(sv[3]);
       LX_TR(tr_cta, jb_x + i, x * 16 + 6);
       if (!full_tile) {
+        // the visible keys of a row are ONE interval of the tile's columns, [lo, lo + width): the prefix-LM mask keeps
+        // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
+        // compare against a per-row constant and a select per element instead of three compares
+        const int lo = kDocs ? ds_row - kv0 : 0;
+        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int kv = kv0 + c * 32 + e;
-            const bool ok = (kv < p.S) && ((kv < p.P) || (kv <= q)) && (!kDocs || kv >= ds_row);
-            if (!ok) sv[c][e] = 0xff800000u;  // -inf
-          }
+          for (int e = 0; e < 32; ++e)
+            if ((uint32_t)(c * 32 + e - lo) >= width) sv[c][e] = 0xff800000u;  // -inf
       }
       float mx4[4];
 #pragma unroll
@@ -1642,6 +1650,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_wait_ld_regs(sv[0]);
         tmem_wait_ld_regs(sv[1]);
         LX_TR(tr_cta, s, 8);
+        // prefix-LM without documents: a kv row inside the sequence is seen by every query if it lies in the prefix, else
+        // by the queries q >= kv: a suffix of this thread's 64 query columns, starting at first_q (one compare per element)
+        const int first_q = (kv >= p.S) ? (1 << 30) : (kv < p.P ? -(1 << 30) : kv - q0 - grp * 64);
         auto block = [&](auto masked_tag) {
           constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
@@ -1661,8 +1672,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               for (int e = 0; e < 4; ++e) {
                 float pe = ex2(fmaf(__uint_as_float(sv[c][i + e]), p.scale_log2, -ls[e]));
                 if (kMasked) {
-                  const int qa = q0 + grp * 64 + c * 32 + i + e;
-                  if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && (!kDocs || kv >= dst4[e]))) pe = 0.f;
+                  if (kDocs) {
+                    const int qa = q0 + grp * 64 + c * 32 + i + e;
+                    if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && kv >= dst4[e])) pe = 0.f;
+                  } else if (c * 32 + i + e < first_q) {   // this kv row is visible to the queries from first_q on
+                    pe = 0.f;
+                  }
                 }
                 pv[e] = pe;
               }
