@@ -165,3 +165,25 @@ def test_attention_bwd_fused_rope_backward(B, S, Hq, Hkv, P, Dh):
     assert rel_err(fused[:, :nq + nk].float().cpu(), two[:, :nq + nk].float().cpu()) <= 1e-2
     assert rel_err(to4(fused[:, :nq].cpu(), Hq), unrotate(dq_ref)) <= 1e-2
     assert rel_err(to4(fused[:, nq:nq + nk].cpu(), Hkv), unrotate(dk_ref)) <= 1e-2
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,P", [(2, 301, 4, 2, 100), (1, 128, 2, 1, 0)])
+def test_attention_backward_writes_stay_inside_their_views(B, S, Hq, Hkv, P):
+    """Canary test (compute-sanitizer is closed on this pool): dq / dk / dv are column views of a larger buffer filled
+    with a sentinel, with spare rows after the last token; nothing outside the three views may change, ragged S
+    included (the kernels' row / column guards)."""
+    torch.manual_seed(3)
+    ld = (Hq + 2 * Hkv) * D
+    g = torch.randn(B * S, ld, device="cuda").bfloat16()
+    q, k, v = _split(g, Hq, Hkv)
+    o, lse = ops.attn_fwd(q, k, v, B, S, Hq, Hkv, D, P)
+    pad = 16
+    big = torch.full((B * S + 8, ld + 2 * pad), 3.0, device="cuda", dtype=torch.bfloat16)
+    inner = big[: B * S, pad : pad + ld]
+    dq, dk, dv = _split(inner, Hq, Hkv)
+    ops.attn_bwd(q, k, v, o, lse, torch.randn(B * S, Hq * D, device="cuda").bfloat16(), dq, dk, dv, B, S, Hq, Hkv, D, P)
+    torch.cuda.synchronize()
+    assert bool((big[B * S :] == 3).all()) and bool((big[:, :pad] == 3).all()) and bool((big[:, pad + ld :] == 3).all())
+    assert not bool((inner == 3).all())
+    # forward outputs: every row written, lse finite
+    assert bool(torch.isfinite(lse).all()) and bool(torch.isfinite(o.float()).all())

@@ -14,7 +14,8 @@ import time
 import pynvml
 
 Hq, Hkv, D = 32, 8, 128
-with_bwd = len(sys.argv) > 1 and sys.argv[1] == "bwd"
+with_bwd = "bwd" in sys.argv[1:]
+with_sdpa = "sdpa" in sys.argv[1:]   # also time cuDNN SDPA (causal configs) the same way
 pynvml.nvmlInit()
 _h = pynvml.nvmlDeviceGetHandleByIndex(0)
 
@@ -93,3 +94,27 @@ for B, S, P in ((8, 2048, 0), (2, 8192, 0), (8, 1756, 1500), (4, 4096, 1024)):
         msb, susb = timeit(lambda: ops.attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, P))
         line += f" | bwd burst {2.5 * fl / msb / 1e9:7.1f} sustained {2.5 * fl / susb / 1e9:7.1f} TFLOP/s [{last_clocks}]"
     print(line, flush=True)
+    if with_sdpa and P == 0:
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+
+        q4 = q.view(B, S, Hq, D).transpose(1, 2).contiguous().requires_grad_(True)
+        k4 = k.view(B, S, Hkv, D).transpose(1, 2).contiguous().requires_grad_(True)
+        v4 = v.view(B, S, Hkv, D).transpose(1, 2).contiguous().requires_grad_(True)
+        do4 = torch.randn(B, Hq, S, D, device="cuda").bfloat16()
+        with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+            def f():
+                return F.scaled_dot_product_attention(q4, k4, v4, is_causal=True, enable_gqa=True)
+
+            def fb():
+                f().backward(do4)
+                q4.grad = k4.grad = v4.grad = None
+
+            ms, sus = timeit(f)
+            line = f"B={B} S={S} P={P}: cuDNN SDPA fwd burst {fl / ms / 1e9:7.1f} sustained {fl / sus / 1e9:7.1f} TFLOP/s [{last_clocks}]"
+            try:
+                mfb, sfb = timeit(fb)
+                line += f" | bwd (fwd+bwd - fwd) burst {2.5 * fl / (mfb - ms) / 1e9:7.1f} sustained {2.5 * fl / (sfb - sus) / 1e9:7.1f} TFLOP/s [{last_clocks}]"
+            except Exception as e:   # autograd inside a graph capture may be refused
+                line += f" | bwd: {str(e)[:80]}"
+        print(line, flush=True)
