@@ -130,6 +130,8 @@ int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_
 
 /* ---- K8/K9: prefix-LM attention (modelling/llama.py:129-137) --------------------------------------
  * mask(q, kv) = (kv < prefix_len) | (q >= kv);  prefix_len = 0 is plain causal.
+ * prefix_len_b: NULL, or int32 [B] with one prefix length per sequence of the batch (then prefix_len is ignored): the
+ * LibriSpeech-shaped batches of train_librispeech.py:36-124 pack utterances of different durations.
  * Optional packed-sequence document-causal mask (train_metamathqa.py:67-70): doc_start / doc_end int32 [B, S] hold the
  * first / last position of the document containing each position (documents are contiguous); visible pairs are
  * additionally restricted to kv >= doc_start[q].  NULL = no document structure.
@@ -139,7 +141,7 @@ int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_
  * descriptor zero-fills the missing half, at half the tensor-core efficiency).  scale = 1/sqrt(D). */
 int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
-                    int64_t prefix_len, const void* doc_start, float scale, void* stream);
+                    int64_t prefix_len, const void* prefix_len_b, const void* doc_start, float scale, void* stream);
 /* dq/dk/dv bf16 with pitches lddq/lddk/lddv; dq_accum fp32 workspace [B,S,Hq,D] (zeroed by the call);
  * delta fp32 workspace [B,Hq,S]. rope_inverse: null, or the fp32 [>= S, D/2, 2] (cos, sin) table of K7: dq and dk then
  * leave the call already rotated back through RoPE (the autograd of apply_rope, llama.py:63-73), which saves the
@@ -148,7 +150,8 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
                     int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
                     int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
-                    const void* doc_start, const void* doc_end, float scale, const void* rope_inverse, void* stream);
+                    const void* prefix_len_b, const void* doc_start, const void* doc_end, float scale,
+                    const void* rope_inverse, void* stream);
 
 /* ---- audio stem (modelling/audio.py:26-31,51-60): Conv1d(k3,s1)+GELU, Conv1d(k3,s2)+GELU -------------------------
  * The convolutions run on llamax_bf16_gemm: with channels-last activations padded by one zero row on each side of a

@@ -70,9 +70,9 @@ SIGNATURES = {
     "llamax_swiglu_fwd": [P, P, I64, P, P, P, I64, I64, P],
     "llamax_swiglu_bwd": [P, P, P, I64, P, P, I64, P, I64, I64, P],
     "llamax_rope_inplace": [P, I64, P, I64, I64, I32, I32, c_int, P],
-    "llamax_attn_fwd": [P, I64, P, I64, P, I64, P, I64, P, I64, I64, I32, I32, I32, I64, P, c_float, P],
+    "llamax_attn_fwd": [P, I64, P, I64, P, I64, P, I64, P, I64, I64, I32, I32, I32, I64, P, P, c_float, P],
     "llamax_attn_bwd": [P, I64, P, I64, P, I64, P, I64, P, P, I64, P, I64, P, I64, P, I64, P, P,
-                        I64, I64, I32, I32, I32, I64, P, P, c_float, P, P],
+                        I64, I64, I32, I32, I32, I64, P, P, P, c_float, P, P],
     "llamax_lora_wgrad": [P, I64, P, I64, P, I64, I64, I32, c_float, P],
     "llamax_lora_bwd_pair": [P, I64, P, I64, P, I64, P, I64, P, I64, P, P, I64, I64, I32, c_float, P],
     "llamax_gelu_bias_fwd": [P, P, P, I64, I64, I32, I32, I32, P],

@@ -70,6 +70,7 @@ struct AttnFwdParams {
   int D;             // real head dim (64 or 128); tiles are always 128 wide, TMA zero-fills columns >= D
   float scale_log2;  // softmax scale * log2(e)
   const int32_t* doc_start;  // [B, S] first position of the document containing each position, or null
+  const int32_t* prefix_b;   // null, or [B]: per-sequence prefix length (overrides P)
 };
 
 namespace fwd {
@@ -121,9 +122,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // dispatched longest-first (the last query tile visits every kv tile); the 4 heads of a GQA group run together
   const int qt = gridDim.z - 1 - blockIdx.z;
   const int h = blockIdx.x, b = blockIdx.y;
+  const int Pb = p.prefix_b ? min(max(p.prefix_b[b], 0), p.S) : p.P;   // prefix length of this sequence
   const int hk = h / (p.Hq / p.Hkv);
   const int q0 = qt * kTile;
-  const int kv_end = min(p.S, max(p.P, q0 + kTile));
+  const int kv_end = min(p.S, max(Pb, q0 + kTile));
   // packed documents: keys before the start of the first row's document are never visible to this tile
   const int j_begin = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
   const int n_kv = (kv_end + kTile - 1) / kTile - j_begin;  // number of visited kv tiles
@@ -242,7 +244,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int st = kNB == 2 ? (j & 1) : 0;
       const int kv0 = (j_begin + j) * kTile;
       // tile needs the element test unless every (q, kv) pair is visible and in range
-      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= Pb) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
       LX_TR(tr_cta, j, 4);
       mbar_wait(&s_full[st], (kNB == 2 ? (j >> 1) : j) & 1);
       tc_fence_after();
@@ -266,7 +268,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
         // compare against a per-row constant and a select per element instead of three compares
         const int lo = kDocs ? ds_row - kv0 : 0;
-        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
+        const uint32_t width = (uint32_t)max(min(p.S, max(Pb, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -417,6 +419,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // grid = (query heads, batch, pairs of query tiles): pairs run backwards so CTAs are dispatched longest-first
   const int pr = gridDim.z - 1 - blockIdx.z;
   const int h = blockIdx.x, b = blockIdx.y;
+  const int Pb = p.prefix_b ? min(max(p.prefix_b[b], 0), p.S) : p.P;   // prefix length of this sequence
   const int hk = h / (p.Hq / p.Hkv);
   // per-tile kv tile ranges [jb_x, je_x); a tile past the end of the sequence has an empty range
   int jb_[2], je_[2];
@@ -424,7 +427,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   for (int x = 0; x < 2; ++x) {
     const int q0 = (2 * pr + x) * kTile;
     if (q0 < p.S) {
-      const int kv_end = min(p.S, max(p.P, q0 + kTile));
+      const int kv_end = min(p.S, max(Pb, q0 + kTile));
       je_[x] = (kv_end + kTile - 1) / kTile;
       jb_[x] = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
     } else {
@@ -564,7 +567,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < n_kv; ++i) {
       const int kv0 = (jb_x + i) * kTile;
       // tile needs the element test unless every (q, kv) pair is visible and in range
-      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= Pb) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
       if (x == 0) LX_TR(tr_cta, jb_x + i, 4);
       mbar_wait(&s_full[x], i & 1);
       tc_fence_after();
@@ -583,7 +586,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
         // compare against a per-row constant and a select per element instead of three compares
         const int lo = kDocs ? ds_row - kv0 : 0;
-        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
+        const uint32_t width = (uint32_t)max(min(p.S, max(Pb, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -741,6 +744,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // grid = (query heads, batch, pairs of query tiles): pairs run backwards so CTAs are dispatched longest-first
   const int pr = gridDim.z - 1 - blockIdx.z;
   const int h = blockIdx.x, b = blockIdx.y;
+  const int Pb = p.prefix_b ? min(max(p.prefix_b[b], 0), p.S) : p.P;   // prefix length of this sequence
   const int hk = h / (p.Hq / p.Hkv);
   // per-tile kv tile ranges [jb_x, je_x); a tile past the end of the sequence has an empty range
   int jb_[2], je_[2];
@@ -748,7 +752,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   for (int x = 0; x < 2; ++x) {
     const int q0 = (2 * pr + x) * kTile;
     if (q0 < p.S) {
-      const int kv_end = min(p.S, max(p.P, q0 + kTile));
+      const int kv_end = min(p.S, max(Pb, q0 + kTile));
       je_[x] = (kv_end + kTile - 1) / kTile;
       jb_[x] = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
     } else {
@@ -892,7 +896,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < n_kv; ++i) {
       const int kv0 = (jb_x + i) * kTile;
       // tile needs the element test unless every (q, kv) pair is visible and in range
-      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= Pb) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
       mbar_wait(&s_full[x], i & 1);
       tc_fence_after();
       uint32_t sv[2][32];
@@ -905,7 +909,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
         // compare against a per-row constant and a select per element instead of three compares
         const int lo = kDocs ? ds_row - kv0 : 0;
-        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
+        const uint32_t width = (uint32_t)max(min(p.S, max(Pb, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -1060,6 +1064,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // grid = (query heads, batch, pairs of query tiles): pairs run backwards so CTAs are dispatched longest-first
   const int pr = gridDim.z - 1 - blockIdx.z;
   const int h = blockIdx.x, b = blockIdx.y;
+  const int Pb = p.prefix_b ? min(max(p.prefix_b[b], 0), p.S) : p.P;   // prefix length of this sequence
   const int hk = h / (p.Hq / p.Hkv);
   // per-tile kv tile ranges [jb_x, je_x); a tile past the end of the sequence has an empty range
   int jb_[2], je_[2];
@@ -1067,7 +1072,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   for (int x = 0; x < 2; ++x) {
     const int q0 = (2 * pr + x) * kTile;
     if (q0 < p.S) {
-      const int kv_end = min(p.S, max(p.P, q0 + kTile));
+      const int kv_end = min(p.S, max(Pb, q0 + kTile));
       je_[x] = (kv_end + kTile - 1) / kTile;
       jb_[x] = kDocs ? p.doc_start[(int64_t)b * p.S + q0] / kTile : 0;
     } else {
@@ -1213,7 +1218,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < n_kv; ++i) {
       const int kv0 = (jb_x + i) * kTile;
       // tile needs the element test unless every (q, kv) pair is visible and in range
-      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= p.P) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
+      const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= Pb) || (kv0 + kTile - 1 <= q0)) && (kv0 >= ds_tile);
       LX_TR(tr_cta, jb_x + i, x * 16 + 4);
       mbar_wait(&s_full[x], i & 1);   // also: PV(i-1) has completed (same issuing thread, in order): O is stable
       tc_fence_after();
@@ -1232,7 +1237,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // kv < max(P, q + 1) (and kv < S), packed documents additionally cut the head (kv >= ds_row) — one unsigned
         // compare against a per-row constant and a select per element instead of three compares
         const int lo = kDocs ? ds_row - kv0 : 0;
-        const uint32_t width = (uint32_t)max(min(p.S, max(p.P, q + 1)) - kv0 - lo, 0);
+        const uint32_t width = (uint32_t)max(min(p.S, max(Pb, q + 1)) - kv0 - lo, 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -1370,6 +1375,7 @@ struct AttnBwdParams {
   const int32_t* doc_start;  // [B, S] or null (packed-sequence document-causal mask)
   const int32_t* doc_end;    // [B, S] last position of the document containing each position
   const float* rope;         // null, or [>= S, D/2, 2] (cos, sin): dk (here) and dq (convert kernel) get the RoPE backward
+  const int32_t* prefix_b;   // null, or [B]: per-sequence prefix length (overrides P)
 };
 
 namespace bwd {
@@ -1438,6 +1444,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // every query tile, the last tile only by the last one); batch elements follow one another so that the fp32 dQ
   // accumulator being reduced into stays L2-resident (one element = 33 MB at 8B shape, S = 2048)
   const int hk = blockIdx.x, jt = blockIdx.y, b = blockIdx.z;
+  const int Pb = p.prefix_b ? min(max(p.prefix_b[b], 0), p.S) : p.P;   // prefix length of this sequence
 #ifdef LX_ATTN_TRACE
   const bool tr_cta = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 &&
                       (warp == 1 || warp == 4 || warp == 12);
@@ -1445,7 +1452,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int kv0 = jt * kKV;
   const int G = p.Hq / p.Hkv;
   const int nq_tiles = (p.S + kQ - 1) / kQ;
-  const int i_start = (kv0 < p.P) ? 0 : kv0 / kQ;  // first query tile that sees this kv tile
+  const int i_start = (kv0 < Pb) ? 0 : kv0 / kQ;  // first query tile that sees this kv tile
   // packed documents: queries after the end of the last kv row's document never see this tile
   const int i_end = kDocs ? min(nq_tiles, p.doc_end[(int64_t)b * p.S + min(kv0 + kKV - 1, p.S - 1)] / kQ + 1) : nq_tiles;
   const int steps_per_head = i_end - i_start;
@@ -1642,7 +1649,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       load_stat(s + 1, nxt_a, nxt_d);            // prefetch next step's stats (global)
       const uint32_t stat_u = s_stat_u + st * (3 * kQ * 4) + grp * 64 * 4;
       const int ds_tile = kDocs ? p.doc_start[(int64_t)b * p.S + min(q0 + kQ - 1, p.S - 1)] : 0;
-      const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= p.P) || (kv0 + kKV - 1 <= q0)) &&
+      const bool full_tile = (kv0 + kKV <= p.S) && (q0 + kQ <= p.S) && ((kv0 + kKV <= Pb) || (kv0 + kKV - 1 <= q0)) &&
                              (kv0 >= ds_tile);
       mbar_wait(s_full, s & 1);
       tc_fence_after();
@@ -1657,7 +1664,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         LX_TR(tr_cta, s, 8);
         // prefix-LM without documents: a kv row inside the sequence is seen by every query if it lies in the prefix, else
         // by the queries q >= kv: a suffix of this thread's 64 query columns, starting at first_q (one compare per element)
-        const int first_q = (kv >= p.S) ? (1 << 30) : (kv < p.P ? -(1 << 30) : kv - q0 - grp * 64);
+        const int first_q = (kv >= p.S) ? (1 << 30) : (kv < Pb ? -(1 << 30) : kv - q0 - grp * 64);
         auto block = [&](auto masked_tag) {
           constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
@@ -1679,7 +1686,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (kMasked) {
                   if (kDocs) {
                     const int qa = q0 + grp * 64 + c * 32 + i + e;
-                    if (!((kv < p.S) && ((kv < p.P) || (kv <= qa)) && kv >= dst4[e])) pe = 0.f;
+                    if (!((kv < p.S) && ((kv < Pb) || (kv <= qa)) && kv >= dst4[e])) pe = 0.f;
                   } else if (c * 32 + i + e < first_q) {   // this kv row is visible to the queries from first_q on
                     pe = 0.f;
                   }
@@ -1910,7 +1917,7 @@ int llamax_debug_attn_trace(void* buf) {
 
 int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
-                    int64_t prefix_len, const void* doc_start, float scale, void* stream) {
+                    int64_t prefix_len, const void* prefix_len_b, const void* doc_start, float scale, void* stream) {
   if (!q || !k || !v || !o || !lse) return set_error(LLAMAX_ERR_ARG, "attn_fwd: null pointer");
   int rc = check_attn_args(B, S, Hq, Hkv, D, prefix_len, "attn_fwd");
   if (rc) return rc;
@@ -1962,6 +1969,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.D = D;
   p.scale_log2 = scale * kLog2e;
   p.doc_start = (const int32_t*)doc_start;
+  p.prefix_b = (const int32_t*)prefix_len_b;
   const unsigned q_tiles = (unsigned)ceil_div(S, fwd::kTile);
   dim3 grid(Hq, (unsigned)B, one_tile ? q_tiles : (q_tiles + 1) / 2);
   kern<<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
@@ -1973,7 +1981,8 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     const void* o, int64_t ldo, const void* lse, const void* dout, int64_t lddo, void* dq,
                     int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dq_accum, void* delta,
                     int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D, int64_t prefix_len,
-                    const void* doc_start, const void* doc_end, float scale, const void* rope_inverse, void* stream) {
+                    const void* prefix_len_b, const void* doc_start, const void* doc_end, float scale,
+                    const void* rope_inverse, void* stream) {
   if ((doc_start == nullptr) != (doc_end == nullptr))
     return set_error(LLAMAX_ERR_ARG, "attn_bwd: doc_start and doc_end go together");
   if (!q || !k || !v || !o || !lse || !dout || !dq || !dk || !dv || !dq_accum || !delta)
@@ -2019,6 +2028,7 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   p.doc_start = (const int32_t*)doc_start;
   p.doc_end = (const int32_t*)doc_end;
   p.rope = (const float*)rope_inverse;
+  p.prefix_b = (const int32_t*)prefix_len_b;
   dim3 grid(Hkv, (unsigned)ceil_div(S, bwd::kKV), (unsigned)B);
   kern<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");

@@ -138,7 +138,10 @@ class LlamaAudio(Llama):
         return emb.transpose(1, 2)
 
     def forward(self, audio: Tensor | None, tokens: Tensor, *, input_pos: Tensor | None = None,
-                labels: Tensor | None = None, prefix_lm: bool = False) -> Tensor:
+                labels: Tensor | None = None, prefix_lm: bool | Tensor = False) -> Tensor:
+        """prefix_lm: False (reference behaviour: causal over [audio ; text]), True (the audio positions are a bidirectional
+        prefix), or an int tensor [B] of per-sequence prefix lengths (utterances shorter than the padded audio: only
+        their own frames are bidirectional)."""
         if input_pos is not None:
             raise NotImplementedError("llamax_b200: input_pos (inference) is outside the fine-tuning hot path")
         x = self.tok_embeddings(tokens)
@@ -147,7 +150,10 @@ class LlamaAudio(Llama):
             prefix = self.embed_audio(audio)
             n_prefix = prefix.shape[1]
             x = torch.cat([prefix, x], dim=1)
-        block_mask = PrefixLM(n_prefix) if (prefix_lm and n_prefix > 0) else None
+        if isinstance(prefix_lm, Tensor):
+            block_mask = PrefixLM(prefix_lm.clamp(max=n_prefix))
+        else:
+            block_mask = PrefixLM(n_prefix) if (prefix_lm and n_prefix > 0) else None
         x = self._run_layers(x, block_mask)
         if n_prefix:
             x = x[:, n_prefix:]  # loss / logits on text positions only

@@ -9,10 +9,11 @@ sm_100a kernels.
   Llama                            llama.py:177-219    embed -> layers -> norm -> output -> cross-entropy
 
 Masking: the reference wires FlexAttention `block_mask`s and dense SDPA `mask`s (llama.py:129-137). The kernels here
-implement the prefix-LM family  mask(q, kv) = (kv < P) | (q >= kv)  (P = 0: causal). Pass it as
-`block_mask=PrefixLM(P)` (or anything with a `.prefix_len` attribute, e.g. a FlexAttention BlockMask produced by
-`prefix_lm_block_mask`). Arbitrary dense masks, KV caches / `input_pos` (the inference path) are out of scope and
-raise.
+implement two mask families: prefix-LM  mask(q, kv) = (kv < P) | (q >= kv)  (P = 0: causal; P an int or one value per
+sequence of the batch) and packed-document causal. Pass `block_mask=PrefixLM(P)` / `DocumentCausal(doc_ids)`, or — as in
+the reference — a FlexAttention BlockMask or a dense boolean `mask`: those are RECOGNISED (their dense form is compared
+with the family rebuilt from the descriptor read off them, `describe_dense_mask`) and raise if they are anything else.
+KV caches / `input_pos` (the inference path) are out of scope and raise.
 """
 
 from __future__ import annotations
@@ -44,10 +45,11 @@ class LlamaConfig(NamedTuple):
 
 
 class PrefixLM:
-    """Mask descriptor: keys [0, prefix_len) are visible to every query, the rest is causal."""
+    """Mask descriptor: keys [0, prefix_len) are visible to every query, the rest is causal. prefix_len: an int, or an
+    int tensor [B] with one prefix length per sequence of the batch (utterances of different durations)."""
 
-    def __init__(self, prefix_len: int):
-        self.prefix_len = int(prefix_len)
+    def __init__(self, prefix_len):
+        self.prefix_len = prefix_len if isinstance(prefix_len, Tensor) else int(prefix_len)
 
     def __repr__(self):
         return f"PrefixLM(prefix_len={self.prefix_len})"
@@ -104,21 +106,100 @@ def _doc_bounds_of(block_mask):
     return (ds, getattr(block_mask, "doc_end", None)) if ds is not None else (None, None)
 
 
-def _prefix_len_of(mask, block_mask, input_pos) -> int:
-    if mask is not None or input_pos is not None:
-        raise NotImplementedError(
-            "llamax_b200: dense `mask` / `input_pos` (KV-cache inference path, llama.py:126-127,135-137) is outside "
-            "the fine-tuning hot path; use block_mask=PrefixLM(P)"
-        )
+class _MaskDesc:
+    """What the kernels understand: a prefix length (int or [B] tensor) and optional packed-document bounds."""
+
+    def __init__(self, prefix_len=0, doc_start=None, doc_end=None):
+        self.prefix_len, self.doc_start, self.doc_end = prefix_len, doc_start, doc_end
+
+
+def describe_dense_mask(m: Tensor) -> _MaskDesc:
+    """Recognise a dense boolean attention mask [L, L] / [B, L, L] / [B, 1, L, L] (True = attend; what the reference hands
+    to SDPA, llama.py:135-137, or what a FlexAttention mask_mod evaluates to) as a member of the two families the kernels
+    implement, by CONSTRUCTION AND COMPARISON: the candidate descriptor is read off the mask (row 0 gives the prefix length,
+    the first visible key of each row gives its document start), the family's mask is rebuilt from it and must equal the
+    input exactly. Anything else (sliding windows, arbitrary mask_mods, head-dependent masks) raises."""
+    if m.dtype is not torch.bool:
+        raise NotImplementedError("llamax_b200: only boolean attention masks are recognised")
+    while m.dim() > 3:
+        if m.shape[1] != 1 and not bool((m[:, :1] == m).all()):
+            raise NotImplementedError("llamax_b200: head-dependent attention masks are not implemented")
+        m = m[:, 0]
+    if m.dim() == 2:
+        m = m[None]
+    Bm, L, L2 = m.shape
+    if L != L2:
+        raise NotImplementedError("llamax_b200: attention masks must be square (training path, no KV cache)")
+    idx = torch.arange(L, device=m.device)
+    causal = idx[:, None] >= idx[None, :]
+    # --- prefix-LM: row 0 sees exactly kv < max(P, 1)
+    P = m[:, 0].sum(dim=1)                                        # [Bm]
+    if bool((((idx[None, None, :] < P[:, None, None]) | causal[None]) == m).all()):
+        P = torch.where(P <= 1, torch.zeros_like(P), P)           # P = 1 is plain causal
+        if Bm == 1 or bool((P == P[0]).all()):
+            return _MaskDesc(int(P[0]))
+        return _MaskDesc(P.to(torch.int32))
+    # --- packed documents (train_metamathqa.py:67-70): causal inside contiguous documents
+    first = m.int().argmax(dim=2)                                 # first visible key of each query row
+    doc_ids = (first[:, 1:] != first[:, :-1]).cumsum(dim=1)
+    doc_ids = torch.cat([torch.zeros_like(doc_ids[:, :1]), doc_ids], dim=1)
+    if bool((((doc_ids[:, :, None] == doc_ids[:, None, :]) & causal[None]) == m).all()):
+        ds, de = ops.doc_bounds(doc_ids)
+        return _MaskDesc(0, ds, de)
+    raise NotImplementedError(
+        "llamax_b200: this attention mask is neither prefix-LM ((kv < P) | (q >= kv)) nor document-causal; the sm_100a "
+        "kernels implement these two families (PrefixLM(P), DocumentCausal(doc_ids))")
+
+
+def describe_block_mask(block_mask) -> _MaskDesc:
+    """A mask descriptor of this package, or a generic FlexAttention BlockMask (llama.py:129-132): its mask_mod is evaluated
+    once on the dense index grid and recognised by describe_dense_mask; the result is cached on the object."""
     if block_mask is None:
-        return 0
+        return _MaskDesc(0)
     p = getattr(block_mask, "prefix_len", None)
-    if p is None:
+    if p is not None:
+        return _MaskDesc(p, *_doc_bounds_of(block_mask))
+    cached = getattr(block_mask, "_llamax_desc", None)
+    if cached is not None:
+        return cached
+    mask_mod = getattr(block_mask, "mask_mod", None)
+    if mask_mod is None:
+        raise NotImplementedError("llamax_b200: block_mask must be PrefixLM / DocumentCausal or a FlexAttention BlockMask")
+    from torch.nn.attention.flex_attention import create_mask
+
+    q_len, kv_len = block_mask.seq_lengths
+    nb = block_mask.kv_num_blocks.shape[0]
+    dense = create_mask(mask_mod, nb, 1, q_len, kv_len, device=block_mask.kv_num_blocks.device)
+    desc = describe_dense_mask(dense)
+    try:
+        block_mask._llamax_desc = desc
+    except Exception:
+        pass
+    return desc
+
+
+_dense_desc_cache: dict = {}
+
+
+def _mask_desc(mask, block_mask, input_pos) -> _MaskDesc:
+    if input_pos is not None:
         raise NotImplementedError(
-            "llamax_b200: block_mask must describe a prefix-LM mask (PrefixLM(P) or prefix_lm_block_mask(P, L)); "
-            "generic FlexAttention mask_mods are not implemented"
-        )
-    return int(p)
+            "llamax_b200: `input_pos` (KV-cache inference path, llama.py:126-127) is outside the fine-tuning hot path")
+    if mask is not None:
+        if block_mask is not None:
+            raise ValueError("pass either mask or block_mask")
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.device)   # the 32 layers get the same tensor
+        hit = _dense_desc_cache.get(key)
+        if hit is None:
+            if len(_dense_desc_cache) > 8:
+                _dense_desc_cache.clear()
+            hit = _dense_desc_cache[key] = describe_dense_mask(mask)
+        return hit
+    return describe_block_mask(block_mask)
+
+
+def _prefix_len_of(mask, block_mask, input_pos):
+    return _mask_desc(mask, block_mask, input_pos).prefix_len
 
 
 def scale_llama3_1_rope(freqs: Tensor) -> Tensor:
@@ -211,13 +292,13 @@ class Attention(nn.Module):
             raise NotImplementedError("llamax_b200: KV-cache decoding is outside the fine-tuning hot path")
         if self.training and self.attn_dropout > 0:
             raise NotImplementedError("llamax_b200: attention dropout is not implemented")
-        prefix_len = _prefix_len_of(mask, block_mask, input_pos)
+        desc = _mask_desc(mask, block_mask, input_pos)
         B, L, _ = x.shape
         q = self.wq(x).view(B, L, self.num_heads, self.head_dim)
         k = self.wk(x).view(B, L, self.num_kv_heads, self.head_dim)
         v = self.wv(x).view(B, L, self.num_kv_heads, self.head_dim)
         q, k = apply_rope(q, rope), apply_rope(k, rope)
-        out = prefix_lm_attention(q, k, v, prefix_len, *_doc_bounds_of(block_mask))
+        out = prefix_lm_attention(q, k, v, desc.prefix_len, desc.doc_start, desc.doc_end)
         return self.wo(out.reshape(B, L, self.num_heads * self.head_dim))
 
 
@@ -264,8 +345,8 @@ class TransformerLayer(nn.Module):
     def forward(self, x: Tensor, rope: Tensor, *, mask: Tensor | None = None, input_pos: Tensor | None = None,
                 block_mask=None) -> Tensor:
         if fused_block_supported(self, x):
-            prefix_len = _prefix_len_of(mask, block_mask, input_pos)
-            return FusedDecoderBlock.apply(x, rope, (self, prefix_len, *_doc_bounds_of(block_mask)),
+            desc = _mask_desc(mask, block_mask, input_pos)
+            return FusedDecoderBlock.apply(x, rope, (self, desc.prefix_len, desc.doc_start, desc.doc_end),
                                            *block_trainables(self))
         # unfused composition (e.g. bf16 base weights): same math, module by module
         x = x + self.attention(self.attention_norm(x), rope, mask=mask, input_pos=input_pos, block_mask=block_mask)

@@ -463,10 +463,23 @@ def cross_entropy_(logits: Tensor, labels: Tensor, loss_sum: Tensor, inv_n: Tens
 
 
 # ---------------------------------------------------------------------------------------------- attention
-def _pairs(S: int, prefix_len: int) -> float:
-    """Unmasked (q, kv) pairs of the prefix-LM mask: S*P + (S-P)(S-P+1)/2."""
+def _pairs(S: int, prefix_len) -> float:
+    """Unmasked (q, kv) pairs of the prefix-LM mask: S*P + (S-P)(S-P+1)/2 (mean over the batch for per-sequence P)."""
+    if isinstance(prefix_len, Tensor):
+        if not TIMING.on:
+            return 0.0          # only the timing report needs it: no device sync on the training path
+        return float(sum(_pairs(S, int(v)) for v in prefix_len.tolist())) / max(1, prefix_len.numel())
     P_ = min(int(prefix_len), S)
     return S * P_ + (S - P_) * (S - P_ + 1) / 2
+
+
+def _prefix_args(prefix_len, B: int, device):
+    """(scalar prefix, int32 [B] device pointer tensor | None) for the C ABI."""
+    if isinstance(prefix_len, Tensor):
+        pb = prefix_len.to(device=device, dtype=torch.int32).reshape(-1).contiguous()
+        assert pb.numel() == B, f"per-sequence prefix_len must have {B} entries"
+        return 0, pb
+    return int(prefix_len), None
 
 
 def doc_bounds(doc_ids: Tensor):
@@ -482,17 +495,19 @@ def doc_bounds(doc_ids: Tensor):
     return start.to(torch.int32).contiguous(), end.to(torch.int32).contiguous()
 
 
-def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, prefix_len: int,
+def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, prefix_len,
              scale: float | None = None, doc_start: Tensor | None = None):
-    """q [B*S, Hq*D] / k, v [B*S, Hkv*D] row views (unit inner stride). Returns (o [B*S, Hq*D], lse [B,Hq,S])."""
+    """q [B*S, Hq*D] / k, v [B*S, Hkv*D] row views (unit inner stride). prefix_len: int, or an int tensor [B] with one
+    prefix length per sequence. Returns (o [B*S, Hq*D], lse [B,Hq,S])."""
     lib, st = _prep(q)
     for t in (q, k, v):
         assert t.dtype is torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == B * S
     o = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.bfloat16)
     lse = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     scale = float(scale) if scale is not None else D ** -0.5
+    p_scalar, p_b = _prefix_args(prefix_len, B, q.device)
     _call(lib, "llamax_attn_fwd",
-          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), B, S, Hq, Hkv, D, int(prefix_len), _p(doc_start), scale, st,),
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), B, S, Hq, Hkv, D, p_scalar, _p(p_b), _p(doc_start), scale, st,),
           "attn_fwd", 4.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return o, lse
 
@@ -509,7 +524,8 @@ def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, sc
     dq_accum = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.float32)
     delta = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
     scale = float(scale) if scale is not None else D ** -0.5
+    p_scalar, p_b = _prefix_args(prefix_len, B, q.device)
     _call(lib, "llamax_attn_bwd",
-          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, int(prefix_len), _p(doc_start), _p(doc_end), scale, _p(rope_inverse), st,),
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, p_scalar, _p(p_b), _p(doc_start), _p(doc_end), scale, _p(rope_inverse), st,),
           "attn_bwd", 10.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return dq, dk, dv

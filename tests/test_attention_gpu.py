@@ -187,3 +187,55 @@ def test_attention_backward_writes_stay_inside_their_views(B, S, Hq, Hkv, P):
     assert not bool((inner == 3).all())
     # forward outputs: every row written, lse finite
     assert bool(torch.isfinite(lse).all()) and bool(torch.isfinite(o.float()).all())
+
+
+def test_per_sequence_prefix_lengths_fwd_bwd():
+    """One prefix length per sequence of the batch (int32 [B] through the C ABI): every sequence matches the oracle run
+    with its own scalar prefix; a constant vector equals the scalar call bit for bit."""
+    B, S, Hq, Hkv = 3, 300, 4, 2
+    Ps = [0, 77, 300]
+    torch.manual_seed(8)
+    qkv = torch.randn(B * S, (Hq + 2 * Hkv) * D).bfloat16()
+    dout = torch.randn(B * S, Hq * D).bfloat16()
+    g = qkv.cuda()
+    qc, kc, vc = _split(g, Hq, Hkv)
+    pb = torch.tensor(Ps, device="cuda", dtype=torch.int32)
+    o, lse = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, pb)
+    dqkv = torch.zeros_like(g)
+    dq, dk, dv = _split(dqkv, Hq, Hkv)
+    ops.attn_bwd(qc, kc, vc, o, lse, dout.cuda(), dq, dk, dv, B, S, Hq, Hkv, D, pb)
+    q, k, v = _split(qkv, Hq, Hkv)
+    to4 = lambda t, H, b: t.reshape(B, S, H, D)[b : b + 1].transpose(1, 2)
+    for b, P in enumerate(Ps):
+        o_ref, dq_ref, dk_ref, dv_ref = R.attention_ref_grads(to4(q, Hq, b), to4(k, Hkv, b), to4(v, Hkv, b), to4(dout, Hq, b), P)
+        assert rel_err(to4(o.cpu(), Hq, b), o_ref) <= 1e-2
+        assert rel_err(to4(dq.cpu(), Hq, b), dq_ref) <= 1e-2
+        assert rel_err(to4(dk.cpu(), Hkv, b), dk_ref) <= 1e-2
+        assert rel_err(to4(dv.cpu(), Hkv, b), dv_ref) <= 1e-2
+    o1, lse1 = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, 77)
+    o2, lse2 = ops.attn_fwd(qc, kc, vc, B, S, Hq, Hkv, D, torch.full((B,), 77, device="cuda", dtype=torch.int32))
+    assert torch.equal(o1, o2) and torch.equal(lse1, lse2)
+
+
+def test_generic_flex_block_mask_is_recognised_by_the_fused_block():
+    """A FlexAttention BlockMask built from a user mask_mod (no llamax tags) and a dense boolean mask drive the fused block
+    exactly like PrefixLM(P); a sliding-window mask_mod raises."""
+    from torch.nn.attention.flex_attention import create_block_mask
+
+    from llamax_b200.modelling import PrefixLM
+    from tests.helpers import build_tiny_llama
+
+    P, B, S = 100, 2, 256
+    model = build_tiny_llama(True, num_layers=1).cuda()
+    layer, cfg = model.layers[0], model.config
+    rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:S].cuda()
+    x = torch.randn(B, S, cfg.embed_dim, device="cuda").bfloat16()
+    want = layer(x, rope, block_mask=PrefixLM(P))
+    bm = create_block_mask(lambda b, h, q, kv: (kv < P) | (q >= kv), None, None, S, S, device="cuda")
+    assert torch.equal(layer(x, rope, block_mask=bm), want)
+    idx = torch.arange(S, device="cuda")
+    dense = ((idx[None, :] < P) | (idx[:, None] >= idx[None, :]))[None, None]
+    assert torch.equal(layer(x, rope, mask=dense), want)
+    sw = create_block_mask(lambda b, h, q, kv: (q >= kv) & (q - kv < 64), None, None, S, S, device="cuda")
+    with pytest.raises(NotImplementedError):
+        layer(x, rope, block_mask=sw)

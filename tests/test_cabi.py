@@ -54,7 +54,7 @@ def test_argument_validation_without_gpu():
     assert lib.llamax_set_gemm_cta_group(2) == 0
     buf = ctypes.create_string_buffer(64)
     p = ctypes.cast(buf, ctypes.c_void_p)
-    rc = lib.llamax_attn_fwd(p, 64, p, 64, p, 64, p, 64, p, 1, 16, 2, 1, 32, 0, None, 1.0, None)
+    rc = lib.llamax_attn_fwd(p, 64, p, 64, p, 64, p, 64, p, 1, 16, 2, 1, 32, 0, None, None, 1.0, None)
     assert rc == -1 and b"head_dim" in lib.llamax_last_error()
 
 

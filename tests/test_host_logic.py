@@ -111,10 +111,12 @@ def test_rope_table_matches_reference(gold):
 def test_mask_plumbing():
     assert L._prefix_len_of(None, None, None) == 0
     assert L._prefix_len_of(None, PrefixLM(17), None) == 17
-    with pytest.raises(NotImplementedError):
-        L._prefix_len_of(torch.ones(4, 4, dtype=torch.bool), None, None)
+    assert L._prefix_len_of(torch.ones(4, 4, dtype=torch.bool), None, None) == 4    # fully bidirectional = prefix 4
+    assert L._prefix_len_of(torch.ones(4, 4, dtype=torch.bool).tril(), None, None) == 0
     with pytest.raises(NotImplementedError):
         L._prefix_len_of(None, object(), None)
+    with pytest.raises(NotImplementedError):
+        L._prefix_len_of(None, None, torch.arange(4))
     model = _tiny()
     with pytest.raises(NotImplementedError):
         model.build_cache(inference=True)
@@ -144,3 +146,31 @@ def test_gemm_tile_order_model_is_a_bijection():
     for nm, nn in [(64, 16), (55, 16), (32, 501), (64, 24)]:
         pick = -8 if nm >= nn else 8
         assert mod.live_panels(nm, nn, pick) <= mod.live_panels(nm, nn, -pick) + 1e-9
+
+
+def test_dense_masks_and_block_masks_are_recognised():
+    """Generic mask ingestion: dense boolean masks / FlexAttention mask_mods are compared with the
+    prefix-LM and document-causal families rebuilt from the descriptor read off them; anything else raises."""
+    import pytest
+
+    from llamax_b200.modelling.llama import describe_dense_mask
+    from oracle import ref_ops as R
+
+    L = 96
+    for P in (0, 1, 17, 96):
+        d = describe_dense_mask(R.prefix_lm_mask(L, P))
+        assert d.prefix_len == (0 if P <= 1 else P) and d.doc_start is None
+    # one prefix length per sequence -> int32 [B]
+    m = torch.stack([R.prefix_lm_mask(L, 5), R.prefix_lm_mask(L, 40)])[:, None]
+    d = describe_dense_mask(m)
+    assert d.prefix_len.tolist() == [5, 40]
+    # packed documents
+    doc_ids = torch.repeat_interleave(torch.arange(3), torch.tensor([30, 1, 65]))[None]
+    d = describe_dense_mask(R.document_causal_mask(doc_ids))
+    assert d.prefix_len == 0 and d.doc_start[0, 30].item() == 30 and d.doc_end[0, 29].item() == 29 and d.doc_start[0, 95].item() == 31
+    # a sliding window is neither
+    idx = torch.arange(L)
+    with pytest.raises(NotImplementedError):
+        describe_dense_mask((idx[:, None] >= idx[None, :]) & (idx[:, None] - idx[None, :] < 8))
+    with pytest.raises(NotImplementedError):
+        describe_dense_mask(torch.ones(L, L))          # not boolean
