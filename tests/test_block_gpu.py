@@ -427,3 +427,36 @@ def test_training_trajectory_follows_oracle():
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) <= 5e-3 * abs(b), (losses, ref_losses)
     assert losses[-1] < losses[0] - 0.05 and ref_losses[-1] < ref_losses[0] - 0.05
+
+
+def test_weight_cache_modes_give_identical_gradients():
+    """The grad_input operand (scale * W)^T is either resident in bf16 ("1": 2 extra bytes per parameter, 14 GB at 8B) or
+    rebuilt per use from the int8 codes into one shared scratch ("0": no extra weight memory, +2 % step time — profiles/
+    r2_bench_1gpu_weight_cache_off.json): the operand holds the same bf16 numbers either way, so the block output is
+    bit-identical and the gradients agree to the fp32-reduction-order noise."""
+    from llamax_b200.modelling import PrefixLM
+    from llamax_b200.modelling import fused_block as FB
+
+    results = []
+    for mode in ("1", "0"):
+        FB.set_weight_cache(mode)
+        try:
+            model = build_tiny_llama(True, num_layers=1).cuda()
+            layer, cfg = model.layers[0], model.config
+            rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:256].cuda()
+            torch.manual_seed(7)
+            x = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16().requires_grad_(True)
+            dout = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16()
+            for _ in range(2):      # second pass: the resident operands are hits
+                x.grad = None
+                for p_ in layer.parameters():
+                    p_.grad = None
+                out = layer(x, rope, block_mask=PrefixLM(64))
+                out.backward(dout)
+            results.append([out.detach(), x.grad.detach()] + [p_.grad.detach() for p_ in layer.parameters() if p_.requires_grad])
+        finally:
+            FB.set_weight_cache("auto")
+    for other in results[1:]:
+        assert torch.equal(results[0][0], other[0])
+        for a, b in zip(results[0][1:], other[1:]):
+            assert rel_err(a, b) <= 5e-3
