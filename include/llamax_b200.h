@@ -77,6 +77,24 @@ int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, voi
 int llamax_bf16_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                                 const llamax_epilogue_t* epi, const void* ab, int64_t ld_ab, void* dab, int64_t ld_dab,
                                 void* g, void* stream);
+/* ---- K4/K5 mixed-input: bf16 activations x frozen INT8 weight, converted inside the GEMM ---------------------------
+ * The int8 weight is read by TMA as stored and expanded to bf16 in shared memory by converter warps (exact: every int8
+ * value is a bf16 value), so neither a de-quantised nor a transposed copy of the weight exists in HBM.
+ *   b_layout = 0, weight-only forward (subclasses/int8.py:118): B8 int8 [N,K] pitch ldb8 (the weight as stored),
+ *     C[m,n] = bf16( bf16(sum_k A[m,k]*B8[n,k]) * b_scale[n] ) [+ epilogue terms]; tail = NULL, K1 = K.
+ *   b_layout = 1, grad_input (subclasses/int8.py:127): B8 int8 [K1,N] pitch ldb8 (the weight as stored: its rows are the
+ *     contraction index; row-concatenated weights that share an input form one operand), b_scale bf16 [K1] folded into
+ *     the operand as bf16(f32(w) * f32(s)) exactly like llamax_dequant_weight(transpose = 1, apply_scale = 1);
+ *     tail: NULL (K1 = K) or bf16 [K-K1, N] pitch ldt (K - K1 <= 64): the LoRA A rows that multiply the dh columns
+ *     A[:, K1:K];  C[m,n] = bf16( sum_{k<K1} A[m,k]*bf16(B8[k,n]*s[k]) + sum_{k>=K1} A[m,k]*tail[k-K1,n] ) [+ LoRA term].
+ * K1 % 64 == 0. Results are bit-identical to llamax_dequant_weight + llamax_bf16_gemm on the same operands. */
+int llamax_bf16_int8_gemm(const void* A, int64_t lda, const void* B8, int64_t ldb8, const void* b_scale, int b_layout,
+                          const void* tail, int64_t ldt, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                          int64_t K1, const llamax_epilogue_t* epi, void* stream);
+/* llamax_bf16_gemm_swiglu_bwd with the b_layout = 1 operand above (B8 = w2 as stored, [K, N] int8; k_scale bf16 [K]). */
+int llamax_bf16_int8_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B8, int64_t ldb8, const void* k_scale,
+                                     int64_t M, int64_t N, int64_t K, const llamax_epilogue_t* epi, const void* ab,
+                                     int64_t ld_ab, void* dab, int64_t ld_dab, void* g, void* stream);
 /* Weight-gradient form: C[m,n] = bf16( sum_k At[k,m] * Bt[k,n] ), At bf16 [K,M] pitch ldat, Bt bf16 [K,N] pitch ldbt
  * (M, N indices contiguous; M % 8 == 0, N % 8 == 0). Both tensors are consumed as stored (MN-major UMMA operands):
  * dW[out,in] = dY[tokens,out]^T X[tokens,in] needs no transposed copies. Rows of Bt may overlap (pitch < N), which is

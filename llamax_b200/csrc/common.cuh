@@ -112,6 +112,21 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "r"(cta)
       : "memory");
 }
+// Same, with the default (CTA-scope release) semantics. The explicit .release.cluster form above costs the arriving
+// thread ~1500 cycles (measured with tools/mixed_gemm_trace.py: it drains the thread's outstanding shared-memory stores
+// to cluster scope first) — fine once per tile, ruinous once per k-block. Use this one when the data the arrive
+// publishes is consumed by the async proxy of the arriving thread's OWN CTA (tensor-core reads of this CTA's shared
+// memory, ordered by fence.proxy.async) and only the barrier lives in the peer.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -138,6 +153,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 #endif
+}
+
+// Same wait with cluster-scope acquire: the arrivals come from threads of the peer CTA that published shared-memory
+// writes (release.cluster) this CTA's tensor-core instruction is about to consume.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+#ifdef LX_WATCHDOG
+  uint32_t polls = 0;
+#endif
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#ifdef LX_WATCHDOG
+    if (!ok && ++polls == (1u << 26)) __trap();
+#endif
+  } while (!ok);
 }
 
 // ----------------------------------------------------------------------------------------------

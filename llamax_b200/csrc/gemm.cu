@@ -25,7 +25,23 @@
 
 #include "llamax_b200.h"
 
+#ifndef LX_MIX_EXP
+#define LX_MIX_EXP 0   // timing experiments on the mixed-input pipeline (tools only): see tools/mixed_gemm_perf.py
+#endif
+
 namespace lx {
+
+#ifdef LX_MIX_TRACE
+// tools-only build: SM-clock timestamps of the mixed-input pipeline's roles (cluster 0, leader CTA), read back through
+// llamax_debug_mix_trace. Row layout: [role 0 = MMA issuer, 1 = converter warp 12][64 k-blocks][8 marks].
+__device__ long long g_mix_trace[2 * 64 * 8];
+#define MIX_MARK(role, idx, m)                                                                       \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (idx) < 64) g_mix_trace[((role) * 64 + (idx)) * 8 + (m)] = clock64();     \
+  } while (0)
+#else
+#define MIX_MARK(role, idx, m) do {} while (0)
+#endif
 
 constexpr int kBM = 128;          // rows of A per CTA
 constexpr int kBN = 256;          // accumulator columns per tile
@@ -56,18 +72,66 @@ struct GemmParams {
   int64_t ld_dab;
   __nv_bfloat16* swi_g;         // optional g = bf16(silu(a)) * b, [M, N] contiguous
   int group;                    // tile-order group (set by the launcher, see tile_coords)
+  // mixed-input variants (kMix): B arrives as int8 and is expanded to bf16 in shared memory
+  const __nv_bfloat16* k_scale; // kMix == 2: per-contraction-index scale folded into the operand, bf16 [K1]
+  int K1;                       // kMix == 2: contraction indices [0, K1) come from the int8 tensor (K1 % 64 == 0),
+                                // [K1, K) from the bf16 tail tensor (LoRA A rows)
 };
 
-template <int CG>
+// kMix != 0 (mixed-input bf16 x int8, CG = 2 only): three rings instead of one. A: kStages x 16 KB (TMA -> MMA);
+// raw: kRawStages x 8 KB int8 boxes of the B half-tile (TMA -> converter warps); B: kBStages x 16 KB bf16 (converter
+// warps -> MMA). The raw ring is what hides the global-memory latency of B (small stages: it can be deep); the B ring
+// only has to cover the local conversion latency. With one ring of {A, B, raw} stages only 5 fit and every stage's
+// round trip contained TMA latency + conversion + MMA: 740-830 TFLOP/s against 1300 for the plain bf16 kernel.
+template <int CG, int kMix = 0>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBKBytes;               // 16 KB
   static constexpr int kBBytes = (kBN / CG) * kBKBytes;        // 32 KB / 16 KB
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRawBytes = kMix ? (kBN / CG) * 64 : 0; // 8 KB of int8
   static constexpr int kStages = CG == 1 ? 4 : 6;
+  static constexpr int kBStages = kMix ? 4 : kStages;          // kMix == 0: B lives in the A ring's stages
+  static constexpr int kRawStages = kMix ? 6 : 1;              // (1: keeps the dead kMix code of plain variants well-formed)
+  static constexpr int kStageBytes = kMix ? kABytes : kABytes + kBBytes;
+  static constexpr int kOffB = kStages * kStageBytes;          // kMix: B ring
+  static constexpr int kOffRaw = kOffB + (kMix ? kBStages * kBBytes : 0);
+  static constexpr int kOffAux = kOffRaw + kRawStages * kRawBytes;
   static constexpr int kAuxBytes = kBN * 4 + kBN * kMaxLoraRank * 4;  // col scale + lora_b (fp32)
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kStages * kStageBytes + kAuxBytes + kBarBytes + 1024;  // + align slack
+  static constexpr int kNumBars = 2 * kStages + 4 + 1 + 2 * kRawStages + (kMix ? 2 * kBStages : 0);
+  static constexpr int kBarBytes = kNumBars * 8 + 16;
+  static constexpr int kTotal = kOffAux + kAuxBytes + kBarBytes + 1024;  // + align slack
+  static_assert(kTotal <= 232448, "GEMM shared memory budget");
 };
+
+constexpr int kMixThreads = 640;        // + warps 12-19: int8 -> bf16 converters of the mixed-input variants
+constexpr int kMixPairs = 4;            // converter warp pairs, round-robin over the k-blocks
+// setmaxnreg budgets. The pool is what the CTA was launched with — 640 threads x 96 registers (launch bound) = 61440,
+// not the whole register file (a first version that summed to 65536 dead-locked in setmaxnreg.inc):
+// 128 x 40 (control) + 256 x 152 (epilogue) + 256 x 64 (converters) = 60416
+constexpr int kMixRegsCtrl = 40, kMixRegsEpi = 152, kMixRegsConv = 64;
+static_assert(128 * kMixRegsCtrl + 256 * kMixRegsEpi + 256 * kMixRegsConv <= kMixThreads * 96, "setmaxnreg pool");
+
+// Exact bf16 pairs of four signed bytes (one raw word): 0x43xx is the bf16 128 + (xx & 0x7f) when bit 7 of xx is
+// clear and the exponent's last bit when it is set, so with t = [0x43, b] per 16-bit lane,
+//   (t & 0x437f) - (t & 0x4380) = (128 + (b & 127)) - (128 | 256) = b as a signed byte, exactly — one byte permute,
+// two logic ops and one packed subtract per two elements, nothing on the conversion (XU) pipe.
+__device__ __forceinline__ uint32_t sub_bf16x2(uint32_t x, uint32_t y) {
+  uint32_t d;
+  asm("sub.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(y));
+  return d;
+}
+__device__ __forceinline__ void s8x4_to_bf16x4(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  const uint32_t t0 = __byte_perm(w, 0x43434343u, 0x4140), t1 = __byte_perm(w, 0x43434343u, 0x4342);
+  lo = sub_bf16x2(t0 & 0x437F437Fu, t0 & 0x43804380u);
+  hi = sub_bf16x2(t1 & 0x437F437Fu, t1 & 0x43804380u);
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // Tile order. One wave = `clusters` consecutive tiles (74 CTA pairs), and the operand panels a wave touches should stay
 // as few as possible: a group takes kGroupM tiles of one dimension and sweeps the other dimension completely, fastest
@@ -117,18 +181,31 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 // kRes: the residual term is read through the same one-group-ahead pipeline as kSwi's a / b (a 16-byte load per 8
 // columns issued right before its use exposed one global-load latency per 8 columns: +37..64 % kernel time on the
 // K = 4096 shapes, whose main loop is only ~16k cycles per tile). Requires resid != C.
-template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using S = GemmSmem<CG>;
+// kMix (mixed-input, bf16 activations x frozen int8 weight; CG = 2, 512 threads): tmB maps the INT8
+// weight as stored; the producer lands its raw [128 x 64]-byte box next to the stage, warps 12-15 expand it to bf16
+// into the B slot of the stage (same 128B-swizzled layout a TMA load of a bf16 operand would have produced) and signal
+// the leader CTA's conv barrier; the MMA issuer waits for both the A bytes and the converted B halves of the pair.
+//   kMix == 1: B8 [N, K] (K contiguous), K-major operand — weight-only forward (subclasses/int8.py:118): exact
+//              bf16(int8) values, the weight scale is applied to the bf16-rounded accumulator by the epilogue.
+//   kMix == 2: B8 [K1, N] (N contiguous) = the weight AS STORED seen from grad_input (subclasses/int8.py:127),
+//              MN-major operand, bf16(f32(w) * f32(k_scale[k])) — bit-identical to llamax_dequant_weight(transpose,
+//              apply_scale) — followed by an optional bf16 tail tmT [K - K1, N] (the LoRA A rows) loaded by TMA
+//              straight into the B slot. Neither a transposed nor a de-quantised copy of the weight exists.
+template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false, int kMix = 0>
+__global__ void __launch_bounds__(kMix ? kMixThreads : kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmT, const GemmParams p) {
+  static_assert(kMix == 0 || (!kInt8 && CG == 2 && !kMN), "mixed-input variants: bf16 accumulate, CTA pairs");
+  using S = GemmSmem<CG, kMix>;
   constexpr int kStages = S::kStages;
   constexpr int kElemPerRow = kInt8 ? 128 : 64;  // K elements per 128 B
   constexpr int kTileM = kBM * CG;               // rows per cluster tile
+  constexpr bool kBmn = kMN || kMix == 2;        // B operand is MN-major in shared memory
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* s_colscale = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
+  float* s_colscale = reinterpret_cast<float*>(smem + S::kOffAux);
   float* s_lorab = s_colscale + kBN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_lorab + kBN * kMaxLoraRank);
   uint64_t* full_bar = bars;
@@ -136,6 +213,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull_bar = bars + 2 * kStages;
   uint64_t* tempty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  // kMix rings: raw int8 boxes (this CTA's barriers) and converted B halves (full: the leader's barrier, arrived on by
+  // the converters of both CTAs; empty: MMA commit, multicast to both CTAs)
+  constexpr int kRawStages = S::kRawStages, kBStages = S::kBStages;
+  uint64_t* raw_full = bars + 2 * kStages + 5;
+  uint64_t* raw_empty = raw_full + kRawStages;
+  uint64_t* conv_bar = raw_empty + kRawStages;
+  uint64_t* bempty_bar = conv_bar + kBStages;
+  uint8_t* b_ring = smem + S::kOffB;
+  uint8_t* raw_ring = smem + S::kOffRaw;
 
   const int warp = threadIdx.x >> 5;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
@@ -161,6 +247,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp of every CTA in the group
     }
+    if constexpr (kMix != 0) {
+      for (int i = 0; i < kRawStages; ++i) {
+        mbar_init(&raw_full[i], 1);
+        mbar_init(&raw_empty[i], 2);       // the two warps of the converting pair
+      }
+      for (int i = 0; i < kBStages; ++i) {
+        mbar_init(&conv_bar[i], 2 * CG);   // one arrive per warp of the converting pair, both CTAs
+        mbar_init(&bempty_bar[i], 1);
+      }
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -171,6 +267,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int kb1 = kMix == 2 ? p.K1 / 64 : num_kb;   // k-blocks fed from the int8 tensor
+
+  // kMix register budget (512 threads start with 128 each; the epilogue variants need up to 168): every role branch
+  // below starts with its warpgroup's setmaxnreg
+  if (kMix != 0 && warp < 4) setmaxnreg_dec<kMixRegsCtrl>();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -187,7 +288,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          if constexpr (kMN) {
+          if constexpr (kMix != 0) {   // A only: the raw B boxes have their own producer (warp 3) and ring
+            if (is_leader) mbar_expect_tx(&full_bar[stage], S::kABytes * 2);
+            tma_load_2d_cg2(sa, &tmA, full_addr + stage * 8, kb * 64, row_a);
+          } else if constexpr (kMN) {
             // boxes of [64 k rows] x [64 mn elements = 128 B]: inner coordinate = mn index, outer = k
             constexpr int kBoxBytes = 64 * 128;
             if constexpr (CG == 1) {
@@ -227,9 +331,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ================================ MMA issuer ================================
     if (is_leader && elect_one()) {
       constexpr uint32_t idesc = kInt8 ? make_idesc(2, 1, kTileM, kBN)
-                                       : make_idesc(1, 1, kTileM, kBN, kMN ? 1 : 0, kMN ? 1 : 0);
+                                       : make_idesc(1, 1, kTileM, kBN, kMN ? 1 : 0, kBmn ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
+      int bstage = 0;
+      uint32_t bphase = 0;
       int local_tile = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
         const int as = local_tile & 1;
@@ -238,27 +344,176 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kBN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if constexpr (kMix != 0) MIX_MARK(0, kb + local_tile * num_kb, 0);
           mbar_wait(&full_bar[stage], phase);
+          if constexpr (kMix != 0) MIX_MARK(0, kb + local_tile * num_kb, 1);
+          if constexpr (kMix != 0) mbar_wait_cluster(&conv_bar[bstage], bphase);
+          if constexpr (kMix != 0) MIX_MARK(0, kb + local_tile * num_kb, 2);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
-          const uint32_t sb = sa + S::kABytes;
+          const uint32_t sb = kMix != 0 ? smem_u32(b_ring + bstage * S::kBBytes) : sa + S::kABytes;
           // K-major: 8-row atoms 1024 B apart, +32 B per k-step inside the swizzle atom (+2 in the addr >> 4 field);
           // MN-major: 64-element mn atoms one 8 KB box apart (LBO), 8-k-row groups 1024 B apart, +16 k rows = 2048 B
           const uint64_t adesc = make_smem_desc_sw128(sa, kMN ? 8192 : 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sb, kMN ? 8192 : 16, 1024);
-          constexpr int kStep = kMN ? 128 : 2;
+          const uint64_t bdesc = make_smem_desc_sw128(sb, kBmn ? 8192 : 16, 1024);
+          constexpr int kStepA = kMN ? 128 : 2, kStepB = kBmn ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < kBKBytes / 32; ++k)
-            umma_ss<kInt8, CG>(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb | k) != 0);
+            umma_ss<kInt8, CG>(d_tmem, adesc + kStepA * k, bdesc + kStepB * k, idesc, (kb | k) != 0);
           if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage], 3);
+          if constexpr (kMix != 0) {
+            umma_commit_cg2(&bempty_bar[bstage], 3);
+            if (++bstage == kBStages) { bstage = 0; bphase ^= 1; }
+            MIX_MARK(0, kb + local_tile * num_kb, 3);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if constexpr (CG == 1) umma_commit(&tfull_bar[as]); else umma_commit_cg2(&tfull_bar[as], 3);
       }
     }
     __syncwarp();
+  } else if (kMix != 0 && warp == 3) {
+    // ================================ raw int8 producer (kMix) ================================
+    if (elect_one()) {
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int tm, tn;
+        tile_coords(tile, num_m, num_n, p.group, tm, tn);
+        const int row_b = tn * kBN + cta_rank * (kBN / CG);
+        for (int kb = 0; kb < kb1; ++kb) {
+          mbar_wait(&raw_empty[rs], rphase ^ 1);
+          mbar_expect_tx(&raw_full[rs], S::kRawBytes);
+          if constexpr (kMix == 1) tma_load_2d(raw_ring + rs * S::kRawBytes, &tmB, &raw_full[rs], kb * 64, row_b);
+          else tma_load_2d(raw_ring + rs * S::kRawBytes, &tmB, &raw_full[rs], row_b, kb * 64);
+          if (++rs == kRawStages) { rs = 0; rphase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (kMix != 0 && warp >= 12) {
+    // ================================ int8 -> bf16 converters (kMix) ================================
+    // Four pairs of warps take the k-blocks round-robin: a pair expands one raw box (512 sixteen-byte chunks, 8 per
+    // thread) into a slot of the B ring. Measured with tools/mixed_gemm_trace.py, one k-block costs a pair ~700-800
+    // cycles of conversion (ALU-pipe bound: byte permutes and logic ops issue at half rate) plus ~600-900 cycles of
+    // serial overhead (two barrier waits, proxy fence, arrives, loop): two warps per scheduler overlap one pair's
+    // overhead with another pair's arithmetic. Lane mappings keep every quarter-warp on 128 contiguous raw bytes and on
+    // eight distinct 16-byte bank groups per store.
+    setmaxnreg_dec<kMixRegsConv>();
+    const int cw = warp - 12, cl = lane_id();
+    const int pair = cw >> 1;
+    const int t2 = (cw & 1) * 32 + cl;       // 0..63 within the pair
+    const uint32_t conv_addr = mapa_u32(smem_u32(&conv_bar[0]), 0);   // the leader's conv barriers
+    int it = 0;                               // k-block counter over all tiles of this CTA (B ring position)
+    int rit = 0;                              // ... counting only the k-blocks that come from the int8 tensor (raw ring)
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int tm, tn;
+      tile_coords(tile, num_m, num_n, p.group, tm, tn);
+      const int row_b = tn * kBN + cta_rank * (kBN / CG);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const bool from_raw = kb < kb1;
+        const int my_rit = rit;
+        rit += from_raw ? 1 : 0;
+        if ((it & (kMixPairs - 1)) != pair) continue;
+        const int bs = it % kBStages;
+        const uint32_t bphase = (it / kBStages) & 1;
+        const uint32_t sb = smem_u32(b_ring + bs * S::kBBytes);
+        if (from_raw) {
+          const int rs = my_rit % kRawStages;
+          const uint32_t rphase = (my_rit / kRawStages) & 1;
+          uint32_t sc[8];
+          if constexpr (kMix == 2) {   // this thread's eight k rows of the box: their scales, in flight during the waits
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sc[j] = *reinterpret_cast<const uint16_t*>(p.k_scale + kb * 64 + j * 8 + (t2 >> 3));
+          }
+          if (cw == 0 && cl == 0) MIX_MARK(1, it >> 2, 0);
+          mbar_wait(&raw_full[rs], rphase);
+          if (cw == 0 && cl == 0) MIX_MARK(1, it >> 2, 1);
+          mbar_wait(&bempty_bar[bs], bphase ^ 1);
+          if (cw == 0 && cl == 0) MIX_MARK(1, it >> 2, 2);
+          const uint32_t sraw = smem_u32(raw_ring + rs * S::kRawBytes);
+#if LX_MIX_EXP == 1
+          if (false)
+#endif
+#pragma unroll
+          for (int half = 0; half < 4; ++half) {
+            uint4 w[2];
+            if constexpr (kMix == 1) {
+              // raw rows of 64 B (n index), chunk c = 16 k values; bf16 tile rows of 128 B, chunk c -> chunks 2c, 2c+1
+              const int c = t2 & 3;
+#pragma unroll
+              for (int j = 0; j < 2; ++j) w[j] = lds_v4(sraw + ((half * 2 + j) * 16 + (t2 >> 2)) * 64 + c * 16);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int r = (half * 2 + j) * 16 + (t2 >> 2);
+                uint4 lo, hi;
+                s8x4_to_bf16x4(w[j].x, lo.x, lo.y); s8x4_to_bf16x4(w[j].y, lo.z, lo.w);
+                s8x4_to_bf16x4(w[j].z, hi.x, hi.y); s8x4_to_bf16x4(w[j].w, hi.z, hi.w);
+                const uint32_t row = sb + r * 128;
+                sts_v4(row + (((2 * c) ^ (r & 7)) << 4), lo);
+                sts_v4(row + (((2 * c + 1) ^ (r & 7)) << 4), hi);
+              }
+            } else {
+              // raw rows of 128 B (k index), chunk c = 16 n values -> box c / 4, bf16 chunks 2 (c % 4), + 1 of row kr.
+              // Lanes c >= 4 store their upper half first: within a quarter-warp the stores of box 0 and box 1 then
+              // fall on different bank groups.
+              const int c = t2 & 7;
+              const bool swp = (c & 4) != 0;
+              const int c2 = 2 * (c & 3) + (swp ? 1 : 0);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) w[j] = lds_v4(sraw + ((half * 2 + j) * 8 + (t2 >> 3)) * 128 + c * 16);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int kr = (half * 2 + j) * 8 + (t2 >> 3);
+                uint4 v = w[j];
+                if (swp) { const uint32_t a0 = v.x, a1 = v.y; v.x = v.z; v.y = v.w; v.z = a0; v.w = a1; }
+                uint4 lo, hi;
+                s8x4_to_bf16x4(v.x, lo.x, lo.y); s8x4_to_bf16x4(v.y, lo.z, lo.w);
+                s8x4_to_bf16x4(v.z, hi.x, hi.y); s8x4_to_bf16x4(v.w, hi.z, hi.w);
+                const uint32_t s16 = sc[half * 2 + j];
+                const uint32_t s2 = s16 | (s16 << 16);
+                lo.x = mul_bf16x2(lo.x, s2); lo.y = mul_bf16x2(lo.y, s2); lo.z = mul_bf16x2(lo.z, s2); lo.w = mul_bf16x2(lo.w, s2);
+                hi.x = mul_bf16x2(hi.x, s2); hi.y = mul_bf16x2(hi.y, s2); hi.z = mul_bf16x2(hi.z, s2); hi.w = mul_bf16x2(hi.w, s2);
+                const uint32_t row = sb + (c >> 2) * 8192 + kr * 128;
+                sts_v4(row + ((c2 ^ (kr & 7)) << 4), lo);
+                sts_v4(row + (((c2 ^ 1) ^ (kr & 7)) << 4), hi);
+              }
+            }
+          }
+          if (cw == 0 && cl == 0) MIX_MARK(1, it >> 2, 3);
+          fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          if (cw == 0 && cl == 0) MIX_MARK(1, it >> 2, 4);
+          __syncwarp();
+          if (cl == 0) {
+            mbar_arrive(&raw_empty[rs]);                      // the raw box has been read (loads completed above)
+            mbar_arrive_remote(&conv_bar[bs], 0);
+          }
+          if (cw == 0 && cl == 0) MIX_MARK(1, it >> 2, 5);
+        } else {
+          // tail k-block (kMix == 2): the bf16 LoRA-A rows go by TMA straight into this CTA's B slot, [64 k] x [64 n]
+          // boxes = the MN-major operand layout. The pair's first warp posts the transaction bytes on the leader's conv
+          // barrier together with its arrive; the second warp just arrives.
+          mbar_wait(&bempty_bar[bs], bphase ^ 1);
+          if (cl == 0) {
+            const uint32_t bar = conv_addr + bs * 8;
+            if ((cw & 1) == 0) {
+              asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar),
+                           "r"((uint32_t)S::kBBytes) : "memory");
+#pragma unroll
+              for (int i = 0; i < kBN / CG / 64; ++i)
+                tma_load_2d_cg2(b_ring + bs * S::kBBytes + i * 8192, &tmT, bar, row_b + i * 64, (kb - kb1) * 64);
+            } else {
+              mbar_arrive_remote(&conv_bar[bs], 0);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
+    if constexpr (kMix != 0) setmaxnreg_inc<kMixRegsEpi>();
     const int ew = warp & 3;                 // TMEM lanes [32*ew, 32*ew+32) (hardware: warp % 4)
     const int ch = (warp - 4) >> 2;          // column half of the tile handled by this warp: chunks 4*ch .. 4*ch+3
     const int et = threadIdx.x - 128;        // 0..255
@@ -597,8 +852,70 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, pp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA, pp);
   if (e != cudaSuccess) return set_cuda_error(e, "gemm: launch");
+  return 0;
+}
+
+// Mixed-input launch (always CTA pairs). kMix == 1: B8 int8 [N, K] pitch ldb8. kMix == 2: B8 int8 [K1, N] pitch ldb8,
+// tail bf16 [K - K1, N] pitch ldt (or null when K == K1).
+template <int kMix, int kRank, bool kSwi = false>
+static int launch_gemm_mix(const void* A, int64_t lda, const void* B8, int64_t ldb8, const void* tail, int64_t ldt,
+                           const GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<2, kMix>;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return set_error(LLAMAX_ERR_ARG, "gemm: empty problem");
+  if ((lda * 2) % 16 || ldb8 % 16 || (reinterpret_cast<uintptr_t>(A) % 16) || (reinterpret_cast<uintptr_t>(B8) % 16))
+    return set_error(LLAMAX_ERR_ARG, "mixed gemm: operand base / leading dimension must be 16-byte aligned");
+  if (!kSwi && (p.N % 8 || p.ldc % 8 || (reinterpret_cast<uintptr_t>(p.C) % 16)))
+    return set_error(LLAMAX_ERR_ARG, "gemm: N and ldc must be multiples of 8, C 16-byte aligned");
+  if (p.resid && (p.ldr % 8 || reinterpret_cast<uintptr_t>(p.resid) % 16))
+    return set_error(LLAMAX_ERR_ARG, "gemm: residual must be 16-byte aligned with ldr % 8 == 0");
+  if (p.lora_rank < 0 || p.lora_rank > kMaxLoraRank || (p.lora_rank % 4))
+    return set_error(LLAMAX_ERR_ARG, "gemm: lora rank must be a multiple of 4 in [0, 16]");
+  CUtensorMap tmA, tmB, tmT;
+  int rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, p.K, p.M, lda, 64, kBM);
+  if (rc) return rc;
+  if constexpr (kMix == 1) {
+    rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B8, p.K, p.N, ldb8, 64, kBN / 2, false);
+    if (rc) return rc;
+    tmT = tmA;
+  } else {
+    if (p.K1 <= 0 || p.K1 % 64 || p.K1 > p.K || p.K - p.K1 > 64 || !p.k_scale)
+      return set_error(LLAMAX_ERR_ARG, "mixed gemm: K1 must be a positive multiple of 64, the tail at most 64 rows");
+    if ((p.K > p.K1) != (tail != nullptr))
+      return set_error(LLAMAX_ERR_ARG, "mixed gemm: tail tensor and K - K1 disagree");
+    rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B8, p.N, p.K1, ldb8, kBN / 2, 64, false);
+    if (rc) return rc;
+    if (tail != nullptr) {
+      if ((ldt * 2) % 16 || reinterpret_cast<uintptr_t>(tail) % 16)
+        return set_error(LLAMAX_ERR_ARG, "mixed gemm: tail must be 16-byte aligned with a pitch multiple of 8");
+      rc = make_tmap_2d(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tail, p.N, p.K - p.K1, ldt, 64, 64);
+      if (rc) return rc;
+    } else {
+      tmT = tmA;
+    }
+  }
+  auto kern = gemm_kernel<false, 2, kRank, false, kSwi, false, kMix>;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::kTotal, "mixed gemm: cudaFuncSetAttribute"))) return rc;
+  const int num_m = (p.M + 2 * kBM - 1) / (2 * kBM), num_n = (p.N + kBN - 1) / kBN;
+  const int clusters = std::min(sm_count() / 2, num_m * num_n);
+  GemmParams pp = p;
+  static const int forced = getenv("LLAMAX_GEMM_GROUP") ? atoi(getenv("LLAMAX_GEMM_GROUP")) : 0;   // A/B switch
+  pp.group = forced != 0 ? forced : (num_m >= num_n ? -kGroupM : kGroupM);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(kMixThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmT, pp);
+  if (e != cudaSuccess) return set_cuda_error(e, "mixed gemm: launch");
   return 0;
 }
 
@@ -1293,6 +1610,12 @@ using namespace lx;
 
 extern "C" {
 
+#ifdef LX_MIX_TRACE
+int llamax_debug_mix_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_mix_trace, sizeof(long long) * 2 * 64 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 int llamax_set_gemm_cta_group(int cg) {
   if (cg != 1 && cg != 2) return set_error(LLAMAX_ERR_ARG, "cta group must be 1 or 2");
   g_gemm_cg = cg;
@@ -1479,6 +1802,58 @@ int llamax_bf16_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B, int64
   if (r == 0) return launch_gemm_r<false, 1, 0, false, true>(A, lda, B, ldb, p, st);
   if (r == 8) return launch_gemm_r<false, 1, 8, false, true>(A, lda, B, ldb, p, st);
   return launch_gemm_r<false, 1, 16, false, true>(A, lda, B, ldb, p, st);
+}
+
+int llamax_bf16_int8_gemm(const void* A, int64_t lda, const void* B8, int64_t ldb8, const void* b_scale, int b_layout,
+                          const void* tail, int64_t ldt, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                          int64_t K1, const llamax_epilogue_t* epi, void* stream) {
+  if (!A || !B8 || !C || !b_scale) return set_error(LLAMAX_ERR_ARG, "bf16_int8_gemm: null pointer");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.C = C; p.ldc = ldc;
+  fill_epilogue(p, epi);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int r = p.lora_rank <= 0 ? 0 : p.lora_rank <= 8 ? 8 : 16;
+  if (b_layout == 0) {   // weight-only forward: bf16(acc) * scale[n]
+    if (tail != nullptr || K1 != K) return set_error(LLAMAX_ERR_ARG, "bf16_int8_gemm: layout 0 has no tail (K1 == K)");
+    p.col_scale = static_cast<const __nv_bfloat16*>(b_scale);
+    p.flags = 2;
+    if (r == 0) return launch_gemm_mix<1, 0>(A, lda, B8, ldb8, nullptr, 0, p, st);
+    if (r == 8) return launch_gemm_mix<1, 8>(A, lda, B8, ldb8, nullptr, 0, p, st);
+    return launch_gemm_mix<1, 16>(A, lda, B8, ldb8, nullptr, 0, p, st);
+  }
+  if (b_layout != 1) return set_error(LLAMAX_ERR_ARG, "bf16_int8_gemm: b_layout must be 0 or 1");
+  p.k_scale = static_cast<const __nv_bfloat16*>(b_scale);
+  p.K1 = (int)K1;
+  if (r == 0) return launch_gemm_mix<2, 0>(A, lda, B8, ldb8, tail, ldt, p, st);
+  if (r == 8) return launch_gemm_mix<2, 8>(A, lda, B8, ldb8, tail, ldt, p, st);
+  return launch_gemm_mix<2, 16>(A, lda, B8, ldb8, tail, ldt, p, st);
+}
+
+int llamax_bf16_int8_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B8, int64_t ldb8, const void* k_scale,
+                                     int64_t M, int64_t N, int64_t K, const llamax_epilogue_t* epi, const void* ab,
+                                     int64_t ld_ab, void* dab, int64_t ld_dab, void* g, void* stream) {
+  if (!A || !B8 || !k_scale || !ab || !dab) return set_error(LLAMAX_ERR_ARG, "bf16_int8_gemm_swiglu_bwd: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(LLAMAX_ERR_ARG, "gemm: empty problem");
+  if (N % 16 || ld_ab % 8 || ld_dab % 8 || ld_ab < 2 * N || ld_dab < 2 * N)
+    return set_error(LLAMAX_ERR_ARG, "bf16_int8_gemm_swiglu_bwd: N % 16 == 0 and pitches % 8 == 0, >= 2N required");
+  if ((reinterpret_cast<uintptr_t>(ab) | reinterpret_cast<uintptr_t>(dab) | reinterpret_cast<uintptr_t>(g)) % 16)
+    return set_error(LLAMAX_ERR_ARG, "bf16_int8_gemm_swiglu_bwd: ab / dab / g must be 16-byte aligned");
+  if (epi != nullptr && epi->resid != nullptr)
+    return set_error(LLAMAX_ERR_ARG, "bf16_int8_gemm_swiglu_bwd: no residual term in this epilogue");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  fill_epilogue(p, epi);
+  p.swi_ab = static_cast<const __nv_bfloat16*>(ab); p.ld_ab = ld_ab;
+  p.swi_dab = static_cast<__nv_bfloat16*>(dab); p.ld_dab = ld_dab;
+  p.swi_g = static_cast<__nv_bfloat16*>(g);
+  p.k_scale = static_cast<const __nv_bfloat16*>(k_scale);
+  p.K1 = (int)K;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int r = p.lora_rank <= 0 ? 0 : p.lora_rank <= 8 ? 8 : 16;
+  if (r == 0) return launch_gemm_mix<2, 0, true>(A, lda, B8, ldb8, nullptr, 0, p, st);
+  if (r == 8) return launch_gemm_mix<2, 8, true>(A, lda, B8, ldb8, nullptr, 0, p, st);
+  return launch_gemm_mix<2, 16, true>(A, lda, B8, ldb8, nullptr, 0, p, st);
 }
 
 int llamax_bf16_gemm_tn(const void* At, int64_t ldat, const void* Bt, int64_t ldbt, void* C, int64_t ldc, int64_t M,

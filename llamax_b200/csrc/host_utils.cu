@@ -95,13 +95,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* ptr, int64_t inner, int64_t outer,
-                 int64_t ld, int box_inner, int box_outer) {
+                 int64_t ld, int box_inner, int box_outer, bool swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(LLAMAX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr; key.d[0] = inner; key.d[1] = outer; key.s[0] = ld; key.box[0] = box_inner; key.box[1] = box_outer;
-  key.dt = (int)dt; key.esz = esz; key.rank = 2;
+  key.dt = (int)dt; key.esz = esz; key.rank = swizzle128 ? 2 : -2;   // the swizzle mode is part of the key
   TmapSlot* slot = tmap_slot(key);
   if (slot->valid && slot->key == key) {
     *map = slot->map;
@@ -112,7 +112,8 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* 
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
     snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(2d) failed: CUresult %d (inner=%lld outer=%lld ld=%lld)",

@@ -11,9 +11,10 @@ int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
 int sm_count();
 
-// rank-2 tensor map: dims {inner, outer}, row pitch ld (elements), box {box_inner, box_outer}, 128B swizzle.
+// rank-2 tensor map: dims {inner, outer}, row pitch ld (elements), box {box_inner, box_outer}, 128B swizzle
+// (swizzle128 = false: the box lands in shared memory as plain rows of box_inner elements).
 int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* ptr, int64_t inner, int64_t outer,
-                 int64_t ld, int box_inner, int box_outer);
+                 int64_t ld, int box_inner, int box_outer, bool swizzle128 = true);
 
 // rank-4 tensor map over a [d3, d2, d1, d0] view (d0 contiguous) with element strides s1, s2, s3.
 int make_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* ptr, const int64_t dims[4],

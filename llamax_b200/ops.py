@@ -193,6 +193,81 @@ def bf16_gemm_swiglu_bwd(A: Tensor, B: Tensor, a: Tensor, b: Tensor, *, out_ab: 
     return out_ab[:, :F], out_ab[:, F : 2 * F], g
 
 
+def bf16_int8_gemm(A: Tensor, W8: Tensor, w_scale: Tensor, *, out: Tensor | None = None, lora_h=None, lora_b=None,
+                   lora_scale=1.0, resid=None) -> Tensor:
+    """Weight-only forward, mixed-input (subclasses/int8.py:118): C = bf16(A[M,K] @ bf16(W8[N,K])^T) * w_scale[n]
+    (+ LoRA + residual). The int8 weight is expanded to bf16 inside the GEMM's shared-memory pipeline: no de-quantised
+    copy of W exists in HBM. Same arithmetic (and bits) as dequant_weight + bf16_gemm(round_before_scale=True)."""
+    lib, st = _prep(A)
+    assert A.dtype is torch.bfloat16 and W8.dtype is torch.int8 and A.dim() == 2 and W8.dim() == 2
+    assert A.stride(1) == 1 and W8.stride(1) == 1 and A.shape[1] == W8.shape[1]
+    M, K = A.shape
+    N = W8.shape[0]
+    w_scale = w_scale.reshape(-1).contiguous()
+    assert w_scale.dtype is torch.bfloat16 and w_scale.numel() == N
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
+    assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
+    _call(lib, "llamax_bf16_int8_gemm",
+          (_p(A), A.stride(0), _p(W8), W8.stride(0), _p(w_scale), 0, None, 0, _p(out), out.stride(0), M, N, K, K,
+           ctypes.byref(ep) if ep is not None else None, st,),
+          "bf16_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))
+    return out
+
+
+def _mixed_bwd_operands(A: Tensor, W8: Tensor, k_scale: Tensor, tail):
+    assert A.dtype is torch.bfloat16 and W8.dtype is torch.int8 and A.dim() == 2 and W8.dim() == 2
+    assert A.stride(1) == 1 and W8.stride(1) == 1
+    K1, N = W8.shape
+    k_scale = k_scale.reshape(-1).contiguous()
+    assert k_scale.dtype is torch.bfloat16 and k_scale.numel() == K1
+    rt = 0
+    if tail is not None:
+        assert tail.dtype is torch.bfloat16 and tail.dim() == 2 and tail.stride(1) == 1 and tail.shape[1] == N
+        rt = tail.shape[0]
+    assert A.shape[1] == K1 + rt, "A must be [M, K1 + tail rows]"
+    return K1, N, rt, k_scale
+
+
+def bf16_int8_gemm_bwd(A: Tensor, W8: Tensor, k_scale: Tensor, *, tail: Tensor | None = None, out: Tensor | None = None,
+                       lora_h=None, lora_b=None, lora_scale=1.0) -> Tensor:
+    """grad_input, mixed-input (subclasses/int8.py:127): C[M,N] = A[:, :K1] @ (k_scale[:, None] * W8[K1,N]) (+ A[:, K1:]
+    @ tail[K-K1, N]) (+ LoRA epilogue). W8 is the frozen weight AS STORED ([out_features, in_features]: the contraction
+    runs over out_features), or row-concatenated weights that share their input; tail = the LoRA A rows whose dh columns
+    follow the gradient blocks in A. Bit-identical to bf16_gemm(A, [dequant_weight(W8, k_scale, transpose, scale) | tail^T])."""
+    lib, st = _prep(A)
+    K1, N, rt, k_scale = _mixed_bwd_operands(A, W8, k_scale, tail)
+    M, K = A.shape
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
+    assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, None)
+    _call(lib, "llamax_bf16_int8_gemm",
+          (_p(A), A.stride(0), _p(W8), W8.stride(0), _p(k_scale), 1, _p(tail), tail.stride(0) if tail is not None else 0,
+           _p(out), out.stride(0), M, N, K, K1, ctypes.byref(ep) if ep is not None else None, st,),
+          "bf16_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))
+    return out
+
+
+def bf16_int8_gemm_swiglu_bwd(A: Tensor, W8: Tensor, k_scale: Tensor, a: Tensor, b: Tensor, *, out_ab: Tensor,
+                              want_g: bool = False, lora_h=None, lora_b=None, lora_scale=1.0):
+    """bf16_gemm_swiglu_bwd with the mixed-input B operand of bf16_int8_gemm_bwd (W8 = w2 as stored, [D, F])."""
+    lib, st = _prep(A)
+    K1, F, rt, k_scale = _mixed_bwd_operands(A, W8, k_scale, None)
+    M, K = A.shape
+    assert a.shape == (M, F) and b.shape == (M, F) and a.stride(1) == 1 and a.stride(0) == b.stride(0)
+    assert b.data_ptr() == a.data_ptr() + 2 * F, "a | b must be adjacent column blocks of one buffer"
+    assert out_ab.dtype is torch.bfloat16 and out_ab.shape[0] == M and out_ab.shape[1] >= 2 * F and out_ab.stride(1) == 1
+    g = torch.empty(M, F, device=A.device, dtype=torch.bfloat16) if want_g else None
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, None)
+    _call(lib, "llamax_bf16_int8_gemm_swiglu_bwd",
+          (_p(A), A.stride(0), _p(W8), W8.stride(0), _p(k_scale), M, F, K, ctypes.byref(ep) if ep is not None else None,
+           _p(a), a.stride(0), _p(out_ab), out_ab.stride(0), _p(g), st,),
+          "bf16_gemm", 2.0 * M * F * K, 0.0, shape=(M, F, K))
+    return out_ab[:, :F], out_ab[:, F : 2 * F], g
+
+
 def bf16_gemm_tn(At: Tensor, Bt: Tensor, *, out: Tensor | None = None) -> Tensor:
     """C[M,N] = At[K,M]^T @ Bt[K,N] (bf16 in/out, fp32 accumulate): the weight-gradient form, both operands consumed as
     stored (rows = the contraction index; row pitches may be smaller than the row length, i.e. overlapping rows)."""

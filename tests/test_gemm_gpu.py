@@ -254,3 +254,91 @@ def test_bf16_gemm_wide_tile_path(M, N, K):
     out = torch.full((M + 8, N + 8), 7.0, device="cuda", dtype=torch.bfloat16)
     ops.bf16_gemm(a, b, out=out[:M, :N])
     assert torch.equal(out[:M, :N], c) and bool((out[M:] == 7).all()) and bool((out[:, N:] == 7).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# mixed-input GEMMs (bf16 activations x int8 weight expanded in shared memory): SURVEY K4 / K5
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,Rk,resid", [(256, 256, 64, 0, False), (512, 768, 1024, 8, True), (300, 264, 208, 0, False),
+                                            (1000, 1032, 4096, 16, True), (77, 6144, 512, 8, False),
+                                            (4096, 4096, 448, 0, False)])   # > 74 tiles: several tiles per CTA pair
+def test_mixed_weight_only_forward_equals_dequant_then_gemm(M, N, K, Rk, resid):
+    """int8.py:118: bf16(x @ bf16(W8)^T) * scale. The in-GEMM int8 -> bf16 expansion is exact, so the mixed kernel must
+    reproduce dequant_weight + bf16_gemm(round_before_scale) bit for bit, and the reference formula within 1e-2."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    W8 = torch.randint(-128, 128, (N, K), dtype=torch.int8, generator=g).cuda()
+    sw = (torch.rand(N, generator=g) * 0.01 + 1e-3).bfloat16().cuda()
+    kw = {}
+    if Rk:
+        kw.update(lora_h=torch.randn(M, Rk, generator=g).bfloat16().cuda(),
+                  lora_b=(torch.randn(N, Rk, generator=g) * 0.05).bfloat16().cuda(), lora_scale=2.0)
+    if resid:
+        kw["resid"] = torch.randn(M, N, generator=g).bfloat16().cuda()
+    canary = torch.full((M + 2, N + 16), 7.0, device="cuda", dtype=torch.bfloat16)
+    out = ops.bf16_int8_gemm(x, W8, sw, out=canary[1 : M + 1, 8 : N + 8], **kw)
+    ref = ops.bf16_gemm(x, ops.dequant_weight(W8, None, transpose=False, apply_scale=False), col_scale=sw,
+                        round_before_scale=True, **kw)
+    assert torch.equal(out, ref)
+    assert (canary[0] == 7).all() and (canary[-1] == 7).all() and (canary[:, :8] == 7).all() and (canary[:, N + 8 :] == 7).all()
+    if not kw:
+        y = (x.cpu().float() @ W8.cpu().float().T).bfloat16() * sw.cpu()
+        assert rel_err(out, y.float()) <= 1e-2
+
+
+@pytest.mark.parametrize("M,N,K1,Rt,Rk", [(256, 256, 64, 0, 0), (512, 768, 1024, 24, 0), (300, 272, 192, 8, 0),
+                                          (1000, 528, 4096, 0, 8), (2048, 4096, 6144, 24, 0), (130, 512, 8192, 16, 16)])
+def test_mixed_grad_input_equals_dequant_then_gemm(M, N, K1, Rt, Rk):
+    """int8.py:127 with the weight consumed AS STORED ([out, in] int8, rows = contraction index), the per-row scale folded
+    in during the expansion, and the LoRA A rows as a bf16 tail: bit-identical to the de-quantised-operand GEMM."""
+    g = torch.Generator().manual_seed(M + N + K1 + Rt)
+    K = K1 + Rt
+    pitch = (K + 63) // 64 * 64
+    dy = torch.zeros(M, pitch).bfloat16().cuda()[:, :K]
+    dy.copy_(torch.randn(M, K, generator=g).bfloat16())
+    W8 = torch.randint(-128, 128, (K1, N), dtype=torch.int8, generator=g).cuda()
+    s = (torch.rand(K1, generator=g) * 0.01 + 1e-3).bfloat16().cuda()
+    tail = (torch.randn(Rt, N, generator=g) * 0.05).bfloat16().cuda() if Rt else None
+    kw = {}
+    if Rk:
+        kw.update(lora_h=torch.randn(M, Rk, generator=g).bfloat16().cuda(),
+                  lora_b=(torch.randn(N, Rk, generator=g) * 0.05).bfloat16().cuda(), lora_scale=1.0)
+    out = ops.bf16_int8_gemm_bwd(dy, W8, s, tail=tail, **kw)
+    wt = torch.zeros(N, pitch, device="cuda", dtype=torch.bfloat16)[:, :K]
+    ops.dequant_weight(W8, s, transpose=True, apply_scale=True, out=wt[:, :K1])
+    if Rt:
+        wt[:, K1:].copy_(tail.t())
+    ref = ops.bf16_gemm(dy, wt, **kw)
+    assert torch.equal(out, ref)
+    if not kw:
+        y = dy.cpu().float() @ torch.cat([W8.cpu().float() * s.cpu().float()[:, None]] + ([tail.cpu().float()] if Rt else []))
+        assert rel_err(out, y) <= 1e-2
+
+
+@pytest.mark.parametrize("M,F,K,R", [(384, 512, 256, 8), (300, 1792, 512, 0)])
+def test_mixed_grad_input_with_swiglu_backward_epilogue(M, F, K, R):
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(M, K, generator=g).bfloat16().cuda()
+    W8 = torch.randint(-128, 128, (K, F), dtype=torch.int8, generator=g).cuda()
+    s = (torch.rand(K, generator=g) * 0.01 + 1e-3).bfloat16().cuda()
+    ab = torch.randn(M, 2 * F, generator=g).bfloat16().cuda()
+    kw = {}
+    if R:
+        kw.update(lora_h=torch.randn(M, R, generator=g).bfloat16().cuda(),
+                  lora_b=(torch.randn(F, R, generator=g) * 0.05).bfloat16().cuda(), lora_scale=1.0)
+    o1 = torch.empty(M, 2 * F + 16, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    da, db, g1 = ops.bf16_int8_gemm_swiglu_bwd(dy, W8, s, ab[:, :F], ab[:, F:], out_ab=o1, want_g=True, **kw)
+    wt = ops.dequant_weight(W8, s, transpose=True, apply_scale=True)
+    da2, db2, g2 = ops.bf16_gemm_swiglu_bwd(dy, wt, ab[:, :F], ab[:, F:], out_ab=o2, want_g=True, **kw)
+    assert torch.equal(da, da2) and torch.equal(db, db2) and torch.equal(g1, g2)
+
+
+def test_mixed_gemm_bad_arguments_raise():
+    from llamax_b200._lib import LlamaxError
+
+    x = torch.randn(128, 96).bfloat16().cuda()
+    W8 = torch.zeros(96, 256, dtype=torch.int8).cuda()
+    s = torch.ones(96).bfloat16().cuda()
+    with pytest.raises(LlamaxError):   # K1 must be a multiple of 64
+        ops.bf16_int8_gemm_bwd(x, W8, s)

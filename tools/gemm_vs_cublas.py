@@ -62,25 +62,30 @@ def sustained(fn, secs=2.0):
     return e0.elapsed_time(e1) / reps, c.summary()
 
 
-shapes = [(16384, 4096, 28688), (16384, 14336, 4096), (16384, 4096, 6168), (16384, 4096, 4096), (8192, 8192, 8192)]
-if len(sys.argv) > 1 and sys.argv[1] == "ncu":
-    M, N, K = shapes[0]
-    a = torch.randn(M, K + 48, device=dev).bfloat16()[:, :K]
-    b = torch.randn(N, K + 48, device=dev).bfloat16()[:, :K]
-    for _ in range(2):
-        ops.bf16_gemm(a, b)
-        torch.matmul(a, b.t())
-    torch.cuda.synchronize()
-    print("ok")
-    sys.exit(0)
+def main():
+    shapes = [(16384, 4096, 28688), (16384, 14336, 4096), (16384, 4096, 6168), (16384, 4096, 4096), (8192, 8192, 8192)]
+    if len(sys.argv) > 1 and sys.argv[1] == "ncu":
+        M, N, K = shapes[0]
+        a = torch.randn(M, K + 48, device=dev).bfloat16()[:, :K]
+        b = torch.randn(N, K + 48, device=dev).bfloat16()[:, :K]
+        for _ in range(2):
+            ops.bf16_gemm(a, b)
+            torch.matmul(a, b.t())
+        torch.cuda.synchronize()
+        print("ok")
+        sys.exit(0)
 
-for (M, N, K) in shapes:
-    Kp = (K + 63) // 64 * 64
-    a = torch.randn(M, Kp, device=dev).bfloat16()[:, :K]          # 128-byte pitches, as the fused block allocates them
-    b = torch.randn(N, Kp, device=dev).bfloat16()[:, :K]
-    fl = 2.0 * M * N * K
-    for name, fn in (("llamax_b200", lambda: ops.bf16_gemm(a, b)), ("cuBLAS", lambda: torch.matmul(a, b.t()))):
-        tb = burst(fn)
-        ts, clk = sustained(fn)
-        print(f"[{M},{N},{K}] {name:12s} burst {fl / tb / 1e9:7.0f} TF/s  sustained {fl / ts / 1e9:7.0f} TF/s  [{clk}]", flush=True)
-    del a, b
+    for (M, N, K) in shapes:
+        Kp = (K + 63) // 64 * 64
+        a = torch.randn(M, Kp, device=dev).bfloat16()[:, :K]          # 128-byte pitches, as the fused block allocates them
+        b = torch.randn(N, Kp, device=dev).bfloat16()[:, :K]
+        fl = 2.0 * M * N * K
+        for name, fn in (("llamax_b200", lambda: ops.bf16_gemm(a, b)), ("cuBLAS", lambda: torch.matmul(a, b.t()))):
+            tb = burst(fn)
+            ts, clk = sustained(fn)
+            print(f"[{M},{N},{K}] {name:12s} burst {fl / tb / 1e9:7.0f} TF/s  sustained {fl / ts / 1e9:7.0f} TF/s  [{clk}]", flush=True)
+        del a, b
+
+
+if __name__ == "__main__":
+    main()
