@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--ref-tokens", type=int, default=512, help="reference arm: positions of the bounded sample per step")
     ap.add_argument("--int8-grad-input", action="store_true",
                     help="OPT-IN, NON-PARITY: grad_input on the int8 tensor path (SURVEY 8 f4); never the headline")
+    ap.add_argument("--mixed-gemm", action="store_true",
+                    help="opt-in: mixed-input bf16 x int8 GEMMs (SURVEY K4/K5) for the weight-only forward and every "
+                         "grad_input; identical results, no bf16 weight operands in HBM")
     return ap.parse_args()
 
 
@@ -365,6 +368,10 @@ def run_ours(args):
         from llamax_b200.modelling import fused_block as _fb
 
         _fb.set_int8_grad_input(True)
+    if args.mixed_gemm:
+        from llamax_b200.modelling import fused_block as _fb
+
+        _fb.set_mixed_gemm(True)
     warmup = max(args.warmup, 3)
     head_wl = "speech" if args.workload == "speech" else "text"
     main = run_workload(args, head_wl, rank, world, device, args.steps, warmup)
@@ -449,6 +456,8 @@ def run_ours(args):
         "config": {"workload": workload_label(args, head_wl, positions),
                    "layers": args.layers, "global_batch": args.batch * world, "seq_len": main["seq"],
                    "int8_mode": "weight-only" if args.weight_only else "dynamic_int8_act", "parallelism": f"dp{world}",
+                   **({"mixed_gemm": "opt-in: bf16 x int8 mixed-input GEMMs (weights expanded inside the GEMM)"}
+                      if args.mixed_gemm else {}),
                    **({"NON_PARITY_OPT_IN": "int8 grad_input (gradients quantised to 8 bit per row): not the reference's "
                                             "numerics, not a headline number"} if args.int8_grad_input else {}),
                    "l2": "per-step working set (>10 GB activations + 7 GB weights) far exceeds the 126 MB L2; no flush needed",

@@ -72,7 +72,37 @@ _INT8_GRAD = os.environ.get("LLAMAX_INT8_GRAD_INPUT", "0") == "1"
 # A/B switch (benchmarking only): "0" runs the w2 grad_input GEMM and the SwiGLU backward as two launches (identical
 # results); default: SwiGLU backward as the GEMM's epilogue, the [M, F] gradient dg never exists in HBM
 _FUSE_SWIGLU_BWD = os.environ.get("LLAMAX_FUSE_SWIGLU_BWD", "1") != "0"
+# OPT-IN: mixed-input GEMMs: the int8 weight is expanded to bf16 INSIDE the GEMM (converter warps between
+# the TMA ring and the tensor core), so the weight-only forward needs no de-quantised scratch and grad_input needs no
+# (scale * W)^T operand at all — wo and w2 are consumed as stored, q|k|v and w1|w3 as row-concatenated int8 copies
+# (4.5 GB at 8B instead of 14.1 GB of bf16 operands). Results are bit-identical to the default path. Default off: at the
+# 1 kW cap the kernel reaches 0.83-0.86 (grad_input) / 0.92-0.97 (forward) of the bf16-operand GEMM — the conversion's
+# integer work costs more than the de-quantisation pass it removes (profiles/r2_mixed_gemm_perf.txt).
+_MIXED = os.environ.get("LLAMAX_MIXED_GEMM", "0") == "1"
 _ones: dict = {}
+
+
+def set_mixed_gemm(on: bool) -> None:
+    global _MIXED
+    _MIXED = bool(on)
+
+
+def _mixed_group_operand(cache: dict, key: str, specs):
+    """Resident int8 [sum N, K] = [W_1; W_2; ...] (rows = the contraction index of grad_input) + concatenated scales; a
+    single weight is used as stored (no copy). None when the shape does not fit the kernel (sum N % 64, K % 16)."""
+    n_total = sum(s.N for s in specs)
+    if n_total % 64 or specs[0].K % 16:
+        return None
+    if len(specs) == 1:
+        return specs[0].w8, specs[0].ws.reshape(-1)
+    sig = tuple((s.w8.data_ptr(), s.w8._version, s.ws.data_ptr(), s.ws._version) for s in specs)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1], hit[2]
+    w8cat = torch.cat([s.w8 for s in specs], 0).contiguous()
+    scat = torch.cat([s.ws.reshape(-1) for s in specs]).contiguous()
+    cache[key] = (sig, w8cat, scat)
+    return w8cat, scat
 
 
 def set_int8_grad_input(on: bool) -> None:
@@ -195,6 +225,8 @@ def _linear(spec: LinearSpec, x_bf16, x_q8, x_qs, h, out=None, resid=None):
         ep["resid"] = resid
     if spec.dynamic:
         return ops.int8_gemm_dequant(x_q8, spec.w8, x_qs, spec.ws, out=out, **ep)
+    if _MIXED and spec.K % 16 == 0:
+        return ops.bf16_int8_gemm(x_bf16, spec.w8, spec.ws, out=out, **ep)
     wd = ops.dequant_weight(spec.w8, None, transpose=False, apply_scale=False,
                             out=_get_scratch(x_bf16.device, spec.N * spec.K)[: spec.N * spec.K].view(spec.N, spec.K))
     return ops.bf16_gemm(x_bf16, wd, col_scale=spec.ws, round_before_scale=True, out=out, **ep)
@@ -270,7 +302,7 @@ def _ffn_up(x1: Tensor, w_fn: Tensor, s1: LinearSpec, s3: LinearSpec, dynamic: b
 
 
 def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tensor | None, a_placed: bool, prep, sink,
-                    need_dx=True, i8=None):
+                    need_dx=True, i8=None, mixed=None):
     """Backward of linears that share one input. dy_cat [M, n_total + r_total]: gradient blocks already written in
     the first n_total columns (block i = specs[i].N columns); the LoRA dh columns are filled here. wt: the
     [K, n_total + r_total] grad_input operand (frozen part valid; A^T columns valid iff a_placed).
@@ -285,7 +317,7 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tenso
         if s.R > 0:
             c0 = n_total + r_off
             bt, at, ht = prep[id(s)]
-            if not a_placed and i8 is None:
+            if not a_placed and i8 is None and mixed is None:
                 wt[:, c0 : c0 + s.R].copy_(at)
             # one pass over dy_i:  dh_i = scale * dy_i @ B_i -> columns [c0, c0+R) of dy_cat;  dB = scale * dy_i^T h_i
             dB = _lora_dh_dB(dy_i, bt, ht, dy_cat[:, c0 : c0 + s.R], s.lora_scale, dht[r_off : r_off + s.R])  # [N, R] fp32
@@ -306,10 +338,13 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tenso
     if i8 is not None:   # opt-in int8 grad_input: (w8t, scat, at_cat [K, r_total] | None)
         dh = dy_cat[:, n_total:] if r_total > 0 else None
         return _grad_input_i8(dy_cat[:, :n_total], i8[0], i8[1], dh, i8[2]), lora_grads
+    if mixed is not None:   # opt-in mixed-input GEMM: int8 rows as stored + the LoRA A rows as the bf16 tail
+        tail = torch.cat([s.lora_a.detach() for s in specs if s.R > 0], 0) if r_total > 0 else None
+        return ops.bf16_int8_gemm_bwd(dy_cat, mixed[0], mixed[1], tail=tail), lora_grads
     return ops.bf16_gemm(dy_cat, wt), lora_grads
 
 
-def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, wt: Tensor | None, prep, sink, i8=None):
+def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, wt: Tensor | None, prep, sink, i8=None, mixed=None):
     """Backward of one linear whose incoming gradient buffer we do not own: LoRA term in the GEMM epilogue."""
     if spec.R > 0:
         bt, at, ht = prep[id(spec)]
@@ -318,12 +353,16 @@ def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, wt: Tensor | No
         dB = sink.emit(_lora_dh_dB(dy, bt, ht, dh, spec.lora_scale, dht), False, spec.lora_b.dtype)  # dh, dh^T, dB
         if i8 is not None:
             dx = _grad_input_i8(dy, i8[0], i8[1], dh, at)
+        elif mixed is not None:
+            dx = ops.bf16_int8_gemm_bwd(dy, mixed[0], mixed[1], lora_h=dh, lora_b=at, lora_scale=1.0)
         else:
             dx = ops.bf16_gemm(dy, wt, lora_h=dh, lora_b=at, lora_scale=1.0)
         dA = sink.emit(ops.lora_wgrad(x_in, None, 1.0, Ht=dht), True, spec.lora_a.dtype)
         return dx, (dA, dB)
     if i8 is not None:
         return _grad_input_i8(dy, i8[0], i8[1], None, None), None
+    if mixed is not None:
+        return ops.bf16_int8_gemm_bwd(dy, mixed[0], mixed[1]), None
     return ops.bf16_gemm(dy, wt), None
 
 
@@ -421,6 +460,12 @@ class FusedDecoderBlock(torch.autograd.Function):
         # that the LoRA columns can be refreshed by the batched prepare below; the shared scratch is filled at its use
         held = {}
         i8 = {}
+        mixed = {}
+        if _MIXED and not _INT8_GRAD:   # opt-in: int8 weights consumed by the mixed-input GEMM, no bf16 operand
+            for key, (specs, rows, width) in shapes.items():
+                op = _mixed_group_operand(cache, key + "_mix", specs)
+                if op is not None:
+                    mixed[key] = op
         if _INT8_GRAD:   # opt-in, non-parity: int8 operands instead of the bf16 ones
             for key, (specs, rows, width) in shapes.items():
                 w8t, scat = _i8_operand(cache, key + "_i8", specs)
@@ -429,13 +474,15 @@ class FusedDecoderBlock(torch.autograd.Function):
                 i8[key] = (w8t, scat, at_cat)
         else:
             for key, (specs, rows, width) in shapes.items():
+                if key in mixed:
+                    continue
                 wt, valid, resident = _operand(cache, key, specs, rows, width, dev)
                 if resident:
                     _fill_operand(wt, valid, specs)
                     held[key] = wt
 
         def operand(key):
-            if _INT8_GRAD:
+            if _INT8_GRAD or key in mixed:
                 return None, True
             if key in held:
                 return held[key], True
@@ -447,6 +494,8 @@ class FusedDecoderBlock(torch.autograd.Function):
         def a_dst(key, n_total, r_off, R):
             if _INT8_GRAD:
                 return i8[key][2][:, r_off : r_off + R] if R > 0 else None
+            if key in mixed:
+                return None
             return held[key][:, n_total + r_off : n_total + r_off + R] if (key in held and R > 0) else None
 
         sink = _GradSink()
@@ -471,12 +520,17 @@ class FusedDecoderBlock(torch.autograd.Function):
             dh2 = torch.empty(M, s2.R, device=dev, dtype=torch.bfloat16)
             dht2 = ops.transposed_rank_buffer(s2.R, M, dev)
             dB2 = sink.emit(_lora_dh_dB(dout2, bt2, ht2, dh2, s2.lora_scale, dht2), False, s2.lora_b.dtype)
-        if fuse:   # dg = dout2 @ (s W2) (+ dh2 @ A2) goes straight through the SwiGLU backward in the GEMM epilogue
+        if fuse and "w2" in mixed:
+            _, _, g = ops.bf16_int8_gemm_swiglu_bwd(dout2, mixed["w2"][0], mixed["w2"][1], a_, b_, out_ab=dab,
+                                                    want_g=s2.R > 0, lora_h=dh2, lora_b=at2, lora_scale=1.0)
+        elif fuse:   # dg = dout2 @ (s W2) (+ dh2 @ A2) goes straight through the SwiGLU backward in the GEMM epilogue
             _, _, g = ops.bf16_gemm_swiglu_bwd(dout2, wt2, a_, b_, out_ab=dab, want_g=s2.R > 0,
                                                lora_h=dh2, lora_b=at2, lora_scale=1.0)
         else:
             if _INT8_GRAD:
                 dg = _grad_input_i8(dout2, i8["w2"][0], i8["w2"][1], dh2, at2)
+            elif "w2" in mixed:
+                dg = ops.bf16_int8_gemm_bwd(dout2, mixed["w2"][0], mixed["w2"][1], lora_h=dh2, lora_b=at2, lora_scale=1.0)
             elif s2.R > 0:
                 dg = ops.bf16_gemm(dout2, wt2, lora_h=dh2, lora_b=at2, lora_scale=1.0)
             else:
@@ -489,7 +543,8 @@ class FusedDecoderBlock(torch.autograd.Function):
 
         # --- w1 | w3 ---
         wt13, placed13 = operand("w13")
-        dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, wt13, placed13, prep, sink, i8=i8.get("w13"))
+        dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, wt13, placed13, prep, sink, i8=i8.get("w13"),
+                                    mixed=mixed.get("w13"))
         del dab
         want_dw_fn, want_dw_an = w_fn.requires_grad, w_an.requires_grad
         dx1, dw_fn = ops.rmsnorm_bwd(dxn2, x1, w_fn.detach(), rstd2, dout2, want_dw=want_dw_fn)
@@ -497,7 +552,7 @@ class FusedDecoderBlock(torch.autograd.Function):
 
         # --- wo ---
         wto, _ = operand("wo")
-        do, go = _single_backward(so, dx1, o, wto, prep, sink, i8=i8.get("wo"))
+        do, go = _single_backward(so, dx1, o, wto, prep, sink, i8=i8.get("wo"), mixed=mixed.get("wo"))
 
         # --- attention ---
         dqkv = _padded_empty(M, nq + 2 * nk + rqkv, dev)
@@ -506,7 +561,7 @@ class FusedDecoderBlock(torch.autograd.Function):
                      doc_start=doc_start, doc_end=doc_end, rope_inverse=rope)   # dq, dk come back un-rotated
         wtqkv, placedqkv = operand("wqkv")
         dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, wtqkv, placedqkv, prep, sink,
-                                     i8=i8.get("wqkv"))
+                                     i8=i8.get("wqkv"), mixed=mixed.get("wqkv"))
         del dqkv
         dx, dw_an = ops.rmsnorm_bwd(dxn1, x2, w_an.detach(), rstd1, dx1, want_dw=want_dw_an)
         sink.flush()   # fp32 dA^T / dB -> parameter-dtype gradients, one launch

@@ -460,3 +460,39 @@ def test_weight_cache_modes_give_identical_gradients():
         assert torch.equal(results[0][0], other[0])
         for a, b in zip(results[0][1:], other[1:]):
             assert rel_err(a, b) <= 5e-3
+
+
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_mixed_input_gemm_mode_gives_identical_block(dynamic):
+    """LLAMAX_MIXED_GEMM=1: the weight-only forward and every grad_input GEMM read the frozen INT8 weights
+    directly (expanded to bf16 inside the GEMM) instead of a de-quantised bf16 operand. The expansion is exact and the
+    scale product is rounded the same way, so the block output and the input gradient are BIT-identical to the default
+    path in both INT8 modes (the parameter gradients only see fp32 reduction-order noise)."""
+    from llamax_b200.modelling import PrefixLM
+    from llamax_b200.modelling import fused_block as FB
+
+    results = []
+    for mixed in (False, True):
+        FB.set_mixed_gemm(mixed)
+        try:
+            model = build_tiny_llama(dynamic, num_layers=1).cuda()
+            layer, cfg = model.layers[0], model.config
+            rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:256].cuda()
+            torch.manual_seed(7)
+            x = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16().requires_grad_(True)
+            dout = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16()
+            for _ in range(2):
+                x.grad = None
+                for p_ in layer.parameters():
+                    p_.grad = None
+                out = layer(x, rope, block_mask=PrefixLM(64))
+                out.backward(dout)
+            if mixed:   # no bf16 grad_input operand was built
+                assert not any(k in layer.__dict__.get("_llamax_bwd_operands", {}) for k in ("w2", "w13", "wo", "wqkv"))
+            results.append([out.detach(), x.grad.detach()] + [p_.grad.detach() for p_ in layer.parameters() if p_.requires_grad])
+        finally:
+            FB.set_mixed_gemm(False)
+    assert torch.equal(results[0][0], results[1][0])
+    assert rel_err(results[1][1], results[0][1]) <= 5e-3   # dQ is reduced with fp32 atomics: a bf16 ulp here and there
+    for a, b in zip(results[0][2:], results[1][2:]):
+        assert rel_err(b, a) <= 5e-3
