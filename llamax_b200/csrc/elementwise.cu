@@ -328,6 +328,137 @@ __global__ void rowquant_ring_kernel(const __nv_bfloat16* __restrict__ x, int64_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-per-row variants of RMSNorm forward (+ quantisation) and of the row quantiser, for rows of <= 4096 elements
+// (the model width). The block-per-row kernels above pay two block reductions per row (four __syncthreads with a
+// shared-memory round trip each) for 16 elements of work per thread: in the step they run at 2.8-3.1 TB/s, neither
+// HBM- nor issue-bound (~15 instructions per element = 37 us of issue per launch against 110 us measured). Here a warp
+// owns a row: lane l holds the 16-byte vectors l, l + 32, ... of the row PACKED (kVec registers quads), every load of
+// the row is in flight at once, both reductions are five shuffles, there is no barrier and no shared memory at all;
+// 16+ warps per SM keep ~100 KB of loads in flight. Arithmetic (and rounding order per element) is that of the
+// kernels above; only the summation order of the mean square differs.
+// kNorm = false: row quantiser alone (w, y, rstd unused).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_l1_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// The row stays PACKED between the passes: without this the compiler keeps the fp32 copies of all 8 * kVec elements alive
+// from one pass to the next (common sub-expression of the unpacking) and spills at 16 vectors per lane.
+template <int kVec>
+__device__ __forceinline__ void keep_packed(uint4 (&pk)[kVec]) {
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) asm volatile("" : "+r"(pk[j].x), "+r"(pk[j].y), "+r"(pk[j].z), "+r"(pk[j].w));
+}
+
+template <int kVec, bool kNorm>
+__global__ void __launch_bounds__(256, 2)
+row_wpr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+               __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int8_t* __restrict__ q8,
+               __nv_bfloat16* __restrict__ qscale, int64_t M, int D, int nvec, float eps) {
+  const int lane = lane_id();
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
+    const __nv_bfloat16* xr = x + row * ldx;
+    uint4 pk[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const int idx = lane + 32 * j;
+      pk[j] = idx < nvec ? ldg_nc_v4(xr + (int64_t)idx * 8) : make_uint4(0, 0, 0, 0);
+    }
+    float amax = 0.f;
+    if constexpr (kNorm) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) {
+        float f[8];
+        unpack8(pk[j], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+      }
+      ss = warp_sum(ss);
+      keep_packed(pk);
+      const float rstd = 1.0f / sqrtf(ss / (float)D + eps);
+      if (lane == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) {
+        const int idx = lane + 32 * j;
+        if (idx < nvec) {
+          float f[8], wf[8];
+          unpack8(pk[j], f);
+          unpack8(ldg_l1_v4(w + (int64_t)idx * 8), wf);   // L1-resident; volatile: stays inside its iteration
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = (f[e] * rstd) * wf[e];
+          pk[j] = pack8(f);   // y, rounded once; the quantiser below reads these bf16 values
+          if (y != nullptr) *reinterpret_cast<uint4*>(y + row * D + (int64_t)idx * 8) = pk[j];
+        }
+        asm volatile("" ::: "memory");   // keeps the iterations (and their 16 fp32 temporaries) apart: 128-register budget
+      }
+    }
+    if (q8 == nullptr) continue;
+    keep_packed(pk);
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      float f[8];
+      unpack8(pk[j], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+    }
+    amax = warp_max(amax);
+    keep_packed(pk);
+    const float s = amax / 127.0f;
+    const float sc = fmaxf(s, 1e-12f);
+    const float inv = 1.0f / sc;
+    const float inv_lo = inv * (1.0f - 0x1p-21f), inv_hi = inv * (1.0f + 0x1p-21f);
+    int8_t* qrow = q8 + row * D;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const int idx = lane + 32 * j;
+      if (idx < nvec) {
+        float f[8];
+        unpack8(pk[j], f);
+        uint32_t c[8];
+        uint32_t differ = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          c[e] = __float_as_uint(__fmaf_rn(f[e], inv_lo, kRoundMagic));
+          differ |= c[e] ^ __float_as_uint(__fmaf_rn(f[e], inv_hi, kRoundMagic));
+        }
+        if (differ) {   // see quant_row_store: the rare vector with a quotient next to a half-integer
+#pragma unroll
+          for (int e = 0; e < 8; ++e) c[e] = __float_as_uint(__fadd_rn(f[e] / sc, kRoundMagic));
+        }
+        *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) =
+            make_uint2(pack4_low_bytes(c[0], c[1], c[2], c[3]), pack4_low_bytes(c[4], c[5], c[6], c[7]));
+      }
+      asm volatile("" ::: "memory");
+    }
+    if (lane == 0) qscale[row] = __float2bfloat16_rn(s);
+  }
+}
+
+// rows of up to 32 * 16 vectors; enough rows to fill the machine; 16-byte aligned rows. LLAMAX_ROW_WPR=1 turns it on:
+// measured isolated it is SLOWER than the ring kernels (rmsnorm + quant 92 vs 79 us, rowquant 51 vs 52 us), see DESIGN.md
+static bool wpr_cfg(int nvec, int64_t M, bool aligned, int& kvec, int& grid) {
+  static const bool enabled = getenv("LLAMAX_ROW_WPR") != nullptr && atoi(getenv("LLAMAX_ROW_WPR")) != 0;   // default off
+  static const int per_sm = getenv("LLAMAX_ROW_WPR_CTAS") ? std::max(1, atoi(getenv("LLAMAX_ROW_WPR_CTAS"))) : 2;
+  if (!enabled || !aligned || nvec > 512 || M < 256) return false;
+  const int v = (nvec + 31) / 32;
+  kvec = v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 8 ? 8 : 16;
+  grid = (int)std::min<int64_t>((M + 7) / 8, (int64_t)sm_count() * per_sm);
+  return true;
+}
+#define LX_DISPATCH_WPR(V_, ...)                            \
+  switch (V_) {                                             \
+    case 1: { constexpr int kV = 1; __VA_ARGS__; } break;   \
+    case 2: { constexpr int kV = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int kV = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int kV = 8; __VA_ARGS__; } break;   \
+    default: { constexpr int kV = 16; __VA_ARGS__; } break; \
+  }
+
+// ------------------------------------------------------------------------------------------------
 // SwiGLU forward: g = bf16( bf16(silu(a)) * b ), optional fused row quantisation
 // ------------------------------------------------------------------------------------------------
 // silu in fp32; the result is rounded to bf16 right away, so the fast exp / divide (~2 ulp fp32) are invisible
@@ -815,8 +946,11 @@ int llamax_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, void* 
   if ((q8 == nullptr) != (qscale == nullptr)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: q8 and qscale go together");
   if (!row_cfg(D, c)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: D must be a multiple of 8 and <= 65536");
   if (M == 0) return 0;
-  int ring_grid, ring_smem;
-  if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
+  int ring_grid, ring_smem, wv, wgrid;
+  if (wpr_cfg(c.nvec, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, wv, wgrid)) {
+    LX_DISPATCH_WPR(wv, row_wpr_kernel<kV, true><<<wgrid, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, D, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, M, (int)D, c.nvec, eps));
+  } else if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
     LX_DISPATCH_V(c.V, {
       LX_RING_SMEM(rmsnorm_fwd_ring_kernel<kV>, ring_smem, "rmsnorm_fwd");
       rmsnorm_fwd_ring_kernel<kV><<<ring_grid, c.threads, ring_smem, (cudaStream_t)stream>>>(
@@ -836,8 +970,11 @@ int llamax_rowquant_int8(const void* x, int64_t ldx, void* q8, void* scale_out, 
   if (!x || !q8 || !scale_out) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: null pointer");
   if (!row_cfg(K, c) || ldx % 8) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: K and ldx must be multiples of 8");
   if (M == 0) return 0;
-  int ring_grid, ring_smem;
-  if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
+  int ring_grid, ring_smem, wv, wgrid;
+  if (wpr_cfg(c.nvec, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, wv, wgrid)) {
+    LX_DISPATCH_WPR(wv, row_wpr_kernel<kV, false><<<wgrid, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, nullptr, nullptr, nullptr, (int8_t*)q8, (bf16*)scale_out, M, (int)K, c.nvec, 0.f));
+  } else if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
     LX_DISPATCH_V(c.V, {
       LX_RING_SMEM(rowquant_ring_kernel<kV>, ring_smem, "rowquant_int8");
       rowquant_ring_kernel<kV><<<ring_grid, c.threads, ring_smem, (cudaStream_t)stream>>>(

@@ -144,6 +144,7 @@ class LlamaAudio(Llama):
         their own frames are bidirectional)."""
         if input_pos is not None:
             raise NotImplementedError("llamax_b200: input_pos (inference) is outside the fine-tuning hot path")
+        label_count = self._count_labels(labels)
         x = self.tok_embeddings(tokens)
         n_prefix = 0
         if audio is not None:
@@ -157,4 +158,4 @@ class LlamaAudio(Llama):
         x = self._run_layers(x, block_mask)
         if n_prefix:
             x = x[:, n_prefix:]  # loss / logits on text positions only
-        return self._head(x, labels)
+        return self._head(x, labels, label_count)

@@ -21,6 +21,8 @@ from __future__ import annotations
 import math
 from typing import NamedTuple
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
@@ -384,6 +386,45 @@ def rms_norm(norm: nn.RMSNorm, x: Tensor) -> Tensor:
     return norm(x)
 
 
+# Row compaction of the LM head (default on; LLAMAX_LM_COMPACT=0 for A/B). Positions whose label is -100 contribute
+# neither to the loss nor to any gradient (F.cross_entropy(ignore_index=-100), llama.py:216-218), so the final norm,
+# the [rows, vocab] logits GEMM, the cross-entropy pass and the grad_input GEMM run on the labelled rows only, gathered
+# into a dense [n, D] matrix; their input gradients are scattered back into zeros. Row results of a GEMM do not depend
+# on the other rows: loss and gradients are unchanged. With MetaMathQA-style batches (prompt positions masked) a
+# quarter to a half of the rows drop out of the largest GEMMs of the step (vocab 128256).
+# The number of labelled rows has to reach the host (GEMM sizes are host-side): it is counted by a tiny kernel at the
+# START of forward() and copied to pinned memory asynchronously; by the time the host reaches the head it has queued
+# the whole forward pass behind that copy, so reading the count does not drain the launch queue.
+_LM_COMPACT = os.environ.get("LLAMAX_LM_COMPACT", "1") != "0"
+
+
+def set_lm_compact(on: bool) -> None:
+    global _LM_COMPACT
+    _LM_COMPACT = bool(on)
+
+
+class _LabelCount:
+    """Asynchronous count of labels != -100 (one step in flight at a time; the pinned word is owned by the model)."""
+
+    def __init__(self, owner: nn.Module, labels: Tensor):
+        self.mask = labels.reshape(-1) != -100
+        pin = owner.__dict__.get("_label_pin")
+        if pin is None:
+            pin = owner.__dict__["_label_pin"] = torch.empty(1, dtype=torch.int64, pin_memory=True)
+        self.pin = pin
+        pin.copy_(self.mask.sum(), non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def rows(self):
+        """(n, idx): number of labelled rows and their indices in order, or (n, None) when every row is labelled."""
+        self.event.synchronize()
+        n = int(self.pin[0])
+        if n == 0 or n == self.mask.numel():
+            return n, None
+        return n, torch.nonzero_static(self.mask, size=n).view(-1)
+
+
 class Llama(nn.Module):
     def __init__(self, config: LlamaConfig) -> None:
         super().__init__()
@@ -410,10 +451,15 @@ class Llama(nn.Module):
                 x = layer(x, rope, block_mask=block_mask)
         return x
 
-    def _head(self, x: Tensor, labels: Tensor | None) -> Tensor:
-        x = rms_norm(self.norm, x)
+    def _count_labels(self, labels: Tensor | None):
+        """Called at the top of forward(): starts the asynchronous count of labelled rows (see _LM_COMPACT)."""
+        if labels is None or not _LM_COMPACT or not labels.is_cuda:
+            return None
+        return _LabelCount(self, labels)
+
+    def _head(self, x: Tensor, labels: Tensor | None, label_count=None) -> Tensor:
         if labels is None:
-            return self.output(x)
+            return self.output(rms_norm(self.norm, x))
         out = self.output
         w = out.weight
         # chunked fast path only for a plain frozen-or-trainable bf16 head: `type(...) is nn.Linear` excludes LoRALinear
@@ -421,8 +467,16 @@ class Llama(nn.Module):
         fast = (type(out) is nn.Linear and out.bias is None and type(w) is nn.Parameter and w.is_cuda
                 and w.dtype is torch.bfloat16 and x.is_cuda and x.dtype is torch.bfloat16 and w.shape[0] % 8 == 0)
         if not fast:
-            logits = out(x)
+            logits = out(rms_norm(self.norm, x))
             return F.cross_entropy(logits.view(-1, logits.shape[-1]).float(), labels.view(-1))
+        labels = labels.reshape(-1)
+        x = x.reshape(-1, x.shape[-1])
+        if label_count is not None:
+            n, idx = label_count.rows()
+            if idx is not None:   # labelled rows only, in order; index_select's backward scatters into zeros
+                x = x.index_select(0, idx)
+                labels = labels.index_select(0, idx)
+        x = rms_norm(self.norm, x)
         return chunked_lm_loss(x, w, labels, self._output_weight_t(x))
 
     def _output_weight_t(self, x: Tensor):
@@ -441,9 +495,10 @@ class Llama(nn.Module):
                 labels: Tensor | None = None) -> Tensor:
         if input_pos is not None:
             raise NotImplementedError("llamax_b200: input_pos (inference) is outside the fine-tuning hot path")
+        label_count = self._count_labels(labels)
         x = self.tok_embeddings(x)
         x = self._run_layers(x, block_mask)
-        return self._head(x, labels)
+        return self._head(x, labels, label_count)
 
 
 class _ChunkedLMLoss(torch.autograd.Function):

@@ -496,3 +496,44 @@ def test_mixed_input_gemm_mode_gives_identical_block(dynamic):
     assert rel_err(results[1][1], results[0][1]) <= 5e-3   # dQ is reduced with fp32 atomics: a bf16 ulp here and there
     for a, b in zip(results[0][2:], results[1][2:]):
         assert rel_err(b, a) <= 5e-3
+
+
+def test_lm_head_row_compaction_changes_nothing():
+    """Rows whose label is -100 are dropped before the final norm / LM head / cross-entropy (llamax_b200.modelling.llama
+    _LM_COMPACT): loss and every gradient equal the all-rows computation (the dropped rows' contributions are exact
+    zeros there), also with ignored positions scattered through the batch and with a whole sequence ignored."""
+    from llamax_b200.modelling import PrefixLM
+    from llamax_b200.modelling import llama as L
+
+    B, S = 3, 256
+    model = build_tiny_llama(True, num_layers=2).cuda()
+    model.build_cache()
+    model.tok_embeddings.requires_grad_(False)
+    model.output.requires_grad_(False)
+    cfg = model.config
+    torch.manual_seed(11)
+    tokens = torch.randint(0, cfg.vocab_size, (B, S), device="cuda")
+    labels = torch.randint(0, cfg.vocab_size, (B, S), device="cuda")
+    labels[:, :70] = -100
+    labels[torch.rand(B, S, device="cuda") < 0.2] = -100
+    labels[2] = -100
+    results = []
+    for on in (False, True):
+        L.set_lm_compact(on)
+        try:
+            for p_ in model.parameters():
+                p_.grad = None
+            loss = model(tokens, labels=labels, block_mask=PrefixLM(64))
+            loss.backward()
+            results.append([loss.detach().float()] + [p_.grad.detach().float().clone() for p_ in model.parameters() if p_.grad is not None])
+        finally:
+            L.set_lm_compact(True)
+    assert len(results[0]) == len(results[1]) > 10
+    assert abs(results[0][0].item() - results[1][0].item()) <= 1e-5 * abs(results[0][0].item())
+    for a, b in zip(results[0][1:], results[1][1:]):
+        assert rel_err(b, a) <= 5e-3   # fp32-atomic reduction order of dQ / LoRA gradients only
+    # every row labelled / no row labelled: the all-rows path
+    full = torch.randint(0, cfg.vocab_size, (B, S), device="cuda")
+    assert torch.isfinite(model(tokens, labels=full, block_mask=PrefixLM(64)))
+    none = torch.full((B, S), -100, device="cuda")
+    assert model(tokens, labels=none, block_mask=PrefixLM(64)).item() == 0.0

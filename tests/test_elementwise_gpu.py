@@ -10,7 +10,9 @@ from tests.helpers import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("M,K", [(64, 512), (300, 4096), (128, 14336), (5, 1792), (1, 8), (3, 32768)])
+# M >= 256 with K <= 4096 runs the warp-per-row kernel, the others the block-per-row / ring kernels
+@pytest.mark.parametrize("M,K", [(64, 512), (300, 4096), (128, 14336), (5, 1792), (1, 8), (3, 32768), (1024, 4096),
+                                 (2048, 512), (257, 1792), (300, 2056), (4100, 8)])
 def test_rowquant_bit_exact(M, K):
     g = torch.Generator().manual_seed(K)
     x = (torch.randn(M, K, generator=g) * 3).bfloat16()
@@ -47,6 +49,9 @@ def test_rowquant_exact_ties_round_half_even():
     assert q_ref[0, 0] == -126 and q_ref[0, 1] == -126 and q_ref[0, 127] == 0 and q_ref[0, 128] == 2   # half-to-even
     q, sc = ops.rowquant_int8(x.cuda())
     assert torch.equal(q.cpu(), q_ref) and torch.equal(sc.cpu(), s_ref)
+    xb = x.repeat(128, 1)                                              # 512 rows: the warp-per-row kernel
+    q, sc = ops.rowquant_int8(xb.cuda())
+    assert torch.equal(q.cpu(), q_ref.repeat(128, 1)) and torch.equal(sc.cpu(), s_ref.repeat(128))
 
 
 def test_rowquant_pitched_input():
@@ -56,7 +61,7 @@ def test_rowquant_pitched_input():
     assert torch.equal(q.cpu(), q_ref) and torch.equal(s.cpu(), s_ref)
 
 
-@pytest.mark.parametrize("M,D", [(64, 512), (300, 4096), (7, 8192)])
+@pytest.mark.parametrize("M,D", [(64, 512), (300, 4096), (7, 8192), (1024, 4096), (2048, 512), (300, 2056)])
 def test_rmsnorm_fwd_bwd(M, D):
     g = torch.Generator().manual_seed(D)
     x = torch.randn(M, D, generator=g).bfloat16()
