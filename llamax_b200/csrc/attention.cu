@@ -1358,6 +1358,362 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 3) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward v5 = v4 made PERSISTENT. One CTA per SM walks a static, length-balanced list of work items (pair of query
+// tiles, head, sequence) and every ring — K / V stages, the S / P / O hand-offs, the XU token — keeps running across
+// items, so that of an item's fixed cost only the O drain stays exposed:
+//   * v4 pays per item (= per CTA): launch, barrier init, TMEM allocation, then Q and the first K from global memory and
+//     the first S MMA before any softmax can start (~2400 cycles, tools/attn_trace.py), and at the end one tile alone in
+//     its last step, the O drain and the tear-down — ~8-12k cycles on items that average ~9 steps of ~3550 cycles at
+//     S = 2048 causal (13.8 items per SM): a quarter of the kernel;
+//   * here the producer loads the next item's Q as soon as both issuers have committed the item's last S MMA (q_empty),
+//     its K / V follow through the ring, and each issuer puts S(0) of the next item right behind its last PV: the next
+//     item's first scores are in TMEM while the softmax warpgroup still normalises and stores O. The first PV of the next
+//     item (accumulate = 0) needs that warpgroup's first P chunk, which it only produces after its O reads: no extra
+//     hand-shake for O.
+// Items are ordered longest first (pairs from the end of the sequence, heads of one kv head adjacent) and dealt to the
+// CTAs in boustrophedon order (round r forwards, round r + 1 backwards), which levels the per-CTA sums of a monotone
+// length list to within one step without a work counter. XU-token arrivals are made conditional so that every arrival
+// has exactly one wait (v4 leaves unmatched arrivals behind at the end of a CTA; here the barrier lives on).
+// Packed-document masks stay on v2 (the token's wait chain is only acyclic when both tiles start at kv tile 0).
+// ------------------------------------------------------------------------------------------------
+namespace fwd5 {
+using namespace fwd4;   // same shared-memory layout, thread roles and register split
+constexpr int kNumBars5 = fwd4::kNumBars + 1 + 2;   // + q_empty, + a second pair of XU-token barriers
+constexpr int kSmemBytes5 = fwd4::kOffBar + kNumBars5 * 8 + 16 + 1024;
+}  // namespace fwd5
+
+template <int kD>
+__global__ void __launch_bounds__(fwd4::kThreads, 1)
+attn_fwd5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p, int n_pairs) {
+  using namespace fwd5;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;     // [tile]
+  uint64_t* p_chunk = bars + 11;   // [tile * 4 + chunk]
+  uint64_t* pv_done = bars + 19;   // [tile]
+  // XU token [item parity][tile]: consecutive items use different barriers. Within an item a tile is never more than one
+  // arrival ahead of the other tile's waits, but tile 0 finishes an item one step before tile 1 and its first arrival of
+  // the next item could otherwise land on a barrier whose previous phase tile 1 has not waited for yet (parity alias).
+  // A tile cannot start item n + 2 before the other has finished item n (q_empty), so two sets are enough.
+  uint64_t* xu_tok = bars + 21;
+  uint64_t* q_empty = bars + 25;   // both issuers have committed the item's last S MMA: the Q tiles may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars5);
+
+  const int warp = threadIdx.x >> 5;
+  const int heads_per_kv = p.Hq / p.Hkv;
+  const int per_pair = p.B * p.Hq;            // items per pair index
+  const int n_items = n_pairs * per_pair;
+  const int G = gridDim.x;
+
+  // item of round r for this CTA; -1 past the end. Rounds alternate direction (see above).
+  auto item_of = [&](int r) {
+    const int k = r * G + ((r & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+    return k < n_items ? k : -1;
+  };
+  // kv tile ranges of an item's two query tiles: [0, je_x); a tile past the end of the sequence has je_x = 0
+  struct Item { int pr, b, h, je0, je1, je, Pb; };
+  auto decode = [&](int k) {
+    Item it;
+    it.pr = n_pairs - 1 - k / per_pair;
+    const int rem = k % per_pair;
+    it.b = rem / p.Hq;
+    it.h = rem % p.Hq;
+    it.Pb = p.prefix_b ? min(max(p.prefix_b[it.b], 0), p.S) : p.P;
+    int je[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int q0 = (2 * it.pr + x) * kTile;
+      je[x] = q0 < p.S ? (min(p.S, max(it.Pb, q0 + kTile)) + kTile - 1) / kTile : 0;
+    }
+    it.je0 = je[0]; it.je1 = je[1]; it.je = max(je[0], je[1]);
+    return it;
+  };
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 2);   // one commit from each tile's issuer
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 2);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&p_chunk[i], 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&xu_tok[i], 4);
+    fence_mbar_init();
+  }
+  if (warp == 3) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsCtrl>();
+    if (warp == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (elect_one()) {
+        uint32_t kvc = 0;   // K / V stages filled so far (ring position across items)
+        for (int r = 0;; ++r) {
+          const int k = item_of(r);
+          if (k < 0) break;
+          const Item it = decode(k);
+          const int hk = it.h / heads_per_kv;
+          mbar_wait(q_empty, (r & 1) ^ 1);   // the previous item's last S MMAs have read Q (first item: passes)
+          mbar_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {   // rows past the end of the sequence are zero-filled
+            tma_load_4d(smem + kOffQ + x * kTileBytes, &tmQ, q_full, 0, it.h, (2 * it.pr + x) * kTile, it.b);
+            tma_load_4d(smem + kOffQ + x * kTileBytes + kTileBytes / 2, &tmQ, q_full, 64, it.h, (2 * it.pr + x) * kTile, it.b);
+          }
+          for (int j = 0; j < it.je; ++j, ++kvc) {
+            const int st = kvc & 1;
+            const uint32_t ph = (kvc >> 1) & 1;
+            mbar_wait(&k_empty[st], ph ^ 1);
+            mbar_expect_tx(&k_full[st], kTileBytes);
+            uint8_t* sk = smem + kOffK + st * kTileBytes;
+            tma_load_4d(sk, &tmK, &k_full[st], 0, hk, j * kTile, it.b);
+            tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, j * kTile, it.b);
+            mbar_wait(&v_empty[st], ph ^ 1);
+            mbar_expect_tx(&v_full[st], kTileBytes);
+            uint8_t* sv = smem + kOffV + st * kTileBytes;
+            tma_load_4d(sv, &tmV, &v_full[st], 0, hk, j * kTile, it.b);
+            tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, j * kTile, it.b);
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp <= 2) {
+      // ------------------------------------ MMA issuer of tile x ------------------------------------
+      // Walks EVERY kv tile of the item, also the one its own query tile does not visit (causal: the first tile of a pair
+      // skips the last kv tile): there it only waits for the stage and releases it, so the K / V barriers always see two
+      // arrivals and neither issuer can run a stage ahead of the other.
+      const int x = warp - 1;
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
+        constexpr uint32_t kHi = desc_hi(1024);
+        const uint32_t loQ = desc_lo(smem_u32(smem + kOffQ), 16) + x * (kTileBytes / 16);
+        const uint32_t loK0 = desc_lo(smem_u32(smem + kOffK), 16), loV0 = desc_lo(smem_u32(smem + kOffV), 16384);
+        const uint32_t tSx = tmem_base + x * 128, tOx = tmem_base + 256 + x * 128;
+        uint32_t kc = 0, vc = 0;   // K / V stages consumed so far
+        uint32_t pvc = 0;          // PV steps issued so far (phase of the P-chunk barriers)
+        for (int r = 0;; ++r) {
+          const int k = item_of(r);
+          if (k < 0) break;
+          const Item it = decode(k);
+          const int je_x = x ? it.je1 : it.je0;
+          auto issue_s = [&](int j) {
+            const int st = kc & 1;
+            mbar_wait(&k_full[st], (kc >> 1) & 1);
+            ++kc;
+            if (j < je_x) {
+              tc_fence_after();
+              const uint32_t loK = loK0 + st * (kTileBytes / 16);
+#pragma unroll
+              for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ss<false, 1>(tSx, desc_join(loQ + dh * 1024 + ks * 2, kHi), desc_join(loK + dh * 1024 + ks * 2, kHi),
+                                    idesc_s, (dh | ks) != 0);
+              umma_commit(&s_full[x]);
+            }
+            umma_commit(&k_empty[st]);
+            // the item's last K tile: once these MMAs (and, in order, all earlier ones) are done Q is no longer needed
+            if (j == it.je - 1) umma_commit(q_empty);
+          };
+          mbar_wait(q_full, r & 1);
+          issue_s(0);
+          for (int j = 0; j < it.je; ++j) {
+            const int st = vc & 1;
+            mbar_wait(&v_full[st], (vc >> 1) & 1);
+            ++vc;
+            if (j < je_x) {
+              const uint32_t loV = loV0 + st * (kTileBytes / 16);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                mbar_wait(&p_chunk[x * 4 + c], pvc & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                  const int ks = c * 2 + k2;   // 16 kv rows per MMA: P columns 8 ks .. 8 ks + 7, V rows 16 ks .. 16 ks + 15
+                  umma_ts_f16(tOx, tSx + ks * 8, desc_join(loV + ((ks >> 2) * 64 + (ks & 3) * 16) * 8, kHi), idesc_pv,
+                              (j | ks) != 0);
+                }
+              }
+              umma_commit(&pv_done[x]);
+              ++pvc;
+            }
+            umma_commit(&v_empty[st]);
+            if (j + 1 < it.je) issue_s(j + 1);   // in order behind PV_x(j), which reads P from the same columns
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------ softmax / correction / epilogue: one warpgroup per query tile ------------
+    setmaxnreg_inc<kRegsSoftmax>();
+    const int x = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int rr = ew * 32 + lane_id();  // row in tile == TMEM lane
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const uint32_t tS = tmem_base + x * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + x * 128 + lane_off;
+    uint32_t sc = 0;             // s_full waits done (= steps of this tile so far, over all items)
+    uint32_t tokw[2] = {0, 0};   // XU-token waits done, per barrier set
+    for (int r = 0;; ++r) {
+      const int k = item_of(r);
+      if (k < 0) break;
+      const Item it = decode(k);
+      const int n0 = it.je0, n1 = it.je1;
+      const int n_kv = x ? n1 : n0;
+      const int q0 = (2 * it.pr + x) * kTile;
+      const int q = q0 + rr;
+      const int Pb = it.Pb;
+      float m_used = -INFINITY, l = 0.f;
+      for (int i = 0; i < n_kv; ++i) {
+        const int kv0 = i * kTile;
+        // tile needs the element test unless every (q, kv) pair is visible and in range
+        const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= Pb) || (kv0 + kTile - 1 <= q0));
+        mbar_wait(&s_full[x], sc & 1);   // also: PV(i-1) has completed (same issuing thread, in order): O is stable
+        ++sc;
+        tc_fence_after();
+        uint32_t sv[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, sv[c]);
+        tmem_wait_ld_regs(sv[0]);
+        tmem_wait_ld_regs(sv[1]);
+        tmem_wait_ld_regs(sv[2]);
+        tmem_wait_ld_regs(sv[3]);
+        if (!full_tile) {
+          // the visible keys of a row are the first `width` columns of the tile: kv < max(P, q + 1) and kv < S
+          const uint32_t width = (uint32_t)max(min(p.S, max(Pb, q + 1)) - kv0, 0);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if ((uint32_t)(c * 32 + e) >= width) sv[c][e] = 0xff800000u;  // -inf
+        }
+        float mx4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          mx4[c] = __uint_as_float(sv[c][0]);
+#pragma unroll
+          for (int e = 1; e < 32; ++e) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][e]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const float m_tile = mx * p.scale_log2;
+        float alpha = 1.f;
+        if (m_tile > m_used + 8.f) {  // lazy rescale: only when the running max grows by more than 2^8
+          alpha = ex2(m_used - m_tile);
+          m_used = m_tile;
+        }
+        if (i > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st_32x32(tO + c * 32, v);
+          }
+          tmem_wait_st();
+        }
+        // XU token (see v4): within an item the exp phases alternate t0(0) t1(0) t0(1) t1(1) ...; tile 1's exp i follows
+        // tile 0's exp i (if tile 0 has one), tile 0's exp i follows tile 1's exp i - 1. Every arrival below has exactly
+        // one wait here, so the barrier phases can be counted across items.
+        if (x == 1 ? (i < n0) : (i > 0 && i - 1 < n1)) {
+          mbar_wait(&xu_tok[(r & 1) * 2 + x], tokw[r & 1] & 1);
+          ++tokw[r & 1];
+        }
+        float m_exp = (m_used == -INFINITY) ? 0.f : m_used;
+        asm volatile("" : "+f"(m_exp));   // pins the exponentials behind the wait (they are pure: ptxas hoists them otherwise)
+        float rowsum = 0.f;
+        uint32_t pc[2][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(sv[c][e]), p.scale_log2, -m_exp));      // -inf -> 0
+            const float p1 = ex2(fmaf(__uint_as_float(sv[c][e + 1]), p.scale_log2, -m_exp));
+            rowsum += p0 + p1;
+            pc[c & 1][e / 2] = pack_bf16(p0, p1);
+          }
+          if (c > 0) {   // chunk c - 1 is in TMEM: hand it to the issuer
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&p_chunk[x * 4 + c - 1]);
+          }
+          tmem_st_32x16(tS + c * 16, pc[c & 1]);
+        }
+        // exponentials done: the other tile may start the exp phase that waits for this one (if it has such a step)
+        if (x == 0 ? (i < n1) : (i + 1 < n0)) {
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(&xu_tok[(r & 1) * 2 + (x ^ 1)]);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&p_chunk[x * 4 + 3]);
+        l = l * alpha + rowsum;
+      }
+      // epilogue of the item: the issuer is already past S(0) of the next one
+      if (n_kv > 0) {
+        mbar_wait(&pv_done[x], (sc - 1) & 1);   // PV steps == S steps of this tile
+        tc_fence_after();
+        const float inv_l = 1.f / l;
+        const bool row_ok = q < p.S;
+        __nv_bfloat16* orow = p.o + ((int64_t)it.b * p.S + q) * p.ldo + (int64_t)it.h * kD;
+#pragma unroll 1
+        for (int c = 0; c < kD / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + c * 32, v);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              uint4 o4;
+              o4.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+              o4.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+              o4.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+              o4.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+              stg_v4(orow + c * 32 + e, o4);
+            }
+          }
+        }
+        if (row_ok) p.lse[((int64_t)it.b * p.Hq + it.h) * p.S + q] = (m_used + log2f(l)) * kLn2;
+        tc_fence_before();
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ================================================================================================
 // backward
 // ================================================================================================
@@ -1931,10 +2287,30 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   static const int version = [] {
     const char* e = getenv("LLAMAX_ATTN_FWD");
     if (getenv("LLAMAX_ATTN_FWD_ONE_TILE") && getenv("LLAMAX_ATTN_FWD_ONE_TILE")[0] == '1') return 1;
-    return (e != nullptr && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 4;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 5;
   }();
-  // packed documents: v4's XU token is off there (see the kernel) and without it v4 loses to v2 -> v2
-  const int version_eff = (version == 4 && doc_start != nullptr) ? 2 : version;
+  // packed documents: the XU token of v4 / v5 is off there (see the kernels) and without it they lose to v2 -> v2
+  const int version_eff = (version >= 4 && doc_start != nullptr) ? 2 : version;
+  if (version_eff == 5) {   // persistent: one CTA per SM over a static item list
+    auto kern5 = D == 128 ? attn_fwd5_kernel<128> : attn_fwd5_kernel<64>;
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern5), fwd5::kSmemBytes5, "attn_fwd: cudaFuncSetAttribute"))) return rc;
+    AttnFwdParams p5;
+    p5.o = (__nv_bfloat16*)o;
+    p5.ldo = ldo;
+    p5.lse = (float*)lse;
+    p5.B = (int)B; p5.S = (int)S; p5.Hq = Hq; p5.Hkv = Hkv;
+    p5.P = (int)std::min<int64_t>(prefix_len, S);
+    p5.D = D;
+    p5.scale_log2 = scale * kLog2e;
+    p5.doc_start = nullptr;
+    p5.prefix_b = (const int32_t*)prefix_len_b;
+    const int n_pairs = (int)((ceil_div(S, fwd::kTile) + 1) / 2);
+    const int64_t n_items = (int64_t)n_pairs * B * Hq;
+    const int grid5 = (int)std::min<int64_t>(n_items, sm_count());
+    kern5<<<grid5, fwd4::kThreads, fwd5::kSmemBytes5, (cudaStream_t)stream>>>(tq, tk, tv, p5, n_pairs);
+    LX_CHECK_LAUNCH("attn_fwd");
+    return 0;
+  }
   const bool one_tile = version_eff == 1;
   auto kern1 = doc_start ? (D == 128 ? attn_fwd_kernel<true, 128> : attn_fwd_kernel<true, 64>)
                          : (D == 128 ? attn_fwd_kernel<false, 128> : attn_fwd_kernel<false, 64>);
