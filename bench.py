@@ -461,7 +461,10 @@ def run_ours(args):
                    **({"NON_PARITY_OPT_IN": "int8 grad_input (gradients quantised to 8 bit per row): not the reference's "
                                             "numerics, not a headline number"} if args.int8_grad_input else {}),
                    "l2": "per-step working set (>10 GB activations + 7 GB weights) far exceeds the 126 MB L2; no flush needed",
-                   "positions_per_step": positions * world, "label_tokens_per_step": n_label * world},
+                   "positions_per_step": positions * world, "label_tokens_per_step": n_label * world,
+                   "lm_head_rows": "final norm / LM head / cross-entropy run on the %d labelled rows per GPU and step only "
+                                   "(rows with label -100 contribute exact zeros to loss and gradients; identical results, "
+                                   "LLAMAX_LM_COMPACT=0 computes all %d rows)" % (n_label, positions)},
         "label_tokens_per_s": round(n_label * world / (ms_step / 1e3), 1),
         "loss": round(float(main["loss"]), 4),
         "clocks": main["clocks"],

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LLAMAX_B200_VERSION 100
+#define LLAMAX_B200_VERSION 101
 
 #define LLAMAX_OK 0
 #define LLAMAX_ERR_ARG (-1)  /* bad argument (shape / alignment / null) */
@@ -44,6 +44,11 @@ typedef struct {
   float lora_scale;   /* alpha / rank */
   const void* resid;  /* bf16 [M, N], row pitch ldr; NULL = none */
   int64_t ldr;
+  /* Column segments for row-concatenated weights that share an input (q | k | v in one launch): output columns
+   * [0, seg_n0) take LoRA-h columns [0, rank), [seg_n0, seg_n1) take [rank, 2 rank), [seg_n1, N) take [2 rank, 3 rank)
+   * of lora_h (whose rows then hold 3 * rank values); lora_b is the row-concatenation [N, rank] of the three B matrices.
+   * seg_n0 = 0: one segment. seg_n0, seg_n1 must be multiples of 256 (the tile width). */
+  int32_t seg_n0, seg_n1;
 } llamax_epilogue_t;
 
 /* ---- K3: int8 x int8 -> int32 GEMM with row/column-scale dequant --------------------------------

@@ -29,6 +29,8 @@ class Epilogue(Structure):
         ("lora_scale", c_float),
         ("resid", P),
         ("ldr", I64),
+        ("seg_n0", I32),
+        ("seg_n1", I32),
     ]
 
 

@@ -64,6 +64,7 @@ struct GemmParams {
   float lora_scale;
   const __nv_bfloat16* resid;
   int64_t ldr;
+  int seg_n0, seg_n1;  // LoRA column segments (0 = none): see llamax_epilogue_t
   int flags;  // 1: dump raw accumulator (int32 / fp32) to C; 2: round to bf16 before the column scale
   // kSwi epilogue (SwiGLU backward fused behind the w2 grad_input GEMM): C is not written
   const __nv_bfloat16* swi_ab;  // [M, 2N] pitch ld_ab: a = w1 x in columns [0, N), b = w3 x in [N, 2N)
@@ -548,13 +549,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tile_coords(t, num_m, num_n, p.group, fm, fn);
       const int n = fn * kBN + et;
       const int frow = fm * kTileM + cta_rank * kBM + ew * 32 + lane_id();
+      const int hoff = p.seg_n0 > 0 ? (fn * kBN >= p.seg_n1 ? 2 * kRank : fn * kBN >= p.seg_n0 ? kRank : 0) : 0;
       ncs = (has_cs && n < p.N) ? (uint32_t) * reinterpret_cast<const uint16_t*>(p.col_scale + n) : 0u;
       nrs = (p.row_scale != nullptr && frow < p.M) ? __bfloat162float(p.row_scale[frow]) : 1.f;
       if constexpr (kRank > 0) {
 #pragma unroll
         for (int r8 = 0; r8 < kRV; ++r8) {
           nlb[r8] = n < p.N ? ldg_nc_v4(p.lora_b + (int64_t)n * kRank + r8 * 8) : make_uint4(0, 0, 0, 0);
-          nh[r8] = frow < p.M ? ldg_nc_v4(p.lora_h + (int64_t)frow * p.ldh + r8 * 8) : make_uint4(0, 0, 0, 0);
+          nh[r8] = frow < p.M ? ldg_nc_v4(p.lora_h + (int64_t)frow * p.ldh + hoff + r8 * 8) : make_uint4(0, 0, 0, 0);
         }
       }
     };
@@ -620,7 +622,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if constexpr (kRank > 0) {
         if (row_ok && !fast_stage) {
-          const __nv_bfloat16* hp = p.lora_h + (int64_t)row * p.ldh;
+          const __nv_bfloat16* hp = p.lora_h + (int64_t)row * p.ldh +
+                                    (p.seg_n0 > 0 ? (col0 >= p.seg_n1 ? 2 * R : col0 >= p.seg_n0 ? R : 0) : 0);
           if (R == kRank) {  // 16-byte vector loads (h rows are 16-byte aligned for rank 8 / 16)
 #pragma unroll
             for (int r = 0; r < kRank; r += 8) {
@@ -810,6 +813,8 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
     return set_error(LLAMAX_ERR_ARG, "gemm: residual must be 16-byte aligned with ldr % 8 == 0");
   if (p.lora_rank < 0 || p.lora_rank > kMaxLoraRank || (p.lora_rank % 4))
     return set_error(LLAMAX_ERR_ARG, "gemm: lora rank must be a multiple of 4 in [0, 16]");
+  if (p.seg_n0 != 0 && (p.seg_n0 % kBN || p.seg_n1 % kBN || p.seg_n0 <= 0 || p.seg_n1 <= p.seg_n0))
+    return set_error(LLAMAX_ERR_ARG, "gemm: LoRA column segments must be increasing multiples of 256");
 
   CUtensorMap tmA, tmB;
   const CUtensorMapDataType dt = kInt8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -1631,6 +1636,8 @@ static void fill_epilogue(GemmParams& p, const llamax_epilogue_t* epi) {
   p.lora_scale = epi->lora_scale;
   p.resid = static_cast<const __nv_bfloat16*>(epi->resid);
   p.ldr = epi->ldr;
+  p.seg_n0 = epi->lora_h ? epi->seg_n0 : 0;
+  p.seg_n1 = epi->lora_h ? epi->seg_n1 : 0;
 }
 
 int llamax_int8_gemm_dequant(const void* A, int64_t lda, const void* B, int64_t ldb, const void* a_scale,

@@ -82,6 +82,20 @@ _MIXED = os.environ.get("LLAMAX_MIXED_GEMM", "0") == "1"
 _ones: dict = {}
 
 
+# A/B switch (benchmarking only): "0" restores three INT8 GEMM launches for wq, wk, wv
+_QKV_ONE_LAUNCH = os.environ.get("LLAMAX_QKV_ONE_LAUNCH", "1") != "0"
+
+
+def _qkv_mergeable(sq, sk, sv, nq: int, nk: int) -> bool:
+    """One launch needs tile-aligned segment boundaries, one LoRA rank / scale for the three (or no LoRA at all) and
+    the shape limits of the concatenated operand."""
+    if nq % 256 or (nq + nk) % 256 or (nq + 2 * nk) % 64 or sq.K % 16:
+        return False
+    if not (sq.R == sk.R == sv.R and sq.R in (0, 8, 16)):
+        return False
+    return sq.R == 0 or (sq.lora_scale == sk.lora_scale == sv.lora_scale)
+
+
 def set_mixed_gemm(on: bool) -> None:
     global _MIXED
     _MIXED = bool(on)
@@ -391,11 +405,23 @@ class FusedDecoderBlock(torch.autograd.Function):
         h_qkv = _lora_down(xn1, (sq, sk, sv))
         nq, nk = Hq * D, Hkv * D
         qkv = torch.empty(M, nq + 2 * nk, device=x.device, dtype=torch.bfloat16)
-        r_off = 0
-        for spec, c0, c1 in ((sq, 0, nq), (sk, nq, nq + nk), (sv, nq + nk, nq + 2 * nk)):
-            h = h_qkv[:, r_off : r_off + spec.R] if spec.R > 0 else None
-            r_off += spec.R
-            _linear(spec, xn1, xq, xs, h, out=qkv[:, c0:c1])
+        if _QKV_ONE_LAUNCH and dyn_qkv and _qkv_mergeable(sq, sk, sv, nq, nk):
+            # ONE INT8 GEMM over the row-concatenated [Wq; Wk; Wv] (a resident 25 MB int8 copy per layer at 8B): N = 6144
+            # instead of 4096 + 1024 + 1024 — the two N = 1024 launches fill 3.5 waves of 74 CTA pairs and ran at 1870 TOP/s
+            # against 2370-2630 for the wide ones. The epilogue picks each column segment's own LoRA-h columns.
+            cache = layer.__dict__.setdefault("_llamax_bwd_operands", {})
+            w8cat, scat = _mixed_group_operand(cache, "wqkv_fwd", (sq, sk, sv))
+            ep = {}
+            if sq.R > 0:
+                ep = dict(lora_h=h_qkv, lora_b=torch.cat([sq.lora_b.detach(), sk.lora_b.detach(), sv.lora_b.detach()], 0),
+                          lora_scale=sq.lora_scale, lora_seg=(nq, nq + nk))
+            ops.int8_gemm_dequant(xq, w8cat, xs, scat, out=qkv, **ep)
+        else:
+            r_off = 0
+            for spec, c0, c1 in ((sq, 0, nq), (sk, nq, nq + nk), (sv, nq + nk, nq + 2 * nk)):
+                h = h_qkv[:, r_off : r_off + spec.R] if spec.R > 0 else None
+                r_off += spec.R
+                _linear(spec, xn1, xq, xs, h, out=qkv[:, c0:c1])
         ops.rope_(qkv, rope, B, S, Hq + Hkv, D)
         o, lse = ops.attn_fwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], B, S, Hq, Hkv, D, prefix_len,
                               doc_start=doc_start)

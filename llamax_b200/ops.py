@@ -89,7 +89,9 @@ def _rows(t: Tensor) -> Tensor:
     return t
 
 
-def make_epilogue(lora_h=None, lora_b=None, lora_scale=1.0, resid=None):
+def make_epilogue(lora_h=None, lora_b=None, lora_scale=1.0, resid=None, lora_seg=None):
+    """lora_seg = (n0, n1): three column segments [0, n0), [n0, n1), [n1, N) that use LoRA-h columns [0, R), [R, 2R),
+    [2R, 3R) (lora_h is [M, 3R], lora_b the row-concatenated [N, R]) — q | k | v in one launch."""
     if lora_h is None and resid is None:
         return None, ()
     ep = Epilogue()
@@ -98,9 +100,15 @@ def make_epilogue(lora_h=None, lora_b=None, lora_scale=1.0, resid=None):
         lora_h = _rows(lora_h)
         lora_b = lora_b.contiguous()
         assert lora_h.dtype is torch.bfloat16 and lora_b.dtype is torch.bfloat16
-        assert lora_b.shape[1] == lora_h.shape[1]
+        rank = lora_b.shape[1]
+        if lora_seg is not None:
+            assert lora_h.shape[1] == 3 * rank and lora_seg[0] % 256 == 0 and lora_seg[1] % 256 == 0
+            assert 0 < lora_seg[0] < lora_seg[1]
+            ep.seg_n0, ep.seg_n1 = int(lora_seg[0]), int(lora_seg[1])
+        else:
+            assert rank == lora_h.shape[1]
         ep.lora_h, ep.ldh = lora_h.data_ptr(), lora_h.stride(0)
-        ep.lora_b, ep.lora_rank, ep.lora_scale = lora_b.data_ptr(), lora_h.shape[1], float(lora_scale)
+        ep.lora_b, ep.lora_rank, ep.lora_scale = lora_b.data_ptr(), rank, float(lora_scale)
         keep += [lora_h, lora_b]
     if resid is not None:
         resid = _rows(resid)
@@ -116,7 +124,7 @@ def set_gemm_cta_group(cg: int):
 
 # ---------------------------------------------------------------------------------------------- GEMMs
 def int8_gemm_dequant(A: Tensor, W: Tensor, a_scale: Tensor, w_scale: Tensor, *, out: Tensor | None = None,
-                      lora_h=None, lora_b=None, lora_scale=1.0, resid=None) -> Tensor:
+                      lora_h=None, lora_b=None, lora_scale=1.0, resid=None, lora_seg=None) -> Tensor:
     """C = dequant(A[M,K] @ W[N,K]^T) (+ LoRA + residual). A, W int8; scales bf16."""
     lib, st = _prep(A)
     assert A.dtype is torch.int8 and W.dtype is torch.int8 and A.dim() == 2 and W.dim() == 2
@@ -130,7 +138,7 @@ def int8_gemm_dequant(A: Tensor, W: Tensor, a_scale: Tensor, w_scale: Tensor, *,
     if out is None:
         out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
     assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
-    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid)
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid, lora_seg)
     _call(lib, "llamax_int8_gemm_dequant",
           (_p(A), A.stride(0), _p(W), W.stride(0), _p(a_scale), _p(w_scale), _p(out), out.stride(0), M, N, K, ctypes.byref(ep) if ep is not None else None, st,),
           "int8_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))

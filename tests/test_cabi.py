@@ -28,14 +28,16 @@ def test_library_exports_every_declared_symbol():
         if name in _lib.SIGNATURES:
             assert len(_lib.SIGNATURES[name]) == len(args), f"{name}: binding has {len(_lib.SIGNATURES[name])} args, header {len(args)}"
     assert set(_lib.SIGNATURES) <= set(declared)
-    assert lib.llamax_version() == 100
+    assert lib.llamax_version() == 101
     assert isinstance(lib.llamax_last_error(), bytes)
 
 
 def test_epilogue_struct_layout_matches_header():
     e = _lib.Epilogue
-    assert [f[0] for f in e._fields_] == ["lora_h", "ldh", "lora_b", "lora_rank", "lora_scale", "resid", "ldr"]
-    assert ctypes.sizeof(e) == 48 and e.lora_rank.offset == 24 and e.lora_scale.offset == 28 and e.resid.offset == 32
+    assert [f[0] for f in e._fields_] == ["lora_h", "ldh", "lora_b", "lora_rank", "lora_scale", "resid", "ldr", "seg_n0",
+                                          "seg_n1"]
+    assert ctypes.sizeof(e) == 56 and e.lora_rank.offset == 24 and e.lora_scale.offset == 28 and e.resid.offset == 32
+    assert e.seg_n0.offset == 48 and e.seg_n1.offset == 52
 
 
 def test_copy_job_struct_layout_matches_header():

@@ -342,3 +342,21 @@ def test_mixed_gemm_bad_arguments_raise():
     s = torch.ones(96).bfloat16().cuda()
     with pytest.raises(LlamaxError):   # K1 must be a multiple of 64
         ops.bf16_int8_gemm_bwd(x, W8, s)
+
+
+@pytest.mark.parametrize("M,K,n0,n1,N,R", [(300, 512, 256, 512, 768, 8), (2048, 4096, 4096, 5120, 6144, 8), (515, 256, 512, 768, 1280, 16)])
+def test_int8_gemm_lora_column_segments_equal_three_launches(M, K, n0, n1, N, R):
+    """q | k | v in ONE launch: column segments [0, n0), [n0, n1), [n1, N) take their own R columns of the shared LoRA-h
+    matrix [M, 3R] and their own rows of the concatenated B; bit-identical to three launches on the three weights."""
+    g = torch.Generator().manual_seed(N + R)
+    A, W = _rand_i8(M, K, gen=g).cuda(), _rand_i8(N, K, gen=g).cuda()
+    sa = (torch.rand(M, generator=g) * 0.1).bfloat16().cuda()
+    sw = (torch.rand(N, generator=g) * 0.01).bfloat16().cuda()
+    h = torch.randn(M, 3 * R, generator=g).bfloat16().cuda()
+    B = (torch.randn(N, R, generator=g) * 0.05).bfloat16().cuda()
+    out = ops.int8_gemm_dequant(A, W, sa, sw, lora_h=h, lora_b=B, lora_scale=2.0, lora_seg=(n0, n1))
+    ref = torch.empty_like(out)
+    for i, (c0, c1) in enumerate(((0, n0), (n0, n1), (n1, N))):
+        ops.int8_gemm_dequant(A, W[c0:c1], sa, sw[c0:c1], out=ref[:, c0:c1], lora_h=h[:, i * R : (i + 1) * R],
+                              lora_b=B[c0:c1].contiguous(), lora_scale=2.0)
+    assert torch.equal(out, ref)
