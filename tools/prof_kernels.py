@@ -54,6 +54,12 @@ for _ in range(reps):
     dab2 = torch.empty(M, 2 * F + 16, device=dev, dtype=torch.bfloat16)
     ops.bf16_gemm_swiglu_bwd(x, wt2, ab[:, :F], ab[:, F:], out_ab=dab2, want_g=True, lora_h=h[:, :8], lora_b=lb)
     del wt2, dab2
+    # 12/13. mixed-input GEMMs (opt-in mode): grad_input of wo from the int8 weight as stored, weight-only forward of wq
+    w8o = torch.randint(-127, 128, (D, D), device=dev, dtype=torch.int8)
+    so = torch.rand(D, device=dev).bfloat16()
+    ops.bf16_int8_gemm_bwd(x, w8o, so)
+    ops.bf16_int8_gemm(x, w8o, so)
+    del w8o
     del ab, qkv, dqkv
 torch.cuda.synchronize()
 print("ok")
