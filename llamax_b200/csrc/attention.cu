@@ -1714,397 +1714,6 @@ attn_fwd5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 3) tmem_dealloc<1>(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Forward v6 = the persistent v5 with TWO softmax warpgroups per query tile. v5's softmax warps are instruction-issue
-// bound with one warp per scheduler and tile (tools/xu_bench.cu: the shipped loop body costs 16 cycles per element pair
-// with one warp per scheduler, 11.5 per scheduler with two), and the two tiles' exp phases are serial (XU token), so a
-// step of a tile pair costs two full exp phases. Here a tile's 128 rows are spread over eight warps in the 16-lane
-// fragment layout (two rows and a quarter of the columns per thread): half the instructions per thread and step, two
-// warps per scheduler inside an exp phase, row maxima by two quad shuffles, nothing through shared memory (v3 split the
-// columns between two thread-per-row warps and paid a barrier + shared-memory exchange per tile for the maxima).
-// The score tile is read from TMEM twice (maxima, then exponentials) instead of being held in 128 registers.
-// ------------------------------------------------------------------------------------------------
-namespace fwd6 {
-constexpr int kThreads6 = 640;   // warps 0-3 control as in v4 / v5; warps 4-11 tile 0, warps 12-19 tile 1
-// setmaxnreg pool = 640 x 96 (launch bound): 128 x 40 + 512 x 104 = 58368
-constexpr int kRegsCtrl6 = 40, kRegsSoftmax6 = 104;
-}  // namespace fwd6
-
-template <int kD>
-__global__ void __launch_bounds__(fwd6::kThreads6, 1)
-attn_fwd6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p, int n_pairs) {
-  using namespace fwd5;
-  using namespace fwd6;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 3;
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 7;
-  uint64_t* s_full = bars + 9;     // [tile]
-  uint64_t* p_chunk = bars + 11;   // [tile * 4 + chunk]
-  uint64_t* pv_done = bars + 19;   // [tile]
-  // XU token [item parity][tile]: consecutive items use different barriers. Within an item a tile is never more than one
-  // arrival ahead of the other tile's waits, but tile 0 finishes an item one step before tile 1 and its first arrival of
-  // the next item could otherwise land on a barrier whose previous phase tile 1 has not waited for yet (parity alias).
-  // A tile cannot start item n + 2 before the other has finished item n (q_empty), so two sets are enough.
-  uint64_t* xu_tok = bars + 21;
-  uint64_t* q_empty = bars + 25;   // both issuers have committed the item's last S MMA: the Q tiles may be overwritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars5);
-
-  const int warp = threadIdx.x >> 5;
-  const int heads_per_kv = p.Hq / p.Hkv;
-  const int per_pair = p.B * p.Hq;            // items per pair index
-  const int n_items = n_pairs * per_pair;
-  const int G = gridDim.x;
-
-  // item of round r for this CTA; -1 past the end. Rounds alternate direction (see above).
-  auto item_of = [&](int r) {
-    const int k = r * G + ((r & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
-    return k < n_items ? k : -1;
-  };
-  // kv tile ranges of an item's two query tiles: [0, je_x); a tile past the end of the sequence has je_x = 0
-  struct Item { int pr, b, h, je0, je1, je, Pb; };
-  auto decode = [&](int k) {
-    Item it;
-    it.pr = n_pairs - 1 - k / per_pair;
-    const int rem = k % per_pair;
-    it.b = rem / p.Hq;
-    it.h = rem % p.Hq;
-    it.Pb = p.prefix_b ? min(max(p.prefix_b[it.b], 0), p.S) : p.P;
-    int je[2];
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-      const int q0 = (2 * it.pr + x) * kTile;
-      je[x] = q0 < p.S ? (min(p.S, max(it.Pb, q0 + kTile)) + kTile - 1) / kTile : 0;
-    }
-    it.je0 = je[0]; it.je1 = je[1]; it.je = max(je[0], je[1]);
-    return it;
-  };
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && elect_one()) {
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 2);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 2);   // one commit from each tile's issuer
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 2);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&pv_done[i], 1);
-    }
-    for (int i = 0; i < 8; ++i) mbar_init(&p_chunk[i], 8);   // eight softmax warps per tile
-    for (int i = 0; i < 4; ++i) mbar_init(&xu_tok[i], 8);
-    fence_mbar_init();
-  }
-  if (warp == 3) {
-    tmem_alloc<1>(tmem_slot, 512);
-    tmem_relinquish<1>();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    setmaxnreg_dec<kRegsCtrl6>();
-    if (warp == 0) {
-      // ------------------------------------ TMA producer ------------------------------------
-      if (elect_one()) {
-        uint32_t kvc = 0;   // K / V stages filled so far (ring position across items)
-        for (int r = 0;; ++r) {
-          const int k = item_of(r);
-          if (k < 0) break;
-          const Item it = decode(k);
-          const int hk = it.h / heads_per_kv;
-          mbar_wait(q_empty, (r & 1) ^ 1);   // the previous item's last S MMAs have read Q (first item: passes)
-          mbar_expect_tx(q_full, 2 * kTileBytes);
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {   // rows past the end of the sequence are zero-filled
-            tma_load_4d(smem + kOffQ + x * kTileBytes, &tmQ, q_full, 0, it.h, (2 * it.pr + x) * kTile, it.b);
-            tma_load_4d(smem + kOffQ + x * kTileBytes + kTileBytes / 2, &tmQ, q_full, 64, it.h, (2 * it.pr + x) * kTile, it.b);
-          }
-          for (int j = 0; j < it.je; ++j, ++kvc) {
-            const int st = kvc & 1;
-            const uint32_t ph = (kvc >> 1) & 1;
-            mbar_wait(&k_empty[st], ph ^ 1);
-            mbar_expect_tx(&k_full[st], kTileBytes);
-            uint8_t* sk = smem + kOffK + st * kTileBytes;
-            tma_load_4d(sk, &tmK, &k_full[st], 0, hk, j * kTile, it.b);
-            tma_load_4d(sk + kTileBytes / 2, &tmK, &k_full[st], 64, hk, j * kTile, it.b);
-            mbar_wait(&v_empty[st], ph ^ 1);
-            mbar_expect_tx(&v_full[st], kTileBytes);
-            uint8_t* sv = smem + kOffV + st * kTileBytes;
-            tma_load_4d(sv, &tmV, &v_full[st], 0, hk, j * kTile, it.b);
-            tma_load_4d(sv + kTileBytes / 2, &tmV, &v_full[st], 64, hk, j * kTile, it.b);
-          }
-        }
-      }
-      __syncwarp();
-    } else if (warp <= 2) {
-      // ------------------------------------ MMA issuer of tile x ------------------------------------
-      // Walks EVERY kv tile of the item, also the one its own query tile does not visit (causal: the first tile of a pair
-      // skips the last kv tile): there it only waits for the stage and releases it, so the K / V barriers always see two
-      // arrivals and neither issuer can run a stage ahead of the other.
-      const int x = warp - 1;
-      if (elect_one()) {
-        constexpr uint32_t idesc_s = make_idesc(1, 1, 128, 128, 0, 0);
-        constexpr uint32_t idesc_pv = make_idesc(1, 1, 128, 128, 0, 1);  // B = V is MN-major
-        constexpr uint32_t kHi = desc_hi(1024);
-        const uint32_t loQ = desc_lo(smem_u32(smem + kOffQ), 16) + x * (kTileBytes / 16);
-        const uint32_t loK0 = desc_lo(smem_u32(smem + kOffK), 16), loV0 = desc_lo(smem_u32(smem + kOffV), 16384);
-        const uint32_t tSx = tmem_base + x * 128, tOx = tmem_base + 256 + x * 128;
-        uint32_t kc = 0, vc = 0;   // K / V stages consumed so far
-        uint32_t pvc = 0;          // PV steps issued so far (phase of the P-chunk barriers)
-        for (int r = 0;; ++r) {
-          const int k = item_of(r);
-          if (k < 0) break;
-          const Item it = decode(k);
-          const int je_x = x ? it.je1 : it.je0;
-          auto issue_s = [&](int j) {
-            const int st = kc & 1;
-            mbar_wait(&k_full[st], (kc >> 1) & 1);
-            ++kc;
-            if (j < je_x) {
-              tc_fence_after();
-              const uint32_t loK = loK0 + st * (kTileBytes / 16);
-#pragma unroll
-              for (int dh = 0; dh < 2; ++dh)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_ss<false, 1>(tSx, desc_join(loQ + dh * 1024 + ks * 2, kHi), desc_join(loK + dh * 1024 + ks * 2, kHi),
-                                    idesc_s, (dh | ks) != 0);
-              umma_commit(&s_full[x]);
-            }
-            umma_commit(&k_empty[st]);
-            // the item's last K tile: once these MMAs (and, in order, all earlier ones) are done Q is no longer needed
-            if (j == it.je - 1) umma_commit(q_empty);
-          };
-          mbar_wait(q_full, r & 1);
-          issue_s(0);
-          for (int j = 0; j < it.je; ++j) {
-            const int st = vc & 1;
-            mbar_wait(&v_full[st], (vc >> 1) & 1);
-            ++vc;
-            if (j < je_x) {
-              const uint32_t loV = loV0 + st * (kTileBytes / 16);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                mbar_wait(&p_chunk[x * 4 + c], pvc & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
-                  const int ks = c * 2 + k2;   // 16 kv rows per MMA: P columns 8 ks .. 8 ks + 7, V rows 16 ks .. 16 ks + 15
-                  umma_ts_f16(tOx, tSx + ks * 8, desc_join(loV + ((ks >> 2) * 64 + (ks & 3) * 16) * 8, kHi), idesc_pv,
-                              (j | ks) != 0);
-                }
-              }
-              umma_commit(&pv_done[x]);
-              ++pvc;
-            }
-            umma_commit(&v_empty[st]);
-            if (j + 1 < it.je) issue_s(j + 1);   // in order behind PV_x(j), which reads P from the same columns
-          }
-        }
-      }
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------ softmax / correction / epilogue: TWO warpgroups per query tile ----------
-    // A warp owns 16 rows of the tile (lanes 16 hf .. 16 hf + 15 of its TMEM quarter) in the 16x256b fragment layout: a
-    // thread holds two rows (lane / 4 and + 8) and, of every 8 columns, the pair 2 (lane % 4), + 1. Row maxima are two
-    // quad shuffles; a packed bf16 pair is one word of the 16x128b store shape, i.e. one 32-bit column of P.
-    setmaxnreg_inc<kRegsSoftmax6>();
-    const int sw = warp - 4;
-    const int x = sw >> 3;
-    const int q4 = warp & 3;                 // TMEM lane quarter (hardware: warp % 4)
-    const int hf = (sw >> 2) & 1;
-    const int lane = lane_id();
-    const int rA = q4 * 32 + hf * 16 + (lane >> 2);   // rows rA and rA + 8 of the tile
-    const int cq = (lane & 3) * 2;
-    const uint32_t lane_off = uint32_t(q4 * 32 + hf * 16) << 16;
-    const uint32_t tS = tmem_base + x * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + x * 128 + lane_off;
-    uint32_t sc = 0;             // s_full waits done (= steps of this tile so far, over all items)
-    uint32_t tokw[2] = {0, 0};   // XU-token waits done, per barrier set
-    for (int r = 0;; ++r) {
-      const int k = item_of(r);
-      if (k < 0) break;
-      const Item it = decode(k);
-      const int n0 = it.je0, n1 = it.je1;
-      const int n_kv = x ? n1 : n0;
-      const int q0 = (2 * it.pr + x) * kTile;
-      const int qA = q0 + rA, qB = qA + 8;
-      const int Pb = it.Pb;
-      float m_used[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-      for (int i = 0; i < n_kv; ++i) {
-        const int kv0 = i * kTile;
-        // tile needs the element test unless every (q, kv) pair is visible and in range
-        const bool full_tile = (kv0 + kTile <= p.S) && ((kv0 + kTile <= Pb) || (kv0 + kTile - 1 <= q0));
-        // visible keys of a row: the first `width` columns of the tile (kv < max(P, q + 1) and kv < S)
-        const uint32_t wA = full_tile ? 128u : (uint32_t)max(min(p.S, max(Pb, qA + 1)) - kv0, 0);
-        const uint32_t wB = full_tile ? 128u : (uint32_t)max(min(p.S, max(Pb, qB + 1)) - kv0, 0);
-        mbar_wait(&s_full[x], sc & 1);   // also: PV(i-1) has completed (same issuing thread, in order): O is stable
-        ++sc;
-        tc_fence_after();
-        uint32_t sv[2][16];
-        // ---- pass 1: row maxima (scores are read again for the exponentials: 64 live registers less)
-        float mxA = -INFINITY, mxB = -INFINITY;
-        tmem_ld_16x256b_x4(tS, sv[0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_wait_ld_regs(sv[c & 1]);
-          if (c < 3) tmem_ld_16x256b_x4(tS + (c + 1) * 32, sv[(c + 1) & 1]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t col = c * 32 + g * 8 + cq;
-            float a0 = __uint_as_float(sv[c & 1][4 * g]), a1 = __uint_as_float(sv[c & 1][4 * g + 1]);
-            float b0 = __uint_as_float(sv[c & 1][4 * g + 2]), b1 = __uint_as_float(sv[c & 1][4 * g + 3]);
-            if (!full_tile) {
-              if (col >= wA) a0 = -INFINITY;
-              if (col + 1 >= wA) a1 = -INFINITY;
-              if (col >= wB) b0 = -INFINITY;
-              if (col + 1 >= wB) b1 = -INFINITY;
-            }
-            mxA = fmaxf(mxA, fmaxf(a0, a1));
-            mxB = fmaxf(mxB, fmaxf(b0, b1));
-          }
-        }
-        mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1));
-        mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1));
-        mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
-        mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
-        float alphaA = 1.f, alphaB = 1.f;
-        {
-          const float mtA = mxA * p.scale_log2, mtB = mxB * p.scale_log2;
-          if (mtA > m_used[0] + 8.f) { alphaA = ex2(m_used[0] - mtA); m_used[0] = mtA; }   // lazy rescale (2^8 headroom)
-          if (mtB > m_used[1] + 8.f) { alphaB = ex2(m_used[1] - mtB); m_used[1] = mtB; }
-        }
-        if (i > 0 && __any_sync(0xffffffffu, alphaA != 1.f || alphaB != 1.f)) {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[16];
-            tmem_ld_16x256b_x4(tO + c * 32, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              v[4 * g] = __float_as_uint(__uint_as_float(v[4 * g]) * alphaA);
-              v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) * alphaA);
-              v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) * alphaB);
-              v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) * alphaB);
-            }
-            tmem_st_16x256b_x4(tO + c * 32, v);
-          }
-          tmem_wait_st();
-        }
-        // XU token (see v5): exp phases of the two tiles alternate; every arrival has exactly one wait
-        if (x == 1 ? (i < n0) : (i > 0 && i - 1 < n1)) {
-          mbar_wait(&xu_tok[(r & 1) * 2 + x], tokw[r & 1] & 1);
-          ++tokw[r & 1];
-        }
-        float meA = (m_used[0] == -INFINITY) ? 0.f : m_used[0];
-        float meB = (m_used[1] == -INFINITY) ? 0.f : m_used[1];
-        asm volatile("" : "+f"(meA), "+f"(meB));   // pins the exponentials behind the wait
-        // ---- pass 2: exponentials, P written over the score columns already consumed (P chunk c = 32-bit columns
-        // 16 c .. 16 c + 15 < 32 c + 32; every warp only touches its own 16 lanes)
-        float sumA = 0.f, sumB = 0.f;
-        uint32_t pc[8];
-        tmem_ld_16x256b_x4(tS, sv[0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_wait_ld_regs(sv[c & 1]);
-          if (c < 3) tmem_ld_16x256b_x4(tS + (c + 1) * 32, sv[(c + 1) & 1]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t col = c * 32 + g * 8 + cq;
-            float a0 = fmaf(__uint_as_float(sv[c & 1][4 * g]), p.scale_log2, -meA);
-            float a1 = fmaf(__uint_as_float(sv[c & 1][4 * g + 1]), p.scale_log2, -meA);
-            float b0 = fmaf(__uint_as_float(sv[c & 1][4 * g + 2]), p.scale_log2, -meB);
-            float b1 = fmaf(__uint_as_float(sv[c & 1][4 * g + 3]), p.scale_log2, -meB);
-            if (!full_tile) {
-              if (col >= wA) a0 = -INFINITY;
-              if (col + 1 >= wA) a1 = -INFINITY;
-              if (col >= wB) b0 = -INFINITY;
-              if (col + 1 >= wB) b1 = -INFINITY;
-            }
-            a0 = ex2(a0); a1 = ex2(a1); b0 = ex2(b0); b1 = ex2(b1);   // -inf -> 0
-            sumA += a0 + a1;
-            sumB += b0 + b1;
-            pc[2 * g] = pack_bf16(a0, a1);
-            pc[2 * g + 1] = pack_bf16(b0, b1);
-          }
-          if (c > 0) {   // chunk c - 1 is in TMEM: hand it to the issuer
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_chunk[x * 4 + c - 1]);
-          }
-          tmem_st_16x128b_x4(tS + c * 16, pc);
-        }
-        // exponentials done: the other tile may start the exp phase that waits for this one (if it has such a step)
-        if (x == 0 ? (i < n1) : (i + 1 < n0)) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&xu_tok[(r & 1) * 2 + (x ^ 1)]);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_chunk[x * 4 + 3]);
-        l[0] = l[0] * alphaA + sumA;
-        l[1] = l[1] * alphaB + sumB;
-      }
-      // epilogue of the item: the issuer is already past S(0) of the next one
-      if (n_kv > 0) {
-        mbar_wait(&pv_done[x], (sc - 1) & 1);   // PV steps == S steps of this tile
-        tc_fence_after();
-#pragma unroll
-        for (int rr2 = 0; rr2 < 2; ++rr2) {     // row sums are spread over the quad
-          l[rr2] += __shfl_xor_sync(0xffffffffu, l[rr2], 1);
-          l[rr2] += __shfl_xor_sync(0xffffffffu, l[rr2], 2);
-        }
-        const float invA = 1.f / l[0], invB = 1.f / l[1];
-        const bool okA = qA < p.S, okB = qB < p.S;
-        __nv_bfloat16* oA = p.o + ((int64_t)it.b * p.S + qA) * p.ldo + (int64_t)it.h * kD + cq;
-        __nv_bfloat16* oB = oA + 8 * p.ldo;
-#pragma unroll 1
-        for (int c = 0; c < kD / 32; ++c) {
-          uint32_t v[16];
-          tmem_ld_16x256b_x4(tO + c * 32, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (okA)
-              *reinterpret_cast<uint32_t*>(oA + c * 32 + g * 8) =
-                  pack_bf16(__uint_as_float(v[4 * g]) * invA, __uint_as_float(v[4 * g + 1]) * invA);
-            if (okB)
-              *reinterpret_cast<uint32_t*>(oB + c * 32 + g * 8) =
-                  pack_bf16(__uint_as_float(v[4 * g + 2]) * invB, __uint_as_float(v[4 * g + 3]) * invB);
-          }
-        }
-        if ((lane & 3) == 0) {
-          float* lse = p.lse + ((int64_t)it.b * p.Hq + it.h) * p.S;
-          if (okA) lse[qA] = (m_used[0] + log2f(l[0])) * kLn2;
-          if (okB) lse[qB] = (m_used[1] + log2f(l[1])) * kLn2;
-        }
-        tc_fence_before();
-      }
-    }
-    tc_fence_before();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 3) tmem_dealloc<1>(tmem_base, 512);
-}
-
 // ================================================================================================
 // backward
 // ================================================================================================
@@ -2678,13 +2287,12 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   static const int version = [] {
     const char* e = getenv("LLAMAX_ATTN_FWD");
     if (getenv("LLAMAX_ATTN_FWD_ONE_TILE") && getenv("LLAMAX_ATTN_FWD_ONE_TILE")[0] == '1') return 1;
-    return (e != nullptr && e[0] >= '1' && e[0] <= '6') ? e[0] - '0' : 5;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 5;
   }();
   // packed documents: the XU token of v4 / v5 is off there (see the kernels) and without it they lose to v2 -> v2
-  const int version_eff = (version >= 4 && doc_start != nullptr) ? 2 : version;   // 6: see attn_fwd6_kernel
-  if (version_eff >= 5) {   // persistent: one CTA per SM over a static item list
-    auto kern5 = version_eff == 6 ? (D == 128 ? attn_fwd6_kernel<128> : attn_fwd6_kernel<64>)
-                                  : (D == 128 ? attn_fwd5_kernel<128> : attn_fwd5_kernel<64>);
+  const int version_eff = (version >= 4 && doc_start != nullptr) ? 2 : version;
+  if (version_eff == 5) {   // persistent: one CTA per SM over a static item list
+    auto kern5 = D == 128 ? attn_fwd5_kernel<128> : attn_fwd5_kernel<64>;
     if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern5), fwd5::kSmemBytes5, "attn_fwd: cudaFuncSetAttribute"))) return rc;
     AttnFwdParams p5;
     p5.o = (__nv_bfloat16*)o;
@@ -2699,8 +2307,7 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
     const int n_pairs = (int)((ceil_div(S, fwd::kTile) + 1) / 2);
     const int64_t n_items = (int64_t)n_pairs * B * Hq;
     const int grid5 = (int)std::min<int64_t>(n_items, sm_count());
-    kern5<<<grid5, version_eff == 6 ? fwd6::kThreads6 : fwd4::kThreads, fwd5::kSmemBytes5, (cudaStream_t)stream>>>(tq, tk, tv, p5,
-                                                                                                                    n_pairs);
+    kern5<<<grid5, fwd4::kThreads, fwd5::kSmemBytes5, (cudaStream_t)stream>>>(tq, tk, tv, p5, n_pairs);
     LX_CHECK_LAUNCH("attn_fwd");
     return 0;
   }
