@@ -82,6 +82,16 @@ int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, voi
 int llamax_bf16_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                                 const llamax_epilogue_t* epi, const void* ab, int64_t ld_ab, void* dab, int64_t ld_dab,
                                 void* g, void* stream);
+/* llamax_bf16_gemm that also returns, per row and group of 128 output columns, the dot product of the bf16-ROUNDED
+ * outputs with a second matrix:  dot_out[(m / S) * (N / 128) + g][m % S] = sum_{c in group g} C[m,c] * other[m,c]
+ * (fp32, layout [M / S, N / 128, S]). With C = dO = grad_input of wo (int8.py:127 + the LoRA term) and other = O this is
+ * the attention backward's delta[b, h, s] (head_dim 128) for free in the epilogue that writes dO: pass it to
+ * llamax_attn_bwd with o = NULL. N % 256 == 0, M % S == 0, other bf16 [M,N] pitch ld_other (must not alias C); epi:
+ * LoRA term only. */
+int llamax_bf16_gemm_rowdot(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
+                            int64_t N, int64_t K, const llamax_epilogue_t* epi, const void* other, int64_t ld_other,
+                            void* dot_out, int64_t S, void* stream);
+
 /* ---- K4/K5 mixed-input: bf16 activations x frozen INT8 weight, converted inside the GEMM ---------------------------
  * The int8 weight is read by TMA as stored and expanded to bf16 in shared memory by converter warps (exact: every int8
  * value is a bf16 value), so neither a de-quantised nor a transposed copy of the weight exists in HBM.
@@ -166,7 +176,8 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     int64_t ldo, void* lse, int64_t B, int64_t S, int32_t Hq, int32_t Hkv, int32_t D,
                     int64_t prefix_len, const void* prefix_len_b, const void* doc_start, float scale, void* stream);
 /* dq/dk/dv bf16 with pitches lddq/lddk/lddv; dq_accum fp32 workspace [B,S,Hq,D] (zeroed by the call);
- * delta fp32 workspace [B,Hq,S]. rope_inverse: null, or the fp32 [>= S, D/2, 2] (cos, sin) table of K7: dq and dk then
+ * delta fp32 workspace [B,Hq,S]; o = NULL: delta already holds sum_d dO * O (e.g. from llamax_bf16_gemm_rowdot) and
+ * the pass over o / dout that computes it is skipped. rope_inverse: null, or the fp32 [>= S, D/2, 2] (cos, sin) table of K7: dq and dk then
  * leave the call already rotated back through RoPE (the autograd of apply_rope, llama.py:63-73), which saves the
  * separate in-place pass over the q|k gradient columns. */
 int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

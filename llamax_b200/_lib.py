@@ -63,6 +63,7 @@ SIGNATURES = {
     "llamax_bf16_gemm": [P, I64, P, I64, P, I64, I64, I64, I64, P, c_int, EP, P],
     "llamax_bf16_gemm_swiglu_bwd": [P, I64, P, I64, I64, I64, I64, EP, P, I64, P, I64, P, P],
     "llamax_bf16_gemm_tn": [P, I64, P, I64, P, I64, I64, I64, I64, P],
+    "llamax_bf16_gemm_rowdot": [P, I64, P, I64, P, I64, I64, I64, I64, EP, P, I64, P, I64, P],
     "llamax_bf16_int8_gemm": [P, I64, P, I64, P, c_int, P, I64, P, I64, I64, I64, I64, I64, EP, P],
     "llamax_bf16_int8_gemm_swiglu_bwd": [P, I64, P, I64, P, I64, I64, I64, EP, P, I64, P, I64, P, P],
     "llamax_dequant_weight": [P, P, P, I64, I64, I64, c_int, c_int, P],

@@ -2361,17 +2361,17 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     const void* rope_inverse, void* stream) {
   if ((doc_start == nullptr) != (doc_end == nullptr))
     return set_error(LLAMAX_ERR_ARG, "attn_bwd: doc_start and doc_end go together");
-  if (!q || !k || !v || !o || !lse || !dout || !dq || !dk || !dv || !dq_accum || !delta)
+  if (!q || !k || !v || !lse || !dout || !dq || !dk || !dv || !dq_accum || !delta)   // o may be NULL: delta is given
     return set_error(LLAMAX_ERR_ARG, "attn_bwd: null pointer");
   int rc = check_attn_args(B, S, Hq, Hkv, D, prefix_len, "attn_bwd");
   if (rc) return rc;
-  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || lddo % 8 || lddq % 8 || lddk % 8 || lddv % 8)
+  if (ldq % 8 || ldk % 8 || ldv % 8 || (o != nullptr && ldo % 8) || lddo % 8 || lddq % 8 || lddk % 8 || lddv % 8)
     return set_error(LLAMAX_ERR_ARG, "attn_bwd: pitches must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = B * S;
   cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)rows * Hq * D * sizeof(float), st);
   if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: memset");
-  {
+  if (o != nullptr) {
     const int64_t warps = rows * ceil_div(Hq, 32 / (D / 8));
     const int blocks = (int)ceil_div(warps * 32, 256);
     if (D == 128)

@@ -65,7 +65,11 @@ struct GemmParams {
   const __nv_bfloat16* resid;
   int64_t ldr;
   int seg_n0, seg_n1;  // LoRA column segments (0 = none): see llamax_epilogue_t
-  int flags;  // 1: dump raw accumulator (int32 / fp32) to C; 2: round to bf16 before the column scale
+  // row-dot mode (flags & 4, kRes kernels): `resid` is not added; dot_out[(m / dot_S) * (N / 128) + g][m % dot_S] =
+  // sum over the 128 columns of group g of bf16(C[m, c]) * resid[m, c]  (the attention backward's delta)
+  float* dot_out;
+  int dot_S;
+  int flags;  // 1: dump raw accumulator (int32 / fp32) to C; 2: round to bf16 before the column scale; 4: row-dot mode
   // kSwi epilogue (SwiGLU backward fused behind the w2 grad_input GEMM): C is not written
   const __nv_bfloat16* swi_ab;  // [M, 2N] pitch ld_ab: a = w1 x in columns [0, N), b = w3 x in [N, 2N)
   int64_t ld_ab;
@@ -675,6 +679,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr bool kSide = kSwi || kRes || (kPipeStage && kRank > 0);   // pipelined side inputs need the registers
       constexpr int kVBufs = kSide ? 1 : 2;
       uint32_t v[kVBufs][32];
+      const bool rowdot = kRes && (p.flags & 4) != 0;
+      float dacc = 0.f;
       if constexpr (!kSide) {
         if (ch * 4 < n_chunks) tmem_ld_32x32(taddr + ch * 4 * 32, v[0]);
       }
@@ -757,10 +763,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (row_ok && col + j8 < p.N) {
                 const uint32_t* r4 = &pa[j8 >> 4][(j8 & 8) >> 1];
                 uint4 o;
-                o.x = pack_bf16(f[0] + bf16_lo(r4[0]), f[1] + bf16_hi(r4[0]));
-                o.y = pack_bf16(f[2] + bf16_lo(r4[1]), f[3] + bf16_hi(r4[1]));
-                o.z = pack_bf16(f[4] + bf16_lo(r4[2]), f[5] + bf16_hi(r4[2]));
-                o.w = pack_bf16(f[6] + bf16_lo(r4[3]), f[7] + bf16_hi(r4[3]));
+                if (rowdot) {   // C is stored as is; the side operand is multiplied with the ROUNDED outputs and summed
+                  o.x = pack_bf16(f[0], f[1]);
+                  o.y = pack_bf16(f[2], f[3]);
+                  o.z = pack_bf16(f[4], f[5]);
+                  o.w = pack_bf16(f[6], f[7]);
+                  dacc += bf16_lo(o.x) * bf16_lo(r4[0]) + bf16_hi(o.x) * bf16_hi(r4[0]) + bf16_lo(o.y) * bf16_lo(r4[1]) +
+                          bf16_hi(o.y) * bf16_hi(r4[1]) + bf16_lo(o.z) * bf16_lo(r4[2]) + bf16_hi(o.z) * bf16_hi(r4[2]) +
+                          bf16_lo(o.w) * bf16_lo(r4[3]) + bf16_hi(o.w) * bf16_hi(r4[3]);
+                } else {
+                  o.x = pack_bf16(f[0] + bf16_lo(r4[0]), f[1] + bf16_hi(r4[0]));
+                  o.y = pack_bf16(f[2] + bf16_lo(r4[1]), f[3] + bf16_hi(r4[1]));
+                  o.z = pack_bf16(f[4] + bf16_lo(r4[2]), f[5] + bf16_hi(r4[2]));
+                  o.w = pack_bf16(f[6] + bf16_lo(r4[3]), f[7] + bf16_hi(r4[3]));
+                }
                 stg_v4(dst + j8, o);
               }
             } else if (row_ok && col + j8 < p.N) {
@@ -779,6 +795,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               stg_v4(dst + j8, o);
             }
           }
+        }
+      }
+      if constexpr (kRes) {
+        // this thread's 128 columns (chunks 4 ch .. 4 ch + 3 of the tile) are one group: [batch][group][position]
+        if (rowdot && row_ok && col0 + ch * 128 < p.N) {
+          const int bb = row / p.dot_S;
+          p.dot_out[((int64_t)bb * (p.N / 128) + (col0 / 128 + ch)) * p.dot_S + (row - bb * p.dot_S)] = dacc;
         }
       }
       tc_fence_before();
@@ -1809,6 +1832,31 @@ int llamax_bf16_gemm_swiglu_bwd(const void* A, int64_t lda, const void* B, int64
   if (r == 0) return launch_gemm_r<false, 1, 0, false, true>(A, lda, B, ldb, p, st);
   if (r == 8) return launch_gemm_r<false, 1, 8, false, true>(A, lda, B, ldb, p, st);
   return launch_gemm_r<false, 1, 16, false, true>(A, lda, B, ldb, p, st);
+}
+
+int llamax_bf16_gemm_rowdot(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M,
+                            int64_t N, int64_t K, const llamax_epilogue_t* epi, const void* other, int64_t ld_other,
+                            void* dot_out, int64_t S, void* stream) {
+  if (!A || !B || !C || !other || !dot_out) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_rowdot: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0 || S <= 0 || M % S) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_rowdot: M must be a multiple of S");
+  if (N % 256) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_rowdot: N must be a multiple of 256 (groups of 128 columns, two per tile)");
+  if (other == C) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_rowdot: `other` must not alias C");
+  if (epi != nullptr && epi->resid != nullptr) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_rowdot: no residual term in this form");
+  if (g_gemm_cg != 2) return set_error(LLAMAX_ERR_ARG, "bf16_gemm_rowdot: needs the CTA-pair configuration");
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.C = C; p.ldc = ldc;
+  fill_epilogue(p, epi);
+  p.resid = static_cast<const __nv_bfloat16*>(other);
+  p.ldr = ld_other;
+  p.dot_out = static_cast<float*>(dot_out);
+  p.dot_S = (int)S;
+  p.flags = 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int r = p.lora_rank <= 0 ? 0 : p.lora_rank <= 8 ? 8 : 16;
+  if (r == 0) return launch_gemm_r<false, 2, 0, false, false, true>(A, lda, B, ldb, p, st);
+  if (r == 8) return launch_gemm_r<false, 2, 8, false, false, true>(A, lda, B, ldb, p, st);
+  return launch_gemm_r<false, 2, 16, false, false, true>(A, lda, B, ldb, p, st);
 }
 
 int llamax_bf16_int8_gemm(const void* A, int64_t lda, const void* B8, int64_t ldb8, const void* b_scale, int b_layout,

@@ -82,6 +82,16 @@ _MIXED = os.environ.get("LLAMAX_MIXED_GEMM", "0") == "1"
 _ones: dict = {}
 
 
+# "1": the attention backward's delta = rowsum(dO * O) comes out of the epilogue of the wo grad_input GEMM (which writes
+# dO) instead of its own pass over O and dO. Measured, same box: attention-backward class 38.6 -> 36.7 ms/step, bf16 GEMM
+# class 195.8 -> 197.3 (the K = 4096 GEMM is epilogue-bound and now reads O), step 401.8 vs 401.4 / 403.2: no gain at the
+# power cap, so the separate pass stays the default.
+_FUSE_DELTA = os.environ.get("LLAMAX_FUSE_DELTA", "0") == "1"
+
+
+def set_fuse_delta(on: bool) -> None:
+    global _FUSE_DELTA
+    _FUSE_DELTA = bool(on)
 # A/B switch (benchmarking only): "0" restores three INT8 GEMM launches for wq, wk, wv
 _QKV_ONE_LAUNCH = os.environ.get("LLAMAX_QKV_ONE_LAUNCH", "1") != "0"
 
@@ -358,8 +368,24 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tenso
     return ops.bf16_gemm(dy_cat, wt), lora_grads
 
 
-def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, wt: Tensor | None, prep, sink, i8=None, mixed=None):
-    """Backward of one linear whose incoming gradient buffer we do not own: LoRA term in the GEMM epilogue."""
+def _single_backward(spec: LinearSpec, dy: Tensor, x_in: Tensor, wt: Tensor | None, prep, sink, i8=None, mixed=None,
+                     rowdot_S: int = 0):
+    """Backward of one linear whose incoming gradient buffer we do not own: LoRA term in the GEMM epilogue.
+    rowdot_S > 0 (wo, head_dim 128, default bf16 operand path): the epilogue that writes dx = dO also returns the
+    attention backward's delta[b, h, s] = sum_d dO * O (x_in is the attention output O): returns (dx, grads, delta)."""
+    if rowdot_S > 0:
+        kw = {}
+        dA = dB = None
+        if spec.R > 0:
+            bt, at, ht = prep[id(spec)]
+            dh = torch.empty(dy.shape[0], spec.R, device=dy.device, dtype=torch.bfloat16)
+            dht = ops.transposed_rank_buffer(spec.R, dy.shape[0], dy.device)
+            dB = sink.emit(_lora_dh_dB(dy, bt, ht, dh, spec.lora_scale, dht), False, spec.lora_b.dtype)
+            kw = dict(lora_h=dh, lora_b=at, lora_scale=1.0)
+        dx, delta = ops.bf16_gemm_rowdot(dy, wt, x_in, rowdot_S, **kw)
+        if spec.R > 0:
+            dA = sink.emit(ops.lora_wgrad(x_in, None, 1.0, Ht=dht), True, spec.lora_a.dtype)
+        return dx, ((dA, dB) if spec.R > 0 else None), delta
     if spec.R > 0:
         bt, at, ht = prep[id(spec)]
         dh = torch.empty(dy.shape[0], spec.R, device=dy.device, dtype=torch.bfloat16)
@@ -578,13 +604,20 @@ class FusedDecoderBlock(torch.autograd.Function):
 
         # --- wo ---
         wto, _ = operand("wo")
-        do, go = _single_backward(so, dx1, o, wto, prep, sink, i8=i8.get("wo"), mixed=mixed.get("wo"))
+        # delta = rowsum(dO * O) per head comes out of the epilogue that writes dO (no separate pass over O and dO)
+        fuse_delta = (_FUSE_DELTA and wto is not None and D == 128 and (Hq * D) % 256 == 0 and not _INT8_GRAD
+                      and "wo" not in mixed)
+        delta = None
+        if fuse_delta:
+            do, go, delta = _single_backward(so, dx1, o, wto, prep, sink, rowdot_S=S)
+        else:
+            do, go = _single_backward(so, dx1, o, wto, prep, sink, i8=i8.get("wo"), mixed=mixed.get("wo"))
 
         # --- attention ---
         dqkv = _padded_empty(M, nq + 2 * nk + rqkv, dev)
         ops.attn_bwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], o, lse, do,
                      dqkv[:, :nq], dqkv[:, nq : nq + nk], dqkv[:, nq + nk : nq + 2 * nk], B, S, Hq, Hkv, D, prefix_len,
-                     doc_start=doc_start, doc_end=doc_end, rope_inverse=rope)   # dq, dk come back un-rotated
+                     doc_start=doc_start, doc_end=doc_end, rope_inverse=rope, delta=delta)   # dq, dk come back un-rotated
         wtqkv, placedqkv = operand("wqkv")
         dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, wtqkv, placedqkv, prep, sink,
                                      i8=i8.get("wqkv"), mixed=mixed.get("wqkv"))

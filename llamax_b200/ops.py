@@ -201,6 +201,27 @@ def bf16_gemm_swiglu_bwd(A: Tensor, B: Tensor, a: Tensor, b: Tensor, *, out_ab: 
     return out_ab[:, :F], out_ab[:, F : 2 * F], g
 
 
+def bf16_gemm_rowdot(A: Tensor, B: Tensor, other: Tensor, S: int, *, lora_h=None, lora_b=None, lora_scale=1.0):
+    """C = A[M,K] @ B[N,K]^T (+ LoRA) and dot[b, g, s] = sum over the 128 columns of group g of C[b*S + s, c] * other[...]
+    (C rounded to bf16 first): with other = the attention output this is the attention backward's delta, produced by the
+    epilogue that writes dO. Returns (C, dot fp32 [M / S, N / 128, S])."""
+    lib, st = _prep(A)
+    assert A.dtype is torch.bfloat16 and B.dtype is torch.bfloat16 and other.dtype is torch.bfloat16
+    assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
+    M, K = A.shape
+    N = B.shape[0]
+    other = _rows(other)
+    assert other.shape == (M, N) and M % S == 0 and N % 256 == 0
+    out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
+    dot = torch.empty(M // S, N // 128, S, device=A.device, dtype=torch.float32)
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, None)
+    _call(lib, "llamax_bf16_gemm_rowdot",
+          (_p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), M, N, K, ctypes.byref(ep) if ep is not None else None,
+           _p(other), other.stride(0), _p(dot), S, st,),
+          "bf16_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))
+    return out, dot
+
+
 def bf16_int8_gemm(A: Tensor, W8: Tensor, w_scale: Tensor, *, out: Tensor | None = None, lora_h=None, lora_b=None,
                    lora_scale=1.0, resid=None) -> Tensor:
     """Weight-only forward, mixed-input (subclasses/int8.py:118): C = bf16(A[M,K] @ bf16(W8[N,K])^T) * w_scale[n]
@@ -596,19 +617,24 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, S: int, Hq: int, Hkv: int,
 
 
 def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, S, Hq, Hkv, D, prefix_len, scale=None, doc_start=None,
-             doc_end=None, rope_inverse=None):
+             doc_end=None, rope_inverse=None, delta=None):
     """Writes dq/dk/dv (row views like q/k/v). rope_inverse: fp32 [>= S, D/2, 2] table -> dq, dk come back already
-    rotated through the RoPE backward (no separate rope_(..., inverse=True) pass needed)."""
+    rotated through the RoPE backward (no separate rope_(..., inverse=True) pass needed). delta: fp32 [B, Hq, S] =
+    sum_d dout * o already computed (bf16_gemm_rowdot): o is then not read and may be None."""
     if rope_inverse is not None:
         assert rope_inverse.dtype is torch.float32 and rope_inverse.is_contiguous()
         assert rope_inverse.shape[0] >= S and rope_inverse.shape[1] == D // 2
     lib, st = _prep(q)
     dout = _rows(dout)
     dq_accum = torch.empty(B * S, Hq * D, device=q.device, dtype=torch.float32)
-    delta = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
+    if delta is None:
+        delta = torch.empty(B, Hq, S, device=q.device, dtype=torch.float32)
+    else:
+        assert delta.dtype is torch.float32 and delta.shape == (B, Hq, S) and delta.is_contiguous()
+        o = None
     scale = float(scale) if scale is not None else D ** -0.5
     p_scalar, p_b = _prefix_args(prefix_len, B, q.device)
     _call(lib, "llamax_attn_bwd",
-          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, p_scalar, _p(p_b), _p(doc_start), _p(doc_end), scale, _p(rope_inverse), st,),
+          (_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0) if o is not None else 0, _p(lse), _p(dout), dout.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(dq_accum), _p(delta), B, S, Hq, Hkv, D, p_scalar, _p(p_b), _p(doc_start), _p(doc_end), scale, _p(rope_inverse), st,),
           "attn_bwd", 10.0 * B * Hq * D * _pairs(S, prefix_len), 0.0)
     return dq, dk, dv

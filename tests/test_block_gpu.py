@@ -537,3 +537,27 @@ def test_lm_head_row_compaction_changes_nothing():
     assert torch.isfinite(model(tokens, labels=full, block_mask=PrefixLM(64)))
     none = torch.full((B, S), -100, device="cuda")
     assert model(tokens, labels=none, block_mask=PrefixLM(64)).item() == 0.0
+
+
+def test_delta_from_gemm_epilogue_mode_matches_default():
+    """LLAMAX_FUSE_DELTA=1: delta of the attention backward from the wo grad_input GEMM's epilogue (head_dim 128)."""
+    from llamax_b200.modelling import PrefixLM
+    from llamax_b200.modelling import fused_block as FB
+
+    results = []
+    for on in (False, True):
+        FB.set_fuse_delta(on)
+        try:
+            model = build_tiny_llama(True, num_layers=1).cuda()
+            layer, cfg = model.layers[0], model.config
+            rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:256].cuda()
+            torch.manual_seed(7)
+            x = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16().requires_grad_(True)
+            dout = torch.randn(2, 256, cfg.embed_dim, device="cuda").bfloat16()
+            out = layer(x, rope, block_mask=PrefixLM(64))
+            out.backward(dout)
+            results.append([x.grad.detach()] + [p_.grad.detach() for p_ in layer.parameters() if p_.requires_grad])
+        finally:
+            FB.set_fuse_delta(False)
+    for a, b in zip(results[0], results[1]):
+        assert rel_err(b, a) <= 5e-3

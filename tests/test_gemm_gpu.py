@@ -360,3 +360,41 @@ def test_int8_gemm_lora_column_segments_equal_three_launches(M, K, n0, n1, N, R)
         ops.int8_gemm_dequant(A, W[c0:c1], sa, sw[c0:c1], out=ref[:, c0:c1], lora_h=h[:, i * R : (i + 1) * R],
                               lora_b=B[c0:c1].contiguous(), lora_scale=2.0)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("M,S,N,K,R", [(512, 256, 512, 256, 8), (1024, 512, 4096, 4096, 8), (300, 100, 256, 192, 0)])
+def test_bf16_gemm_rowdot_epilogue(M, S, N, K, R):
+    """The grad_input GEMM of wo also returns delta[b, h, s] = sum_d dO * O (groups of 128 columns = heads): C is
+    bit-identical to the plain GEMM and the dot products equal those of the stored (rounded) C in fp32."""
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).bfloat16().cuda()
+    B = (torch.randn(N, K, generator=g) * 0.05).bfloat16().cuda()
+    O = torch.randn(M, N, generator=g).bfloat16().cuda()
+    kw = {}
+    if R:
+        kw.update(lora_h=torch.randn(M, R, generator=g).bfloat16().cuda(),
+                  lora_b=(torch.randn(N, R, generator=g) * 0.05).bfloat16().cuda(), lora_scale=1.0)
+    C, dot = ops.bf16_gemm_rowdot(A, B, O, S, **kw)
+    assert torch.equal(C, ops.bf16_gemm(A, B, **kw))
+    ref = (C.float() * O.float()).view(M // S, S, N // 128, 128).sum(-1).permute(0, 2, 1)
+    assert dot.shape == ref.shape
+    assert rel_err(dot, ref) <= 1e-5
+
+
+def test_attention_backward_with_given_delta_equals_internal():
+    B, S, Hq, Hkv, D = 2, 384, 8, 2, 128
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B * S, (Hq + 2 * Hkv) * D, generator=g).bfloat16().cuda()
+    q, k, v = qkv[:, : Hq * D], qkv[:, Hq * D : (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D :]
+    o, lse = ops.attn_fwd(q, k, v, B, S, Hq, Hkv, D, 100)
+    do = torch.randn(B * S, Hq * D, generator=g).bfloat16().cuda()
+    outs = []
+    for given in (False, True):
+        d = torch.zeros_like(qkv)
+        delta = None
+        if given:
+            delta = (do.float() * o.float()).view(B, S, Hq, D).sum(-1).permute(0, 2, 1).contiguous()
+        ops.attn_bwd(q, k, v, None if given else o, lse, do, d[:, : Hq * D], d[:, Hq * D : (Hq + Hkv) * D], d[:, (Hq + Hkv) * D :],
+                     B, S, Hq, Hkv, D, 100, delta=delta)
+        outs.append(d)
+    assert rel_err(outs[1], outs[0]) <= 2e-3
