@@ -900,6 +900,14 @@ static int launch_gemm_mix(const void* A, int64_t lda, const void* B8, int64_t l
     return set_error(LLAMAX_ERR_ARG, "gemm: residual must be 16-byte aligned with ldr % 8 == 0");
   if (p.lora_rank < 0 || p.lora_rank > kMaxLoraRank || (p.lora_rank % 4))
     return set_error(LLAMAX_ERR_ARG, "gemm: lora rank must be a multiple of 4 in [0, 16]");
+  if constexpr (kMix == 2) {   // argument checks before any driver call
+    if (p.K1 <= 0 || p.K1 % 64 || p.K1 > p.K || p.K - p.K1 > 64 || !p.k_scale)
+      return set_error(LLAMAX_ERR_ARG, "mixed gemm: K1 must be a positive multiple of 64, the tail at most 64 rows");
+    if ((p.K > p.K1) != (tail != nullptr))
+      return set_error(LLAMAX_ERR_ARG, "mixed gemm: tail tensor and K - K1 disagree");
+    if (tail != nullptr && ((ldt * 2) % 16 || reinterpret_cast<uintptr_t>(tail) % 16))
+      return set_error(LLAMAX_ERR_ARG, "mixed gemm: tail must be 16-byte aligned with a pitch multiple of 8");
+  }
   CUtensorMap tmA, tmB, tmT;
   int rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, p.K, p.M, lda, 64, kBM);
   if (rc) return rc;
@@ -908,15 +916,9 @@ static int launch_gemm_mix(const void* A, int64_t lda, const void* B8, int64_t l
     if (rc) return rc;
     tmT = tmA;
   } else {
-    if (p.K1 <= 0 || p.K1 % 64 || p.K1 > p.K || p.K - p.K1 > 64 || !p.k_scale)
-      return set_error(LLAMAX_ERR_ARG, "mixed gemm: K1 must be a positive multiple of 64, the tail at most 64 rows");
-    if ((p.K > p.K1) != (tail != nullptr))
-      return set_error(LLAMAX_ERR_ARG, "mixed gemm: tail tensor and K - K1 disagree");
     rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B8, p.N, p.K1, ldb8, kBN / 2, 64, false);
     if (rc) return rc;
     if (tail != nullptr) {
-      if ((ldt * 2) % 16 || reinterpret_cast<uintptr_t>(tail) % 16)
-        return set_error(LLAMAX_ERR_ARG, "mixed gemm: tail must be 16-byte aligned with a pitch multiple of 8");
       rc = make_tmap_2d(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tail, p.N, p.K - p.K1, ldt, 64, 64);
       if (rc) return rc;
     } else {

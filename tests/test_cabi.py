@@ -78,3 +78,41 @@ def test_new_gemm_entry_points_validate_arguments_without_gpu():
     mis = ctypes.c_void_p(p.value + 2)
     assert lib.llamax_bf16_gemm_swiglu_bwd(p, 64, p, 64, 16, 32, 64, None, mis, 64, p, 64, None, None) == -1
     assert b"aligned" in lib.llamax_last_error()
+
+
+def test_round2_entry_points_validate_arguments_without_gpu():
+    """Mixed-input GEMMs, the row-dot GEMM and the segmented LoRA epilogue reject bad arguments before any launch."""
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(512)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    # mixed-input: null pointers; layout 0 has no tail; layout must be 0 / 1; K1 multiple of 64; tail and K - K1 agree
+    assert lib.llamax_bf16_int8_gemm(None, 64, p, 64, p, 0, None, 0, p, 64, 16, 64, 64, 64, None, None) == -1
+    assert b"null" in lib.llamax_last_error()
+    assert lib.llamax_bf16_int8_gemm(p, 64, p, 64, p, 0, p, 64, p, 64, 16, 64, 64, 64, None, None) == -1
+    assert b"no tail" in lib.llamax_last_error()
+    assert lib.llamax_bf16_int8_gemm(p, 64, p, 64, p, 2, None, 0, p, 64, 16, 64, 64, 64, None, None) == -1
+    assert b"b_layout" in lib.llamax_last_error()
+    assert lib.llamax_bf16_int8_gemm(p, 96, p, 64, p, 1, None, 0, p, 64, 16, 64, 96, 96, None, None) == -1
+    assert b"multiple of 64" in lib.llamax_last_error()
+    assert lib.llamax_bf16_int8_gemm(p, 128, p, 64, p, 1, None, 0, p, 64, 16, 64, 72, 64, None, None) == -1
+    assert b"disagree" in lib.llamax_last_error()
+    assert lib.llamax_bf16_int8_gemm_swiglu_bwd(p, 64, p, 64, None, 16, 32, 64, None, p, 64, p, 64, None, None) == -1
+    assert b"null" in lib.llamax_last_error()
+    # row-dot GEMM: N % 256, M % S, aliasing
+    assert lib.llamax_bf16_gemm_rowdot(p, 64, p, 64, p, 128, 16, 128, 64, None, p, 128, p, 16, None) == -1
+    assert b"multiple of 256" in lib.llamax_last_error()
+    assert lib.llamax_bf16_gemm_rowdot(p, 64, p, 64, p, 256, 16, 256, 64, None, p, 256, p, 5, None) == -1
+    assert b"multiple of S" in lib.llamax_last_error()
+    q = ctypes.cast(ctypes.create_string_buffer(64), ctypes.c_void_p)
+    assert lib.llamax_bf16_gemm_rowdot(p, 64, p, 64, q, 256, 16, 256, 64, None, q, 256, p, 16, None) == -1
+    assert b"alias" in lib.llamax_last_error()
+    # LoRA column segments must be increasing multiples of the tile width
+    ep = _lib.Epilogue()
+    ep.lora_h, ep.ldh, ep.lora_b, ep.lora_rank, ep.lora_scale = p.value, 24, p.value, 8, 1.0
+    ep.seg_n0, ep.seg_n1 = 100, 200
+    assert lib.llamax_int8_gemm_dequant(p, 64, p, 64, p, p, p, 768, 16, 768, 64, ctypes.byref(ep), None) == -1
+    assert b"segments" in lib.llamax_last_error()
+    # attention backward accepts o = NULL (delta given) but still rejects the other null pointers
+    assert lib.llamax_attn_bwd(p, 64, p, 64, p, 64, None, 0, p, None, 64, p, 64, p, 64, p, 64, p, p,
+                               1, 16, 2, 1, 128, 0, None, None, None, 1.0, None, None) == -1
+    assert b"null" in lib.llamax_last_error()
