@@ -25,10 +25,6 @@
 
 #include "llamax_b200.h"
 
-#ifndef LX_MIX_EXP
-#define LX_MIX_EXP 0   // timing experiments on the mixed-input pipeline (tools only): see tools/mixed_gemm_perf.py
-#endif
-
 namespace lx {
 
 #ifdef LX_MIX_TRACE
@@ -438,9 +434,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&bempty_bar[bs], bphase ^ 1);
           if (cw == 0 && cl == 0) MIX_MARK(1, it >> 2, 2);
           const uint32_t sraw = smem_u32(raw_ring + rs * S::kRawBytes);
-#if LX_MIX_EXP == 1
-          if (false)
-#endif
 #pragma unroll
           for (int half = 0; half < 4; ++half) {
             uint4 w[2];

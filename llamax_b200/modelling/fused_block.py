@@ -111,7 +111,7 @@ def set_mixed_gemm(on: bool) -> None:
     _MIXED = bool(on)
 
 
-def _mixed_group_operand(cache: dict, key: str, specs):
+def _concat_int8_operand(cache: dict, key: str, specs):
     """Resident int8 [sum N, K] = [W_1; W_2; ...] (rows = the contraction index of grad_input) + concatenated scales; a
     single weight is used as stored (no copy). None when the shape does not fit the kernel (sum N % 64, K % 16)."""
     n_total = sum(s.N for s in specs)
@@ -436,7 +436,7 @@ class FusedDecoderBlock(torch.autograd.Function):
             # instead of 4096 + 1024 + 1024 — the two N = 1024 launches fill 3.5 waves of 74 CTA pairs and ran at 1870 TOP/s
             # against 2370-2630 for the wide ones. The epilogue picks each column segment's own LoRA-h columns.
             cache = layer.__dict__.setdefault("_llamax_bwd_operands", {})
-            w8cat, scat = _mixed_group_operand(cache, "wqkv_fwd", (sq, sk, sv))
+            w8cat, scat = _concat_int8_operand(cache, "wqkv_fwd", (sq, sk, sv))
             ep = {}
             if sq.R > 0:
                 ep = dict(lora_h=h_qkv, lora_b=torch.cat([sq.lora_b.detach(), sk.lora_b.detach(), sv.lora_b.detach()], 0),
@@ -515,7 +515,7 @@ class FusedDecoderBlock(torch.autograd.Function):
         mixed = {}
         if _MIXED and not _INT8_GRAD:   # opt-in: int8 weights consumed by the mixed-input GEMM, no bf16 operand
             for key, (specs, rows, width) in shapes.items():
-                op = _mixed_group_operand(cache, key + "_mix", specs)
+                op = _concat_int8_operand(cache, key + "_mix", specs)
                 if op is not None:
                     mixed[key] = op
         if _INT8_GRAD:   # opt-in, non-parity: int8 operands instead of the bf16 ones

@@ -11,7 +11,7 @@ from tools.gemm_vs_cublas import burst, sustained
 
 dev = "cuda"
 M = 16384
-QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"   # timing-experiment builds (results may be wrong): two shapes, no check
+QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"   # two shapes only, no equality check
 # grad_input shapes (N = in_features, K1 = sum of out_features, tail = LoRA rows): wqkv, wo, w1|w3, w2
 for name, N, K1, Rt in (("wqkv-bwd", 4096, 6144, 24), ("wo-bwd", 4096, 4096, 0), ("w13-bwd", 4096, 28672, 16), ("w2-bwd", 14336, 4096, 0)):
     if QUICK and name != "wo-bwd":
