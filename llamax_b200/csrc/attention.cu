@@ -9,14 +9,19 @@
 //
 // Optional packed-sequence document mask: additionally kv >= doc_start[q] (tiles outside a row's document skipped).
 //
-// Forward  : CTA = (128 query rows, 1 query head). warp0 TMA, warp1 MMA issue, warps4-7 softmax (thread = row).
-//            S = Q K^T double-buffered in TMEM, read once into registers; P (bf16 pairs) is written back over the
-//            score columns and consumed by the PV MMA straight from TMEM; O accumulates in TMEM with lazy
-//            rescaling; exp2-domain online softmax, LSE saved in natural log.
-// Backward : CTA = (128 kv rows, 1 kv head), loops over the group's query heads x 64-row query tiles.
-//            S^T = K Q^T and dP^T = V dO^T in TMEM (thread = kv row), P^T / dS^T staged through smem,
-//            dV += P^T dO and dK += dS^T Q accumulate in TMEM for the whole CTA lifetime,
-//            dQ^T = K^T dS^T goes TMEM -> fp32 smem tile -> cp.reduce.async.bulk add into an fp32 buffer.
+// Forward  : default = attn_fwd5_kernel, persistent: one CTA per SM walks a length-balanced list of items (pair of
+//            128-row query tiles, query head, sequence); warp0 TMA, warps1-2 MMA issue (one per tile), two softmax
+//            warpgroups (thread = row). Per tile S = Q K^T in TMEM is read once into registers, P (bf16 pairs) is written
+//            back over the score columns in four chunks and consumed by the PV MMA straight from TMEM, O accumulates
+//            in TMEM with lazy rescaling; exp2-domain online softmax, LSE saved in natural log. Older forms kept behind
+//            LLAMAX_ATTN_FWD (1: one tile per CTA, 2: two tiles / one issuer — also the packed-document path, 3: two
+//            threads per row, 4: v5 without the persistent loop).
+// Backward : CTA = (128 kv rows, 1 kv head), loops over the group's query heads x 128-row query tiles; every MMA is
+//            128 x 128 x 16. S^T = K Q^T and dP^T = V dO^T in TMEM (thread = kv row); P^T goes back to TMEM as bf16 pairs
+//            (A operand of dV += P^T dO straight from TMEM), dS^T through smem (dK += dS^T Q, dQ^T = K^T dS^T); dV, dK
+//            accumulate in TMEM for the CTA lifetime; dQ^T is drained to registers and reduced into an fp32 buffer with
+//            coalesced red.global.add; RoPE's backward is applied to dK in the epilogue and to dQ in the fp32 -> bf16
+//            convert. See the comment block above attn_bwd_kernel for the TMEM aliasing and the MMA issue order.
 // head_dim 128 natively; head_dim 64 runs on the same 128-wide tiles (TMA zero-fills the missing half).
 #include <type_traits>
 
