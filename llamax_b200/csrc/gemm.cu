@@ -10,6 +10,10 @@
 // Fused epilogue options: LoRA up-projection (modelling/lora.py:43), residual add (modelling/llama.py:172-173), and
 // (kSwi) the SwiGLU backward behind the w2 grad_input GEMM (modelling/llama.py:152 differentiated).
 // kMN: both operands stored [K, M] / [K, N] (weight-gradient form dW = dY^T X), consumed as MN-major UMMA operands.
+// kRes: residual (or, in row-dot mode, the attention output for delta = rowsum(dO * O)) read through a prefetch pipeline.
+// kMix: mixed-input variants: B arrives as the frozen INT8 weight and is expanded to bf16 by converter
+//       warps between the TMA ring and the tensor core (640 threads, three rings; see the comment above gemm_kernel).
+// gemm_wide_kernel: 512 x 256 outputs per CTA-pair visit for long contractions without an epilogue (further down).
 //
 // Structure (per CTA, 384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warp3 idle,
 // warps4-11 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, one per column half of the
