@@ -26,6 +26,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 
 #include "llamax_b200.h"
 
@@ -990,7 +991,7 @@ constexpr int kSmem = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 __nv_bfloat16* __restrict__ C, int64_t ldc, int M, int N, int K, int group) {
+                 __nv_bfloat16* __restrict__ C, int64_t ldc, int M, int N, int K, int group, int* wave_sync) {
   using namespace wd;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1041,11 +1042,29 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_addr = mapa_u32(smem_u32(&full_bar[0]), 0);
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int visit_p = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++visit_p) {
         int tm, tn;
         tile_coords(tile, num_m, num_n, group, tm, tn);
         const int row_a = tm * 512 + cta_rank * 256;
         const int row_b = tn * kBN + cta_rank * 128;
+        if (wave_sync != nullptr && visit_p > 0) {
+          // Wave alignment. The CTA pairs of a wave share operand panels (one 512-row A panel is read by ~8 pairs, one B
+          // panel by ~9) and with K = 28688 a wave's live panels are 2-3 x the L2, so the sharing only works while the pairs
+          // walk K in step — and nothing re-aligned them between visits: after the first visit they drift apart and
+          // every pair fetches its panels from DRAM on its own (ncu: 7.1 GB per launch, L2 hit 61 %). Every producer
+          // checks in at the start of a visit and waits for the other producers of that visit: 3.0 GB, L2 hit 77 %,
+          // 2.62 -> 2.41 ms under ncu, 1327-1341 -> 1377-1379 TFLOP/s sustained at the 1 kW cap (less DRAM traffic =
+          // higher clocks), same box. All pairs are co-resident (persistent grid, one CTA per SM); the wait is bounded
+          // all the same, so that a device shared with another stream's kernel can only lose the alignment, not hang.
+          const int expected = 2 * min(num_clusters, num_tiles - visit_p * num_clusters);
+          atomicAdd(&wave_sync[visit_p], 1);
+          int seen;
+          uint32_t polls = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(wave_sync + visit_p) : "memory");
+          } while (seen < expected && ++polls < (1u << 14));
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -1174,7 +1193,34 @@ static int launch_gemm_wide(const void* A, int64_t lda, const void* B, int64_t l
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wide_kernel, tmA, tmB, (__nv_bfloat16*)C, ldc, M, N, K, group);
+  // Wave-alignment counters (see the producer): one int per visit, a slot of kSyncInts per launch out of a per-device ring
+  // (concurrent launches from other streams / threads get different slots), zeroed in stream order before the launch.
+  // LLAMAX_GEMM_WAVESYNC=0 turns the alignment off (A/B).
+  int* wave_sync = nullptr;
+  static const bool use_sync = !(getenv("LLAMAX_GEMM_WAVESYNC") != nullptr && atoi(getenv("LLAMAX_GEMM_WAVESYNC")) == 0);
+  constexpr int kSyncInts = 128, kSyncSlots = 64, kMaxDev = 16;
+  const int visits = (num_m * num_n + clusters - 1) / clusters;
+  if (use_sync && visits > 1 && visits <= kSyncInts) {
+    static std::mutex mu;
+    static int* ring[kMaxDev] = {nullptr};
+    static std::atomic<unsigned> next_slot{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < kMaxDev) {
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (ring[dev] == nullptr && cudaMalloc(&ring[dev], (size_t)kSyncSlots * kSyncInts * sizeof(int)) != cudaSuccess) {
+          ring[dev] = nullptr;
+          (void)cudaGetLastError();
+        }
+      }
+      if (ring[dev] != nullptr) {
+        wave_sync = ring[dev] + (size_t)(next_slot.fetch_add(1) % kSyncSlots) * kSyncInts;
+        if (cudaMemsetAsync(wave_sync, 0, kSyncInts * sizeof(int), stream) != cudaSuccess) wave_sync = nullptr;
+      }
+    }
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wide_kernel, tmA, tmB, (__nv_bfloat16*)C, ldc, M, N, K, group, wave_sync);
   if (e != cudaSuccess) return set_cuda_error(e, "wide gemm: launch");
   return 0;
 }
