@@ -70,6 +70,8 @@ struct GemmParams {
   // sum over the 128 columns of group g of bf16(C[m, c]) * resid[m, c]  (the attention backward's delta)
   float* dot_out;
   int dot_S;
+  int* wave_sync;   // wave alignment counters (one per sync point) or null; sync_every: visits between two sync points
+  int sync_every;
   int flags;  // 1: dump raw accumulator (int32 / fp32) to C; 2: round to bf16 before the column scale; 4: row-dot mode
   // kSwi epilogue (SwiGLU backward fused behind the w2 grad_input GEMM): C is not written
   const __nv_bfloat16* swi_ab;  // [M, 2N] pitch ld_ab: a = w1 x in columns [0, N), b = w3 x in [N, 2N)
@@ -285,11 +287,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_addr = CG == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int visit_p = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++visit_p) {
         int tm, tn;
         tile_coords(tile, num_m, num_n, p.group, tm, tn);
         const int row_a = tm * kTileM + cta_rank * kBM;
         const int row_b = tn * kBN + cta_rank * (kBN / CG);
+        if (p.wave_sync != nullptr && visit_p > 0 && visit_p % p.sync_every == 0) {   // see gemm_wide_kernel
+          const int expected = CG * min(num_clusters, num_tiles - visit_p * num_clusters);
+          int* ctr = p.wave_sync + visit_p / p.sync_every;
+          atomicAdd(ctr, 1);
+          int seen;
+          uint32_t polls = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+          } while (seen < expected && ++polls < (1u << 14));
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * S::kStageBytes;
@@ -818,6 +831,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// Wave-alignment counters (see the producer of gemm_wide_kernel): one int per sync point, a slot of kSyncInts per launch
+// out of a per-device ring (concurrent launches from other streams / threads get different slots), zeroed in stream
+// order before the launch. Returns null when the feature is off, the launch has too many sync points, or allocation fails.
+static int* acquire_wave_sync(int points, cudaStream_t stream) {
+  static const bool use_sync = !(getenv("LLAMAX_GEMM_WAVESYNC") != nullptr && atoi(getenv("LLAMAX_GEMM_WAVESYNC")) == 0);
+  constexpr int kSyncInts = 128, kSyncSlots = 64, kMaxDev = 16;
+  if (!use_sync || points > kSyncInts) return nullptr;
+  static std::mutex mu;
+  static int* ring[kMaxDev] = {nullptr};
+  static std::atomic<unsigned> next_slot{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (ring[dev] == nullptr && cudaMalloc(&ring[dev], (size_t)kSyncSlots * kSyncInts * sizeof(int)) != cudaSuccess) {
+      ring[dev] = nullptr;
+      (void)cudaGetLastError();
+    }
+  }
+  if (ring[dev] == nullptr) return nullptr;
+  int* slot = ring[dev] + (size_t)(next_slot.fetch_add(1) % kSyncSlots) * kSyncInts;
+  if (cudaMemsetAsync(slot, 0, kSyncInts * sizeof(int), stream) != cudaSuccess) return nullptr;
+  return slot;
+}
+
 template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false>
 static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
@@ -865,6 +904,19 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
     static const int forced = getenv("LLAMAX_GEMM_GROUP") ? atoi(getenv("LLAMAX_GEMM_GROUP")) : 0;   // A/B switch
     const int num_m = (p.M + kBM * CG - 1) / (kBM * CG), num_n = (p.N + kBN - 1) / kBN;
     pp.group = forced != 0 ? forced : (num_m >= num_n ? -kGroupM : kGroupM);
+    // Wave alignment every `sync_every` visits (see gemm_wide_kernel). Measured per kernel form, sustained, same box
+    // (tools/sync_every_ab.py): the w2 grad_input GEMM with the SwiGLU-backward epilogue — the form that moves the most
+    // DRAM bytes per flop (5.8 GB per launch) — gains 2.5 % at any period 1..8 (1016-1026 -> 1044-1050 TFLOP/s); the
+    // INT8 forward GEMM (2429-2437 -> 2291-2414 TOP/s) and the short-K bf16 GEMMs (1292-1295 -> 1270-1291) lose: their
+    // operand panels fit the L2 whatever the drift, and the barrier only adds a wait. Default: that one form, period 2.
+    // LLAMAX_GEMM_SYNC_EVERY overrides the period for every form (0 = off).
+    static const int forced_sync = getenv("LLAMAX_GEMM_SYNC_EVERY") ? atoi(getenv("LLAMAX_GEMM_SYNC_EVERY")) : -1;
+    const int sync_every = forced_sync >= 0 ? forced_sync : (kSwi ? 2 : 0);
+    const int visits = (num_tiles + clusters - 1) / clusters;
+    if (sync_every > 0 && visits > sync_every) {
+      pp.wave_sync = acquire_wave_sync(visits / sync_every + 1, stream);
+      pp.sync_every = sync_every;
+    }
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
@@ -1193,33 +1245,8 @@ static int launch_gemm_wide(const void* A, int64_t lda, const void* B, int64_t l
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // Wave-alignment counters (see the producer): one int per visit, a slot of kSyncInts per launch out of a per-device ring
-  // (concurrent launches from other streams / threads get different slots), zeroed in stream order before the launch.
-  // LLAMAX_GEMM_WAVESYNC=0 turns the alignment off (A/B).
-  int* wave_sync = nullptr;
-  static const bool use_sync = !(getenv("LLAMAX_GEMM_WAVESYNC") != nullptr && atoi(getenv("LLAMAX_GEMM_WAVESYNC")) == 0);
-  constexpr int kSyncInts = 128, kSyncSlots = 64, kMaxDev = 16;
   const int visits = (num_m * num_n + clusters - 1) / clusters;
-  if (use_sync && visits > 1 && visits <= kSyncInts) {
-    static std::mutex mu;
-    static int* ring[kMaxDev] = {nullptr};
-    static std::atomic<unsigned> next_slot{0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < kMaxDev) {
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        if (ring[dev] == nullptr && cudaMalloc(&ring[dev], (size_t)kSyncSlots * kSyncInts * sizeof(int)) != cudaSuccess) {
-          ring[dev] = nullptr;
-          (void)cudaGetLastError();
-        }
-      }
-      if (ring[dev] != nullptr) {
-        wave_sync = ring[dev] + (size_t)(next_slot.fetch_add(1) % kSyncSlots) * kSyncInts;
-        if (cudaMemsetAsync(wave_sync, 0, kSyncInts * sizeof(int), stream) != cudaSuccess) wave_sync = nullptr;
-      }
-    }
-  }
+  int* wave_sync = visits > 1 ? acquire_wave_sync(visits, stream) : nullptr;   // LLAMAX_GEMM_WAVESYNC=0: off (A/B)
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wide_kernel, tmA, tmB, (__nv_bfloat16*)C, ldc, M, N, K, group, wave_sync);
   if (e != cudaSuccess) return set_cuda_error(e, "wide gemm: launch");
   return 0;
