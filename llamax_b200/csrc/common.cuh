@@ -517,7 +517,15 @@ __device__ __forceinline__ uint32_t mul_bf16x2(uint32_t x, uint32_t y) {
 }
 
 // sigmoid in fp32 (fast exp / divide, ~2 ulp; every use is rounded to bf16 right after)
-__device__ __forceinline__ float sigmoid_f(float a) { return __fdividef(1.0f, 1.0f + __expf(-a)); }
+// exp(-a) through ex2.approx.ftz: the non-ftz form __expf compiles to spends a compare and two predicated multiplies per
+// element on denormal RESULTS (ex2(x/2)^2 below 2^-126); here the result only ever feeds 1 + exp(-a), where anything below
+// 2^-126 rounds away — same value bit for bit, three instructions less.
+__device__ __forceinline__ float exp_neg_f(float a) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * -1.4426950216293334961f));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_f(float a) { return __fdividef(1.0f, 1.0f + exp_neg_f(a)); }
 
 // SwiGLU backward for TWO adjacent elements held as packed bf16 pairs (modelling/llama.py:143-152 differentiated,
 // with the reference's bf16 roundings: sl = bf16(silu(a)), dsl = bf16(dg * b), outputs bf16):

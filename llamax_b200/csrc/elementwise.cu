@@ -89,6 +89,32 @@ __device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t a, uint32_t b, uint
   return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
+// The rare vector (a quotient within ~2^-20 of a half-integer), redone with the reference's exact divisions. Out of line on
+// purpose: inlined, the eight IEEE divisions are ~250 instructions per call site, and the warp-per-row kernels (16 call
+// sites per row) grew to 70 KB of code whose hot path kept missing the instruction cache (ncu: `no_instruction` the top
+// stall, 2.9 warps per issue slot).
+__device__ __noinline__ uint2 quant_vec_exact(float f0, float f1, float f2, float f3, float f4, float f5, float f6,
+                                              float f7, float sc) {
+  const float f[8] = {f0, f1, f2, f3, f4, f5, f6, f7};
+  uint32_t c[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) c[e] = __float_as_uint(__fadd_rn(f[e] / sc, kRoundMagic));
+  return make_uint2(pack4_low_bytes(c[0], c[1], c[2], c[3]), pack4_low_bytes(c[4], c[5], c[6], c[7]));
+}
+
+// Eight int8 codes of one 16-byte vector (see the comment above kRoundMagic)
+__device__ __forceinline__ uint2 quant_vec(const float (&f)[8], float sc, float inv_lo, float inv_hi) {
+  uint32_t c[8];
+  uint32_t differ = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    c[e] = __float_as_uint(__fmaf_rn(f[e], inv_lo, kRoundMagic));
+    differ |= c[e] ^ __float_as_uint(__fmaf_rn(f[e], inv_hi, kRoundMagic));
+  }
+  if (differ) return quant_vec_exact(f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], sc);
+  return make_uint2(pack4_low_bytes(c[0], c[1], c[2], c[3]), pack4_low_bytes(c[4], c[5], c[6], c[7]));
+}
+
 template <int kMaxV>
 __device__ __forceinline__ void quant_row_store(const float (&v)[kMaxV][8], int nvec, float amax, int8_t* qrow,
                                                 __nv_bfloat16* scale_out) {
@@ -99,22 +125,7 @@ __device__ __forceinline__ void quant_row_store(const float (&v)[kMaxV][8], int 
 #pragma unroll
   for (int j = 0; j < kMaxV; ++j) {
     const int idx = threadIdx.x + j * blockDim.x;
-    if (idx < nvec) {
-      uint32_t w[8];
-      uint32_t differ = 0;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        w[e] = __float_as_uint(__fmaf_rn(v[j][e], inv_lo, kRoundMagic));
-        differ |= w[e] ^ __float_as_uint(__fmaf_rn(v[j][e], inv_hi, kRoundMagic));
-      }
-      if (differ) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(__fadd_rn(v[j][e] / sc, kRoundMagic));
-      }
-      const uint32_t lo = pack4_low_bytes(w[0], w[1], w[2], w[3]);
-      const uint32_t hi = pack4_low_bytes(w[4], w[5], w[6], w[7]);
-      *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) = make_uint2(lo, hi);
-    }
+    if (idx < nvec) *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) = quant_vec(v[j], sc, inv_lo, inv_hi);
   }
   if (threadIdx.x == 0) *scale_out = __float2bfloat16_rn(s);
 }
@@ -328,85 +339,111 @@ __global__ void rowquant_ring_kernel(const __nv_bfloat16* __restrict__ x, int64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-per-row variants of RMSNorm forward (+ quantisation) and of the row quantiser, for rows of <= 4096 elements
-// (the model width). The block-per-row kernels above pay two block reductions per row (four __syncthreads with a
-// shared-memory round trip each) for 16 elements of work per thread: in the step they run at 2.8-3.1 TB/s, neither
-// HBM- nor issue-bound (~15 instructions per element = 37 us of issue per launch against 110 us measured). Here a warp
-// owns a row: lane l holds the 16-byte vectors l, l + 32, ... of the row PACKED (kVec registers quads), every load of
-// the row is in flight at once, both reductions are five shuffles, there is no barrier and no shared memory at all;
-// 16+ warps per SM keep ~100 KB of loads in flight. Arithmetic (and rounding order per element) is that of the
-// kernels above; only the summation order of the mean square differs.
+// Warp-per-row RMSNorm forward (+ quantisation) and row quantiser, for rows of <= 4096 elements (the model width): the
+// default for those rows. Measured at the clocks of a power-capped step (tools/ew_sustained.py: each pass right after a long
+// GEMM, SM ~1.2 GHz) a device copy keeps 5.3 TB/s while the block-per-row ring kernels above reach 2.3-2.5: they issue
+// ~32 instructions per element, two thirds of them per-ROW cost (two block reductions with four barriers, the scale
+// arithmetic with its IEEE divisions, loop and address arithmetic) that 256 threads each pay for only 16 elements.
+// Here a warp owns a row, lane l the 16-byte vectors l, l + 32, ...: the per-row cost is paid once per 128 elements per
+// lane, both reductions are five shuffles, there is no barrier. The first version of this kernel loaded the row straight
+// into registers and was SLOWER than the ring kernels (92 vs 79 us): nothing overlapped a warp's load with its arithmetic
+// and the warps of an SM fell into step. Now every warp keeps the NEXT row of its walk in flight as cp.async copies into a
+// warp-private two-stage shared-memory ring (each lane copies exactly the slots it reads: cp.async.wait_group is the only
+// synchronisation), the passes read the row from shared memory, and only the rounded output row stays in registers
+// (packed) between the normalisation and the quantiser. The row maximum is taken on the packed bf16 pairs (one logic op +
+// one HMNMX2 per two elements). Arithmetic and rounding order per element are those of the kernels above; only the
+// summation order of the mean square differs.
 // kNorm = false: row quantiser alone (w, y, rstd unused).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ldg_l1_v4(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+constexpr int kWprWarps = 4;
+
+__device__ __forceinline__ uint32_t absmax_bf16x2(uint32_t acc, uint32_t v) {
+  uint32_t a = v & 0x7fff7fffu, r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(acc), "r"(a));
   return r;
 }
 
-// The row stays PACKED between the passes: without this the compiler keeps the fp32 copies of all 8 * kVec elements alive
-// from one pass to the next (common sub-expression of the unpacking) and spills at 16 vectors per lane.
-template <int kVec>
-__device__ __forceinline__ void keep_packed(uint4 (&pk)[kVec]) {
-#pragma unroll
-  for (int j = 0; j < kVec; ++j) asm volatile("" : "+r"(pk[j].x), "+r"(pk[j].y), "+r"(pk[j].z), "+r"(pk[j].w));
-}
-
-template <int kVec, bool kNorm>
-__global__ void __launch_bounds__(256, 2)
+// kFull: the row has exactly 32 * kVec vectors (the model width with kVec = 16): no per-vector bounds branch, so the
+// passes are straight-line code the compiler can schedule across vectors (and ~30 % less of it)
+template <int kVec, bool kNorm, bool kFull>
+__global__ void __launch_bounds__(32 * kWprWarps, 3)
 row_wpr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int8_t* __restrict__ q8,
                __nv_bfloat16* __restrict__ qscale, int64_t M, int D, int nvec, float eps) {
-  const int lane = lane_id();
-  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
-    const __nv_bfloat16* xr = x + row * ldx;
-    uint4 pk[kVec];
-#pragma unroll
-    for (int j = 0; j < kVec; ++j) {
-      const int idx = lane + 32 * j;
-      pk[j] = idx < nvec ? ldg_nc_v4(xr + (int64_t)idx * 8) : make_uint4(0, 0, 0, 0);
-    }
-    float amax = 0.f;
-    if constexpr (kNorm) {
-      float ss = 0.f;
+  extern __shared__ uint4 ring[];   // [warp][stage][32 * kVec], then (kNorm) the norm weight [32 * kVec]
+  const int lane = lane_id(), wib = threadIdx.x >> 5;
+  constexpr int kSlots = 32 * kVec;
+  uint4* my = ring + wib * 2 * kSlots;
+  const uint4* wsm = ring + kWprWarps * 2 * kSlots;
+  if constexpr (kNorm) {
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+      ring[kWprWarps * 2 * kSlots + i] = *reinterpret_cast<const uint4*>(w + (int64_t)i * 8);
+    __syncthreads();
+  }
+  const int64_t warps = (int64_t)gridDim.x * kWprWarps;
+  auto issue = [&](int stage, int64_t row) {
+    if (row < M) {
+      const __nv_bfloat16* xr = x + row * ldx;
 #pragma unroll
       for (int j = 0; j < kVec; ++j) {
-        float f[8];
-        unpack8(pk[j], f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+        const int idx = lane + 32 * j;
+        if (kFull || idx < nvec) cp_async_16(my + stage * kSlots + idx, xr + (int64_t)idx * 8);
       }
-      ss = warp_sum(ss);
-      keep_packed(pk);
+    }
+    cp_async_commit();
+  };
+  int64_t row = (int64_t)blockIdx.x * kWprWarps + wib;
+  issue(0, row);
+  int stage = 0;
+  for (; row < M; row += warps) {
+    issue(stage ^ 1, row + warps);
+    cp_async_wait<1>();
+    const uint4* cur = my + stage * kSlots;
+    stage ^= 1;
+    uint4 pk[kVec];
+    if constexpr (kNorm) {
+      float ss4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains: three warps per scheduler do not hide a 128-deep one
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) {
+        if (kFull || lane + 32 * j < nvec) {
+          float f[8];
+          unpack8(cur[lane + 32 * j], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ss4[e & 3] = fmaf(f[e], f[e], ss4[e & 3]);
+        }
+      }
+      const float ss = warp_sum((ss4[0] + ss4[1]) + (ss4[2] + ss4[3]));
       const float rstd = 1.0f / sqrtf(ss / (float)D + eps);
       if (lane == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
 #pragma unroll
       for (int j = 0; j < kVec; ++j) {
         const int idx = lane + 32 * j;
-        if (idx < nvec) {
+        pk[j] = make_uint4(0, 0, 0, 0);
+        if (kFull || idx < nvec) {
           float f[8], wf[8];
-          unpack8(pk[j], f);
-          unpack8(ldg_l1_v4(w + (int64_t)idx * 8), wf);   // L1-resident; volatile: stays inside its iteration
+          unpack8(cur[idx], f);
+          unpack8(wsm[idx], wf);
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = (f[e] * rstd) * wf[e];
           pk[j] = pack8(f);   // y, rounded once; the quantiser below reads these bf16 values
           if (y != nullptr) *reinterpret_cast<uint4*>(y + row * D + (int64_t)idx * 8) = pk[j];
         }
-        asm volatile("" ::: "memory");   // keeps the iterations (and their 16 fp32 temporaries) apart: 128-register budget
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) pk[j] = (kFull || lane + 32 * j < nvec) ? cur[lane + 32 * j] : make_uint4(0, 0, 0, 0);
     }
     if (q8 == nullptr) continue;
-    keep_packed(pk);
+    uint32_t m4[4] = {0, 0, 0, 0};   // running maxima of |.| on packed bf16 pairs (exact: a maximum rounds nothing)
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
-      float f[8];
-      unpack8(pk[j], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+      m4[0] = absmax_bf16x2(m4[0], pk[j].x);
+      m4[1] = absmax_bf16x2(m4[1], pk[j].y);
+      m4[2] = absmax_bf16x2(m4[2], pk[j].z);
+      m4[3] = absmax_bf16x2(m4[3], pk[j].w);
     }
-    amax = warp_max(amax);
-    keep_packed(pk);
+    const uint32_t m2 = absmax_bf16x2(absmax_bf16x2(m4[0], m4[1]), absmax_bf16x2(m4[2], m4[3]));
+    const float amax = warp_max(fmaxf(bf16_lo(m2), bf16_hi(m2)));
     const float s = amax / 127.0f;
     const float sc = fmaxf(s, 1e-12f);
     const float inv = 1.0f / sc;
@@ -415,38 +452,27 @@ row_wpr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bflo
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
       const int idx = lane + 32 * j;
-      if (idx < nvec) {
+      if (kFull || idx < nvec) {
         float f[8];
         unpack8(pk[j], f);
-        uint32_t c[8];
-        uint32_t differ = 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          c[e] = __float_as_uint(__fmaf_rn(f[e], inv_lo, kRoundMagic));
-          differ |= c[e] ^ __float_as_uint(__fmaf_rn(f[e], inv_hi, kRoundMagic));
-        }
-        if (differ) {   // see quant_row_store: the rare vector with a quotient next to a half-integer
-#pragma unroll
-          for (int e = 0; e < 8; ++e) c[e] = __float_as_uint(__fadd_rn(f[e] / sc, kRoundMagic));
-        }
-        *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) =
-            make_uint2(pack4_low_bytes(c[0], c[1], c[2], c[3]), pack4_low_bytes(c[4], c[5], c[6], c[7]));
+        *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) = quant_vec(f, sc, inv_lo, inv_hi);
       }
-      asm volatile("" ::: "memory");
     }
     if (lane == 0) qscale[row] = __float2bfloat16_rn(s);
   }
+  cp_async_wait<0>();
 }
 
-// rows of up to 32 * 16 vectors; enough rows to fill the machine; 16-byte aligned rows. LLAMAX_ROW_WPR=1 turns it on:
-// measured isolated it is SLOWER than the ring kernels (rmsnorm + quant 92 vs 79 us, rowquant 51 vs 52 us), see DESIGN.md
-static bool wpr_cfg(int nvec, int64_t M, bool aligned, int& kvec, int& grid) {
-  static const bool enabled = getenv("LLAMAX_ROW_WPR") != nullptr && atoi(getenv("LLAMAX_ROW_WPR")) != 0;   // default off
-  static const int per_sm = getenv("LLAMAX_ROW_WPR_CTAS") ? std::max(1, atoi(getenv("LLAMAX_ROW_WPR_CTAS"))) : 2;
-  if (!enabled || !aligned || nvec > 512 || M < 256) return false;
+// rows of up to 32 * 16 vectors, 16-byte aligned, enough of them to fill the machine. LLAMAX_ROW_WPR=0 falls back to the
+// block-per-row ring kernels (A/B).
+static bool wpr_cfg(int nvec, int64_t M, bool aligned, int& kvec, int& grid, int& smem, bool norm) {
+  static const bool enabled = getenv("LLAMAX_ROW_WPR") == nullptr || atoi(getenv("LLAMAX_ROW_WPR")) != 0;
+  static const int per_sm = getenv("LLAMAX_ROW_WPR_CTAS") ? std::max(1, atoi(getenv("LLAMAX_ROW_WPR_CTAS"))) : 3;
+  if (!enabled || !aligned || nvec > 512 || M < 1024) return false;
   const int v = (nvec + 31) / 32;
   kvec = v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 8 ? 8 : 16;
-  grid = (int)std::min<int64_t>((M + 7) / 8, (int64_t)sm_count() * per_sm);
+  smem = (kWprWarps * 2 + (norm ? 1 : 0)) * 32 * kvec * 16;
+  grid = (int)std::min<int64_t>((M + kWprWarps - 1) / kWprWarps, (int64_t)sm_count() * per_sm);
   return true;
 }
 #define LX_DISPATCH_WPR(V_, ...)                            \
@@ -462,7 +488,7 @@ static bool wpr_cfg(int nvec, int64_t M, bool aligned, int& kvec, int& grid) {
 // SwiGLU forward: g = bf16( bf16(silu(a)) * b ), optional fused row quantisation
 // ------------------------------------------------------------------------------------------------
 // silu in fp32; the result is rounded to bf16 right away, so the fast exp / divide (~2 ulp fp32) are invisible
-__device__ __forceinline__ float silu_f(float a) { return __fdividef(a, 1.0f + __expf(-a)); }
+__device__ __forceinline__ float silu_f(float a) { return __fdividef(a, 1.0f + exp_neg_f(a)); }
 
 template <int kMaxV>
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
@@ -494,6 +520,94 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __n
     amax = block_reduce<true>(amax, sm);
     quant_row_store(v, nvec, amax, q8 + row * F, qscale + row);
   }
+}
+
+// Ring variant of the forward (default when it fits): persistent CTAs, the a and b rows of the next kRingStages - 1 rows of
+// the CTA's walk in flight as cp.async copies (168 KB for F = 14336: one 512-thread CTA per SM), g kept PACKED in registers
+// between the activation and the quantiser (row maximum on bf16 pairs), one barrier per row. The one-CTA-per-row kernel
+// above exposes load -> activation -> reduction -> quantiser -> store once per CTA with two CTAs per SM to overlap them:
+// 3.6 TB/s at the clocks of a power-capped step (tools/ew_sustained.py) where a device copy keeps 5.8.
+template <int kMaxV>
+__global__ void __launch_bounds__(512, 1)
+swiglu_fwd_ring_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int64_t ld,
+                       __nv_bfloat16* __restrict__ g, int8_t* __restrict__ q8, __nv_bfloat16* __restrict__ qscale,
+                       int64_t M, int F, int nvec) {
+  extern __shared__ uint4 ring[];   // [stage][a | b][slots]
+  __shared__ float sm[2][32];
+  const int slots = blockDim.x * kMaxV;
+  const int nw = blockDim.x >> 5;
+  const uint32_t ring_s = smem_u32(ring) + threadIdx.x * 16;   // this thread's first slot of stage 0, stream a
+  const int64_t b_off = (b - a) * 2;                            // byte offset from a's row to b's (one buffer, same pitch)
+  auto issue = [&](int stage, int64_t row) {
+    if (row < M) {
+      // row base computed once; per vector one 64-bit add and one 32-bit add
+      const char* src = reinterpret_cast<const char*>(a + row * ld) + threadIdx.x * 16;
+      const uint32_t dst = ring_s + stage * 2 * slots * 16;
+#pragma unroll
+      for (int j = 0; j < kMaxV; ++j) {
+        const int idx = threadIdx.x + j * blockDim.x;
+        if (idx < nvec) {
+          const char* sj = src + (int64_t)(j * blockDim.x) * 16;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * blockDim.x * 16), "l"(sj) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (slots + j * blockDim.x) * 16),
+                       "l"(sj + b_off) : "memory");
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kRingStages; ++s) issue(s, blockIdx.x + (int64_t)s * gridDim.x);
+  int stage = 0, par = 0;
+  for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+    cp_async_wait<kRingStages - 1>();
+    const uint4* st = ring + (int64_t)stage * 2 * slots;
+    uint32_t wg[kMaxV][4];
+    uint32_t m2 = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wg[j][e] = 0;
+      if (idx < nvec) {
+        const uint4 ua = st[idx], ub = st[slots + idx];
+        const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // bf16(silu(a)) for two elements, then the bf16 product with b (exact product, one rounding)
+          wg[j][e] = mul_bf16x2(pack_bf16(silu_f(bf16_lo(wa[e])), silu_f(bf16_hi(wa[e]))), wb[e]);
+          m2 = absmax_bf16x2(m2, wg[j][e]);
+        }
+        if (g != nullptr)
+          *reinterpret_cast<uint4*>(g + row * F + (int64_t)idx * 8) = make_uint4(wg[j][0], wg[j][1], wg[j][2], wg[j][3]);
+      }
+    }
+    issue(stage, row + (int64_t)kRingStages * gridDim.x);   // refill the stage just consumed
+    stage = stage + 1 == kRingStages ? 0 : stage + 1;
+    if (q8 == nullptr) continue;
+    float amax = warp_max(fmaxf(bf16_lo(m2), bf16_hi(m2)));
+    if (lane_id() == 0) sm[par][threadIdx.x >> 5] = amax;
+    __syncthreads();   // one barrier per row: sm[par] is rewritten two rows later, after every thread passed the next one
+    amax = sm[par][0];
+    for (int i = 1; i < nw; ++i) amax = fmaxf(amax, sm[par][i]);
+    par ^= 1;
+    const float s = amax / 127.0f;
+    const float sc = fmaxf(s, 1e-12f);
+    const float inv = 1.0f / sc;
+    const float inv_lo = inv * (1.0f - 0x1p-21f), inv_hi = inv * (1.0f + 0x1p-21f);
+    int8_t* qrow = q8 + row * F;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float f[8];
+        unpack8(make_uint4(wg[j][0], wg[j][1], wg[j][2], wg[j][3]), f);
+        *reinterpret_cast<uint2*>(qrow + (int64_t)idx * 8) = quant_vec(f, sc, inv_lo, inv_hi);
+      }
+    }
+    if (threadIdx.x == 0) qscale[row] = __float2bfloat16_rn(s);
+  }
+  cp_async_wait<0>();
 }
 
 // SwiGLU backward (grid-stride over 16-byte vectors)
@@ -614,6 +728,127 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   }
 }
 
+// Ring variant (default when it fits): two 16-byte vectors per thread instead of one (per-row fixed cost — reduction,
+// loop and address arithmetic — amortised over 16 elements, not 8: the kernel above issues 32 instructions per element and
+// runs at 2.9 TB/s at the clocks of a power-capped step where a device copy keeps 5.3), the three input streams of the next
+// kRingStages - 1 rows of the CTA's walk in flight as cp.async copies into shared memory (no registers held by the
+// prefetch; every thread copies exactly the slots it reads itself, so cp.async.wait_group is the only synchronisation of
+// the ring), and ONE barrier per row: the per-warp partial sums go to one of two alternating shared-memory rows.
+template <int kMaxV>
+__global__ void __launch_bounds__(256, 2)
+rmsnorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                        const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
+                        const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+                        float* __restrict__ dw_partial, int64_t M, int D, int nvec) {
+  extern __shared__ uint4 ring[];   // [stage][stream: x, dy, dres][slots]
+  __shared__ float sm[2][32];
+  const int slots = blockDim.x * kMaxV;
+  const int nstream = dres != nullptr ? 3 : 2;
+  const int nw = blockDim.x >> 5;
+  float wf[kMaxV][8], dwacc[kMaxV][8];
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int idx = threadIdx.x + j * blockDim.x;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dwacc[j][e] = 0.f;
+    if (idx < nvec) unpack8(*reinterpret_cast<const uint4*>(w + (int64_t)idx * 8), wf[j]);
+  }
+  const uint32_t ring_s = smem_u32(ring) + threadIdx.x * 16;
+  auto issue = [&](int stage, int64_t row) {
+    if (row < M) {
+      const int64_t off = (row * D + threadIdx.x * 8) * 2;   // byte offset of this thread's first vector in every stream
+      const uint32_t dst = ring_s + stage * 3 * slots * 16;
+#pragma unroll
+      for (int j = 0; j < kMaxV; ++j) {
+        const int idx = threadIdx.x + j * blockDim.x;
+        if (idx < nvec) {
+          const int64_t oj = off + (int64_t)(j * blockDim.x) * 16;
+          const uint32_t dj = dst + j * blockDim.x * 16;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dj), "l"(reinterpret_cast<const char*>(x) + oj) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dj + slots * 16),
+                       "l"(reinterpret_cast<const char*>(dy) + oj) : "memory");
+          if (nstream == 3)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dj + 2 * slots * 16),
+                         "l"(reinterpret_cast<const char*>(dres) + oj) : "memory");
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kRingStages; ++s) issue(s, blockIdx.x + (int64_t)s * gridDim.x);
+  int stage = 0, par = 0;
+  float rs_next = blockIdx.x < M ? rstd[blockIdx.x] : 0.f;   // one row ahead: its L2 latency is never on the critical path
+  for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+    const float rs = rs_next;
+    if (row + gridDim.x < M) rs_next = rstd[row + gridDim.x];
+    cp_async_wait<kRingStages - 1>();
+    const uint4* st = ring + (int64_t)stage * 3 * slots;
+    float xh[kMaxV][8], gy[kMaxV][8];
+    uint4 cres[kMaxV];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float dyf[8];
+        unpack8(st[idx], xh[j]);
+        unpack8(st[slots + idx], dyf);
+        if (nstream == 3) cres[j] = st[2 * slots + idx];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[j][e] *= rs;
+          dwacc[j][e] = fmaf(dyf[e], xh[j][e], dwacc[j][e]);
+          gy[j][e] = dyf[e] * wf[j][e];
+          dot = fmaf(gy[j][e], xh[j][e], dot);
+        }
+      }
+    }
+    issue(stage, row + (int64_t)kRingStages * gridDim.x);   // refill the stage just consumed (all reads are in registers)
+    stage = stage + 1 == kRingStages ? 0 : stage + 1;
+    dot = warp_sum(dot);
+    if (lane_id() == 0) sm[par][threadIdx.x >> 5] = dot;
+    __syncthreads();
+    // the row after next writes sm[par] again: every thread has passed the next row's barrier by then, i.e. has read it
+    if (nw == 8) {
+      const float4 a = *reinterpret_cast<const float4*>(&sm[par][0]), b = *reinterpret_cast<const float4*>(&sm[par][4]);
+      dot = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+    } else {
+      dot = 0.f;
+      for (int i = 0; i < nw; ++i) dot += sm[par][i];
+    }
+    par ^= 1;
+    dot = dot / (float)D;
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float o[8];
+        if (nstream == 3) unpack8(cres[j], o);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] += rs * (gy[j][e] - xh[j][e] * dot);
+        *reinterpret_cast<uint4*>(dx + row * D + (int64_t)idx * 8) = pack8(o);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (dw_partial != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kMaxV; ++j) {
+      const int idx = threadIdx.x + j * blockDim.x;
+      if (idx < nvec) {
+        float* dst = dw_partial + (int64_t)blockIdx.x * D + (int64_t)idx * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(dwacc[j][0], dwacc[j][1], dwacc[j][2], dwacc[j][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(dwacc[j][4], dwacc[j][5], dwacc[j][6], dwacc[j][7]);
+      }
+    }
+  }
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int nparts,
                                        int64_t D) {
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -626,22 +861,39 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, __nv_b
 // ------------------------------------------------------------------------------------------------
 // RoPE in place, interleaved pairs (modelling/llama.py:63-73).  One thread = 8 bf16 = 4 pairs.
 // ------------------------------------------------------------------------------------------------
-__global__ void rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ rope, int64_t rows,
-                            int S, int nheads, int D, int inverse) {
-  const int vec_per_row = nheads * D / 8;
-  const int64_t total = rows * vec_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / vec_per_row;
-    const int c = (int)(i - row * vec_per_row) * 8;  // column within the row
-    const int s = (int)(row % S);
-    const int d = c % D;                             // offset inside the head, multiple of 8
-    __nv_bfloat16* p = x + row * ld + c;
+// grid = (row pairs, column chunks of 256 vectors): the row (and its position s = row % S) is uniform per CTA and the column
+// comes from the thread index — no 64-bit division per thread. The first version (one grid-stride loop over
+// rows * vectors with `i / vec_per_row`, `row % S`) spent ~19 instructions per element, most of them in those two
+// divisions, and was issue-bound at the clocks of a power-capped step (3.2 TB/s where a device copy keeps 5.3).
+constexpr int kRopeRows = 2;   // rows per thread: both rows' loads are in flight before the first is rotated
+__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld,
+                                                   const float* __restrict__ rope, int64_t rows, int S,
+                                                   int vec_per_row, int D, int inverse) {
+  const int v = blockIdx.y * 256 + threadIdx.x;
+  if (v >= vec_per_row) return;
+  const int c = v * 8;                               // column within the row
+  const int d = (D & (D - 1)) == 0 ? (c & (D - 1)) : c % D;   // offset inside the head, multiple of 8
+  uint4 in[kRopeRows];
+  float4 cs0[kRopeRows], cs1[kRopeRows];
+#pragma unroll
+  for (int r = 0; r < kRopeRows; ++r) {
+    const int64_t row = (int64_t)blockIdx.x * kRopeRows + r;
+    if (row < rows) {
+      const int s = (int)((unsigned)row % (unsigned)S);   // uniform per CTA; rows < 2^31 (checked by the launcher)
+      in[r] = ldg_nc_v4(x + row * ld + c);
+      const float4* cs = reinterpret_cast<const float4*>(rope + ((int64_t)s * (D / 2) + d / 2) * 2);
+      cs0[r] = __ldg(cs);                            // (c0,s0,c1,s1)
+      cs1[r] = __ldg(cs + 1);                        // (c2,s2,c3,s3)
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRopeRows; ++r) {
+    const int64_t row = (int64_t)blockIdx.x * kRopeRows + r;
+    if (row >= rows) break;
     float f[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(p), f);
-    const float4* cs = reinterpret_cast<const float4*>(rope + ((int64_t)s * (D / 2) + d / 2) * 2);
-    const float4 cs0 = cs[0], cs1 = cs[1];  // (c0,s0,c1,s1), (c2,s2,c3,s3)
-    const float cc[4] = {cs0.x, cs0.z, cs1.x, cs1.z};
-    float sn[4] = {cs0.y, cs0.w, cs1.y, cs1.w};
+    unpack8(in[r], f);
+    const float cc[4] = {cs0[r].x, cs0[r].z, cs1[r].x, cs1[r].z};
+    float sn[4] = {cs0[r].y, cs0[r].w, cs1[r].y, cs1[r].w};
     if (inverse) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) sn[e] = -sn[e];
@@ -652,7 +904,7 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, const flo
       o[2 * e] = __fsub_rn(__fmul_rn(f[2 * e], cc[e]), __fmul_rn(f[2 * e + 1], sn[e]));
       o[2 * e + 1] = __fadd_rn(__fmul_rn(f[2 * e + 1], cc[e]), __fmul_rn(f[2 * e], sn[e]));
     }
-    *reinterpret_cast<uint4*>(p) = pack8(o);
+    *reinterpret_cast<uint4*>(x + row * ld + c) = pack8(o);
   }
 }
 
@@ -946,10 +1198,20 @@ int llamax_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, void* 
   if ((q8 == nullptr) != (qscale == nullptr)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: q8 and qscale go together");
   if (!row_cfg(D, c)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_fwd: D must be a multiple of 8 and <= 65536");
   if (M == 0) return 0;
-  int ring_grid, ring_smem, wv, wgrid;
-  if (wpr_cfg(c.nvec, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, wv, wgrid)) {
-    LX_DISPATCH_WPR(wv, row_wpr_kernel<kV, true><<<wgrid, 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, D, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, M, (int)D, c.nvec, eps));
+  int ring_grid, ring_smem, wv, wgrid, wsmem;
+  if (wpr_cfg(c.nvec, M, ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) % 16) == 0, wv, wgrid, wsmem,
+              true)) {
+    LX_DISPATCH_WPR(wv, {
+      if (c.nvec == 32 * kV) {
+        LX_RING_SMEM((row_wpr_kernel<kV, true, true>), wsmem, "rmsnorm_fwd");
+        row_wpr_kernel<kV, true, true><<<wgrid, 32 * kWprWarps, wsmem, (cudaStream_t)stream>>>(
+            (const bf16*)x, D, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, M, (int)D, c.nvec, eps);
+      } else {
+        LX_RING_SMEM((row_wpr_kernel<kV, true, false>), wsmem, "rmsnorm_fwd");
+        row_wpr_kernel<kV, true, false><<<wgrid, 32 * kWprWarps, wsmem, (cudaStream_t)stream>>>(
+            (const bf16*)x, D, (const bf16*)w, (bf16*)y, (float*)rstd, (int8_t*)q8, (bf16*)qscale, M, (int)D, c.nvec, eps);
+      }
+    });
   } else if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
     LX_DISPATCH_V(c.V, {
       LX_RING_SMEM(rmsnorm_fwd_ring_kernel<kV>, ring_smem, "rmsnorm_fwd");
@@ -970,10 +1232,19 @@ int llamax_rowquant_int8(const void* x, int64_t ldx, void* q8, void* scale_out, 
   if (!x || !q8 || !scale_out) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: null pointer");
   if (!row_cfg(K, c) || ldx % 8) return set_error(LLAMAX_ERR_ARG, "rowquant_int8: K and ldx must be multiples of 8");
   if (M == 0) return 0;
-  int ring_grid, ring_smem, wv, wgrid;
-  if (wpr_cfg(c.nvec, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, wv, wgrid)) {
-    LX_DISPATCH_WPR(wv, row_wpr_kernel<kV, false><<<wgrid, 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, ldx, nullptr, nullptr, nullptr, (int8_t*)q8, (bf16*)scale_out, M, (int)K, c.nvec, 0.f));
+  int ring_grid, ring_smem, wv, wgrid, wsmem;
+  if (wpr_cfg(c.nvec, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, wv, wgrid, wsmem, false)) {
+    LX_DISPATCH_WPR(wv, {
+      if (c.nvec == 32 * kV) {
+        LX_RING_SMEM((row_wpr_kernel<kV, false, true>), wsmem, "rowquant_int8");
+        row_wpr_kernel<kV, false, true><<<wgrid, 32 * kWprWarps, wsmem, (cudaStream_t)stream>>>(
+            (const bf16*)x, ldx, nullptr, nullptr, nullptr, (int8_t*)q8, (bf16*)scale_out, M, (int)K, c.nvec, 0.f);
+      } else {
+        LX_RING_SMEM((row_wpr_kernel<kV, false, false>), wsmem, "rowquant_int8");
+        row_wpr_kernel<kV, false, false><<<wgrid, 32 * kWprWarps, wsmem, (cudaStream_t)stream>>>(
+            (const bf16*)x, ldx, nullptr, nullptr, nullptr, (int8_t*)q8, (bf16*)scale_out, M, (int)K, c.nvec, 0.f);
+      }
+    });
   } else if (ring_cfg(c, M, (reinterpret_cast<uintptr_t>(x) % 16) == 0, ring_grid, ring_smem)) {
     LX_DISPATCH_V(c.V, {
       LX_RING_SMEM(rowquant_ring_kernel<kV>, ring_smem, "rowquant_int8");
@@ -995,6 +1266,24 @@ int llamax_swiglu_fwd(const void* a, const void* b, int64_t ld, void* g, void* q
   if ((q8 == nullptr) != (qscale == nullptr)) return set_error(LLAMAX_ERR_ARG, "swiglu_fwd: q8 and qscale go together");
   if (!row_cfg(F, c) || ld % 8) return set_error(LLAMAX_ERR_ARG, "swiglu_fwd: F and ld must be multiples of 8");
   if (M == 0) return 0;
+  static const bool ring_on = getenv("LLAMAX_SWIGLU_RING") == nullptr || atoi(getenv("LLAMAX_SWIGLU_RING")) != 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) % 16) == 0;
+  const int smem = kRingStages * 2 * c.threads * c.V * 16;
+  if (ring_on && aligned && c.V <= 4 && smem <= 200 * 1024) {
+    const int per_sm = std::max(1, std::min((216 * 1024) / (smem + 1280), 2048 / c.threads));
+    const int grid = sm_count() * per_sm;
+    if (M >= (int64_t)grid * 2) {
+      LX_DISPATCH_V(c.V, {
+        if constexpr (kV <= 4) {
+          LX_RING_SMEM(swiglu_fwd_ring_kernel<kV>, smem, "swiglu_fwd");
+          swiglu_fwd_ring_kernel<kV><<<grid, c.threads, smem, (cudaStream_t)stream>>>(
+              (const bf16*)a, (const bf16*)b, ld, (bf16*)g, (int8_t*)q8, (bf16*)qscale, M, (int)F, c.nvec);
+        }
+      });
+      LX_CHECK_LAUNCH("swiglu_fwd");
+      return 0;
+    }
+  }
   LX_DISPATCH_V(c.V, swiglu_fwd_kernel<kV><<<(unsigned)M, c.threads, 0, (cudaStream_t)stream>>>(
       (const bf16*)a, (const bf16*)b, ld, (bf16*)g, (int8_t*)q8, (bf16*)qscale, (int)F, c.nvec));
   LX_CHECK_LAUNCH("swiglu_fwd");
@@ -1020,6 +1309,22 @@ int llamax_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void*
   if (!dy || !x || !w || !rstd || !dx) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: null pointer");
   if (!row_cfg(D, c, true)) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: D must be a multiple of 8 and <= 65536");
   if (nparts <= 0 || nparts > 4096) return set_error(LLAMAX_ERR_ARG, "rmsnorm_bwd: nparts out of range");
+  // ring kernel: rows of up to 256 threads x 2 vectors (the model width), 16-byte aligned streams, a few rows per CTA
+  static const bool ring_on = getenv("LLAMAX_RMSNORM_BWD_RING") == nullptr || atoi(getenv("LLAMAX_RMSNORM_BWD_RING")) != 0;
+  RowCfg cr;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+                         reinterpret_cast<uintptr_t>(dres)) % 16) == 0;
+  if (ring_on && aligned && row_cfg(D, cr) && cr.threads <= 256 && cr.V <= 2 && M >= (int64_t)nparts * 2) {
+    const int smem = kRingStages * 3 * cr.threads * cr.V * 16;
+    LX_DISPATCH_V(cr.V, {
+      LX_RING_SMEM(rmsnorm_bwd_ring_kernel<kV>, smem, "rmsnorm_bwd");
+      rmsnorm_bwd_ring_kernel<kV><<<nparts, cr.threads, smem, (cudaStream_t)stream>>>(
+          (const bf16*)dy, (const bf16*)x, (const bf16*)w, (const float*)rstd, (const bf16*)dres, (bf16*)dx,
+          (float*)dw_partial, M, (int)D, cr.nvec);
+    });
+    LX_CHECK_LAUNCH("rmsnorm_bwd");
+    return 0;
+  }
   LX_DISPATCH_V(c.V, rmsnorm_bwd_kernel<kV><<<nparts, c.threads, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, (const bf16*)x, (const bf16*)w, (const float*)rstd, (const bf16*)dres, (bf16*)dx,
       (float*)dw_partial, M, (int)D, c.nvec));
@@ -1039,11 +1344,14 @@ int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_
                         int inverse, void* stream) {
   if (!x || !rope) return set_error(LLAMAX_ERR_ARG, "rope: null pointer");
   if (D % 8 || ld % 8) return set_error(LLAMAX_ERR_ARG, "rope: D and ld must be multiples of 8");
-  const int64_t total = B * S * (nheads * D / 8);
-  if (total == 0) return 0;
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-  rope_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)x, ld, (const float*)rope, B * S, (int)S, nheads, D,
-                                                        inverse);
+  const int64_t rows = B * S;
+  const int vec_per_row = nheads * D / 8;
+  if (rows == 0 || vec_per_row == 0) return 0;
+  if (rows > 0x7fffffffLL) return set_error(LLAMAX_ERR_ARG, "rope: more than 2^31 - 1 rows");
+  if (reinterpret_cast<uintptr_t>(x) % 16) return set_error(LLAMAX_ERR_ARG, "rope: x must be 16-byte aligned");
+  dim3 grid((unsigned)((rows + kRopeRows - 1) / kRopeRows), (unsigned)((vec_per_row + 255) / 256));
+  rope_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)x, ld, (const float*)rope, rows, (int)S, vec_per_row, D,
+                                                      inverse);
   LX_CHECK_LAUNCH("rope");
   return 0;
 }

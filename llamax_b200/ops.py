@@ -389,7 +389,8 @@ def rmsnorm_bwd(dy: Tensor, x: Tensor, w: Tensor, rstd: Tensor, dres: Tensor | N
         dres2 = _rows(dres)
         assert dres2.is_contiguous()
     dx = torch.empty_like(x2)
-    nparts = max(1, min(int(M), 4 * torch.cuda.get_device_properties(x.device).multi_processor_count))
+    # two persistent CTAs per SM (the ring kernel's residency): one wave, no re-ramp of the prefetch rings
+    nparts = max(1, min(int(M), 2 * torch.cuda.get_device_properties(x.device).multi_processor_count))
     partial = torch.empty(nparts, D, device=x.device, dtype=torch.float32) if want_dw else None
     _call(lib, "llamax_rmsnorm_bwd",
           (_p(dy2), _p(x2), _p(w), _p(rstd), _p(dres2), _p(dx), _p(partial), nparts, M, D, st,),
