@@ -1847,8 +1847,16 @@ int llamax_lora_bwd_pair(const void* dY, int64_t lddy, const void* Bt, int64_t l
   cudaStream_t st = (cudaStream_t)stream;
   const int m_blocks = (int)((M + 127) / 128);
   const int total_chunks = (int)((N + 127) / 128);
-  // enough CTAs for ~2.5 waves; a split streams at least 8 tiles
-  int splits = std::max(1, std::min(total_chunks / 8, (5 * sm_count() / 2 + m_blocks - 1) / m_blocks));
+  // Enough token blocks to cover most of the SMs (16 k tokens: 128 of 148): no split — one wave, every CTA streams its
+  // whole row of tiles through one pipeline fill, dh is final in the CTA (no fp32 partial buffer, its memset and the
+  // convert launch). Measured at the clocks of a power-capped step (tools/ew_sustained.py): dY [M, 4096] 66.6 -> 57.2 us,
+  // [M, 14336] 134.9 -> 126.8 us against the 3-way split. Fewer token blocks: enough CTAs for ~2.5 waves, a split streams
+  // at least 8 tiles.
+  int splits = m_blocks * 4 >= sm_count() * 3
+                   ? 1
+                   : std::max(1, std::min(total_chunks / 8, (5 * sm_count() / 2 + m_blocks - 1) / m_blocks));
+  static const int splits_env = getenv("LLAMAX_LORA_PAIR_SPLITS") ? atoi(getenv("LLAMAX_LORA_PAIR_SPLITS")) : 0;   // A/B only
+  if (splits_env > 0) splits = std::min(splits_env, total_chunks);
   int chunks_per_split = (total_chunks + splits - 1) / splits;
   splits = (total_chunks + chunks_per_split - 1) / chunks_per_split;
   cudaError_t e = cudaMemsetAsync(dB, 0, (size_t)N * R * sizeof(float), st);

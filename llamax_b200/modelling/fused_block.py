@@ -62,6 +62,12 @@ _CACHE_MODE = os.environ.get("LLAMAX_WEIGHT_CACHE", "auto")
 _CACHE_HEADROOM = 24 << 30
 # A/B switch (benchmarking only): "0" restores the two-pass LoRA backward (skinny dh GEMM + lora_wgrad per linear)
 _LORA_PAIR = os.environ.get("LLAMAX_LORA_PAIR", "1") != "0"
+# The adapters of linears that share an input (wq | wk | wv, w1 | w3) take ONE lora_bwd_pair launch over the concatenated
+# gradient [M, sum N] with a block-diagonal scale * B^T [sum R, sum N]: dh of every adapter comes out of the same pass
+# (the off-diagonal zeros contribute exact zeros) and each dB is its diagonal block of the [sum N, sum R] result —
+# bit-identical to one launch per adapter, whose fixed cost (two memsets, prologue, pipeline fill and drain: ~25 us at the
+# clocks of a power-capped step, more than the streaming time of the [M, 1024] wk / wv gradients) is paid once. "0": A/B.
+_LORA_GROUP_PAIR = os.environ.get("LLAMAX_LORA_GROUP_PAIR", "1") != "0"
 
 
 # OPT-IN, NON-PARITY mode (the reference author's TODO at subclasses/int8.py:105): grad_input =
@@ -276,21 +282,51 @@ class _GradSink:
         self.jobs = []
 
 
-def _lora_prepare(items, M: int, device):
+def _lora_prepare(items, M: int, device, groups=()):
     """items: (spec, h [M,R] view, a_dst | None). ONE batched launch builds, per adapter,
     bt = scale * B^T [R,N] (operand of dh), A^T (into a_dst = its columns of a resident grad_input operand, else
-    into a fresh [K,R] buffer) and ht = h^T [R,M] (operand of dB). Returns {id(spec): (bt, at, ht)}."""
+    into a fresh [K,R] buffer) and ht = h^T [R,M] (operand of dB). Returns {id(spec): (bt, at, ht)}.
+    groups: (key, specs, cache) for adapters that share an input and take one merged lora_bwd_pair launch: their bt
+    are the diagonal blocks of one [sum R, sum N] operand (kept per layer in `cache`: the off-diagonal zeros are
+    written once) and their ht consecutive rows of one [sum R, M] buffer; prep[("group", key)] = (bt_cat, ht_cat)."""
     prep, jobs = {}, []
+    placed = {}
+    for key, specs, cache in groups:
+        if not _group_mergeable(specs):
+            continue
+        sig = tuple((s.R, s.N) for s in specs)
+        r_tot, n_tot = sum(s.R for s in specs), sum(s.N for s in specs)
+        ent = cache.get("bt_" + key)
+        if ent is None or ent[0] != sig or ent[1].device != torch.device(device):
+            ent = (sig, torch.zeros(r_tot, n_tot, device=device, dtype=torch.bfloat16))
+            cache["bt_" + key] = ent
+        bt_cat = ent[1]
+        ht_cat = ops.transposed_rank_buffer(r_tot, M, device)
+        r_off = n_off = 0
+        for s in specs:
+            placed[id(s)] = (bt_cat[r_off : r_off + s.R, n_off : n_off + s.N], ht_cat[r_off : r_off + s.R])
+            r_off += s.R
+            n_off += s.N
+        prep[("group", key)] = (bt_cat, ht_cat)
     for s, h, a_dst in items:
         if s.R == 0:
             continue
-        bt = torch.empty(s.R, s.N, device=device, dtype=torch.bfloat16)
+        if id(s) in placed:
+            bt, ht = placed[id(s)]
+        else:
+            bt = torch.empty(s.R, s.N, device=device, dtype=torch.bfloat16)
+            ht = ops.transposed_rank_buffer(s.R, M, device)
         at = a_dst if a_dst is not None else torch.empty(s.K, s.R, device=device, dtype=torch.bfloat16)
-        ht = ops.transposed_rank_buffer(s.R, M, device)
         jobs += [(s.lora_b.detach(), bt, s.lora_scale, True), (s.lora_a.detach(), at, 1.0, True), (h, ht, 1.0, True)]
         prep[id(s)] = (bt, at, ht)
     ops.batched_copy(jobs)
     return prep
+
+
+def _group_mergeable(specs) -> bool:
+    r_tot = sum(s.R for s in specs)
+    return (_LORA_PAIR and _LORA_GROUP_PAIR and len(specs) > 1 and all(s.R > 0 for s in specs) and r_tot <= 32
+            and all(s.lora_scale == specs[0].lora_scale for s in specs) and all(s.N % 8 == 0 for s in specs))
 
 
 def _lora_dh_dB(dy: Tensor, bt: Tensor, ht: Tensor, out_dh: Tensor, scale: float, out_dht: Tensor) -> Tensor:
@@ -326,7 +362,7 @@ def _ffn_up(x1: Tensor, w_fn: Tensor, s1: LinearSpec, s3: LinearSpec, dynamic: b
 
 
 def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tensor | None, a_placed: bool, prep, sink,
-                    need_dx=True, i8=None, mixed=None):
+                    need_dx=True, i8=None, mixed=None, group_key=None):
     """Backward of linears that share one input. dy_cat [M, n_total + r_total]: gradient blocks already written in
     the first n_total columns (block i = specs[i].N columns); the LoRA dh columns are filled here. wt: the
     [K, n_total + r_total] grad_input operand (frozen part valid; A^T columns valid iff a_placed).
@@ -336,7 +372,24 @@ def _group_backward(specs, dy_cat: Tensor, n_total: int, x_in: Tensor, wt: Tenso
     n_off, r_off = 0, 0
     lora_grads = []
     dht = ops.transposed_rank_buffer(r_total, dy_cat.shape[0], dy_cat.device) if r_total > 0 else None
-    for s in specs:
+    merged = prep.get(("group", group_key)) if group_key is not None else None
+    if merged is not None:   # one pass over [M, n_total] for all adapters of the group (see _LORA_GROUP_PAIR)
+        bt_cat, ht_cat = merged
+        if not a_placed and i8 is None and mixed is None:
+            for s in specs:
+                wt[:, n_total + r_off : n_total + r_off + s.R].copy_(prep[id(s)][1])
+                r_off += s.R
+        dB_cat = ops.lora_bwd_pair(dy_cat[:, :n_total], bt_cat, None, dy_cat[:, n_total : n_total + r_total],
+                                   specs[0].lora_scale, Ht=ht_cat, out_dht=dht)   # [n_total, r_total] fp32
+        r_off = 0
+        for s in specs:
+            lora_grads.append([None, sink.emit(dB_cat[n_off : n_off + s.N, r_off : r_off + s.R], False, s.lora_b.dtype)])
+            n_off += s.N
+            r_off += s.R
+        specs_loop = ()
+    else:
+        specs_loop = specs
+    for s in specs_loop:
         dy_i = dy_cat[:, n_off : n_off + s.N]
         if s.R > 0:
             c0 = n_total + r_off
@@ -558,7 +611,7 @@ class FusedDecoderBlock(torch.autograd.Function):
             (so, h_o, None),
             (s1, h_13[:, : s1.R] if s1.R else None, a_dst("w13", 2 * F_, 0, s1.R)),
             (s3, h_13[:, s1.R :] if s3.R else None, a_dst("w13", 2 * F_, s1.R, s3.R)),
-            (s2, h_2, None)), M, dev)
+            (s2, h_2, None)), M, dev, groups=(("wqkv", (sq, sk, sv), cache), ("w13", (s1, s3), cache)))
 
         # --- w2 ---  (needs g = silu(a) * b only for dA of w2: re-materialised by the SwiGLU backward kernel)
         dab = _padded_empty(M, 2 * F_ + r13, dev)
@@ -596,7 +649,7 @@ class FusedDecoderBlock(torch.autograd.Function):
         # --- w1 | w3 ---
         wt13, placed13 = operand("w13")
         dxn2, g13 = _group_backward((s1, s3), dab, 2 * F_, xn2, wt13, placed13, prep, sink, i8=i8.get("w13"),
-                                    mixed=mixed.get("w13"))
+                                    mixed=mixed.get("w13"), group_key="w13")
         del dab
         want_dw_fn, want_dw_an = w_fn.requires_grad, w_an.requires_grad
         dx1, dw_fn = ops.rmsnorm_bwd(dxn2, x1, w_fn.detach(), rstd2, dout2, want_dw=want_dw_fn)
@@ -620,7 +673,7 @@ class FusedDecoderBlock(torch.autograd.Function):
                      doc_start=doc_start, doc_end=doc_end, rope_inverse=rope, delta=delta)   # dq, dk come back un-rotated
         wtqkv, placedqkv = operand("wqkv")
         dxn1, gqkv = _group_backward((sq, sk, sv), dqkv, nq + 2 * nk, xn1, wtqkv, placedqkv, prep, sink,
-                                     i8=i8.get("wqkv"), mixed=mixed.get("wqkv"))
+                                     i8=i8.get("wqkv"), mixed=mixed.get("wqkv"), group_key="wqkv")
         del dqkv
         dx, dw_an = ops.rmsnorm_bwd(dxn1, x2, w_an.detach(), rstd1, dx1, want_dw=want_dw_an)
         sink.flush()   # fp32 dA^T / dB -> parameter-dtype gradients, one launch

@@ -59,7 +59,11 @@ cases = [
     ("lora_wgrad [M,D]^T [M,8]", lambda: ops.lora_wgrad(x, h, 1.0), 2.0 * M * (D + 8)),
     ("lora_bwd_pair dY[M,F]", lambda: ops.lora_bwd_pair(ab[:, :F], bt, h, dh, 1.0), 2.0 * M * (F + 16)),
     ("lora_bwd_pair dY[M,D]", lambda: ops.lora_bwd_pair(x, btd, h, dh, 1.0), 2.0 * M * (D + 16)),
+    ("lora_bwd_pair dY[M,1024]", lambda: ops.lora_bwd_pair(x[:, :1024], btd[:, :1024], h, dh, 1.0), 2.0 * M * (1024 + 16)),
 ]
+only = os.environ.get("EW_ONLY")
+if only:
+    cases = [c for c in cases if any(k in c[0] for k in only.split(","))]
 
 
 def smi():
