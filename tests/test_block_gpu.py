@@ -561,3 +561,34 @@ def test_delta_from_gemm_epilogue_mode_matches_default():
             FB.set_fuse_delta(False)
     for a, b in zip(results[0], results[1]):
         assert rel_err(b, a) <= 5e-3
+
+
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_grouped_lora_backward_equals_one_launch_per_adapter(dynamic, monkeypatch):
+    """wq|wk|wv and w1|w3 take ONE lora_bwd_pair launch each over a block-diagonal scale*B^T (fused_block._LORA_GROUP_PAIR):
+    dh (hence the input gradient's LoRA term) must be the bits of the per-adapter launches — the off-diagonal zeros add
+    exact zeros — and every dB the diagonal block of the merged result (equal up to the order of the fp32 L2 reductions)."""
+    import llamax_b200.modelling.fused_block as FB
+    from llamax_b200.modelling import PrefixLM
+
+    results = []
+    for grouped in (True, False):
+        monkeypatch.setattr(FB, "_LORA_GROUP_PAIR", grouped)
+        model = build_tiny_llama(dynamic, num_layers=1).cuda()      # helpers give every lora_b non-zero values
+        layer, cfg = model.layers[0], model.config
+        rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:512].cuda()
+        torch.manual_seed(5)
+        x = torch.randn(2, 512, cfg.embed_dim, device="cuda").bfloat16().requires_grad_(True)
+        dout = torch.randn(2, 512, cfg.embed_dim, device="cuda").bfloat16()
+        out = layer(x, rope, block_mask=PrefixLM(300))
+        out.backward(dout)
+        names = [n for n, p in layer.named_parameters() if p.requires_grad]
+        results.append((out.detach(), x.grad.detach().clone(),
+                        {n: p.grad.detach().clone() for n, p in layer.named_parameters() if p.requires_grad}))
+        assert any(n.endswith("wk.lora_b") for n in names) and any(n.endswith("w3.lora_a") for n in names)
+    (o1, dx1, g1), (o0, dx0, g0) = results
+    assert torch.equal(o1, o0)
+    assert rel_err(dx1, dx0) <= 5e-3          # dQ is reduced with fp32 atomics: a bf16 ulp here and there, run to run
+    assert g1.keys() == g0.keys()
+    for n in g1:
+        assert g1[n].shape == g0[n].shape and rel_err(g1[n], g0[n]) <= 5e-3, n

@@ -10,9 +10,11 @@ from tests.helpers import rel_err
 pytestmark = pytest.mark.gpu
 
 
-# M >= 256 with K <= 4096 runs the warp-per-row kernel, the others the block-per-row / ring kernels
+# M >= 1024 with K <= 4096 runs the warp-per-row kernel (K = 32 * 8 * {1, 2, 4, 8, 16}: the branch-free kFull form; 3000, 1792:
+# the bounds-checked one), the others the block-per-row / ring kernels
 @pytest.mark.parametrize("M,K", [(64, 512), (300, 4096), (128, 14336), (5, 1792), (1, 8), (3, 32768), (1024, 4096),
-                                 (2048, 512), (257, 1792), (300, 2056), (4100, 8)])
+                                 (2048, 512), (257, 1792), (300, 2056), (4100, 8), (1100, 3000), (1030, 1792),
+                                 (1500, 2048)])
 def test_rowquant_bit_exact(M, K):
     g = torch.Generator().manual_seed(K)
     x = (torch.randn(M, K, generator=g) * 3).bfloat16()
@@ -61,7 +63,9 @@ def test_rowquant_pitched_input():
     assert torch.equal(q.cpu(), q_ref) and torch.equal(s.cpu(), s_ref)
 
 
-@pytest.mark.parametrize("M,D", [(64, 512), (300, 4096), (7, 8192), (1024, 4096), (2048, 512), (300, 2056)])
+# M >= 1024, D <= 4096: warp-per-row forward; M >= 592, D <= 4096: ring backward; the others the block-per-row kernels
+@pytest.mark.parametrize("M,D", [(64, 512), (300, 4096), (7, 8192), (1024, 4096), (2048, 512), (300, 2056), (1100, 3000),
+                                 (700, 4096)])
 def test_rmsnorm_fwd_bwd(M, D):
     g = torch.Generator().manual_seed(D)
     x = torch.randn(M, D, generator=g).bfloat16()
@@ -81,7 +85,8 @@ def test_rmsnorm_fwd_bwd(M, D):
     assert dw2 is None and rel_err(dx2, dx_ref) <= 1e-2
 
 
-@pytest.mark.parametrize("M,F", [(64, 1792), (100, 14336)])
+# (600, 14336), (2400, 1792), (2400, 1000): the persistent ring kernel (enough rows per resident CTA); the others one CTA per row
+@pytest.mark.parametrize("M,F", [(64, 1792), (100, 14336), (600, 14336), (2400, 1792), (2400, 1000)])
 def test_swiglu_fwd_bwd(M, F):
     g = torch.Generator().manual_seed(F)
     ab = (torch.randn(M, 2 * F, generator=g) * 2).bfloat16()
@@ -92,6 +97,10 @@ def test_swiglu_fwd_bwd(M, F):
     assert (gg.cpu() != g_ref).float().mean().item() < 1e-3
     q_ref, s_ref = R.quantize_int8_rowwise(gg.cpu())
     assert torch.equal(q8.cpu(), q_ref) and torch.equal(qs.cpu(), s_ref)
+    none_g, q8b, qsb = ops.swiglu_fwd(abc[:, :F], abc[:, F:], quant=True, want_g=False)      # codes without writing g
+    assert none_g is None and torch.equal(q8b, q8) and torch.equal(qsb, qs)
+    g_only, q_none, _ = ops.swiglu_fwd(abc[:, :F], abc[:, F:], quant=False)                     # g without the quantiser
+    assert q_none is None and torch.equal(g_only, gg)
     dg = torch.randn(M, F, generator=g).bfloat16()
     da_ref, db_ref = R.swiglu_bwd_f32(dg, a, b)
     wide = torch.zeros(M, 2 * F + 16, dtype=torch.bfloat16, device="cuda")
