@@ -157,7 +157,8 @@ int llamax_swiglu_bwd(const void* dg, const void* a, const void* b, int64_t ld, 
 /* ---- K7: RoPE (modelling/llama.py:63-73), interleaved pairs, fp32 math, in place ------------------
  * x bf16 [B*S, ...] row pitch ld; rotates `nheads` heads of width D starting at column 0.
  * rope fp32 [S, D/2, 2] (cos, sin) (build_rope, llama.py:54-60).  inverse = 1 applies the transpose
- * (the backward of apply_rope). */
+ * (the backward of apply_rope).  x 16-byte aligned, ld and D multiples of 8, fewer than 2^31 rows; anything else
+ * returns LLAMAX_ERR_ARG. */
 int llamax_rope_inplace(void* x, int64_t ld, const void* rope, int64_t B, int64_t S, int32_t nheads, int32_t D,
                         int inverse, void* stream);
 

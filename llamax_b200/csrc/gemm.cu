@@ -1772,10 +1772,14 @@ int llamax_bf16_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, voi
   // long contractions without an epilogue (w1|w3 grad_input, LM-head grad_input): 512 x 256 outputs per CTA-pair visit
   static const bool no_wide = getenv("LLAMAX_GEMM_WIDE") != nullptr && getenv("LLAMAX_GEMM_WIDE")[0] == '0';  // A/B switch
   static const int wide_min_k = getenv("LLAMAX_GEMM_WIDE_MINK") ? atoi(getenv("LLAMAX_GEMM_WIDE_MINK")) : 8192;   // A/B
-  // ... and very wide outputs (the LM-head logits GEMM [8192, 128256, 4096]: its 1 GB B operand streams once per group of
-  // m-tiles, and 512-row tiles halve the number of groups: 1106-1113 -> 1230-1236 TFLOP/s sustained, same box; the
-  // short-K GEMMs with N = 4096 lose 4 % on the wide tile and stay on the 256 x 256 kernel)
-  if (plain && !no_wide && g_gemm_cg == 2 && (K >= wide_min_k || (N >= 32768 && K >= 2048)) && M >= 1024 && N >= 256 && N % 8 == 0 && ldc % 8 == 0 &&
+  // Very wide outputs with a short contraction (the LM-head logits GEMM [8192, 128256, 4096]) stay on the 256 x 256 kernel:
+  // back to back at the power cap the wide tile looked better there (1106-1113 -> 1230-1236 TFLOP/s, tools/wide_mink_ab.py),
+  // but INSIDE the step, where the LM head runs at the clocks the lighter passes before it leave, it is slower — 7.1 ms
+  // (1203-1222 TFLOP/s) against 5.5-5.7 ms (1509-1573) in the bench line's per-shape table, same code otherwise.
+  // LLAMAX_GEMM_WIDE_LMHEAD=1 puts those shapes on the wide tile again (A/B).
+  static const bool wide_lmhead = getenv("LLAMAX_GEMM_WIDE_LMHEAD") != nullptr && getenv("LLAMAX_GEMM_WIDE_LMHEAD")[0] == '1';
+  if (plain && !no_wide && g_gemm_cg == 2 && (K >= wide_min_k || (wide_lmhead && N >= 32768 && K >= 2048)) && M >= 1024 &&
+      N >= 256 && N % 8 == 0 && ldc % 8 == 0 &&
       lda % 8 == 0 && ldb % 8 == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0 &&
       reinterpret_cast<uintptr_t>(C) % 16 == 0)
     return launch_gemm_wide(A, lda, B, ldb, C, ldc, (int)M, (int)N, (int)K, (cudaStream_t)stream);
