@@ -348,9 +348,9 @@ __global__ void rowquant_ring_kernel(const __nv_bfloat16* __restrict__ x, int64_
 // lane, both reductions are five shuffles, there is no barrier. The first version of this kernel loaded the row straight
 // into registers and was SLOWER than the ring kernels (92 vs 79 us): nothing overlapped a warp's load with its arithmetic
 // and the warps of an SM fell into step. Now every warp keeps the NEXT row of its walk in flight as cp.async copies into a
-// warp-private two-stage shared-memory ring (each lane copies exactly the slots it reads: cp.async.wait_group is the only
-// synchronisation), the passes read the row from shared memory, and only the rounded output row stays in registers
-// (packed) between the normalisation and the quantiser. The row maximum is taken on the packed bf16 pairs (one logic op +
+// warp-private shared-memory row buffer (each lane copies exactly the slots it reads: cp.async.wait_group is the only
+// synchronisation): the row is pulled into registers (packed) when it has arrived and its slots are refilled at once, so one
+// row per warp is in flight for the whole time the current one is worked on. The row maximum is taken on the packed bf16 pairs (one logic op +
 // one HMNMX2 per two elements). Arithmetic and rounding order per element are those of the kernels above; only the
 // summation order of the mean square differs.
 // kNorm = false: row quantiser alone (w, y, rstd unused).
@@ -366,51 +366,51 @@ __device__ __forceinline__ uint32_t absmax_bf16x2(uint32_t acc, uint32_t v) {
 // kFull: the row has exactly 32 * kVec vectors (the model width with kVec = 16): no per-vector bounds branch, so the
 // passes are straight-line code the compiler can schedule across vectors (and ~30 % less of it)
 template <int kVec, bool kNorm, bool kFull>
-__global__ void __launch_bounds__(32 * kWprWarps, 3)
+__global__ void __launch_bounds__(32 * kWprWarps, kNorm ? 3 : 4)   // the norm variant spills below 168 registers
 row_wpr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int8_t* __restrict__ q8,
                __nv_bfloat16* __restrict__ qscale, int64_t M, int D, int nvec, float eps) {
-  extern __shared__ uint4 ring[];   // [warp][stage][32 * kVec], then (kNorm) the norm weight [32 * kVec]
+  extern __shared__ uint4 ring[];   // [warp][32 * kVec] (one row in flight per warp), then (kNorm) the norm weight [32 * kVec]
   const int lane = lane_id(), wib = threadIdx.x >> 5;
   constexpr int kSlots = 32 * kVec;
-  uint4* my = ring + wib * 2 * kSlots;
-  const uint4* wsm = ring + kWprWarps * 2 * kSlots;
+  uint4* my = ring + wib * kSlots;
+  const uint4* wsm = ring + kWprWarps * kSlots;
   if constexpr (kNorm) {
     for (int i = threadIdx.x; i < nvec; i += blockDim.x)
-      ring[kWprWarps * 2 * kSlots + i] = *reinterpret_cast<const uint4*>(w + (int64_t)i * 8);
+      ring[kWprWarps * kSlots + i] = *reinterpret_cast<const uint4*>(w + (int64_t)i * 8);
     __syncthreads();
   }
   const int64_t warps = (int64_t)gridDim.x * kWprWarps;
-  auto issue = [&](int stage, int64_t row) {
+  auto issue = [&](int64_t row) {
     if (row < M) {
       const __nv_bfloat16* xr = x + row * ldx;
 #pragma unroll
       for (int j = 0; j < kVec; ++j) {
         const int idx = lane + 32 * j;
-        if (kFull || idx < nvec) cp_async_16(my + stage * kSlots + idx, xr + (int64_t)idx * 8);
+        if (kFull || idx < nvec) cp_async_16(my + idx, xr + (int64_t)idx * 8);
       }
     }
     cp_async_commit();
   };
   int64_t row = (int64_t)blockIdx.x * kWprWarps + wib;
-  issue(0, row);
-  int stage = 0;
+  issue(row);
   for (; row < M; row += warps) {
-    issue(stage ^ 1, row + warps);
-    cp_async_wait<1>();
-    const uint4* cur = my + stage * kSlots;
-    stage ^= 1;
+    // the row arrives in registers (packed), and its slots are refilled at once with the warp's next row: one row per warp
+    // in flight for the whole time the current one is worked on, at half the shared memory of a two-stage ring (16 instead
+    // of 12 warps per SM for the quantiser alone)
+    cp_async_wait<0>();
     uint4 pk[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) pk[j] = (kFull || lane + 32 * j < nvec) ? my[lane + 32 * j] : make_uint4(0, 0, 0, 0);
+    issue(row + warps);
     if constexpr (kNorm) {
-      float ss4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains: three warps per scheduler do not hide a 128-deep one
+      float ss4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains: few warps per scheduler do not hide a 128-deep one
 #pragma unroll
       for (int j = 0; j < kVec; ++j) {
-        if (kFull || lane + 32 * j < nvec) {
-          float f[8];
-          unpack8(cur[lane + 32 * j], f);
+        float f[8];
+        unpack8(pk[j], f);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) ss4[e & 3] = fmaf(f[e], f[e], ss4[e & 3]);
-        }
+        for (int e = 0; e < 8; ++e) ss4[e & 3] = fmaf(f[e], f[e], ss4[e & 3]);
       }
       const float ss = warp_sum((ss4[0] + ss4[1]) + (ss4[2] + ss4[3]));
       const float rstd = 1.0f / sqrtf(ss / (float)D + eps);
@@ -418,10 +418,9 @@ row_wpr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bflo
 #pragma unroll
       for (int j = 0; j < kVec; ++j) {
         const int idx = lane + 32 * j;
-        pk[j] = make_uint4(0, 0, 0, 0);
         if (kFull || idx < nvec) {
           float f[8], wf[8];
-          unpack8(cur[idx], f);
+          unpack8(pk[j], f);
           unpack8(wsm[idx], wf);
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = (f[e] * rstd) * wf[e];
@@ -429,9 +428,6 @@ row_wpr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bflo
           if (y != nullptr) *reinterpret_cast<uint4*>(y + row * D + (int64_t)idx * 8) = pk[j];
         }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kVec; ++j) pk[j] = (kFull || lane + 32 * j < nvec) ? cur[lane + 32 * j] : make_uint4(0, 0, 0, 0);
     }
     if (q8 == nullptr) continue;
     uint32_t m4[4] = {0, 0, 0, 0};   // running maxima of |.| on packed bf16 pairs (exact: a maximum rounds nothing)
@@ -467,11 +463,12 @@ row_wpr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bflo
 // block-per-row ring kernels (A/B).
 static bool wpr_cfg(int nvec, int64_t M, bool aligned, int& kvec, int& grid, int& smem, bool norm) {
   static const bool enabled = getenv("LLAMAX_ROW_WPR") == nullptr || atoi(getenv("LLAMAX_ROW_WPR")) != 0;
-  static const int per_sm = getenv("LLAMAX_ROW_WPR_CTAS") ? std::max(1, atoi(getenv("LLAMAX_ROW_WPR_CTAS"))) : 3;
+  static const int per_sm_env = getenv("LLAMAX_ROW_WPR_CTAS") ? std::max(1, atoi(getenv("LLAMAX_ROW_WPR_CTAS"))) : 0;
+  const int per_sm = per_sm_env > 0 ? per_sm_env : (norm ? 3 : 4);   // = the kernels' launch bounds (registers)
   if (!enabled || !aligned || nvec > 512 || M < 1024) return false;
   const int v = (nvec + 31) / 32;
   kvec = v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 8 ? 8 : 16;
-  smem = (kWprWarps * 2 + (norm ? 1 : 0)) * 32 * kvec * 16;
+  smem = (kWprWarps + (norm ? 1 : 0)) * 32 * kvec * 16;
   grid = (int)std::min<int64_t>((M + kWprWarps - 1) / kWprWarps, (int64_t)sm_count() * per_sm);
   return true;
 }
