@@ -2288,7 +2288,8 @@ int llamax_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if ((rc = make_head_tmap(&tk, k, ldk, B, S, Hkv, D, fwd::kTile))) return rc;
   if ((rc = make_head_tmap(&tv, v, ldv, B, S, Hkv, D, fwd::kTile))) return rc;
   // A/B switch: LLAMAX_ATTN_FWD = 1 (one query tile per CTA), 2 (two tiles, thread per row, one issuer), 3 (two tiles,
-  // two threads per row), 4 (default: two tiles, thread per row, chunked P hand-off, one issuer per tile)
+  // two threads per row), 4 (two tiles, thread per row, chunked P hand-off, one issuer per tile), 5 (default: v4 made
+  // persistent, one CTA per SM over a static item list)
   static const int version = [] {
     const char* e = getenv("LLAMAX_ATTN_FWD");
     if (getenv("LLAMAX_ATTN_FWD_ONE_TILE") && getenv("LLAMAX_ATTN_FWD_ONE_TILE")[0] == '1') return 1;
