@@ -534,7 +534,8 @@ swiglu_fwd_ring_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16*
   const int slots = blockDim.x * kMaxV;
   const int nw = blockDim.x >> 5;
   const uint32_t ring_s = smem_u32(ring) + threadIdx.x * 16;   // this thread's first slot of stage 0, stream a
-  const int64_t b_off = (b - a) * 2;                            // byte offset from a's row to b's (one buffer, same pitch)
+  // byte offset from a row of a to the same row of b (same pitch; normally two column blocks of one buffer)
+  const int64_t b_off = reinterpret_cast<const char*>(b) - reinterpret_cast<const char*>(a);
   auto issue = [&](int stage, int64_t row) {
     if (row < M) {
       // row base computed once; per vector one 64-bit add and one 32-bit add

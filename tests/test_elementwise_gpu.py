@@ -101,6 +101,9 @@ def test_swiglu_fwd_bwd(M, F):
     assert none_g is None and torch.equal(q8b, q8) and torch.equal(qsb, qs)
     g_only, q_none, _ = ops.swiglu_fwd(abc[:, :F], abc[:, F:], quant=False)                     # g without the quantiser
     assert q_none is None and torch.equal(g_only, gg)
+    a_sep, b_sep = abc[:, :F].contiguous(), abc[:, F:].contiguous()                            # two allocations, pitch F
+    g_sep, q_sep, s_sep = ops.swiglu_fwd(a_sep, b_sep, quant=True)
+    assert torch.equal(g_sep, gg) and torch.equal(q_sep, q8) and torch.equal(s_sep, qs)
     dg = torch.randn(M, F, generator=g).bfloat16()
     da_ref, db_ref = R.swiglu_bwd_f32(dg, a, b)
     wide = torch.zeros(M, 2 * F + 16, dtype=torch.bfloat16, device="cuda")
