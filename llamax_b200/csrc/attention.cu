@@ -2186,16 +2186,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // delta[b,h,s] = sum_d dO * O. 16-byte loads: D / 8 lanes per (row, head), so a warp covers 2 (D = 128) or 4 (D = 64)
 // heads of one row; the 8-byte-per-lane version ran at half the HBM rate.
 template <int D>
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ dout,
-                                  int64_t lddo, float* __restrict__ delta, int64_t rows, int S, int Hq) {
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo,
+                                                         const __nv_bfloat16* __restrict__ dout, int64_t lddo,
+                                                         float* __restrict__ delta, int S, int Hq) {
+  // grid = (rows, groups of 8 warps): the row is uniform per CTA and the head comes from the warp index — the first version
+  // derived both from one flat warp index with two 64-bit divisions per thread, more instructions than the dot product
   constexpr int kLanes = D / 8;                 // lanes per head: 16 or 8
   constexpr int kHeadsPerWarp = 32 / kLanes;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int groups = (Hq + kHeadsPerWarp - 1) / kHeadsPerWarp;   // warps per row
-  if (w >= rows * groups) return;
-  const int64_t row = w / groups;
-  const int h = (int)(w - row * groups) * kHeadsPerWarp + lane / kLanes;
+  const int grp = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int h = grp * kHeadsPerWarp + lane / kLanes;
+  if (grp * kHeadsPerWarp >= Hq) return;        // whole warp
+  const int64_t row = blockIdx.x;
   float s = 0.f;
   if (h < Hq) {
     const int c = h * D + (lane % kLanes) * 8;
@@ -2208,39 +2210,56 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t l
 #pragma unroll
   for (int off = kLanes / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if (h < Hq && (lane % kLanes) == 0) {
-    const int64_t bb = row / S, ss = row - bb * S;
-    delta[(bb * Hq + h) * S + ss] = s;
+    const unsigned bb = blockIdx.x / (unsigned)S, ss = blockIdx.x - bb * (unsigned)S;   // rows < 2^31 (launcher)
+    delta[((int64_t)bb * Hq + h) * S + ss] = s;
   }
 }
 
-// dq_accum fp32 [B, Hq, S, D] -> dq bf16 [B*S, Hq*D] (row pitch lddq); one thread = 8 head-dim elements
+// dq_accum fp32 [B, Hq, S, D] -> dq bf16 [B*S, Hq*D] (row pitch lddq); one thread = 2 x 8 head-dim elements.
+// grid = (B * Hq, chunks of 512 vectors of one head's [S, D] slab): batch and head are uniform per CTA, position and column
+// come from the thread index by a shift and a mask (the first version: four 64-bit divisions per thread and vector)
 template <int D>
-__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t lddq,
-                                       int64_t B, int S, int Hq, const float* __restrict__ rope) {
-  const int64_t total = B * Hq * (int64_t)S * (D / 8);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % (D / 8)) * 8;
-    int64_t r = i / (D / 8);          // (b * Hq + h) * S + s
-    const int s_ = (int)(r % S);
-    r /= S;
-    const int h = (int)(r % Hq);
-    const int64_t b = r / Hq;
-    const float* src = acc + (((b * Hq + h) * S + s_) * D + c);
-    float4 a = *reinterpret_cast<const float4*>(src);
-    float4 b4 = *reinterpret_cast<const float4*>(src + 4);
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc,
+                                                              __nv_bfloat16* __restrict__ dq, int64_t lddq, int S,
+                                                              int Hq, const float* __restrict__ rope) {
+  constexpr int kVecs = D / 8;
+  const unsigned bh = blockIdx.x, b = bh / (unsigned)Hq, h = bh - b * (unsigned)Hq;
+  const float* slab = acc + (int64_t)bh * S * D;
+  const int nvec = S * kVecs;
+  float4 lo[2], hi[2], t0[2], t1[2];
+  int t[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    t[k] = blockIdx.y * 512 + k * 256 + threadIdx.x;
+    if (t[k] < nvec) {
+      const float* src = slab + (int64_t)t[k] * 8;
+      lo[k] = __ldcs(reinterpret_cast<const float4*>(src));       // read once: streaming
+      hi[k] = __ldcs(reinterpret_cast<const float4*>(src + 4));
+      if (rope != nullptr) {
+        const int s_ = t[k] / kVecs, c = (t[k] % kVecs) * 8;
+        const float4* cs = reinterpret_cast<const float4*>(rope + ((int64_t)s_ * (D / 2) + c / 2) * 2);
+        t0[k] = __ldg(cs);
+        t1[k] = __ldg(cs + 1);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (t[k] >= nvec) continue;
+    const int s_ = t[k] / kVecs, c = (t[k] % kVecs) * 8;
+    float4 a = lo[k], b4 = hi[k];
     if (rope != nullptr) {  // RoPE backward on the fp32 sums (one rounding fewer than rotating the bf16 result)
-      const float4* cs = reinterpret_cast<const float4*>(rope + ((int64_t)s_ * (D / 2) + c / 2) * 2);
-      const float4 t0 = cs[0], t1 = cs[1];
-      a = make_float4(a.x * t0.x + a.y * t0.y, a.y * t0.x - a.x * t0.y, a.z * t0.z + a.w * t0.w, a.w * t0.z - a.z * t0.w);
-      b4 = make_float4(b4.x * t1.x + b4.y * t1.y, b4.y * t1.x - b4.x * t1.y, b4.z * t1.z + b4.w * t1.w,
-                       b4.w * t1.z - b4.z * t1.w);
+      const float4 u0 = t0[k], u1 = t1[k];
+      a = make_float4(a.x * u0.x + a.y * u0.y, a.y * u0.x - a.x * u0.y, a.z * u0.z + a.w * u0.w, a.w * u0.z - a.z * u0.w);
+      b4 = make_float4(b4.x * u1.x + b4.y * u1.y, b4.y * u1.x - b4.x * u1.y, b4.z * u1.z + b4.w * u1.w,
+                       b4.w * u1.z - b4.z * u1.w);
     }
     uint4 o4;
     o4.x = pack_bf16(a.x, a.y);
     o4.y = pack_bf16(a.z, a.w);
     o4.z = pack_bf16(b4.x, b4.y);
     o4.w = pack_bf16(b4.z, b4.w);
-    *reinterpret_cast<uint4*>(dq + (b * S + s_) * lddq + (int64_t)h * D + c) = o4;
+    *reinterpret_cast<uint4*>(dq + ((int64_t)b * S + s_) * lddq + (int64_t)h * D + c) = o4;
   }
 }
 
@@ -2258,6 +2277,9 @@ static int check_attn_args(int64_t B, int64_t S, int Hq, int Hkv, int D, int64_t
   if (D != 128 && D != 64) return set_error(LLAMAX_ERR_ARG, "attention: head_dim must be 64 or 128");
   if (B <= 0 || S <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv) return set_error(LLAMAX_ERR_ARG, "attention: bad B/S/H");
   if (P < 0) return set_error(LLAMAX_ERR_ARG, "attention: prefix_len < 0");
+  // grids are indexed by rows and by (batch, head) pairs, 32-bit position arithmetic inside the side kernels
+  if (B * S > 0x7fffffffLL || B * Hq > 0x7fffffffLL || S * 16 > 0x7fffffffLL)
+    return set_error(LLAMAX_ERR_ARG, "attention: B * S, B * Hq and 16 * S must be below 2^31");
   (void)who;
   return 0;
 }
@@ -2378,14 +2400,14 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)rows * Hq * D * sizeof(float), st);
   if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd: memset");
   if (o != nullptr) {
-    const int64_t warps = rows * ceil_div(Hq, 32 / (D / 8));
-    const int blocks = (int)ceil_div(warps * 32, 256);
+    const int groups = (int)ceil_div(Hq, 32 / (D / 8));   // warps per row
+    dim3 dgrid((unsigned)rows, (unsigned)ceil_div(groups, 8));
     if (D == 128)
-      attn_delta_kernel<128><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
-                                                     (float*)delta, rows, (int)S, Hq);
+      attn_delta_kernel<128><<<dgrid, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
+                                                    (float*)delta, (int)S, Hq);
     else
-      attn_delta_kernel<64><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
-                                                    (float*)delta, rows, (int)S, Hq);
+      attn_delta_kernel<64><<<dgrid, 256, 0, st>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)dout, lddo,
+                                                   (float*)delta, (int)S, Hq);
     LX_CHECK_LAUNCH("attn_bwd: delta");
   }
   CUtensorMap tq, tk, tv, tdo;
@@ -2415,14 +2437,13 @@ int llamax_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   kern<<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(tq, tk, tv, tdo, p);
   LX_CHECK_LAUNCH("attn_bwd");
   {
-    const int64_t total = rows * (Hq * D / 8);
-    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+    dim3 cgrid((unsigned)(B * Hq), (unsigned)ceil_div(S * (D / 8), 512));
     if (D == 128)
-      attn_dq_convert_kernel<128><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq,
-                                                             (const float*)rope_inverse);
+      attn_dq_convert_kernel<128><<<cgrid, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, (int)S, Hq,
+                                                          (const float*)rope_inverse);
     else
-      attn_dq_convert_kernel<64><<<blocks, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, B, (int)S, Hq,
-                                                            (const float*)rope_inverse);
+      attn_dq_convert_kernel<64><<<cgrid, 256, 0, st>>>((const float*)dq_accum, (__nv_bfloat16*)dq, lddq, (int)S, Hq,
+                                                         (const float*)rope_inverse);
     LX_CHECK_LAUNCH("attn_bwd: dq convert");
   }
   return 0;
