@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LLAMAX_B200_VERSION 101
+#define LLAMAX_B200_VERSION 102
 
 #define LLAMAX_OK 0
 #define LLAMAX_ERR_ARG (-1)  /* bad argument (shape / alignment / null) */
@@ -49,6 +49,12 @@ typedef struct {
    * of lora_h (whose rows then hold 3 * rank values); lora_b is the row-concatenation [N, rank] of the three B matrices.
    * seg_n0 = 0: one segment. seg_n0, seg_n1 must be multiples of 256 (the tile width). */
   int32_t seg_n0, seg_n1;
+  /* RoPE in the epilogue (llamax_int8_gemm_dequant only; modelling/llama.py:63-73 applied to the projection's bf16 output,
+   * bit-identical to llamax_rope_inplace on the stored result): rope fp32 [rope_S, 64, 2] (cos, sin), 32-byte aligned,
+   * head_dim 128; output columns [0, rope_cols) are rotated (rope_cols a multiple of 256: the q | k block of a q | k | v
+   * launch), position = row % rope_S. NULL = none. Not combinable with resid; LoRA rank 0 or 8. */
+  const void* rope;
+  int32_t rope_S, rope_cols;
 } llamax_epilogue_t;
 
 /* ---- K3: int8 x int8 -> int32 GEMM with row/column-scale dequant --------------------------------

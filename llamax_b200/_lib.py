@@ -31,6 +31,9 @@ class Epilogue(Structure):
         ("ldr", I64),
         ("seg_n0", I32),
         ("seg_n1", I32),
+        ("rope", P),
+        ("rope_S", I32),
+        ("rope_cols", I32),
     ]
 
 

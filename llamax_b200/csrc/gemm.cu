@@ -81,6 +81,10 @@ struct GemmParams {
   __nv_bfloat16* swi_g;         // optional g = bf16(silu(a)) * b, [M, N] contiguous
   int group;                    // tile-order group (set by the launcher, see tile_coords)
   // mixed-input variants (kMix): B arrives as int8 and is expanded to bf16 in shared memory
+  // kRope epilogue (INT8 q | k | v projection): RoPE applied to the bf16-rounded outputs of columns [0, rope_cols) before
+  // the store; rope fp32 [rope_S, 64, 2] (cos, sin), head_dim 128, position = row % rope_S
+  const float* rope;
+  int rope_S, rope_cols;
   const __nv_bfloat16* k_scale; // kMix == 2: per-contraction-index scale folded into the operand, bf16 [K1]
   int K1;                       // kMix == 2: contraction indices [0, K1) come from the int8 tensor (K1 % 64 == 0),
                                 // [K1, K) from the bf16 tail tensor (LoRA A rows)
@@ -199,11 +203,13 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 //              MN-major operand, bf16(f32(w) * f32(k_scale[k])) — bit-identical to llamax_dequant_weight(transpose,
 //              apply_scale) — followed by an optional bf16 tail tmT [K - K1, N] (the LoRA A rows) loaded by TMA
 //              straight into the B slot. Neither a transposed nor a de-quantised copy of the weight exists.
-template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false, int kMix = 0>
+template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false, int kMix = 0,
+          bool kRope = false>
 __global__ void __launch_bounds__(kMix ? kMixThreads : kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmT, const GemmParams p) {
   static_assert(kMix == 0 || (!kInt8 && CG == 2 && !kMN), "mixed-input variants: bf16 accumulate, CTA pairs");
+  static_assert(!kRope || (kRes && kInt8 && !kSwi && kMix == 0), "RoPE epilogue: a mode of the INT8 side-input (kRes) variant");
   using S = GemmSmem<CG, kMix>;
   constexpr int kStages = S::kStages;
   constexpr int kElemPerRow = kInt8 ? 128 : 64;  // K elements per 128 B
@@ -659,12 +665,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // (two epilogue warps per scheduler cannot hide a global-load latency by themselves); oda / odb / odg collect
       // the packed results of a group for one 32 B store each.
       uint32_t pa[2][8], pb[2][8], oda[8], odb[8], odg[8];
+      const unsigned rope_pos = kRope ? (unsigned)row % (unsigned)p.rope_S : 0u;
       auto swi_load = [&](int c16, uint32_t(&da)[8], uint32_t(&db)[8]) {   // c16: first of 16 columns
         if constexpr (kSwi) {
           if (row_ok && c16 < p.N) {
             const __nv_bfloat16* ap = p.swi_ab + (int64_t)row * p.ld_ab + c16;
             ldg_nc_32B(ap, da, swi_wide);
             ldg_nc_32B(ap + p.N, db, swi_wide);
+          }
+        } else if constexpr (kRope) {   // (cos, sin) of this row's position for the 8 pairs of 16 columns: 2 x 32 B
+          if (row_ok && c16 < p.rope_cols) {
+            const float* tp = p.rope + ((int64_t)rope_pos * 64 + ((c16 & 127) >> 1)) * 2;
+            ldg_nc_32B(tp, da, true);
+            ldg_nc_32B(tp + 8, db, true);
           }
         } else if constexpr (kRes) {   // residual row segment (N % 8 == 0: the last group may be half a group)
           if (row_ok && c16 < p.N) {
@@ -690,7 +703,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr bool kSide = kSwi || kRes || (kPipeStage && kRank > 0);   // pipelined side inputs need the registers
       constexpr int kVBufs = kSide ? 1 : 2;
       uint32_t v[kVBufs][32];
-      const bool rowdot = kRes && (p.flags & 4) != 0;
+      const bool rowdot = kRes && !kRope && (p.flags & 4) != 0;
       float dacc = 0.f;
       if constexpr (!kSide) {
         if (ch * 4 < n_chunks) tmem_ld_32x32(taddr + ch * 4 * 32, v[0]);
@@ -767,6 +780,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 stg_32B(dp, oda, swi_wide);
                 stg_32B(dp + p.N, odb, swi_wide);
                 if (p.swi_g != nullptr) stg_32B(p.swi_g + (int64_t)row * p.N + c16, odg, swi_wide);
+              }
+            } else if constexpr (kRope) {
+              if (j8 == 0) swi_load(col + 16, pa[1], pb[1]);
+              if (j8 == 16 && cc + 1 < n_chunks) swi_load(col + 32, pa[0], pb[0]);
+              if (row_ok && col + j8 < p.N) {
+                uint32_t o[4] = {pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])};
+                if (col + j8 < p.rope_cols) {
+                  // the linear's bf16 output, rotated pair by pair exactly like rope_kernel (separate products and
+                  // sum, each rounded: modelling/llama.py:63-73), rounded to bf16 again
+                  const uint32_t* t = (j8 & 8) ? pb[j8 >> 4] : pa[j8 >> 4];
+#pragma unroll
+                  for (int w = 0; w < 4; ++w) {
+                    const float x0 = bf16_lo(o[w]), x1 = bf16_hi(o[w]);
+                    const float cw = __uint_as_float(t[2 * w]), sw = __uint_as_float(t[2 * w + 1]);
+                    o[w] = pack_bf16(__fsub_rn(__fmul_rn(x0, cw), __fmul_rn(x1, sw)),
+                                     __fadd_rn(__fmul_rn(x1, cw), __fmul_rn(x0, sw)));
+                  }
+                }
+                stg_v4(dst + j8, make_uint4(o[0], o[1], o[2], o[3]));
               }
             } else if constexpr (kRes) {
               if (j8 == 0) swi_load(col + 16, pa[1], pb[1]);
@@ -857,7 +889,7 @@ static int* acquire_wave_sync(int points, cudaStream_t stream) {
   return slot;
 }
 
-template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false>
+template <bool kInt8, int CG, int kRank, bool kMN = false, bool kSwi = false, bool kRes = false, bool kRope = false>
 static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
   using S = GemmSmem<CG>;
@@ -892,7 +924,7 @@ static int launch_gemm_r(const void* A, int64_t lda, const void* B, int64_t ldb,
     if (rc) return rc;
   }
 
-  auto kern = gemm_kernel<kInt8, CG, kRank, kMN, kSwi, kRes>;
+  auto kern = gemm_kernel<kInt8, CG, kRank, kMN, kSwi, kRes, 0, kRope>;
   if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::kTotal, "gemm: cudaFuncSetAttribute"))) return rc;
   const int num_sms = sm_count();
   const int num_tiles = ((p.M + kBM * CG - 1) / (kBM * CG)) * ((p.N + kBN - 1) / kBN);
@@ -1002,6 +1034,20 @@ static int launch_gemm_mix(const void* A, int64_t lda, const void* B8, int64_t l
 template <bool kInt8, int CG>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
                        cudaStream_t stream) {
+  if constexpr (kInt8 && CG == 2) {
+    // q | k | v projection with RoPE in the epilogue (opt-in): the side-input pipeline of the residual variant reads the
+    // (cos, sin) table instead; no residual in this form
+    if (p.rope != nullptr) {
+      if (p.resid != nullptr || (p.flags & 1) || p.rope_S <= 0 || p.rope_cols <= 0 || p.rope_cols % kBN ||
+          p.rope_cols > p.N || reinterpret_cast<uintptr_t>(p.rope) % 32)
+        return set_error(LLAMAX_ERR_ARG, "gemm: RoPE epilogue needs no residual, rope_S > 0, rope_cols a multiple of 256 "
+                                         "within N and a 32-byte aligned table");
+      if (p.lora_rank <= 0) return launch_gemm_r<kInt8, CG, 0, false, false, true, true>(A, lda, B, ldb, p, stream);
+      if (p.lora_rank <= 8) return launch_gemm_r<kInt8, CG, 8, false, false, true, true>(A, lda, B, ldb, p, stream);
+      return set_error(LLAMAX_ERR_ARG, "gemm: RoPE epilogue supports LoRA rank 0 or 8");
+    }
+  }
+  if (p.rope != nullptr) return set_error(LLAMAX_ERR_ARG, "gemm: RoPE epilogue exists for the INT8 GEMM with CTA pairs only");
   if constexpr (kInt8) {
     // forward projections with the residual connection (wo, w2): pipelined residual reads; needs resid != C and a
     // 16-byte aligned residual (rows start on 16-byte boundaries when ldr % 8 == 0)
@@ -1733,6 +1779,9 @@ static void fill_epilogue(GemmParams& p, const llamax_epilogue_t* epi) {
   p.ldr = epi->ldr;
   p.seg_n0 = epi->lora_h ? epi->seg_n0 : 0;
   p.seg_n1 = epi->lora_h ? epi->seg_n1 : 0;
+  p.rope = static_cast<const float*>(epi->rope);
+  p.rope_S = epi->rope_S;
+  p.rope_cols = epi->rope_cols;
 }
 
 int llamax_int8_gemm_dequant(const void* A, int64_t lda, const void* B, int64_t ldb, const void* a_scale,

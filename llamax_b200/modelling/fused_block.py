@@ -100,6 +100,10 @@ def set_fuse_delta(on: bool) -> None:
     _FUSE_DELTA = bool(on)
 # A/B switch (benchmarking only): "0" restores three INT8 GEMM launches for wq, wk, wv
 _QKV_ONE_LAUNCH = os.environ.get("LLAMAX_QKV_ONE_LAUNCH", "1") != "0"
+# RoPE applied by the epilogue of the single q | k | v INT8 launch instead of the in-place pass over
+# q | k (bit-identical; removes 2.0 ms/step of HBM pass and adds its arithmetic and a 64 B table read per 16 outputs to an
+# epilogue that is the critical path at K = 4096: measured in DESIGN.md). head_dim 128, dynamic INT8, LoRA rank 0 or 8.
+_ROPE_EPILOGUE = os.environ.get("LLAMAX_ROPE_EPILOGUE", "0") == "1"
 
 
 def _qkv_mergeable(sq, sk, sv, nq: int, nk: int) -> bool:
@@ -484,6 +488,7 @@ class FusedDecoderBlock(torch.autograd.Function):
         h_qkv = _lora_down(xn1, (sq, sk, sv))
         nq, nk = Hq * D, Hkv * D
         qkv = torch.empty(M, nq + 2 * nk, device=x.device, dtype=torch.bfloat16)
+        rope_done = False
         if _QKV_ONE_LAUNCH and dyn_qkv and _qkv_mergeable(sq, sk, sv, nq, nk):
             # ONE INT8 GEMM over the row-concatenated [Wq; Wk; Wv] (a resident 25 MB int8 copy per layer at 8B): N = 6144
             # instead of 4096 + 1024 + 1024 — the two N = 1024 launches fill 3.5 waves of 74 CTA pairs and ran at 1870 TOP/s
@@ -494,6 +499,10 @@ class FusedDecoderBlock(torch.autograd.Function):
             if sq.R > 0:
                 ep = dict(lora_h=h_qkv, lora_b=torch.cat([sq.lora_b.detach(), sk.lora_b.detach(), sv.lora_b.detach()], 0),
                           lora_scale=sq.lora_scale, lora_seg=(nq, nq + nk))
+            if (_ROPE_EPILOGUE and D == 128 and sq.R in (0, 8) and (nq + nk) % 256 == 0 and rope.dtype is torch.float32
+                    and rope.is_contiguous() and rope.shape[0] >= S and rope.data_ptr() % 32 == 0):
+                ep["rope"] = (rope, S, nq + nk)
+                rope_done = True
             ops.int8_gemm_dequant(xq, w8cat, xs, scat, out=qkv, **ep)
         else:
             r_off = 0
@@ -501,7 +510,8 @@ class FusedDecoderBlock(torch.autograd.Function):
                 h = h_qkv[:, r_off : r_off + spec.R] if spec.R > 0 else None
                 r_off += spec.R
                 _linear(spec, xn1, xq, xs, h, out=qkv[:, c0:c1])
-        ops.rope_(qkv, rope, B, S, Hq + Hkv, D)
+        if not rope_done:
+            ops.rope_(qkv, rope, B, S, Hq + Hkv, D)
         o, lse = ops.attn_fwd(qkv[:, :nq], qkv[:, nq : nq + nk], qkv[:, nq + nk :], B, S, Hq, Hkv, D, prefix_len,
                               doc_start=doc_start)
         oq = osc = None

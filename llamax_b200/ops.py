@@ -89,10 +89,11 @@ def _rows(t: Tensor) -> Tensor:
     return t
 
 
-def make_epilogue(lora_h=None, lora_b=None, lora_scale=1.0, resid=None, lora_seg=None):
+def make_epilogue(lora_h=None, lora_b=None, lora_scale=1.0, resid=None, lora_seg=None, rope=None):
     """lora_seg = (n0, n1): three column segments [0, n0), [n0, n1), [n1, N) that use LoRA-h columns [0, R), [R, 2R),
-    [2R, 3R) (lora_h is [M, 3R], lora_b the row-concatenated [N, R]) — q | k | v in one launch."""
-    if lora_h is None and resid is None:
+    [2R, 3R) (lora_h is [M, 3R], lora_b the row-concatenated [N, R]) — q | k | v in one launch.
+    rope = (table fp32 [S, 64, 2], S, rope_cols): RoPE on output columns [0, rope_cols) in the INT8 GEMM's epilogue."""
+    if lora_h is None and resid is None and rope is None:
         return None, ()
     ep = Epilogue()
     keep = []
@@ -115,6 +116,11 @@ def make_epilogue(lora_h=None, lora_b=None, lora_scale=1.0, resid=None, lora_seg
         assert resid.dtype is torch.bfloat16
         ep.resid, ep.ldr = resid.data_ptr(), resid.stride(0)
         keep.append(resid)
+    if rope is not None:
+        table, S, cols = rope
+        assert table.dtype is torch.float32 and table.is_contiguous() and table.shape[0] >= S and table.shape[1:] == (64, 2)
+        ep.rope, ep.rope_S, ep.rope_cols = table.data_ptr(), int(S), int(cols)
+        keep.append(table)
     return ep, keep
 
 
@@ -124,8 +130,9 @@ def set_gemm_cta_group(cg: int):
 
 # ---------------------------------------------------------------------------------------------- GEMMs
 def int8_gemm_dequant(A: Tensor, W: Tensor, a_scale: Tensor, w_scale: Tensor, *, out: Tensor | None = None,
-                      lora_h=None, lora_b=None, lora_scale=1.0, resid=None, lora_seg=None) -> Tensor:
-    """C = dequant(A[M,K] @ W[N,K]^T) (+ LoRA + residual). A, W int8; scales bf16."""
+                      lora_h=None, lora_b=None, lora_scale=1.0, resid=None, lora_seg=None, rope=None) -> Tensor:
+    """C = dequant(A[M,K] @ W[N,K]^T) (+ LoRA + residual). A, W int8; scales bf16.
+    rope = (table, S, rope_cols): apply_rope on output columns [0, rope_cols) in the epilogue (head_dim 128)."""
     lib, st = _prep(A)
     assert A.dtype is torch.int8 and W.dtype is torch.int8 and A.dim() == 2 and W.dim() == 2
     assert A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] == W.shape[1]
@@ -138,7 +145,7 @@ def int8_gemm_dequant(A: Tensor, W: Tensor, a_scale: Tensor, w_scale: Tensor, *,
     if out is None:
         out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16)
     assert out.dtype is torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
-    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid, lora_seg)
+    ep, keep = make_epilogue(lora_h, lora_b, lora_scale, resid, lora_seg, rope)
     _call(lib, "llamax_int8_gemm_dequant",
           (_p(A), A.stride(0), _p(W), W.stride(0), _p(a_scale), _p(w_scale), _p(out), out.stride(0), M, N, K, ctypes.byref(ep) if ep is not None else None, st,),
           "int8_gemm", 2.0 * M * N * K, 0.0, shape=(M, N, K))

@@ -592,3 +592,31 @@ def test_grouped_lora_backward_equals_one_launch_per_adapter(dynamic, monkeypatc
     assert g1.keys() == g0.keys()
     for n in g1:
         assert g1[n].shape == g0[n].shape and rel_err(g1[n], g0[n]) <= 5e-3, n
+
+
+def test_rope_in_qkv_epilogue_changes_nothing(monkeypatch):
+    """fused_block._ROPE_EPILOGUE (opt-in): the block's output and gradients with RoPE applied by the q | k | v GEMM's
+    epilogue equal those with the separate in-place pass (head_dim 128: the 8B-shape attention at reduced width)."""
+    import llamax_b200.modelling.fused_block as FB
+    from llamax_b200.modelling import PrefixLM
+    from llamax_b200.modelling.llama import LlamaConfig
+
+    cfg = LlamaConfig(1024, 1, 128, 8, 2, 2048, max_seq_len=512, vocab_size=512, rope_base=500000, is_llama3_1=True)
+    results = []
+    for fused in (True, False):
+        monkeypatch.setattr(FB, "_ROPE_EPILOGUE", fused)
+        model = build_tiny_llama(True, num_layers=1, config=cfg).cuda()
+        layer = model.layers[0]
+        rope = R.build_rope(cfg.head_dim, cfg.max_seq_len, cfg.rope_base, cfg.is_llama3_1)[:384].contiguous().cuda()
+        torch.manual_seed(3)
+        x = torch.randn(2, 384, cfg.embed_dim, device="cuda").bfloat16().requires_grad_(True)
+        dout = torch.randn(2, 384, cfg.embed_dim, device="cuda").bfloat16()
+        out = layer(x, rope, block_mask=PrefixLM(100))
+        out.backward(dout)
+        results.append((out.detach(), x.grad.detach().clone(),
+                        [p.grad.detach().clone() for p in layer.parameters() if p.requires_grad]))
+    (o1, dx1, g1), (o0, dx0, g0) = results
+    assert torch.equal(o1, o0)
+    assert rel_err(dx1, dx0) <= 5e-3 and len(g1) == len(g0) > 10
+    for a, b in zip(g1, g0):
+        assert rel_err(a, b) <= 5e-3

@@ -28,16 +28,17 @@ def test_library_exports_every_declared_symbol():
         if name in _lib.SIGNATURES:
             assert len(_lib.SIGNATURES[name]) == len(args), f"{name}: binding has {len(_lib.SIGNATURES[name])} args, header {len(args)}"
     assert set(_lib.SIGNATURES) <= set(declared)
-    assert lib.llamax_version() == 101
+    assert lib.llamax_version() == 102
     assert isinstance(lib.llamax_last_error(), bytes)
 
 
 def test_epilogue_struct_layout_matches_header():
     e = _lib.Epilogue
     assert [f[0] for f in e._fields_] == ["lora_h", "ldh", "lora_b", "lora_rank", "lora_scale", "resid", "ldr", "seg_n0",
-                                          "seg_n1"]
-    assert ctypes.sizeof(e) == 56 and e.lora_rank.offset == 24 and e.lora_scale.offset == 28 and e.resid.offset == 32
+                                          "seg_n1", "rope", "rope_S", "rope_cols"]
+    assert ctypes.sizeof(e) == 72 and e.lora_rank.offset == 24 and e.lora_scale.offset == 28 and e.resid.offset == 32
     assert e.seg_n0.offset == 48 and e.seg_n1.offset == 52
+    assert e.rope.offset == 56 and e.rope_S.offset == 64 and e.rope_cols.offset == 68      # ABI version 102
 
 
 def test_copy_job_struct_layout_matches_header():

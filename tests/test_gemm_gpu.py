@@ -398,3 +398,32 @@ def test_attention_backward_with_given_delta_equals_internal():
                      B, S, Hq, Hkv, D, 100, delta=delta)
         outs.append(d)
     assert rel_err(outs[1], outs[0]) <= 2e-3
+
+
+@pytest.mark.parametrize("M,S,rank", [(512, 256, 8), (600, 200, 0), (2048, 2048, 8)])
+def test_int8_gemm_rope_epilogue_equals_separate_pass(M, S, rank):
+    """RoPE in the epilogue of the single q | k | v INT8 launch (llamax_epilogue_t.rope) gives the bits of the
+    GEMM followed by llamax_rope_inplace on its q | k columns (modelling/llama.py:63-73 on the projection's bf16 output);
+    the v columns are untouched. Ragged M (rows past the last full tile), positions wrapping every S rows."""
+    torch.manual_seed(M + rank)
+    K, Hq, Hkv, D = 512, 8, 2, 128
+    nq, nk = Hq * D, Hkv * D                       # 1024 + 256 | 256: rope_cols = 1280 = 5 tiles
+    N = nq + 2 * nk
+    A = torch.randint(-127, 128, (M, K), dtype=torch.int8, device="cuda")
+    W = torch.randint(-127, 128, (N, K), dtype=torch.int8, device="cuda")
+    a_s = (torch.rand(M, device="cuda") * 0.02 + 0.001).bfloat16()
+    w_s = (torch.rand(N, device="cuda") * 0.02 + 0.001).bfloat16()
+    rope = R.build_rope(D, 4096, 500000, True)[:S].contiguous().cuda()
+    kw = {}
+    if rank:
+        kw = dict(lora_h=torch.randn(M, 3 * rank, device="cuda").bfloat16(),
+                  lora_b=(torch.randn(N, rank, device="cuda") * 0.1).bfloat16(), lora_scale=2.0, lora_seg=(nq, nq + nk))
+    ref = ops.int8_gemm_dequant(A, W, a_s, w_s, **kw)
+    v_before = ref[:, nq + nk :].clone()
+    B = (M + S - 1) // S
+    pad = torch.zeros(B * S, N, dtype=torch.bfloat16, device="cuda")
+    pad[:M] = ref
+    ops.rope_(pad, rope, B, S, Hq + Hkv, D)         # the separate in-place pass over q | k
+    fused = ops.int8_gemm_dequant(A, W, a_s, w_s, rope=(rope, S, nq + nk), **kw)
+    assert torch.equal(fused[:, : nq + nk], pad[:M, : nq + nk])
+    assert torch.equal(fused[:, nq + nk :], v_before)
