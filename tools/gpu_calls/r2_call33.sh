@@ -1,5 +1,3 @@
-# re-entry check of HEAD (container re-created): suite, smoke, default bench line, reference arm
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/r2_bench_1gpu_reentry.json 2> gpurun_out/r2_bench_1gpu_reentry.err; echo "bench rc=$?"
-tail -c 600 gpurun_out/r2_bench_1gpu_reentry.json
+REPS=2 python tools/prof_rows.py > gpurun_out/plain_rows.log 2>&1 &&
+REPS=2 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base function -k regex:'row_wpr_kernel|rmsnorm_bwd_ring_kernel|swiglu_fwd_ring_kernel' -s 4 -c 4 -o gpurun_out/prof_rows python tools/prof_rows.py > gpurun_out/ncu_rows.log 2>&1
+echo "rc=$?"; tail -3 gpurun_out/ncu_rows.log; ls -la gpurun_out/prof_rows.ncu-rep

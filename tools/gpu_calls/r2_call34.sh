@@ -1,4 +1,5 @@
-# 2-GPU check of HEAD: NCCL DP parity test + the driver's torchrun launch of bench.py at N=2 (both arms)
-timeout 600 python -m pytest tests/test_dp_nccl_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 8 --warmup 3 > gpurun_out/r2_bench_2gpu_reentry.json 2> gpurun_out/r2_bench_2gpu_reentry.err; echo "bench2 rc=$?"
-tail -c 1500 gpurun_out/r2_bench_2gpu_reentry.json | head -c 1500
+timeout 600 python -m pytest tests/test_elementwise_gpu.py tests/test_block_gpu.py tests/test_gemm_gpu.py -m gpu -x -q 2>&1 | tail -5
+echo "== new defaults"; timeout 300 python tools/ew_sustained.py 12 | grep -E "copy|rmsnorm|rowquant|swiglu|rope|load"
+echo "== isolated"; timeout 300 python tools/ew_perf.py 2>/dev/null | head -8
+REPS=2 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base function -k regex:'row_wpr_kernel|rmsnorm_bwd_ring_kernel|swiglu_fwd_ring_kernel' -s 4 -c 4 -o gpurun_out/prof_rows2 python tools/prof_rows.py > gpurun_out/ncu_rows2.log 2>&1
+echo "rc=$?"
