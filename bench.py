@@ -393,6 +393,7 @@ def run_ours(args):
         pass
     steps = args.steps
     positions, n_label = main["positions"], main["n_label"]
+    assert head_wl != "text" or n_label == text_label_count(args)   # the reference arm states the same figure without a batch
     ms_step = main["ms"] / steps
     value = positions * world / (ms_step / 1e3)
     e2e_value = positions * world / (main["ms_e2e"] / steps / 1e3)
@@ -453,18 +454,10 @@ def run_ours(args):
         "warmup": warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8 fwd (int32 acc) / bf16 bwd" if not args.weight_only else "bf16 (int8 weights)",
         "data": "synthetic",
-        "config": {"workload": workload_label(args, head_wl, positions),
-                   "layers": args.layers, "global_batch": args.batch * world, "seq_len": main["seq"],
-                   "int8_mode": "weight-only" if args.weight_only else "dynamic_int8_act", "parallelism": f"dp{world}",
-                   **({"mixed_gemm": "opt-in: bf16 x int8 mixed-input GEMMs (weights expanded inside the GEMM)"}
-                      if args.mixed_gemm else {}),
-                   **({"NON_PARITY_OPT_IN": "int8 grad_input (gradients quantised to 8 bit per row): not the reference's "
-                                            "numerics, not a headline number"} if args.int8_grad_input else {}),
-                   "l2": "per-step working set (>10 GB activations + 7 GB weights) far exceeds the 126 MB L2; no flush needed",
-                   "positions_per_step": positions * world, "label_tokens_per_step": n_label * world,
-                   "lm_head_rows": "final norm / LM head / cross-entropy run on the %d labelled rows per GPU and step only "
-                                   "(rows with label -100 contribute exact zeros to loss and gradients; identical results, "
-                                   "LLAMAX_LM_COMPACT=0 computes all %d rows)" % (n_label, positions)},
+        "config": workload_config(args, world, head_wl, positions, n_label),
+        "lm_head_rows": "final norm / LM head / cross-entropy run on the %d labelled rows per GPU and step only "
+                        "(rows with label -100 contribute exact zeros to loss and gradients; identical results, "
+                        "LLAMAX_LM_COMPACT=0 computes all %d rows)" % (n_label, positions),
         "label_tokens_per_s": round(n_label * world / (ms_step / 1e3), 1),
         "loss": round(float(main["loss"]), 4),
         "clocks": main["clocks"],
@@ -515,6 +508,30 @@ def workload_label(args, workload, positions=None):
     return ("Llama-3.1-8B shape, frozen INT8 base + LoRA r=%d, %s, seq %d batch %d per GPU" %
             (args.rank, "MetaMathQA-shaped text SFT (causal)" if workload == "text"
              else "LibriSpeech-shaped 30 s audio prefix (1500) + 256 text, prefix-LM", seq, args.batch))
+
+
+def text_label_count(args):
+    """Labelled positions per GPU and step of the synthetic text batch (make_batch: the first quarter of every sequence
+    is prompt, the last position has no successor)."""
+    return args.batch * (args.seq - args.seq // 4 - 1)
+
+
+def workload_config(args, world, workload, positions, n_label):
+    """`config` of the JSON line: the workload only, identical for both arms (`--impl reference` times a bounded sample
+    of exactly this workload on the host cores; what its sample is goes into its `cpu_baseline.sample`). Notes about
+    how one arm computes the workload are top-level keys of that arm's line, not part of `config`."""
+    cfg = {"workload": workload_label(args, workload, positions),
+           "layers": args.layers, "global_batch": args.batch * world, "seq_len": positions // args.batch,
+           "int8_mode": "weight-only" if args.weight_only else "dynamic_int8_act", "parallelism": f"dp{world}"}
+    if args.mixed_gemm:
+        cfg["mixed_gemm"] = "opt-in: bf16 x int8 mixed-input GEMMs (weights expanded inside the GEMM)"
+    if args.int8_grad_input:
+        cfg["NON_PARITY_OPT_IN"] = ("int8 grad_input (gradients quantised to 8 bit per row): not the reference's "
+                                    "numerics, not a headline number")
+    cfg["l2"] = "per-step working set (>10 GB activations + 7 GB weights) far exceeds the 126 MB L2; no flush needed"
+    cfg["positions_per_step"] = positions * world
+    cfg["label_tokens_per_step"] = n_label * world
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------ reference (CPU)
@@ -630,11 +647,10 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * base["seconds_per_step"], 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16/int8 (CPU)",
            "data": "synthetic",
-           "config": {"workload": workload_label(args, "text"), "layers": args.layers, "global_batch": args.batch,
-                      "seq_len": args.seq,
-                      "int8_mode": "weight-only" if args.weight_only else "dynamic_int8_act", "parallelism": "cpu",
-                      "sample": "bounded: one sequence of %d positions per step through all %d blocks + head (of the "
-                                "%d x %d batch)" % (base["positions_per_step"], args.layers, args.batch, args.seq)},
+           "config": workload_config(args, max(1, args.gpus), "text", args.batch * args.seq, text_label_count(args)),
+           "reference_sample": "bounded: one sequence of %d positions per step through all %d blocks + head (of the "
+                               "%d x %d batch), host cores only" % (base["positions_per_step"], args.layers, args.batch,
+                                                                    args.seq),
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(wall, 1)}
