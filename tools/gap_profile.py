@@ -3,7 +3,8 @@
     ahead, the launch queue is never empty and only the hardware's kernel-to-kernel turnaround is left;
 (2) a CUPTI kernel trace of one step (torch.profiler): sum of the idle intervals between consecutive kernels, and the
     kernels after which the longest ones occur.
-Usage: python tools/gap_profile.py [layers]      (run under gpurun; prints a table)
+(3) device time per kernel name from the same trace (library and torch kernels included).
+Usage: python tools/gap_profile.py [layers] [text|speech]      (run under gpurun; prints tables)
 """
 import os
 import sys
@@ -21,17 +22,21 @@ import bench  # noqa: E402
 
 def main():
     layers = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    workload = sys.argv[2] if len(sys.argv) > 2 else "text"
     args = SimpleNamespace(layers=layers, weight_only=False, rank=8, batch=8, seq=2048)
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
-    model, cfg = bench.build_model(args, dev, "text")
+    model, cfg = bench.build_model(args, dev, workload)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.0, fused=True)
-    host, positions, _ = bench.make_batch(args, cfg, 0, "text")
+    host, positions, _ = bench.make_batch(args, cfg, 0, workload)
     batch = {k: v.to(dev) for k, v in host.items()}
 
     def step():
-        loss = model(batch["tokens"], labels=batch["labels"], block_mask=None)
+        if workload == "text":
+            loss = model(batch["tokens"], labels=batch["labels"], block_mask=None)
+        else:
+            loss = model(batch["audio"], batch["tokens"], labels=batch["labels"], prefix_lm=True)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -81,6 +86,14 @@ def main():
     print(f"kernels {len(evs)}   span {span / 1e3:.2f} ms   busy (sum of durations) {busy / 1e3:.2f} ms   "
           f"idle between kernels {total_gap / 1e3:.2f} ms  ({100 * total_gap / span:.2f} %)")
     print("gap histogram (us -> count):", dict(sorted(hist.items())))
+    by_name = defaultdict(lambda: [0, 0.0])
+    for e in evs:
+        d = by_name[e.name[:90]]
+        d[0] += 1
+        d[1] += e.time_range.end - e.time_range.start
+    print("device time per kernel name (top 40):")
+    for name, (n, tot) in sorted(by_name.items(), key=lambda kv: -kv[1][1])[:40]:
+        print(f"  {tot / 1e3:8.3f} ms  {100 * tot / busy:5.2f} %  n={n:5d}  {name}")
     print("largest idle totals by (previous kernel -> next kernel):")
     for (a, b), (n, tot, mx) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
         print(f"  {tot / 1e3:7.3f} ms  n={n:5d}  max {mx:7.1f} us   {a}  ->  {b}")
