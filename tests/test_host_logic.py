@@ -174,3 +174,25 @@ def test_dense_masks_and_block_masks_are_recognised():
         describe_dense_mask((idx[:, None] >= idx[None, :]) & (idx[:, None] - idx[None, :] < 8))
     with pytest.raises(NotImplementedError):
         describe_dense_mask(torch.ones(L, L))          # not boolean
+
+
+def test_bench_arms_share_one_config(monkeypatch):
+    """bench.py: the GPU arm and `--impl reference` describe the same workload with the same `config` dict (one builder);
+    the labelled-token count the reference arm states by formula equals the count of the synthetic batch."""
+    import os
+    import sys
+    from types import SimpleNamespace
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)   # no CUDA driver in the CPU suite
+    for batch, seq, gpus in ((8, 2048, 1), (8, 2048, 8), (2, 512, 2)):
+        a = SimpleNamespace(layers=32, batch=batch, seq=seq, weight_only=False, rank=8, mixed_gemm=False,
+                            int8_grad_input=False, gpus=gpus)
+        host, positions, n_label = bench.make_batch(a, SimpleNamespace(vocab_size=128256), 0, "text")
+        assert positions == batch * seq and n_label == bench.text_label_count(a)
+        ours = bench.workload_config(a, gpus, "text", positions, n_label)
+        ref = bench.workload_config(a, max(1, a.gpus), "text", a.batch * a.seq, bench.text_label_count(a))
+        assert ours == ref and ours["parallelism"] == f"dp{gpus}" and ours["global_batch"] == batch * gpus
+        assert "l2" in ours and ours["label_tokens_per_step"] == n_label * gpus
